@@ -1,0 +1,153 @@
+/*
+ * llmvox_b200 -- C ABI of the B200-native LLMVoX speech-synthesis hot path.
+ *
+ * One engine per GPU.  Plain pointers and sizes only (no torch types).  Every entry point returns an
+ * int status (LVX_OK == 0); lvx_last_error() gives the message of the last failure on the calling
+ * thread.  An engine is externally serialised (no internal locking) and re-entrant across engines.
+ * "h_" arguments are host pointers, "d_" arguments are device pointers on the engine's GPU, "stream" is
+ * a cudaStream_t passed as void* (NULL = the legacy default stream).  All work is enqueued on that
+ * stream; nothing in the decode / vocode entry points synchronises the host.
+ *
+ * The reference (sabbirhossainujjal/LLMVoX) has no FFI: its boundary is the Python object protocol of
+ * inference/model_handler.py:45-63 driven by streaming_server.py:250-426.  Each entry point below names
+ * the reference interface it replaces; llmvox_b200/model_handler.py is the host-side mirror that binds
+ * them with ctypes.
+ */
+#ifndef LLMVOX_B200_H
+#define LLMVOX_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LVX_OK 0
+#define LVX_ERR_INVALID 1   /* bad argument / unsupported configuration */
+#define LVX_ERR_CUDA 2      /* a CUDA runtime call failed */
+#define LVX_ERR_STATE 3     /* call order (weights not finalised, slot not open, ...) */
+#define LVX_ERR_CAPACITY 4  /* KV pages, context, workspace or slot capacity exceeded */
+
+#define LVX_PRECISION_FP32 0 /* fp32 weights, activations and KV cache; FMA-pipe GEMMs (parity mode)   */
+#define LVX_PRECISION_BF16 1 /* bf16 GEMM operands + KV cache, fp32 accumulate/residual; tcgen05 GEMMs */
+
+typedef struct lvx_engine lvx_engine;
+
+/* Architecture + capacity.  Fields mirror the reference's GPTConfig (src/model.py:135-146), the frame75
+ * WavTokenizer yaml (WavTokenizer/configs/...frame75...yaml:39-65) and configs/inference_config.py. */
+typedef struct lvx_config {
+  int32_t n_layer, n_head, n_embd, block_size, vocab_size, bias;       /* GPT: 4, 8, 768, 8192, 4096, 0 */
+  int32_t text_vocab, text_dim, code_dim, n_codes;                     /* 386, 256, 512, 4096            */
+  int32_t voc_dim, voc_inter, voc_layers, voc_ada_rows, n_fft, hop;    /* 768, 2304, 12, 4, 1280, 320    */
+  int32_t max_sessions;     /* session slots resident on this GPU                                      */
+  int32_t max_context;      /* decode steps (= KV tokens) a slot may hold, <= block_size               */
+  int32_t kv_page_tokens;   /* tokens per KV page (16)                                                 */
+  int32_t kv_pages;         /* pages in the pool; 0 = max_sessions * ceil(max_context / page_tokens)   */
+  int32_t max_batch;        /* sessions stepped by one lvx_decode_steps call                           */
+  int32_t max_vocode_frames;/* codes one lvx_vocode launch group may carry (workspace sizing)          */
+  int32_t precision;        /* LVX_PRECISION_*                                                         */
+  int32_t pad_token_id;     /* 384: text id fed once a session's text is exhausted (:316-320)          */
+  int32_t eoa_token_id;     /* 453                                                                     */
+} lvx_config;
+
+/* Sampler.  greedy != 0 (or top_k == 1): argmax with lowest-index tie break = the hot loop's
+ * softmax->argmax (streaming_server.py:342-346).  Otherwise the semantics of GPT.generate
+ * (src/model.py:397-406): logits / temperature; keep entries >= the top_k-th largest (ties kept,
+ * top_k <= 0 disables); softmax; one draw by inverse CDF in index order against a uniform from
+ * Philox4x32-10(seed; slot, step) -- or d_uniform[i] for session i of the call when non-NULL. */
+typedef struct lvx_sampling {
+  int32_t greedy;
+  int32_t top_k;
+  float temperature;
+  uint64_t seed;
+  const float* d_uniform;
+} lvx_sampling;
+
+const char* lvx_last_error(void);
+int lvx_version(void);
+
+/* Fills *cfg with the english-tiny / frame75 architecture and default capacities. */
+int lvx_config_default(lvx_config* cfg);
+
+/* Replaces ModelHandler.__init__ (inference/model_handler.py:48-63): allocates weights, KV pool, session
+ * state and workspaces on `device`. */
+int lvx_engine_create(const lvx_config* cfg, int device, lvx_engine** out);
+int lvx_engine_destroy(lvx_engine* e);
+
+/* Weight upload, one tensor at a time, fp32 host data, using the reference's state-dict key names
+ * (e.g. "transformer.h.0.attn.c_attn.weight", "backbone.convnext.3.pwconv1.weight",
+ * "feature_extractor.encodec.quantizer.vq.layers.0._codebook.embed", "head.istft.window") plus
+ * "text_table" for T5 encoder.embed_tokens (model_handler.py:105).  Replaces load_state_dict at
+ * model_handler.py:163 and WavTokenizer/decoder/pretrained.py:113.  Unknown names are an error; keys of
+ * the unused SEANet encoder/decoder must be filtered by the caller. */
+int lvx_load_tensor(lvx_engine* e, const char* name, const float* h_data, const int64_t* shape, int ndim);
+/* Checks every tensor arrived, builds derived tensors (tap-major conv weights, fused q|k|v, windowed iDFT
+ * basis, bf16 copies).  Must precede any compute call. */
+int lvx_finalize_weights(lvx_engine* e);
+
+/* Session slots.  open == the per-sentence state reset of streaming_server.py:268-282 / :404-416
+ * (kvcache = None, speech_gen_index = 0): context 0, no text, KV pages released. */
+int lvx_session_open(lvx_engine* e, const int32_t* h_slots, int n, void* stream);
+int lvx_session_close(lvx_engine* e, const int32_t* h_slots, int n, void* stream);
+
+/* Appends text ids to sessions: ids of session i are h_ids[h_offsets[i] .. h_offsets[i+1]).  Replaces the
+ * per-word tokenizer -> tensor -> .to(device) -> llm_model(ids) of streaming_server.py:306-315 (the
+ * embedding gather itself happens inside the decode step). */
+int lvx_feed_text(lvx_engine* e, const int32_t* h_slots, const int32_t* h_offsets, const int32_t* h_ids,
+                  int n, void* stream);
+
+/* n_steps decode steps for n sessions, batched: the loop body of streaming_server.py:323-354 (input
+ * assembly a4, GPT.forward a5-a8 with a paged KV cache, pick a9) with no host sync per token.  Step t of a
+ * session consumes text id t (pad_token_id beyond its text), the previous code's codebook row (zeros at
+ * t = 0) and position t; the new code is appended to the session's device-side code history. */
+int lvx_decode_steps(lvx_engine* e, const int32_t* h_slots, int n, int n_steps, const lvx_sampling* s,
+                     void* stream);
+
+/* Test hook: ONE step that also returns the logits (n x vocab fp32, device) and the picked codes (n,
+ * device, may be NULL).  With d_forced_codes != NULL the code stored in the history (and therefore fed
+ * back at the next step) is d_forced_codes[i] instead of the pick: teacher forcing. */
+int lvx_decode_step_logits(lvx_engine* e, const int32_t* h_slots, int n, const lvx_sampling* s,
+                           const int32_t* d_forced_codes, float* d_logits, int32_t* d_codes, void* stream);
+
+/* Drop-in for `model(emb, kvcache)` (streaming_server.py:341 -> src/model.py:201-237): the caller supplies
+ * the assembled, normalised input row of each session (n x n_embd fp32, device) and its position (the
+ * reference's T-1); returns logits (n x vocab fp32, device) and appends K/V.  No code is recorded. */
+int lvx_decode_step_embeds(lvx_engine* e, const int32_t* h_slots, int n, const float* d_emb,
+                           const int32_t* h_positions, float* d_logits, void* stream);
+
+/* Copies codes [start, start+count) of each session's history to d_out (n x count int32, device). */
+int lvx_gather_codes(lvx_engine* e, const int32_t* h_slots, int n, int start, int count, int32_t* d_out,
+                     void* stream);
+/* Host mirror of a slot's context length (codes decoded so far). */
+int lvx_session_length(lvx_engine* e, int slot, int32_t* out_len);
+
+/* Replaces wavtokenizer.codes_to_features(codes) (pretrained.py:209-239): n codes -> n x code_dim fp32
+ * rows (channels-last; the reference returns the transpose (1, 512, n)). */
+int lvx_codes_to_features(lvx_engine* e, const int32_t* d_codes, int n, float* d_out, void* stream);
+/* Replaces llm_model(ids) (model_handler.py:105): n ids -> n x text_dim fp32 rows. */
+int lvx_text_embed(lvx_engine* e, const int32_t* d_ids, int n, float* d_out, void* stream);
+
+/* Replaces codes_to_features + wavtokenizer.decode(features, bandwidth_id) (streaming_server.py:363-365 ->
+ * pretrained.py:192-207 -> models.py:223-235, heads.py:53-66, spectral_ops.py:33-75) for a ragged batch of
+ * INDEPENDENT chunks: chunk i holds codes d_codes[h_cu[i] .. h_cu[i+1]) and yields hop * len_i samples at
+ * d_pcm[hop * h_cu[i]].  Conv padding, GroupNorm statistics, the pos_net attention and the iSTFT edge
+ * envelope are per chunk, exactly as a separate reference call per chunk. */
+int lvx_vocode(lvx_engine* e, const int32_t* d_codes, const int32_t* h_cu, int n_chunks, int bandwidth_id,
+               float* d_pcm, void* stream);
+
+/* Test hook: runs lvx_vocode's pipeline up to `stage` for ONE chunk and copies that activation
+ * (len x width fp32, channels-last) to d_out.  Stages: 0 embed conv, 1 pos_net[0], 2 pos_net[0..2] (after
+ * attention), 3 pos_net output (after final GroupNorm), 4 backbone output (after final LayerNorm),
+ * 5 windowed iDFT frames (len x n_fft). */
+int lvx_vocode_stage(lvx_engine* e, const int32_t* d_codes, int len, int bandwidth_id, int stage,
+                     float* d_out, void* stream);
+
+/* Counters for bench.py's "gpu_launches": kernels launched by this engine since creation. */
+int64_t lvx_kernel_launches(const lvx_engine* e);
+/* Bytes of device memory the engine allocated. */
+int64_t lvx_device_bytes(const lvx_engine* e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LLMVOX_B200_H */

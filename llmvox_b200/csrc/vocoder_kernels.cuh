@@ -1,0 +1,286 @@
+// WavTokenizer-decoder kernels other than the GEMMs (a3, a11-a13).  Activations are channels-last
+// (rows = frames, 768 contiguous channels) in a PADDED RAGGED layout: chunk i owns rows
+// [row0_i, row0_i + L_i); ROW_PAD zero rows precede the first chunk and follow every chunk, so the k=3 / k=7
+// convolutions (as multi-tap GEMMs) read zeros at chunk edges exactly like the reference's per-chunk
+// zero padding.  row_chunk[r] = chunk index of row r, or -1 for a padding row.
+#pragma once
+#include "common.cuh"
+
+namespace lvx {
+
+constexpr int ROW_PAD = 3;
+
+struct ChunkInfo {
+  int row0;  // first row of the chunk in the padded layout
+  int len;   // frames
+  int out0;  // first frame in the packed (unpadded) order == h_cu[i]
+  int s_off; // element offset of this chunk's L x Lp score matrix
+};
+
+// ---------------------------------------------------------------------------------------------------
+// GroupNorm statistics (WavTokenizer/decoder/models.py:15-16: 32 groups, eps 1e-6): mean / rstd over
+// (C/32 channels x L frames) per (chunk, group).  One CTA per (group, chunk); two passes.
+// ---------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) groupnorm_stats_kernel(const float* __restrict__ x,
+                                                              const ChunkInfo* __restrict__ chunks, float eps,
+                                                              float2* __restrict__ stats) {
+  constexpr int G = 32, CPG = C / G, V = CPG / 4;
+  __shared__ float red[32];
+  const int g = blockIdx.x, ch = blockIdx.y;
+  const ChunkInfo ci = chunks[ch];
+  const int items = ci.len * V;
+  const float* base = x + (size_t)ci.row0 * C + g * CPG;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < items; i += 256) {
+    const float4 v = load4(base + (size_t)(i / V) * C + (i % V) * 4);
+    s += (v.x + v.y) + (v.z + v.w);
+  }
+  const float n = (float)(ci.len * CPG);
+  const float mean = block_sum(s, red) / n;
+  float q = 0.f;
+  for (int i = threadIdx.x; i < items; i += 256) {
+    const float4 v = load4(base + (size_t)(i / V) * C + (i % V) * 4);
+    const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float var = block_sum(q, red) / n;
+  if (threadIdx.x == 0) stats[(size_t)ch * G + g] = make_float2(mean, 1.0f / sqrtf(var + eps));
+}
+
+// GroupNorm apply (+ optional swish, models.py:10-12) -> GEMM operand type.  One thread per float4.
+template <typename TOut, int C>
+__global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float* __restrict__ x, int rows,
+                                                              const int* __restrict__ row_chunk,
+                                                              const float2* __restrict__ stats,
+                                                              const float* __restrict__ w, const float* __restrict__ b,
+                                                              int swish, TOut* __restrict__ out) {
+  constexpr int G = 32, CPG = C / G;
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  const int row = (int)(i / (C / 4)), c = (int)(i % (C / 4)) * 4;
+  if (row >= rows) return;
+  const int ch = row_chunk[row];
+  if (ch < 0) return;
+  const float2 st = stats[(size_t)ch * G + c / CPG];
+  const float4 v = load4(x + (size_t)row * C + c), ww = load4(w + c), bb = load4(b + c);
+  float r[4] = {(v.x - st.x) * st.y * ww.x + bb.x, (v.y - st.x) * st.y * ww.y + bb.y,
+                (v.z - st.x) * st.y * ww.z + bb.z, (v.w - st.x) * st.y * ww.w + bb.w};
+  if (swish) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r[k] = r[k] / (1.0f + expf(-r[k]));
+  }
+  store4(out + (size_t)row * C + c, make_float4(r[0], r[1], r[2], r[3]));
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pos_net tail + backbone.norm (models.py:213,226-228): GroupNorm apply (affine) then AdaLayerNorm
+// (LN eps 1e-6 no affine, * scale[bw] + shift[bw]; modules.py:81-86) -> new fp32 residual stream.
+// One warp per row.
+// ---------------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(256) groupnorm_adaln_kernel(const float* __restrict__ x, int rows,
+                                                              const int* __restrict__ row_chunk,
+                                                              const float2* __restrict__ stats,
+                                                              const float* __restrict__ gw, const float* __restrict__ gb,
+                                                              const float* __restrict__ scale,
+                                                              const float* __restrict__ shift, float eps,
+                                                              float* __restrict__ out_gn, float* __restrict__ out) {
+  constexpr int G = 32, CPG = C / G, V = C / 128;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int ch = row_chunk[row];
+  if (ch < 0) return;
+  float4 v[V];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    const float2 st = stats[(size_t)ch * G + c / CPG];
+    const float4 a = load4(x + (size_t)row * C + c), ww = load4(gw + c), bb = load4(gb + c);
+    v[i] = make_float4((a.x - st.x) * st.y * ww.x + bb.x, (a.y - st.x) * st.y * ww.y + bb.y,
+                       (a.z - st.x) * st.y * ww.z + bb.z, (a.w - st.x) * st.y * ww.w + bb.w);
+    if (out_gn) store4(out_gn + (size_t)row * C + c, v[i]);
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(s) * (1.0f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += a * a + b * b + c * c + d * d;
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / C) + eps);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    const float4 sc = load4(scale + c), sh = load4(shift + c);
+    store4(out + (size_t)row * C + c,
+           make_float4((v[i].x - mean) * rstd * sc.x + sh.x, (v[i].y - mean) * rstd * sc.y + sh.y,
+                       (v[i].z - mean) * rstd * sc.z + sh.z, (v[i].w - mean) * rstd * sc.w + sh.w));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ConvNeXt front half (modules.py:45-51): depthwise Conv1d k=7 pad 3 (zero padding at CHUNK edges) +
+// bias, then AdaLayerNorm.  One warp per frame; the 7 neighbour rows come through L1/L2.
+// dw weights are stored tap-major [7][C].
+// ---------------------------------------------------------------------------------------------------
+template <typename TOut, int C>
+__global__ void __launch_bounds__(256) dwconv_adaln_kernel(const float* __restrict__ x, int rows,
+                                                           const int* __restrict__ row_chunk,
+                                                           const ChunkInfo* __restrict__ chunks,
+                                                           const float* __restrict__ dw_w, const float* __restrict__ dw_b,
+                                                           const float* __restrict__ scale,
+                                                           const float* __restrict__ shift, float eps,
+                                                           TOut* __restrict__ out) {
+  constexpr int V = C / 128;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int ch = row_chunk[row];
+  if (ch < 0) return;
+  const ChunkInfo ci = chunks[ch];
+  float4 v[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) v[i] = load4(dw_b + (lane + 32 * i) * 4);
+#pragma unroll
+  for (int t = 0; t < 7; ++t) {
+    const int r = row + t - 3;
+    if (r < ci.row0 || r >= ci.row0 + ci.len) continue;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const int c = (lane + 32 * i) * 4;
+      const float4 a = load4(x + (size_t)r * C + c), w = load4(dw_w + t * C + c);
+      v[i].x = fmaf(a.x, w.x, v[i].x);
+      v[i].y = fmaf(a.y, w.y, v[i].y);
+      v[i].z = fmaf(a.z, w.z, v[i].z);
+      v[i].w = fmaf(a.w, w.w, v[i].w);
+    }
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) s += v[i].x + v[i].y + v[i].z + v[i].w;
+  const float mean = warp_sum(s) * (1.0f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += a * a + b * b + c * c + d * d;
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) * (1.0f / C) + eps);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    const float4 sc = load4(scale + c), sh = load4(shift + c);
+    store4(out + (size_t)row * C + c,
+           make_float4((v[i].x - mean) * rstd * sc.x + sh.x, (v[i].y - mean) * rstd * sc.y + sh.y,
+                       (v[i].z - mean) * rstd * sc.z + sh.z, (v[i].w - mean) * rstd * sc.w + sh.w));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Row softmax of the pos_net attention scores (models.py:117-118; the C^-0.5 scale is the GEMM's alpha).
+// Scores of chunk i: L x Lp fp32 at s_off (Lp = L rounded up to 4; pad columns are written as zeros so the
+// P.V GEMM may read them).  One warp per row.  Output type = GEMM operand type, in place for fp32.
+// ---------------------------------------------------------------------------------------------------
+template <typename TOut>
+__global__ void __launch_bounds__(256) attn_softmax_kernel(const float* __restrict__ S, TOut* __restrict__ P,
+                                                           const ChunkInfo* __restrict__ chunks,
+                                                           const int* __restrict__ row_chunk, int rows) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const int ch = row_chunk[row];
+  if (ch < 0) return;
+  const ChunkInfo ci = chunks[ch];
+  const int L = ci.len, Lp = (L + 3) & ~3;
+  const size_t off = (size_t)ci.s_off + (size_t)(row - ci.row0) * Lp;
+  const float* s = S + off;
+  float mx = -INFINITY;
+  for (int j = lane; j < L; j += 32) mx = fmaxf(mx, s[j]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < L; j += 32) sum += expf(s[j] - mx);
+  sum = warp_sum(sum);
+  const float inv = 1.0f / sum;
+  TOut* p = P + off;
+  for (int j = lane; j < Lp; j += 32) store1(p + j, j < L ? expf(s[j] - mx) * inv : 0.f);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ISTFT head activation (heads.py:54-65): columns [0,641) = log-magnitude, [641,1282) = phase ->
+// S = min(exp(m), 100) * (cos p, sin p), written as the iDFT GEMM's A operand
+// [re_0..re_640 | im_0..im_640 | zero pad to ldo].
+// ---------------------------------------------------------------------------------------------------
+template <typename TOut>
+__global__ void __launch_bounds__(256) head_activation_kernel(const float* __restrict__ raw, int ld_raw, int rows,
+                                                              const int* __restrict__ row_chunk, int bins,
+                                                              TOut* __restrict__ out, int ldo) {
+  const int row = blockIdx.y;
+  if (row >= rows || row_chunk[row] < 0) return;
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= ldo) return;
+  const float* r = raw + (size_t)row * ld_raw;
+  float v = 0.f;
+  if (j < 2 * bins) {
+    const int k = j < bins ? j : j - bins;
+    const float mag = fminf(expf(r[k]), 100.0f);
+    const float ph = r[bins + k];
+    v = mag * (j < bins ? cosf(ph) : sinf(ph));
+  }
+  store1(out + (size_t)row * ldo + j, v);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Overlap-add + "same" trim + window-envelope normalisation (spectral_ops.py:59-73).  frames[r, n] already
+// carries the Hann window (folded into the iDFT basis).  Output sample t of a chunk sits at padded position
+// p = t + (n_fft - hop) / 2 and sums frames i with i*hop <= p < i*hop + n_fft, 0 <= i < L; the envelope is
+// the same sum over window^2.  One thread per output sample.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) overlap_add_kernel(const float* __restrict__ frames, int ldf,
+                                                          const ChunkInfo* __restrict__ chunks,
+                                                          const float* __restrict__ window, int n_fft, int hop,
+                                                          float* __restrict__ pcm) {
+  const ChunkInfo ci = chunks[blockIdx.y];
+  const int t = blockIdx.x * 256 + threadIdx.x;
+  if (t >= ci.len * hop) return;
+  const int p = t + (n_fft - hop) / 2;
+  int i_lo = (p - n_fft + hop) / hop;  // ceil((p - n_fft + 1) / hop) for p - n_fft + 1 > 0
+  if (p - n_fft + 1 <= 0) i_lo = 0;
+  int i_hi = p / hop;
+  if (i_hi > ci.len - 1) i_hi = ci.len - 1;
+  float y = 0.f, env = 0.f;
+  for (int i = i_lo; i <= i_hi; ++i) {
+    const int n = p - i * hop;
+    const float w = window[n];
+    y += frames[(size_t)(ci.row0 + i) * ldf + n];
+    env += w * w;
+  }
+  pcm[(size_t)ci.out0 * hop + t] = y / env;
+}
+
+__global__ void build_row_chunk_kernel(const ChunkInfo* __restrict__ chunks, int n_chunks, int* __restrict__ row_chunk,
+                                       int* __restrict__ code_rows) {
+  const ChunkInfo ci = chunks[blockIdx.x];
+  for (int j = threadIdx.x; j < ci.len; j += blockDim.x) {
+    row_chunk[ci.row0 + j] = blockIdx.x;
+    code_rows[ci.out0 + j] = ci.row0 + j;
+  }
+}
+
+// copy valid rows of a padded activation to packed order (test hook)
+__global__ void unpad_rows_kernel(const float* __restrict__ src, int ld, int width, const int* __restrict__ code_rows,
+                                  int n, float* __restrict__ dst) {
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  const float* s = src + (size_t)code_rows[i] * ld;
+  for (int c = threadIdx.x; c < width; c += blockDim.x) dst[(size_t)i * width + c] = s[c];
+}
+template <typename T>
+__global__ void unpad_rows_typed_kernel(const T* __restrict__ src, int ld, int width, const int* __restrict__ code_rows,
+                                        int n, float* __restrict__ dst) {
+  const int i = blockIdx.x;
+  if (i >= n) return;
+  const T* s = src + (size_t)code_rows[i] * ld;
+  for (int c = threadIdx.x; c < width; c += blockDim.x) dst[(size_t)i * width + c] = load1(s + c);
+}
+
+}  // namespace lvx

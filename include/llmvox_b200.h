@@ -118,6 +118,11 @@ int lvx_decode_step_embeds(lvx_engine* e, const int32_t* h_slots, int n, const f
 /* Copies codes [start, start+count) of each session's history to d_out (n x count int32, device). */
 int lvx_gather_codes(lvx_engine* e, const int32_t* h_slots, int n, int start, int count, int32_t* d_out,
                      void* stream);
+/* Ragged form: codes [h_starts[i], h_starts[i] + h_counts[i]) of session i, packed back to back in d_out
+ * (sum of counts int32, device) -- the chunk cut `speech_outputs[:dump_size]` of streaming_server.py:359-360
+ * for many sessions at once. */
+int lvx_gather_code_ranges(lvx_engine* e, const int32_t* h_slots, const int32_t* h_starts, const int32_t* h_counts,
+                           int n, int32_t* d_out, void* stream);
 /* Host mirror of a slot's context length (codes decoded so far). */
 int lvx_session_length(lvx_engine* e, int slot, int32_t* out_len);
 
@@ -135,12 +140,25 @@ int lvx_text_embed(lvx_engine* e, const int32_t* d_ids, int n, float* d_out, voi
 int lvx_vocode(lvx_engine* e, const int32_t* d_codes, const int32_t* h_cu, int n_chunks, int bandwidth_id,
                float* d_pcm, void* stream);
 
+/* Same, from features: replaces wavtokenizer.decode(features, bandwidth_id) alone (pretrained.py:192-207) for
+ * callers that already hold codes_to_features' output.  d_feats is channels-last: row h_cu[i] + t = frame t of
+ * chunk i, code_dim fp32 values (the reference tensor is (1, code_dim, L); the host mirror transposes). */
+int lvx_vocode_features(lvx_engine* e, const float* d_feats, const int32_t* h_cu, int n_chunks, int bandwidth_id,
+                        float* d_pcm, void* stream);
+
 /* Test hook: runs lvx_vocode's pipeline up to `stage` for ONE chunk and copies that activation
  * (len x width fp32, channels-last) to d_out.  Stages: 0 embed conv, 1 pos_net[0], 2 pos_net[0..2] (after
  * attention), 3 pos_net output (after final GroupNorm), 4 backbone output (after final LayerNorm),
  * 5 windowed iDFT frames (len x n_fft). */
 int lvx_vocode_stage(lvx_engine* e, const int32_t* d_codes, int len, int bandwidth_id, int stage,
                      float* d_out, void* stream);
+
+/* Test hook: C (M x N fp32) = A (a_rows x tap_K fp32, row-major) . W (N x K fp32, row-major)^T through the
+ * engine's own GEMM path for its precision (FMA-pipe fp32, or tcgen05 with operands rounded to bf16).  With
+ * taps > 1 (K = taps * tap_K) column k = tap * tap_K + c of row m reads A[m + tap - taps / 2, c], rows outside
+ * [0, M) reading as zero: the conv-as-GEMM form of the vocoder's k = 3 / k = 7 convolutions. */
+int lvx_test_gemm(lvx_engine* e, const float* d_A, const float* d_W, int M, int N, int K, int taps, float* d_C,
+                  void* stream);
 
 /* Counters for bench.py's "gpu_launches": kernels launched by this engine since creation. */
 int64_t lvx_kernel_launches(const lvx_engine* e);

@@ -1,0 +1,49 @@
+"""Builds the CUDA engine (C-ABI shared library) in-tree for sm_100a with nvcc."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libllmvox_b200.so")
+SOURCES = ["engine.cu"]
+HEADERS = ["common.cuh", "decode_kernels.cuh", "gemm.cuh", "tc_gemm.cuh", "vocoder_kernels.cuh",
+           os.path.join("..", "..", "include", "llmvox_b200.h")]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: llmvox_b200 has no CPU fallback and needs the CUDA toolkit to build")
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
+    return any(os.path.exists(d) and os.path.getmtime(d) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """nvcc -gencode arch=compute_100a,code=sm_100a ... -> llmvox_b200/libllmvox_b200.so"""
+    if not force and not needs_build():
+        return LIB
+    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+           "-Xcompiler", "-fPIC", "-shared", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force=True, verbose=True))

@@ -1,0 +1,1292 @@
+// llmvox_b200 engine: the C ABI of include/llmvox_b200.h on top of the kernels in this directory.
+//
+// One engine per GPU.  Host code here only sequences kernels on the caller's stream; the decode /
+// vocode entry points never synchronise the host.  The reference interfaces each entry point replaces are
+// cited in the header.
+#include "../../include/llmvox_b200.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "decode_kernels.cuh"
+#include "gemm.cuh"
+#include "tc_gemm.cuh"
+#include "vocoder_kernels.cuh"
+
+namespace lvx {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& msg) { g_last_error = msg; }
+
+enum DT { F32 = 0, B16 = 1 };
+static inline size_t dt_size(DT t) { return t == F32 ? 4 : 2; }
+
+struct Tensor {
+  std::vector<int64_t> shape;
+  size_t n = 0;
+  float* d = nullptr;
+  bool loaded = false;
+};
+
+// A GEMM weight in the (N, K) row-major layout the kernels read, in both storage types.
+struct GemmW {
+  float* f32 = nullptr;
+  bf16* b16 = nullptr;
+  int N = 0, K = 0, ld = 0;
+  TmaDesc tma;  // bf16 mode: tensor map of the (N, K) matrix
+};
+
+__global__ void cast_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16_rn(in[i]);
+}
+// conv weight (O, C, T) -> tap-major GEMM weight (O, T*C): out[o][t*C + c] = in[o][c][t]
+__global__ void conv_to_tapmajor_kernel(const float* __restrict__ in, float* __restrict__ out, int O, int C, int T) {
+  const size_t n = (size_t)O * C * T;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int t = (int)((i / C) % T);
+    const int o = (int)(i / ((size_t)C * T));
+    out[i] = in[((size_t)o * C + c) * T + t];
+  }
+}
+// depthwise weight (C, 1, 7) -> (7, C)
+__global__ void dw_to_tapmajor_kernel(const float* __restrict__ in, float* __restrict__ out, int C, int T) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C * T) out[(i % T) * C + i / T] = in[i];
+}
+__global__ void set_ctx_kernel(const int* __restrict__ slots, const int* __restrict__ pos, int n, SessionState st) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) st.ctx_len[slots[i]] = pos[i] + 1;
+}
+// page-table patch list: (slot, index, page) triples
+__global__ void patch_pages_kernel(const int* __restrict__ upd, int n, SessionState st) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) st.page_table[(size_t)upd[3 * i] * st.max_pages + upd[3 * i + 1]] = upd[3 * i + 2];
+}
+// padded codebook gather: row r of the padded layout <- codebook[codes[out0 + r - row0]] or zeros
+template <typename TOut>
+__global__ void gather_codebook_padded_kernel(const int* __restrict__ codes, const float* __restrict__ codebook,
+                                              int width, int n_codes, const int* __restrict__ row_chunk,
+                                              const ChunkInfo* __restrict__ chunks, TOut* __restrict__ out) {
+  const int r = blockIdx.x, ch = row_chunk[r];
+  TOut* o = out + (size_t)r * width;
+  if (ch < 0) {
+    for (int c = threadIdx.x * 4; c < width; c += blockDim.x * 4) store4(o + c, make_float4(0.f, 0.f, 0.f, 0.f));
+    return;
+  }
+  const ChunkInfo ci = chunks[ch];
+  int code = codes[ci.out0 + (r - ci.row0)];
+  code = min(max(code, 0), n_codes - 1);
+  const float* src = codebook + (size_t)code * width;
+  for (int c = threadIdx.x * 4; c < width; c += blockDim.x * 4) store4(o + c, load4(src + c));
+}
+// padded feature copy: row r <- feats[out0 + r - row0] (packed, channels-last fp32) or zeros
+template <typename TOut>
+__global__ void copy_feats_padded_kernel(const float* __restrict__ feats, int width, const int* __restrict__ row_chunk,
+                                         const ChunkInfo* __restrict__ chunks, TOut* __restrict__ out) {
+  const int r = blockIdx.x, ch = row_chunk[r];
+  TOut* o = out + (size_t)r * width;
+  if (ch < 0) {
+    for (int c = threadIdx.x * 4; c < width; c += blockDim.x * 4) store4(o + c, make_float4(0.f, 0.f, 0.f, 0.f));
+    return;
+  }
+  const ChunkInfo ci = chunks[ch];
+  const float* src = feats + (size_t)(ci.out0 + (r - ci.row0)) * width;
+  for (int c = threadIdx.x * 4; c < width; c += blockDim.x * 4) store4(o + c, load4(src + c));
+}
+__global__ void gather_code_ranges_kernel(const int* __restrict__ slots, const int* __restrict__ starts,
+                                          const int* __restrict__ offs, SessionState st, int* __restrict__ out) {
+  const int b = blockIdx.x, slot = slots[b];
+  const int cnt = offs[b + 1] - offs[b];
+  for (int j = threadIdx.x; j < cnt; j += blockDim.x)
+    out[offs[b] + j] = st.codes[(size_t)slot * st.max_context + starts[b] + j];
+}
+// LayerNorm output split into bf16 hi / lo / hi thirds of a (rows, 3C) operand ("bf16x3" along K)
+template <int C>
+__global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x, int rows, int width, int ld_in,
+                                                     bf16* __restrict__ out, int seg, int ld_out) {
+  // out[r, 0:seg) = hi, [seg, 2seg) = lo, [2seg, 3seg) = hi; columns >= width are zero
+  const int r = blockIdx.y;
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (r >= rows || j >= seg) return;
+  float v = j < width ? x[(size_t)r * ld_in + j] : 0.f;
+  const bf16 hi = __float2bfloat16_rn(v);
+  const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+  bf16* o = out + (size_t)r * ld_out;
+  o[j] = hi;
+  o[seg + j] = lo;
+  o[2 * seg + j] = hi;
+}
+
+}  // namespace lvx
+
+using namespace lvx;
+
+struct lvx_engine {
+  lvx_config cfg;
+  int device = 0;
+  bool finalized = false;
+  int64_t launches = 0;
+  int64_t bytes = 0;
+  std::vector<void*> allocs;
+  std::map<std::string, Tensor> w;
+
+  // ---- GPT derived
+  struct Layer {
+    float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
+    GemmW attn, proj, fc, proj2;
+    float *attn_b, *proj_b, *fc_b, *proj2_b;
+  };
+  std::vector<Layer> layers;
+  float *lnf_w = nullptr, *lnf_b = nullptr;
+  GemmW lm_head;
+  // ---- vocoder derived
+  struct Res {
+    float *n1w, *n1b, *n2w, *n2b, *c1b, *c2b;
+    GemmW c1, c2;
+  };
+  struct CNX {
+    float *dw_w, *dw_b, *scale, *shift, *b1, *b2, *gamma;
+    GemmW pw1, pw2;
+  };
+  GemmW embed;
+  float* embed_b = nullptr;
+  Res res[4];
+  float *at_nw = nullptr, *at_nb = nullptr, *at_qkv_b = nullptr, *at_proj_b = nullptr;
+  GemmW at_qkv, at_proj;
+  float *pn5_w = nullptr, *pn5_b = nullptr, *norm_scale = nullptr, *norm_shift = nullptr;
+  std::vector<CNX> cnx;
+  float *fln_w = nullptr, *fln_b = nullptr, *head_b = nullptr, *window = nullptr;
+  GemmW head, idft;
+  int spec_ld = 0, raw_ld = 0;
+
+  // ---- sessions
+  SessionState st{};
+  void* kv = nullptr;
+  long long pool_pages = 0;
+  int max_pages = 0;
+  std::vector<int> h_len, h_text_len, h_open, h_npages, free_pages, stamp;
+  std::vector<std::vector<int>> h_pages;
+  int stamp_ctr = 0;
+  int *d_slots = nullptr, *d_aux = nullptr, *d_ids = nullptr, *d_upd = nullptr;
+  // ---- decode workspace
+  int Bp = 0;
+  float *x = nullptr, *qkv = nullptr, *logits = nullptr;
+  void *h = nullptr, *y = nullptr, *g = nullptr;
+  // ---- vocoder workspace
+  int R_max = 0;
+  long long score_cap = 0;
+  ChunkInfo* d_chunks = nullptr;
+  GemmProblem *d_prob_s = nullptr, *d_prob_pv = nullptr;
+  int *row_chunk = nullptr, *code_rows = nullptr;
+  int max_chunks = 0;
+  void *v_feats = nullptr, *v_h = nullptr, *v_big = nullptr, *v_spec = nullptr, *v_P = nullptr, *v_h3 = nullptr;
+  float *v_x = nullptr, *v_t = nullptr, *v_raw = nullptr, *v_frames = nullptr, *v_S = nullptr;
+  float2* v_stats = nullptr;
+  TcWorkspace tcw;
+
+  DT adt() const { return cfg.precision == LVX_PRECISION_BF16 ? B16 : F32; }
+};
+
+#define LAUNCHED(e)                                                                                  \
+  do {                                                                                               \
+    (e)->launches++;                                                                                 \
+    cudaError_t _le = cudaGetLastError();                                                            \
+    if (_le != cudaSuccess) {                                                                        \
+      lvx::set_error(std::string("kernel launch: ") + cudaGetErrorString(_le) + " (" + __FILE__ + ":" + \
+                     std::to_string(__LINE__) + ")");                                                \
+      return LVX_ERR_CUDA;                                                                           \
+    }                                                                                                \
+  } while (0)
+
+template <typename T>
+static int dev_alloc(lvx_engine* e, T** p, size_t count) {
+  void* q = nullptr;
+  size_t bytes = std::max<size_t>(count * sizeof(T), 256);
+  LVX_CUDA(cudaMalloc(&q, bytes));
+  LVX_CUDA(cudaMemset(q, 0, bytes));
+  e->allocs.push_back(q);
+  e->bytes += (int64_t)bytes;
+  *p = reinterpret_cast<T*>(q);
+  return LVX_OK;
+}
+static int dev_alloc_bytes(lvx_engine* e, void** p, size_t bytes) {
+  unsigned char* q = nullptr;
+  LVX_TRY(dev_alloc<unsigned char>(e, &q, bytes));
+  *p = q;
+  return LVX_OK;
+}
+
+static void expect(lvx_engine* e, const std::string& name, std::vector<int64_t> shape) {
+  Tensor t;
+  t.shape = shape;
+  t.n = 1;
+  for (auto s : shape) t.n *= (size_t)s;
+  e->w[name] = t;
+}
+
+static void declare_tensors(lvx_engine* e) {
+  const lvx_config& c = e->cfg;
+  const int64_t C = c.n_embd, D = c.voc_dim, I = c.voc_inter;
+  expect(e, "text_table", {c.text_vocab, c.text_dim});
+  expect(e, "transformer.wpe.weight", {c.block_size, C});
+  for (int i = 0; i < c.n_layer; ++i) {
+    const std::string p = "transformer.h." + std::to_string(i) + ".";
+    expect(e, p + "ln_1.weight", {C});
+    expect(e, p + "attn.c_attn.weight", {3 * C, C});
+    expect(e, p + "attn.c_proj.weight", {C, C});
+    expect(e, p + "ln_2.weight", {C});
+    expect(e, p + "mlp.c_fc.weight", {4 * C, C});
+    expect(e, p + "mlp.c_proj.weight", {C, 4 * C});
+    if (c.bias) {
+      expect(e, p + "ln_1.bias", {C});
+      expect(e, p + "ln_2.bias", {C});
+      expect(e, p + "attn.c_attn.bias", {3 * C});
+      expect(e, p + "attn.c_proj.bias", {C});
+      expect(e, p + "mlp.c_fc.bias", {4 * C});
+      expect(e, p + "mlp.c_proj.bias", {C});
+    }
+  }
+  expect(e, "transformer.ln_f.weight", {C});
+  if (c.bias) expect(e, "transformer.ln_f.bias", {C});
+  expect(e, "lm_head.weight", {c.vocab_size, C});
+  expect(e, "feature_extractor.encodec.quantizer.vq.layers.0._codebook.embed", {c.n_codes, c.code_dim});
+  expect(e, "backbone.embed.weight", {D, c.code_dim, 7});
+  expect(e, "backbone.embed.bias", {D});
+  for (int i : {0, 1, 3, 4}) {
+    const std::string p = "backbone.pos_net." + std::to_string(i) + ".";
+    for (const char* n : {"1", "2"}) {
+      expect(e, p + "norm" + n + ".weight", {D});
+      expect(e, p + "norm" + n + ".bias", {D});
+      expect(e, p + "conv" + n + ".weight", {D, D, 3});
+      expect(e, p + "conv" + n + ".bias", {D});
+    }
+  }
+  expect(e, "backbone.pos_net.2.norm.weight", {D});
+  expect(e, "backbone.pos_net.2.norm.bias", {D});
+  for (const char* n : {"q", "k", "v", "proj_out"}) {
+    expect(e, std::string("backbone.pos_net.2.") + n + ".weight", {D, D, 1});
+    expect(e, std::string("backbone.pos_net.2.") + n + ".bias", {D});
+  }
+  expect(e, "backbone.pos_net.5.weight", {D});
+  expect(e, "backbone.pos_net.5.bias", {D});
+  expect(e, "backbone.norm.scale.weight", {c.voc_ada_rows, D});
+  expect(e, "backbone.norm.shift.weight", {c.voc_ada_rows, D});
+  for (int i = 0; i < c.voc_layers; ++i) {
+    const std::string p = "backbone.convnext." + std::to_string(i) + ".";
+    expect(e, p + "dwconv.weight", {D, 1, 7});
+    expect(e, p + "dwconv.bias", {D});
+    expect(e, p + "norm.scale.weight", {c.voc_ada_rows, D});
+    expect(e, p + "norm.shift.weight", {c.voc_ada_rows, D});
+    expect(e, p + "pwconv1.weight", {I, D});
+    expect(e, p + "pwconv1.bias", {I});
+    expect(e, p + "pwconv2.weight", {D, I});
+    expect(e, p + "pwconv2.bias", {D});
+    expect(e, p + "gamma", {D});
+  }
+  expect(e, "backbone.final_layer_norm.weight", {D});
+  expect(e, "backbone.final_layer_norm.bias", {D});
+  expect(e, "head.out.weight", {c.n_fft + 2, D});
+  expect(e, "head.out.bias", {c.n_fft + 2});
+  expect(e, "head.istft.window", {c.n_fft});
+}
+
+extern "C" const char* lvx_last_error(void) { return g_last_error.c_str(); }
+extern "C" int lvx_version(void) { return 100; }
+
+extern "C" int lvx_config_default(lvx_config* cfg) {
+  LVX_CHECK(cfg != nullptr, LVX_ERR_INVALID, "cfg is NULL");
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->n_layer = 4; cfg->n_head = 8; cfg->n_embd = 768; cfg->block_size = 8192; cfg->vocab_size = 4096; cfg->bias = 0;
+  cfg->text_vocab = 386; cfg->text_dim = 256; cfg->code_dim = 512; cfg->n_codes = 4096;
+  cfg->voc_dim = 768; cfg->voc_inter = 2304; cfg->voc_layers = 12; cfg->voc_ada_rows = 4; cfg->n_fft = 1280; cfg->hop = 320;
+  cfg->max_sessions = 256;
+  cfg->max_context = 1024;
+  cfg->kv_page_tokens = 16;
+  cfg->kv_pages = 0;
+  cfg->max_batch = 256;
+  cfg->max_vocode_frames = 32768;
+  cfg->precision = LVX_PRECISION_FP32;
+  cfg->pad_token_id = 384;
+  cfg->eoa_token_id = 453;
+  return LVX_OK;
+}
+
+static int engine_alloc(lvx_engine* e) {
+  const lvx_config& c = e->cfg;
+  const int S = c.max_sessions, B = c.max_batch, C = c.n_embd;
+  const DT a = e->adt();
+  // sessions
+  e->max_pages = ceil_div(c.max_context, c.kv_page_tokens);
+  e->pool_pages = c.kv_pages > 0 ? c.kv_pages : (long long)S * e->max_pages;
+  e->st.max_context = c.max_context;
+  e->st.max_pages = e->max_pages;
+  LVX_TRY(dev_alloc(e, &e->st.ctx_len, S));
+  LVX_TRY(dev_alloc(e, &e->st.text_len, S));
+  LVX_TRY(dev_alloc(e, &e->st.text_ids, (size_t)S * c.max_context));
+  LVX_TRY(dev_alloc(e, &e->st.codes, (size_t)S * c.max_context));
+  LVX_TRY(dev_alloc(e, &e->st.page_table, (size_t)S * e->max_pages));
+  const size_t kv_elems = (size_t)c.n_layer * 2 * e->pool_pages * c.kv_page_tokens * C;
+  LVX_TRY(dev_alloc_bytes(e, &e->kv, kv_elems * dt_size(a)));
+  e->h_len.assign(S, 0);
+  e->h_text_len.assign(S, 0);
+  e->h_open.assign(S, 0);
+  e->stamp.assign(S, 0);
+  e->h_pages.assign(S, {});
+  e->free_pages.resize(e->pool_pages);
+  for (long long i = 0; i < e->pool_pages; ++i) e->free_pages[i] = (int)(e->pool_pages - 1 - i);
+  LVX_TRY(dev_alloc(e, &e->d_slots, B));
+  LVX_TRY(dev_alloc(e, &e->d_aux, 2 * B + 2));
+  LVX_TRY(dev_alloc(e, &e->d_ids, (size_t)B * c.max_context));
+  LVX_TRY(dev_alloc(e, &e->d_upd, (size_t)3 * B * e->max_pages));
+  // decode workspace (rows padded to the tensor-core tile so TMA boxes stay in bounds)
+  const int Bp = ceil_div(B, 128) * 128;
+  e->Bp = Bp;
+  LVX_TRY(dev_alloc(e, &e->x, (size_t)Bp * C));
+  LVX_TRY(dev_alloc(e, &e->qkv, (size_t)Bp * 3 * C));
+  LVX_TRY(dev_alloc(e, &e->logits, (size_t)Bp * c.vocab_size));
+  LVX_TRY(dev_alloc_bytes(e, &e->h, (size_t)Bp * C * dt_size(a)));
+  LVX_TRY(dev_alloc_bytes(e, &e->y, (size_t)Bp * C * dt_size(a)));
+  LVX_TRY(dev_alloc_bytes(e, &e->g, (size_t)Bp * 4 * C * dt_size(a)));
+  // vocoder workspace
+  const int D = c.voc_dim, I = c.voc_inter;
+  e->R_max = ceil_div(c.max_vocode_frames + 2 * ROW_PAD, 128) * 128 + 128;
+  e->max_chunks = c.max_vocode_frames;
+  e->raw_ld = (c.n_fft + 2 + 3) & ~3;
+  e->spec_ld = ceil_div(c.n_fft + 2, 64) * 64;
+  e->score_cap = (long long)c.max_vocode_frames * 1280;
+  const size_t R = e->R_max;
+  LVX_TRY(dev_alloc(e, &e->d_chunks, e->max_chunks));
+  LVX_TRY(dev_alloc(e, &e->d_prob_s, e->max_chunks));
+  LVX_TRY(dev_alloc(e, &e->d_prob_pv, e->max_chunks));
+  LVX_TRY(dev_alloc(e, &e->row_chunk, R));
+  LVX_TRY(dev_alloc(e, &e->code_rows, R));
+  LVX_TRY(dev_alloc_bytes(e, &e->v_feats, R * c.code_dim * dt_size(a)));
+  LVX_TRY(dev_alloc(e, &e->v_x, R * D));
+  LVX_TRY(dev_alloc(e, &e->v_t, R * D));
+  LVX_TRY(dev_alloc_bytes(e, &e->v_h, R * D * dt_size(a)));
+  LVX_TRY(dev_alloc_bytes(e, &e->v_big, R * std::max<size_t>((size_t)std::max(I, 3 * D) * dt_size(a), (size_t)e->spec_ld * 4)));
+  LVX_TRY(dev_alloc(e, &e->v_raw, R * e->raw_ld));
+  LVX_TRY(dev_alloc(e, &e->v_frames, R * c.n_fft));
+  LVX_TRY(dev_alloc(e, &e->v_S, (size_t)e->score_cap));
+  LVX_TRY(dev_alloc_bytes(e, &e->v_P, (size_t)e->score_cap * dt_size(a)));
+  LVX_TRY(dev_alloc(e, &e->v_stats, (size_t)e->max_chunks * 32));
+  if (a == B16) {
+    LVX_TRY(dev_alloc_bytes(e, &e->v_spec, R * 3 * e->spec_ld * sizeof(bf16)));
+    LVX_TRY(dev_alloc_bytes(e, &e->v_h3, R * 3 * D * sizeof(bf16)));
+  } else {
+    LVX_TRY(dev_alloc_bytes(e, &e->v_spec, R * e->spec_ld * sizeof(float)));
+  }
+  return LVX_OK;
+}
+
+extern "C" int lvx_engine_create(const lvx_config* cfg, int device, lvx_engine** out) {
+  LVX_CHECK(cfg && out, LVX_ERR_INVALID, "cfg / out is NULL");
+  const lvx_config& c = *cfg;
+  LVX_CHECK(c.n_embd == 768 && c.voc_dim == 768, LVX_ERR_INVALID,
+            "kernels are specialised for n_embd == voc_dim == 768 (english-tiny / frame75)");
+  LVX_CHECK(c.n_head > 0 && c.n_embd % c.n_head == 0 && c.n_embd / c.n_head == 96, LVX_ERR_INVALID,
+            "kernels are specialised for head_dim 96");
+  LVX_CHECK(c.text_dim + c.code_dim == c.n_embd && c.text_dim % 4 == 0, LVX_ERR_INVALID, "text_dim + code_dim != n_embd");
+  LVX_CHECK(c.vocab_size > 0 && c.vocab_size <= 4096 && c.vocab_size % 4 == 0, LVX_ERR_INVALID, "vocab_size must be <= 4096");
+  LVX_CHECK(c.n_fft == 4 * c.hop && c.n_fft % 64 == 0, LVX_ERR_INVALID, "iSTFT kernels need n_fft == 4 * hop");
+  LVX_CHECK(c.max_sessions > 0 && c.max_batch > 0 && c.max_batch <= c.max_sessions, LVX_ERR_INVALID, "bad session capacity");
+  LVX_CHECK(c.max_context > 0 && c.max_context <= c.block_size, LVX_ERR_INVALID, "max_context must be <= block_size");
+  LVX_CHECK(c.kv_page_tokens > 0 && c.max_vocode_frames > 0, LVX_ERR_INVALID, "bad capacity");
+  LVX_CHECK(c.voc_inter % 64 == 0 && c.code_dim % 64 == 0, LVX_ERR_INVALID, "voc_inter / code_dim must be multiples of 64");
+  LVX_CHECK(c.precision == LVX_PRECISION_FP32 || c.precision == LVX_PRECISION_BF16, LVX_ERR_INVALID, "bad precision");
+  int ndev = 0;
+  LVX_CUDA(cudaGetDeviceCount(&ndev));
+  LVX_CHECK(device >= 0 && device < ndev, LVX_ERR_INVALID, "no such CUDA device");
+  LVX_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  LVX_CUDA(cudaGetDeviceProperties(&prop, device));
+  LVX_CHECK(prop.major == 10, LVX_ERR_INVALID,
+            std::string("llmvox_b200 is built for sm_100a only; device is sm_") + std::to_string(prop.major) +
+                std::to_string(prop.minor));
+  lvx_engine* e = new lvx_engine();
+  e->cfg = c;
+  e->device = device;
+  declare_tensors(e);
+  int s = engine_alloc(e);
+  if (s == LVX_OK && c.precision == LVX_PRECISION_BF16) s = tc_init(&e->tcw, prop.multiProcessorCount);
+  if (s != LVX_OK) {
+    lvx_engine_destroy(e);
+    return s;
+  }
+  *out = e;
+  return LVX_OK;
+}
+
+extern "C" int lvx_engine_destroy(lvx_engine* e) {
+  if (!e) return LVX_OK;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  for (void* p : e->allocs) cudaFree(p);
+  for (auto& kv : e->w)
+    if (kv.second.d) cudaFree(kv.second.d);
+  delete e;
+  return LVX_OK;
+}
+
+extern "C" int lvx_load_tensor(lvx_engine* e, const char* name, const float* h_data, const int64_t* shape, int ndim) {
+  LVX_CHECK(e && name && h_data && shape, LVX_ERR_INVALID, "NULL argument");
+  LVX_CHECK(!e->finalized, LVX_ERR_STATE, "weights already finalised");
+  auto it = e->w.find(name);
+  LVX_CHECK(it != e->w.end(), LVX_ERR_INVALID, std::string("unknown tensor name: ") + name);
+  Tensor& t = it->second;
+  bool ok = (int)t.shape.size() == ndim;
+  for (int i = 0; ok && i < ndim; ++i) ok = t.shape[i] == shape[i];
+  // the position table may be shorter than block_size (only max_context rows are ever read)
+  if (!ok && it->first == "transformer.wpe.weight" && ndim == 2 && shape[1] == t.shape[1] && shape[0] >= e->cfg.max_context &&
+      shape[0] <= t.shape[0]) {
+    t.shape[0] = shape[0];
+    t.n = (size_t)shape[0] * shape[1];
+    ok = true;
+  }
+  LVX_CHECK(ok, LVX_ERR_INVALID, std::string("shape mismatch for ") + name);
+  LVX_CUDA(cudaSetDevice(e->device));
+  if (!t.d) {
+    LVX_CUDA(cudaMalloc(&t.d, std::max<size_t>(t.n * sizeof(float), 256)));
+    e->bytes += (int64_t)(t.n * sizeof(float));
+  }
+  LVX_CUDA(cudaMemcpy(t.d, h_data, t.n * sizeof(float), cudaMemcpyHostToDevice));
+  t.loaded = true;
+  return LVX_OK;
+}
+
+static float* W(lvx_engine* e, const std::string& name) {
+  auto it = e->w.find(name);
+  return it == e->w.end() ? nullptr : it->second.d;
+}
+
+// Registers an (N, K) fp32 matrix as a GEMM weight; bf16 mode adds the bf16 copy and its tensor map.
+static int make_gemm_w(lvx_engine* e, GemmW* g, float* f32, int N, int K, int ld) {
+  g->f32 = f32;
+  g->N = N;
+  g->K = K;
+  g->ld = ld;
+  if (e->adt() == B16) {
+    const size_t n = (size_t)N * ld;
+    LVX_TRY(dev_alloc(e, &g->b16, n));
+    cast_bf16_kernel<<<std::min<size_t>(4096, (n + 255) / 256), 256>>>(f32, g->b16, n);
+    LAUNCHED(e);
+    LVX_TRY(tc_make_desc(&g->tma, g->b16, N, K, ld));
+  }
+  return LVX_OK;
+}
+
+static int make_conv_w(lvx_engine* e, GemmW* g, const std::string& name, int O, int Cin, int T) {
+  float* dst = nullptr;
+  LVX_TRY(dev_alloc(e, &dst, (size_t)O * Cin * T));
+  const size_t n = (size_t)O * Cin * T;
+  conv_to_tapmajor_kernel<<<std::min<size_t>(4096, (n + 255) / 256), 256>>>(W(e, name), dst, O, Cin, T);
+  LAUNCHED(e);
+  return make_gemm_w(e, g, dst, O, Cin * T, Cin * T);
+}
+
+extern "C" int lvx_finalize_weights(lvx_engine* e) {
+  LVX_CHECK(e, LVX_ERR_INVALID, "engine is NULL");
+  LVX_CHECK(!e->finalized, LVX_ERR_STATE, "weights already finalised");
+  for (auto& kv : e->w) LVX_CHECK(kv.second.loaded, LVX_ERR_STATE, std::string("tensor not loaded: ") + kv.first);
+  LVX_CUDA(cudaSetDevice(e->device));
+  const lvx_config& c = e->cfg;
+  const int C = c.n_embd, D = c.voc_dim, I = c.voc_inter;
+  e->layers.resize(c.n_layer);
+  for (int i = 0; i < c.n_layer; ++i) {
+    const std::string p = "transformer.h." + std::to_string(i) + ".";
+    auto& L = e->layers[i];
+    L.ln1_w = W(e, p + "ln_1.weight");
+    L.ln2_w = W(e, p + "ln_2.weight");
+    L.ln1_b = W(e, p + "ln_1.bias");
+    L.ln2_b = W(e, p + "ln_2.bias");
+    L.attn_b = W(e, p + "attn.c_attn.bias");
+    L.proj_b = W(e, p + "attn.c_proj.bias");
+    L.fc_b = W(e, p + "mlp.c_fc.bias");
+    L.proj2_b = W(e, p + "mlp.c_proj.bias");
+    LVX_TRY(make_gemm_w(e, &L.attn, W(e, p + "attn.c_attn.weight"), 3 * C, C, C));
+    LVX_TRY(make_gemm_w(e, &L.proj, W(e, p + "attn.c_proj.weight"), C, C, C));
+    LVX_TRY(make_gemm_w(e, &L.fc, W(e, p + "mlp.c_fc.weight"), 4 * C, C, C));
+    LVX_TRY(make_gemm_w(e, &L.proj2, W(e, p + "mlp.c_proj.weight"), C, 4 * C, 4 * C));
+  }
+  e->lnf_w = W(e, "transformer.ln_f.weight");
+  e->lnf_b = W(e, "transformer.ln_f.bias");
+  LVX_TRY(make_gemm_w(e, &e->lm_head, W(e, "lm_head.weight"), c.vocab_size, C, C));
+
+  // vocoder
+  LVX_TRY(make_conv_w(e, &e->embed, "backbone.embed.weight", D, c.code_dim, 7));
+  e->embed_b = W(e, "backbone.embed.bias");
+  const int ridx[4] = {0, 1, 3, 4};
+  for (int r = 0; r < 4; ++r) {
+    const std::string p = "backbone.pos_net." + std::to_string(ridx[r]) + ".";
+    auto& R = e->res[r];
+    R.n1w = W(e, p + "norm1.weight"); R.n1b = W(e, p + "norm1.bias");
+    R.n2w = W(e, p + "norm2.weight"); R.n2b = W(e, p + "norm2.bias");
+    R.c1b = W(e, p + "conv1.bias");   R.c2b = W(e, p + "conv2.bias");
+    LVX_TRY(make_conv_w(e, &R.c1, p + "conv1.weight", D, D, 3));
+    LVX_TRY(make_conv_w(e, &R.c2, p + "conv2.weight", D, D, 3));
+  }
+  {
+    const std::string p = "backbone.pos_net.2.";
+    e->at_nw = W(e, p + "norm.weight");
+    e->at_nb = W(e, p + "norm.bias");
+    float *wq = nullptr, *bq = nullptr;
+    LVX_TRY(dev_alloc(e, &wq, (size_t)3 * D * D));
+    LVX_TRY(dev_alloc(e, &bq, (size_t)3 * D));
+    const char* names[3] = {"q", "k", "v"};
+    for (int j = 0; j < 3; ++j) {
+      LVX_CUDA(cudaMemcpy(wq + (size_t)j * D * D, W(e, p + names[j] + ".weight"), (size_t)D * D * sizeof(float),
+                          cudaMemcpyDeviceToDevice));
+      LVX_CUDA(cudaMemcpy(bq + (size_t)j * D, W(e, p + names[j] + ".bias"), (size_t)D * sizeof(float),
+                          cudaMemcpyDeviceToDevice));
+    }
+    e->at_qkv_b = bq;
+    LVX_TRY(make_gemm_w(e, &e->at_qkv, wq, 3 * D, D, D));
+    LVX_TRY(make_gemm_w(e, &e->at_proj, W(e, p + "proj_out.weight"), D, D, D));
+    e->at_proj_b = W(e, p + "proj_out.bias");
+  }
+  e->pn5_w = W(e, "backbone.pos_net.5.weight");
+  e->pn5_b = W(e, "backbone.pos_net.5.bias");
+  e->norm_scale = W(e, "backbone.norm.scale.weight");
+  e->norm_shift = W(e, "backbone.norm.shift.weight");
+  e->cnx.resize(c.voc_layers);
+  for (int i = 0; i < c.voc_layers; ++i) {
+    const std::string p = "backbone.convnext." + std::to_string(i) + ".";
+    auto& X = e->cnx[i];
+    LVX_TRY(dev_alloc(e, &X.dw_w, (size_t)7 * D));
+    dw_to_tapmajor_kernel<<<ceil_div(7 * D, 256), 256>>>(W(e, p + "dwconv.weight"), X.dw_w, D, 7);
+    LAUNCHED(e);
+    X.dw_b = W(e, p + "dwconv.bias");
+    X.scale = W(e, p + "norm.scale.weight");
+    X.shift = W(e, p + "norm.shift.weight");
+    X.b1 = W(e, p + "pwconv1.bias");
+    X.b2 = W(e, p + "pwconv2.bias");
+    X.gamma = W(e, p + "gamma");
+    LVX_TRY(make_gemm_w(e, &X.pw1, W(e, p + "pwconv1.weight"), I, D, D));
+    LVX_TRY(make_gemm_w(e, &X.pw2, W(e, p + "pwconv2.weight"), D, I, I));
+  }
+  e->fln_w = W(e, "backbone.final_layer_norm.weight");
+  e->fln_b = W(e, "backbone.final_layer_norm.bias");
+  e->head_b = W(e, "head.out.bias");
+  e->window = W(e, "head.istft.window");
+  const int NF = c.n_fft, bins = NF / 2 + 1;
+  // windowed inverse real DFT basis (spectral_ops.py:56-57): frame[n] = w[n]/N * sum_k c_k (Re_k cos - Im_k sin),
+  // c_0 = c_{N/2} = 1 else 2; irfft ignores Im of the DC and Nyquist bins.
+  std::vector<float> hw(NF);
+  LVX_CUDA(cudaMemcpy(hw.data(), e->window, NF * sizeof(float), cudaMemcpyDeviceToHost));
+  if (e->adt() == F32) {
+    LVX_TRY(make_gemm_w(e, &e->head, W(e, "head.out.weight"), NF + 2, D, D));
+    std::vector<float> basis((size_t)NF * e->spec_ld, 0.f);
+    for (int n = 0; n < NF; ++n)
+      for (int k = 0; k < bins; ++k) {
+        const double ang = 2.0 * M_PI * (double)(((long long)k * n) % NF) / NF;
+        const double ck = (k == 0 || k == NF / 2) ? 1.0 : 2.0;
+        basis[(size_t)n * e->spec_ld + k] = (float)(hw[n] * ck * cos(ang) / NF);
+        basis[(size_t)n * e->spec_ld + bins + k] = (k == 0 || k == NF / 2) ? 0.f : (float)(-hw[n] * 2.0 * sin(ang) / NF);
+      }
+    float* db = nullptr;
+    LVX_TRY(dev_alloc(e, &db, basis.size()));
+    LVX_CUDA(cudaMemcpy(db, basis.data(), basis.size() * sizeof(float), cudaMemcpyHostToDevice));
+    LVX_TRY(make_gemm_w(e, &e->idft, db, NF, 2 * bins, e->spec_ld));
+  } else {
+    // bf16 mode keeps the head Linear and the iDFT at ~fp32 accuracy with three bf16 products laid side by
+    // side along K:  a.w ~= a_hi.w_hi + a_lo.w_hi + a_hi.w_lo  ->  A' = [hi | lo | hi], W' = [hi | hi | lo].
+    auto split3 = [&](const std::vector<float>& src, int N, int K, int seg, GemmW* g) -> int {
+      std::vector<float> w3((size_t)N * 3 * seg, 0.f);
+      for (int n = 0; n < N; ++n)
+        for (int k = 0; k < K; ++k) {
+          const float v = src[(size_t)n * K + k];
+          const float hi = __bfloat162float(__float2bfloat16_rn(v));
+          const float lo = v - hi;
+          w3[(size_t)n * 3 * seg + k] = hi;
+          w3[(size_t)n * 3 * seg + seg + k] = hi;
+          w3[(size_t)n * 3 * seg + 2 * seg + k] = lo;
+        }
+      float* d = nullptr;
+      LVX_TRY(dev_alloc(e, &d, w3.size()));
+      LVX_CUDA(cudaMemcpy(d, w3.data(), w3.size() * sizeof(float), cudaMemcpyHostToDevice));
+      return make_gemm_w(e, g, d, N, 3 * seg, 3 * seg);
+    };
+    std::vector<float> hwt((size_t)(NF + 2) * D);
+    LVX_CUDA(cudaMemcpy(hwt.data(), W(e, "head.out.weight"), hwt.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    LVX_TRY(split3(hwt, NF + 2, D, D, &e->head));
+    std::vector<float> basis((size_t)NF * 2 * bins, 0.f);
+    for (int n = 0; n < NF; ++n)
+      for (int k = 0; k < bins; ++k) {
+        const double ang = 2.0 * M_PI * (double)(((long long)k * n) % NF) / NF;
+        const double ck = (k == 0 || k == NF / 2) ? 1.0 : 2.0;
+        basis[(size_t)n * 2 * bins + k] = (float)(hw[n] * ck * cos(ang) / NF);
+        basis[(size_t)n * 2 * bins + bins + k] = (k == 0 || k == NF / 2) ? 0.f : (float)(-hw[n] * 2.0 * sin(ang) / NF);
+      }
+    LVX_TRY(split3(basis, NF, 2 * bins, e->spec_ld, &e->idft));
+  }
+  LVX_CUDA(cudaDeviceSynchronize());
+  e->finalized = true;
+  return LVX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ GEMM dispatch
+// C = epilogue(A . W^T).  fp32 mode: FMA-pipe kernel.  bf16 mode: tcgen05 kernel (tc_gemm.cuh) when the
+// problem is a plain (optionally multi-tap) GEMM against a registered weight.
+static int run_gemm(lvx_engine* e, GemmParams p, const GemmW& w, DT ta, DT tc, cudaStream_t st) {
+  if (!p.a_cap) p.a_cap = p.row_chunk || p.taps > 1 ? e->R_max : e->Bp;
+  p.N = w.N;
+  p.K = w.K;
+  p.ldw = w.ld;
+  if (e->adt() == F32) {
+    p.W = w.f32;
+    cudaError_t err = launch_gemm_simt<float, float, float>(p, st);
+    e->launches++;
+    LVX_CHECK(err == cudaSuccess, LVX_ERR_CUDA, std::string("gemm launch: ") + cudaGetErrorString(err));
+    return LVX_OK;
+  }
+  LVX_CHECK(ta == B16, LVX_ERR_INVALID, "bf16 mode GEMM needs a bf16 A operand");
+  p.W = w.b16;
+  int s = tc_gemm(&e->tcw, p, w.tma, tc == B16, st);
+  e->launches++;
+  return s;
+}
+
+static int run_gemm_batched(lvx_engine* e, GemmParams p, DT ta, DT tw, DT tc, cudaStream_t st) {
+  cudaError_t err;
+  if (ta == F32)
+    err = launch_gemm_simt<float, float, float>(p, st);
+  else if (tc == B16)
+    err = launch_gemm_simt<bf16, bf16, bf16>(p, st);
+  else
+    err = launch_gemm_simt<bf16, bf16, float>(p, st);
+  (void)tw;
+  e->launches++;
+  LVX_CHECK(err == cudaSuccess, LVX_ERR_CUDA, std::string("gemm launch: ") + cudaGetErrorString(err));
+  return LVX_OK;
+}
+
+template <int C>
+static int run_layernorm(lvx_engine* e, const float* x, int rows, const float* w, const float* b, float eps,
+                         const int* row_chunk, void* out, cudaStream_t st) {
+  if (rows <= 0) return LVX_OK;
+  if (e->adt() == F32)
+    layernorm_kernel<float, C><<<ceil_div(rows, 8), 256, 0, st>>>(x, rows, w, b, eps, row_chunk, (float*)out);
+  else
+    layernorm_kernel<bf16, C><<<ceil_div(rows, 8), 256, 0, st>>>(x, rows, w, b, eps, row_chunk, (bf16*)out);
+  LAUNCHED(e);
+  return LVX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ sessions
+static int check_engine(lvx_engine* e) {
+  LVX_CHECK(e, LVX_ERR_INVALID, "engine is NULL");
+  LVX_CHECK(e->finalized, LVX_ERR_STATE, "lvx_finalize_weights has not been called");
+  LVX_CUDA(cudaSetDevice(e->device));
+  return LVX_OK;
+}
+
+static int check_slots(lvx_engine* e, const int32_t* h_slots, int n, bool must_be_open) {
+  LVX_CHECK(h_slots && n > 0, LVX_ERR_INVALID, "no slots given");
+  LVX_CHECK(n <= e->cfg.max_batch, LVX_ERR_CAPACITY, "more sessions than max_batch in one call");
+  ++e->stamp_ctr;
+  for (int i = 0; i < n; ++i) {
+    const int s = h_slots[i];
+    LVX_CHECK(s >= 0 && s < e->cfg.max_sessions, LVX_ERR_INVALID, "slot out of range");
+    LVX_CHECK(e->stamp[s] != e->stamp_ctr, LVX_ERR_INVALID, "duplicate slot in one call");
+    e->stamp[s] = e->stamp_ctr;
+    if (must_be_open) LVX_CHECK(e->h_open[s], LVX_ERR_STATE, "slot is not open");
+  }
+  return LVX_OK;
+}
+
+static int upload_slots(lvx_engine* e, const int32_t* h_slots, int n, cudaStream_t st) {
+  LVX_CUDA(cudaMemcpyAsync(e->d_slots, h_slots, n * sizeof(int), cudaMemcpyHostToDevice, st));
+  return LVX_OK;
+}
+
+static void release_pages(lvx_engine* e, int slot) {
+  for (int p : e->h_pages[slot]) e->free_pages.push_back(p);
+  e->h_pages[slot].clear();
+}
+
+// makes sure every slot owns pages for `tokens[i]` KV tokens; patches the device page table
+static int ensure_pages(lvx_engine* e, const int32_t* h_slots, int n, const std::vector<int>& tokens, cudaStream_t st) {
+  std::vector<int> upd;
+  for (int i = 0; i < n; ++i) {
+    const int s = h_slots[i];
+    const int need = ceil_div(tokens[i], e->cfg.kv_page_tokens);
+    while ((int)e->h_pages[s].size() < need) {
+      LVX_CHECK(!e->free_pages.empty(), LVX_ERR_CAPACITY, "KV page pool exhausted");
+      const int pg = e->free_pages.back();
+      e->free_pages.pop_back();
+      upd.push_back(s);
+      upd.push_back((int)e->h_pages[s].size());
+      upd.push_back(pg);
+      e->h_pages[s].push_back(pg);
+    }
+  }
+  if (!upd.empty()) {
+    const int m = (int)upd.size() / 3;
+    LVX_CUDA(cudaMemcpyAsync(e->d_upd, upd.data(), upd.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    patch_pages_kernel<<<ceil_div(m, 256), 256, 0, st>>>(e->d_upd, m, e->st);
+    LAUNCHED(e);
+  }
+  return LVX_OK;
+}
+
+extern "C" int lvx_session_open(lvx_engine* e, const int32_t* h_slots, int n, void* stream) {
+  LVX_TRY(check_engine(e));
+  LVX_TRY(check_slots(e, h_slots, n, false));
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int i = 0; i < n; ++i) {
+    const int s = h_slots[i];
+    release_pages(e, s);
+    e->h_len[s] = 0;
+    e->h_text_len[s] = 0;
+    e->h_open[s] = 1;
+  }
+  LVX_TRY(upload_slots(e, h_slots, n, st));
+  reset_sessions_kernel<<<ceil_div(n, 256), 256, 0, st>>>(e->d_slots, n, e->st);
+  LAUNCHED(e);
+  return LVX_OK;
+}
+
+extern "C" int lvx_session_close(lvx_engine* e, const int32_t* h_slots, int n, void* stream) {
+  LVX_TRY(check_engine(e));
+  LVX_TRY(check_slots(e, h_slots, n, false));
+  (void)stream;
+  for (int i = 0; i < n; ++i) {
+    release_pages(e, h_slots[i]);
+    e->h_open[h_slots[i]] = 0;
+  }
+  return LVX_OK;
+}
+
+extern "C" int lvx_feed_text(lvx_engine* e, const int32_t* h_slots, const int32_t* h_offsets, const int32_t* h_ids, int n,
+                             void* stream) {
+  LVX_TRY(check_engine(e));
+  LVX_TRY(check_slots(e, h_slots, n, true));
+  LVX_CHECK(h_offsets && h_ids, LVX_ERR_INVALID, "NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  LVX_CHECK(h_offsets[0] == 0, LVX_ERR_INVALID, "offsets must start at 0");
+  for (int i = 0; i < n; ++i) {
+    const int cnt = h_offsets[i + 1] - h_offsets[i];
+    LVX_CHECK(cnt >= 0, LVX_ERR_INVALID, "offsets must be non-decreasing");
+    LVX_CHECK(e->h_text_len[h_slots[i]] + cnt <= e->cfg.max_context, LVX_ERR_CAPACITY, "text longer than max_context");
+  }
+  const int total = h_offsets[n];
+  for (int i = 0; i < total; ++i)
+    LVX_CHECK(h_ids[i] >= 0 && h_ids[i] < e->cfg.text_vocab, LVX_ERR_INVALID, "text id out of range");
+  if (total == 0) return LVX_OK;
+  LVX_TRY(upload_slots(e, h_slots, n, st));
+  LVX_CUDA(cudaMemcpyAsync(e->d_aux, h_offsets, (n + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+  LVX_CUDA(cudaMemcpyAsync(e->d_ids, h_ids, total * sizeof(int), cudaMemcpyHostToDevice, st));
+  scatter_text_kernel<<<n, 128, 0, st>>>(e->d_slots, e->d_aux, e->d_ids, e->st);
+  LAUNCHED(e);
+  for (int i = 0; i < n; ++i) e->h_text_len[h_slots[i]] += h_offsets[i + 1] - h_offsets[i];
+  return LVX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ decode
+// One GPT.forward over n session rows whose residual stream x is already assembled (src/model.py:220-234).
+static int gpt_body(lvx_engine* e, int n, const int* pos_override, cudaStream_t st) {
+  const lvx_config& c = e->cfg;
+  const int C = c.n_embd;
+  const DT a = e->adt();
+  for (int l = 0; l < c.n_layer; ++l) {
+    auto& L = e->layers[l];
+    LVX_TRY(run_layernorm<768>(e, e->x, n, L.ln1_w, L.ln1_b, 1e-5f, nullptr, e->h, st));
+    GemmParams p;
+    p.A = e->h; p.C = e->qkv; p.M = n; p.lda = C; p.ldc = 3 * C; p.bias = L.attn_b;
+    LVX_TRY(run_gemm(e, p, L.attn, a, F32, st));
+    dim3 grid(n, c.n_head);
+    if (a == F32)
+      decode_attention_kernel<float, float, 96><<<grid, 128, 0, st>>>(e->qkv, (float*)e->kv, e->d_slots, e->st, pos_override, l,
+                                                                       c.n_head, c.kv_page_tokens, e->pool_pages, 0, (float*)e->y);
+    else
+      decode_attention_kernel<bf16, bf16, 96><<<grid, 128, 0, st>>>(e->qkv, (bf16*)e->kv, e->d_slots, e->st, pos_override, l,
+                                                                     c.n_head, c.kv_page_tokens, e->pool_pages, 0, (bf16*)e->y);
+    LAUNCHED(e);
+    GemmParams q;
+    q.A = e->y; q.C = e->x; q.M = n; q.lda = C; q.ldc = C; q.bias = L.proj_b; q.residual = e->x; q.ldr = C;
+    LVX_TRY(run_gemm(e, q, L.proj, a, F32, st));
+    LVX_TRY(run_layernorm<768>(e, e->x, n, L.ln2_w, L.ln2_b, 1e-5f, nullptr, e->h, st));
+    GemmParams f;
+    f.A = e->h; f.C = e->g; f.M = n; f.lda = C; f.ldc = 4 * C; f.bias = L.fc_b; f.act = ACT_GELU_TANH;
+    LVX_TRY(run_gemm(e, f, L.fc, a, a, st));
+    GemmParams r;
+    r.A = e->g; r.C = e->x; r.M = n; r.lda = 4 * C; r.ldc = C; r.bias = L.proj2_b; r.residual = e->x; r.ldr = C;
+    LVX_TRY(run_gemm(e, r, L.proj2, a, F32, st));
+  }
+  LVX_TRY(run_layernorm<768>(e, e->x, n, e->lnf_w, e->lnf_b, 1e-5f, nullptr, e->h, st));
+  return LVX_OK;
+}
+
+static int lm_head_logits(lvx_engine* e, int n, float* d_logits, cudaStream_t st) {
+  GemmParams p;
+  p.A = e->h; p.C = d_logits; p.M = n; p.lda = e->cfg.n_embd; p.ldc = e->cfg.vocab_size;
+  return run_gemm(e, p, e->lm_head, e->adt(), F32, st);
+}
+
+static SamplerArgs sampler_args(const lvx_sampling* s) {
+  SamplerArgs a{};
+  a.greedy = (!s || s->greedy || s->top_k == 1) ? 1 : 0;
+  a.top_k = s ? s->top_k : 0;
+  a.temperature = s ? s->temperature : 1.0f;
+  a.seed = s ? s->seed : 0;
+  a.uniform = s ? s->d_uniform : nullptr;
+  a.record = 1;
+  return a;
+}
+
+static int decode_one_step(lvx_engine* e, int n, const SamplerArgs& sa, float* d_logits, cudaStream_t st) {
+  const lvx_config& c = e->cfg;
+  assemble_input_kernel<<<n, c.n_embd / 4, 0, st>>>(e->d_slots, e->st, W(e, "text_table"),
+                                                    W(e, "feature_extractor.encodec.quantizer.vq.layers.0._codebook.embed"),
+                                                    W(e, "transformer.wpe.weight"), c.text_dim, c.code_dim, c.pad_token_id, 0, e->x);
+  LAUNCHED(e);
+  LVX_TRY(gpt_body(e, n, nullptr, st));
+  LVX_TRY(lm_head_logits(e, n, d_logits, st));
+  sampler_kernel<4096><<<n, 256, 0, st>>>(d_logits, c.vocab_size, e->d_slots, e->st, sa);
+  LAUNCHED(e);
+  return LVX_OK;
+}
+
+static int prepare_decode(lvx_engine* e, const int32_t* h_slots, int n, int n_steps, cudaStream_t st) {
+  LVX_TRY(check_slots(e, h_slots, n, true));
+  std::vector<int> need(n);
+  for (int i = 0; i < n; ++i) {
+    need[i] = e->h_len[h_slots[i]] + n_steps;
+    LVX_CHECK(need[i] <= e->cfg.max_context, LVX_ERR_CAPACITY, "session would exceed max_context");
+  }
+  LVX_TRY(upload_slots(e, h_slots, n, st));
+  LVX_TRY(ensure_pages(e, h_slots, n, need, st));
+  return LVX_OK;
+}
+
+extern "C" int lvx_decode_steps(lvx_engine* e, const int32_t* h_slots, int n, int n_steps, const lvx_sampling* s, void* stream) {
+  LVX_TRY(check_engine(e));
+  LVX_CHECK(n_steps > 0, LVX_ERR_INVALID, "n_steps must be positive");
+  cudaStream_t st = (cudaStream_t)stream;
+  LVX_TRY(prepare_decode(e, h_slots, n, n_steps, st));
+  SamplerArgs sa = sampler_args(s);
+  LVX_CHECK(sa.greedy || sa.temperature > 0.f, LVX_ERR_INVALID, "temperature must be positive");
+  LVX_CHECK(!(sa.uniform && n_steps > 1), LVX_ERR_INVALID, "d_uniform supplies one draw per session: use n_steps == 1");
+  for (int t = 0; t < n_steps; ++t) LVX_TRY(decode_one_step(e, n, sa, e->logits, st));
+  for (int i = 0; i < n; ++i) e->h_len[h_slots[i]] += n_steps;
+  return LVX_OK;
+}
+
+extern "C" int lvx_decode_step_logits(lvx_engine* e, const int32_t* h_slots, int n, const lvx_sampling* s,
+                                      const int32_t* d_forced_codes, float* d_logits, int32_t* d_codes, void* stream) {
+  LVX_TRY(check_engine(e));
+  LVX_CHECK(d_logits, LVX_ERR_INVALID, "d_logits is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  LVX_TRY(prepare_decode(e, h_slots, n, 1, st));
+  SamplerArgs sa = sampler_args(s);
+  LVX_CHECK(sa.greedy || sa.temperature > 0.f, LVX_ERR_INVALID, "temperature must be positive");
+  sa.forced = d_forced_codes;
+  sa.out_codes = d_codes;
+  LVX_TRY(decode_one_step(e, n, sa, d_logits, st));
+  for (int i = 0; i < n; ++i) e->h_len[h_slots[i]] += 1;
+  return LVX_OK;
+}
+
+extern "C" int lvx_decode_step_embeds(lvx_engine* e, const int32_t* h_slots, int n, const float* d_emb,
+                                      const int32_t* h_positions, float* d_logits, void* stream) {
+  LVX_TRY(check_engine(e));
+  LVX_CHECK(d_emb && h_positions && d_logits, LVX_ERR_INVALID, "NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  LVX_TRY(check_slots(e, h_slots, n, true));
+  std::vector<int> need(n);
+  for (int i = 0; i < n; ++i) {
+    // the reference's cache holds exactly T-1 tokens when the caller feeds T rows (src/model.py:74-79)
+    LVX_CHECK(h_positions[i] == e->h_len[h_slots[i]], LVX_ERR_STATE, "position != tokens held by the session's cache");
+    need[i] = h_positions[i] + 1;
+    LVX_CHECK(need[i] <= e->cfg.max_context, LVX_ERR_CAPACITY, "session would exceed max_context");
+  }
+  LVX_TRY(upload_slots(e, h_slots, n, st));
+  LVX_TRY(ensure_pages(e, h_slots, n, need, st));
+  int* d_pos = e->d_aux;
+  LVX_CUDA(cudaMemcpyAsync(d_pos, h_positions, n * sizeof(int), cudaMemcpyHostToDevice, st));
+  add_wpe_kernel<<<n, 192, 0, st>>>(d_emb, d_pos, W(e, "transformer.wpe.weight"), e->cfg.n_embd, e->x);
+  LAUNCHED(e);
+  LVX_TRY(gpt_body(e, n, d_pos, st));
+  LVX_TRY(lm_head_logits(e, n, d_logits, st));
+  set_ctx_kernel<<<ceil_div(n, 256), 256, 0, st>>>(e->d_slots, d_pos, n, e->st);
+  LAUNCHED(e);
+  for (int i = 0; i < n; ++i) e->h_len[h_slots[i]] += 1;
+  return LVX_OK;
+}
+
+extern "C" int lvx_gather_codes(lvx_engine* e, const int32_t* h_slots, int n, int start, int count, int32_t* d_out, void* stream) {
+  LVX_TRY(check_engine(e));
+  LVX_TRY(check_slots(e, h_slots, n, false));
+  LVX_CHECK(d_out && start >= 0 && count > 0 && start + count <= e->cfg.max_context, LVX_ERR_INVALID, "bad range");
+  for (int i = 0; i < n; ++i)
+    LVX_CHECK(start + count <= e->h_len[h_slots[i]], LVX_ERR_STATE, "range beyond the codes decoded so far");
+  cudaStream_t st = (cudaStream_t)stream;
+  LVX_TRY(upload_slots(e, h_slots, n, st));
+  gather_codes_kernel<<<n, 128, 0, st>>>(e->d_slots, e->st, start, count, d_out);
+  LAUNCHED(e);
+  return LVX_OK;
+}
+
+extern "C" int lvx_gather_code_ranges(lvx_engine* e, const int32_t* h_slots, const int32_t* h_starts, const int32_t* h_counts,
+                                      int n, int32_t* d_out, void* stream) {
+  LVX_TRY(check_engine(e));
+  LVX_TRY(check_slots(e, h_slots, n, false));
+  LVX_CHECK(h_starts && h_counts && d_out, LVX_ERR_INVALID, "NULL argument");
+  std::vector<int> offs(n + 1, 0);
+  for (int i = 0; i < n; ++i) {
+    LVX_CHECK(h_starts[i] >= 0 && h_counts[i] >= 0 && h_starts[i] + h_counts[i] <= e->h_len[h_slots[i]], LVX_ERR_STATE,
+              "range beyond the codes decoded so far");
+    offs[i + 1] = offs[i] + h_counts[i];
+  }
+  if (offs[n] == 0) return LVX_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  LVX_TRY(upload_slots(e, h_slots, n, st));
+  LVX_CUDA(cudaMemcpyAsync(e->d_aux, offs.data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+  LVX_CUDA(cudaMemcpyAsync(e->d_ids, h_starts, n * sizeof(int), cudaMemcpyHostToDevice, st));
+  gather_code_ranges_kernel<<<n, 128, 0, st>>>(e->d_slots, e->d_ids, e->d_aux, e->st, d_out);
+  LAUNCHED(e);
+  return LVX_OK;
+}
+
+extern "C" int lvx_session_length(lvx_engine* e, int slot, int32_t* out_len) {
+  LVX_CHECK(e && out_len, LVX_ERR_INVALID, "NULL argument");
+  LVX_CHECK(slot >= 0 && slot < e->cfg.max_sessions, LVX_ERR_INVALID, "slot out of range");
+  *out_len = e->h_len[slot];
+  return LVX_OK;
+}
+
+extern "C" int lvx_codes_to_features(lvx_engine* e, const int32_t* d_codes, int n, float* d_out, void* stream) {
+  LVX_TRY(check_engine(e));
+  LVX_CHECK(d_codes && d_out && n > 0, LVX_ERR_INVALID, "bad argument");
+  gather_rows_kernel<float><<<n, 128, 0, (cudaStream_t)stream>>>(
+      d_codes, W(e, "feature_extractor.encodec.quantizer.vq.layers.0._codebook.embed"), e->cfg.code_dim, n, d_out,
+      e->cfg.code_dim, nullptr);
+  LAUNCHED(e);
+  return LVX_OK;
+}
+
+extern "C" int lvx_text_embed(lvx_engine* e, const int32_t* d_ids, int n, float* d_out, void* stream) {
+  LVX_TRY(check_engine(e));
+  LVX_CHECK(d_ids && d_out && n > 0, LVX_ERR_INVALID, "bad argument");
+  gather_rows_kernel<float><<<n, 64, 0, (cudaStream_t)stream>>>(d_ids, W(e, "text_table"), e->cfg.text_dim, n, d_out,
+                                                                 e->cfg.text_dim, nullptr);
+  LAUNCHED(e);
+  return LVX_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ vocoder
+struct VocGroup {
+  std::vector<ChunkInfo> chunks;
+  int R = 0;        // padded rows
+  int frames = 0;   // valid rows
+  int code0 = 0;    // first code of the group in the caller's packed order
+  int max_len = 0;
+  long long s_elems = 0;
+};
+
+static int groupnorm(lvx_engine* e, const VocGroup& g, const float* x, const float* w, const float* b, int swish, void* out,
+                     cudaStream_t st) {
+  dim3 grid(32, (unsigned)g.chunks.size());
+  groupnorm_stats_kernel<768><<<grid, 256, 0, st>>>(x, e->d_chunks, 1e-6f, e->v_stats);
+  LAUNCHED(e);
+  const long long items = (long long)g.R * (768 / 4);
+  if (e->adt() == F32)
+    groupnorm_apply_kernel<float, 768><<<(unsigned)((items + 255) / 256), 256, 0, st>>>(x, g.R, e->row_chunk, e->v_stats, w, b,
+                                                                                         swish, (float*)out);
+  else
+    groupnorm_apply_kernel<bf16, 768><<<(unsigned)((items + 255) / 256), 256, 0, st>>>(x, g.R, e->row_chunk, e->v_stats, w, b,
+                                                                                        swish, (bf16*)out);
+  LAUNCHED(e);
+  return LVX_OK;
+}
+
+static int conv_gemm(lvx_engine* e, const VocGroup& g, const void* A, int Cin, int taps, const GemmW& w, const float* bias,
+                     float* out, const float* residual, cudaStream_t st) {
+  GemmParams p;
+  p.A = A; p.C = out; p.M = g.R; p.lda = Cin; p.ldc = e->cfg.voc_dim; p.a_rows = g.R;
+  p.taps = taps; p.tap_K = Cin; p.tap_pad = taps / 2;
+  p.bias = bias; p.residual = residual; p.ldr = e->cfg.voc_dim; p.row_chunk = e->row_chunk;
+  return run_gemm(e, p, w, e->adt(), F32, st);
+}
+
+static int resnet_block(lvx_engine* e, const VocGroup& g, const lvx_engine::Res& r, cudaStream_t st) {
+  const int D = e->cfg.voc_dim;
+  LVX_TRY(groupnorm(e, g, e->v_x, r.n1w, r.n1b, 1, e->v_h, st));
+  LVX_TRY(conv_gemm(e, g, e->v_h, D, 3, r.c1, r.c1b, e->v_t, nullptr, st));
+  LVX_TRY(groupnorm(e, g, e->v_t, r.n2w, r.n2b, 1, e->v_h, st));
+  LVX_TRY(conv_gemm(e, g, e->v_h, D, 3, r.c2, r.c2b, e->v_x, e->v_x, st));
+  return LVX_OK;
+}
+
+// stage: -1 = full pipeline; otherwise stop after that stage and copy the activation to d_stage_out
+static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes, const float* d_feats, int bw, float* d_pcm,
+                        int stage, float* d_stage_out, cudaStream_t st) {
+  const lvx_config& c = e->cfg;
+  const int D = c.voc_dim, I = c.voc_inter;
+  const DT a = e->adt();
+  const int nch = (int)g.chunks.size();
+  const int32_t* codes = d_codes ? d_codes + g.code0 : nullptr;
+  auto dump = [&](const float* src, int ld, int width) -> int {
+    unpad_rows_kernel<<<g.frames, 256, 0, st>>>(src, ld, width, e->code_rows, g.frames, d_stage_out);
+    LAUNCHED(e);
+    return LVX_OK;
+  };
+  // layout
+  LVX_CUDA(cudaMemcpyAsync(e->d_chunks, g.chunks.data(), nch * sizeof(ChunkInfo), cudaMemcpyHostToDevice, st));
+  LVX_CUDA(cudaMemsetAsync(e->row_chunk, 0xFF, (size_t)g.R * sizeof(int), st));
+  build_row_chunk_kernel<<<nch, 128, 0, st>>>(e->d_chunks, nch, e->row_chunk, e->code_rows);
+  LAUNCHED(e);
+  // a3: codebook gather (pretrained.py:209-239), channels-last
+  const float* codebook = W(e, "feature_extractor.encodec.quantizer.vq.layers.0._codebook.embed");
+  if (d_feats) {
+    const float* f = d_feats + (size_t)g.code0 * c.code_dim;
+    if (a == F32)
+      copy_feats_padded_kernel<float><<<g.R, 128, 0, st>>>(f, c.code_dim, e->row_chunk, e->d_chunks, (float*)e->v_feats);
+    else
+      copy_feats_padded_kernel<bf16><<<g.R, 128, 0, st>>>(f, c.code_dim, e->row_chunk, e->d_chunks, (bf16*)e->v_feats);
+  } else if (a == F32)
+    gather_codebook_padded_kernel<float><<<g.R, 128, 0, st>>>(codes, codebook, c.code_dim, c.n_codes, e->row_chunk, e->d_chunks,
+                                                               (float*)e->v_feats);
+  else
+    gather_codebook_padded_kernel<bf16><<<g.R, 128, 0, st>>>(codes, codebook, c.code_dim, c.n_codes, e->row_chunk, e->d_chunks,
+                                                              (bf16*)e->v_feats);
+  LAUNCHED(e);
+  // backbone.embed: Conv1d 512 -> 768, k7 (models.py:224)
+  LVX_TRY(conv_gemm(e, g, e->v_feats, c.code_dim, 7, e->embed, e->embed_b, e->v_x, nullptr, st));
+  if (stage == 0) return dump(e->v_x, D, D);
+  // pos_net (models.py:203-216)
+  LVX_TRY(resnet_block(e, g, e->res[0], st));
+  if (stage == 1) return dump(e->v_x, D, D);
+  LVX_TRY(resnet_block(e, g, e->res[1], st));
+  {
+    // AttnBlock (models.py:107-127)
+    LVX_TRY(groupnorm(e, g, e->v_x, e->at_nw, e->at_nb, 0, e->v_h, st));
+    GemmParams p;
+    p.A = e->v_h; p.C = e->v_big; p.M = g.R; p.lda = D; p.ldc = 3 * D; p.bias = e->at_qkv_b; p.row_chunk = e->row_chunk;
+    LVX_TRY(run_gemm(e, p, e->at_qkv, a, a, st));
+    std::vector<GemmProblem> ps(nch), pv(nch);
+    for (int i = 0; i < nch; ++i) {
+      const ChunkInfo& ci = g.chunks[i];
+      const int L = ci.len, Lp = (L + 3) & ~3;
+      ps[i] = GemmProblem{(long long)ci.row0 * 3 * D, (long long)ci.row0 * 3 * D + D, (long long)ci.s_off, L, L, D, 0, Lp};
+      pv[i] = GemmProblem{(long long)ci.s_off, (long long)ci.row0 * 3 * D + 2 * D, (long long)ci.row0 * D, L, D, L, Lp, 0};
+    }
+    LVX_CUDA(cudaMemcpyAsync(e->d_prob_s, ps.data(), nch * sizeof(GemmProblem), cudaMemcpyHostToDevice, st));
+    LVX_CUDA(cudaMemcpyAsync(e->d_prob_pv, pv.data(), nch * sizeof(GemmProblem), cudaMemcpyHostToDevice, st));
+    GemmParams s;
+    s.A = e->v_big; s.W = e->v_big; s.C = e->v_S; s.batch = e->d_prob_s; s.n_batch = nch; s.lda = 3 * D; s.ldw = 3 * D;
+    s.max_M = g.max_len; s.max_N = g.max_len; s.alpha = 1.0f / sqrtf((float)D);
+    LVX_TRY(run_gemm_batched(e, s, a, a, F32, st));
+    if (a == F32)
+      attn_softmax_kernel<float><<<ceil_div(g.R, 8), 256, 0, st>>>(e->v_S, e->v_S, e->d_chunks, e->row_chunk, g.R);
+    else
+      attn_softmax_kernel<bf16><<<ceil_div(g.R, 8), 256, 0, st>>>(e->v_S, (bf16*)e->v_P, e->d_chunks, e->row_chunk, g.R);
+    LAUNCHED(e);
+    GemmParams o;
+    o.A = (a == F32) ? (void*)e->v_S : e->v_P; o.W = e->v_big; o.C = e->v_h; o.batch = e->d_prob_pv; o.n_batch = nch;
+    o.ldw = 3 * D; o.ldc = D; o.w_kn = 1; o.max_M = g.max_len; o.max_N = D;
+    LVX_TRY(run_gemm_batched(e, o, a, a, a, st));
+    GemmParams q;
+    q.A = e->v_h; q.C = e->v_x; q.M = g.R; q.lda = D; q.ldc = D; q.bias = e->at_proj_b; q.residual = e->v_x; q.ldr = D;
+    q.row_chunk = e->row_chunk;
+    LVX_TRY(run_gemm(e, q, e->at_proj, a, F32, st));
+  }
+  if (stage == 2) return dump(e->v_x, D, D);
+  LVX_TRY(resnet_block(e, g, e->res[2], st));
+  LVX_TRY(resnet_block(e, g, e->res[3], st));
+  // pos_net[5] GroupNorm + backbone.norm AdaLayerNorm (models.py:213,226-228)
+  {
+    dim3 grid(32, (unsigned)nch);
+    groupnorm_stats_kernel<768><<<grid, 256, 0, st>>>(e->v_x, e->d_chunks, 1e-6f, e->v_stats);
+    LAUNCHED(e);
+    groupnorm_adaln_kernel<768><<<ceil_div(g.R, 8), 256, 0, st>>>(e->v_x, g.R, e->row_chunk, e->v_stats, e->pn5_w, e->pn5_b,
+                                                                   e->norm_scale + (size_t)bw * D, e->norm_shift + (size_t)bw * D,
+                                                                   1e-6f, stage == 3 ? e->v_t : nullptr, e->v_x);
+    LAUNCHED(e);
+    if (stage == 3) return dump(e->v_t, D, D);
+  }
+  // 12 x ConvNeXtBlock (modules.py:43-60)
+  for (int i = 0; i < c.voc_layers; ++i) {
+    auto& X = e->cnx[i];
+    if (a == F32)
+      dwconv_adaln_kernel<float, 768><<<ceil_div(g.R, 8), 256, 0, st>>>(e->v_x, g.R, e->row_chunk, e->d_chunks, X.dw_w, X.dw_b,
+                                                                         X.scale + (size_t)bw * D, X.shift + (size_t)bw * D, 1e-6f,
+                                                                         (float*)e->v_h);
+    else
+      dwconv_adaln_kernel<bf16, 768><<<ceil_div(g.R, 8), 256, 0, st>>>(e->v_x, g.R, e->row_chunk, e->d_chunks, X.dw_w, X.dw_b,
+                                                                        X.scale + (size_t)bw * D, X.shift + (size_t)bw * D, 1e-6f,
+                                                                        (bf16*)e->v_h);
+    LAUNCHED(e);
+    GemmParams p;
+    p.A = e->v_h; p.C = e->v_big; p.M = g.R; p.lda = D; p.ldc = I; p.bias = X.b1; p.act = ACT_GELU_ERF; p.row_chunk = e->row_chunk;
+    LVX_TRY(run_gemm(e, p, X.pw1, a, a, st));
+    GemmParams q;
+    q.A = e->v_big; q.C = e->v_x; q.M = g.R; q.lda = I; q.ldc = D; q.bias = X.b2; q.col_scale = X.gamma; q.residual = e->v_x;
+    q.ldr = D; q.row_chunk = e->row_chunk;
+    LVX_TRY(run_gemm(e, q, X.pw2, a, F32, st));
+  }
+  // final_layer_norm (models.py:234) + head.out (heads.py:53)
+  const int NF = c.n_fft, bins = NF / 2 + 1;
+  if (a == F32) {
+    layernorm_kernel<float, 768><<<ceil_div(g.R, 8), 256, 0, st>>>(e->v_x, g.R, e->fln_w, e->fln_b, 1e-6f, e->row_chunk, (float*)e->v_h);
+    LAUNCHED(e);
+    if (stage == 4) return dump((float*)e->v_h, D, D);
+    GemmParams p;
+    p.A = e->v_h; p.C = e->v_raw; p.M = g.R; p.lda = D; p.ldc = e->raw_ld; p.bias = e->head_b; p.row_chunk = e->row_chunk;
+    LVX_TRY(run_gemm(e, p, e->head, a, F32, st));
+    dim3 grid(ceil_div(e->spec_ld, 256), g.R);
+    head_activation_kernel<float><<<grid, 256, 0, st>>>(e->v_raw, e->raw_ld, g.R, e->row_chunk, bins, (float*)e->v_spec, e->spec_ld);
+    LAUNCHED(e);
+    GemmParams q;
+    q.A = e->v_spec; q.C = e->v_frames; q.M = g.R; q.lda = e->spec_ld; q.ldc = NF; q.row_chunk = e->row_chunk;
+    LVX_TRY(run_gemm(e, q, e->idft, a, F32, st));
+  } else {
+    layernorm_kernel<float, 768><<<ceil_div(g.R, 8), 256, 0, st>>>(e->v_x, g.R, e->fln_w, e->fln_b, 1e-6f, e->row_chunk, e->v_t);
+    LAUNCHED(e);
+    if (stage == 4) return dump(e->v_t, D, D);
+    dim3 g3(ceil_div(D, 256), g.R);
+    split3_kernel<768><<<g3, 256, 0, st>>>(e->v_t, g.R, D, D, (bf16*)e->v_h3, D, 3 * D);
+    LAUNCHED(e);
+    GemmParams p;
+    p.A = e->v_h3; p.C = e->v_raw; p.M = g.R; p.lda = 3 * D; p.ldc = e->raw_ld; p.bias = e->head_b; p.row_chunk = e->row_chunk;
+    LVX_TRY(run_gemm(e, p, e->head, a, F32, st));
+    dim3 grid(ceil_div(e->spec_ld, 256), g.R);
+    // fp32 spectrum into v_frames' storage is not possible (needed later); reuse v_big as fp32 scratch
+    float* spec32 = (float*)e->v_big;
+    head_activation_kernel<float><<<grid, 256, 0, st>>>(e->v_raw, e->raw_ld, g.R, e->row_chunk, bins, spec32, e->spec_ld);
+    LAUNCHED(e);
+    dim3 g4(ceil_div(e->spec_ld, 256), g.R);
+    split3_kernel<768><<<g4, 256, 0, st>>>(spec32, g.R, e->spec_ld, e->spec_ld, (bf16*)e->v_spec, e->spec_ld, 3 * e->spec_ld);
+    LAUNCHED(e);
+    GemmParams q;
+    q.A = e->v_spec; q.C = e->v_frames; q.M = g.R; q.lda = 3 * e->spec_ld; q.ldc = NF; q.row_chunk = e->row_chunk;
+    LVX_TRY(run_gemm(e, q, e->idft, a, F32, st));
+  }
+  if (stage == 5) return dump(e->v_frames, NF, NF);
+  // overlap-add + trim + envelope (spectral_ops.py:59-73)
+  dim3 grid(ceil_div(g.max_len * c.hop, 256), nch);
+  overlap_add_kernel<<<grid, 256, 0, st>>>(e->v_frames, NF, e->d_chunks, e->window, NF, c.hop, d_pcm + (size_t)g.code0 * c.hop);
+  LAUNCHED(e);
+  return LVX_OK;
+}
+
+static int plan_groups(lvx_engine* e, const int32_t* h_cu, int n_chunks, std::vector<VocGroup>* out) {
+  LVX_CHECK(h_cu && n_chunks > 0, LVX_ERR_INVALID, "no chunks given");
+  LVX_CHECK(h_cu[0] == 0, LVX_ERR_INVALID, "h_cu must start at 0");
+  VocGroup g;
+  g.R = ROW_PAD;
+  g.code0 = 0;
+  for (int i = 0; i < n_chunks; ++i) {
+    const int L = h_cu[i + 1] - h_cu[i];
+    LVX_CHECK(L > 0, LVX_ERR_INVALID, "empty chunk (the reference never decodes zero codes)");
+    LVX_CHECK(L <= e->cfg.max_vocode_frames, LVX_ERR_CAPACITY, "chunk longer than max_vocode_frames");
+    const long long Lp = (L + 3) & ~3;
+    LVX_CHECK((long long)L * Lp <= e->score_cap, LVX_ERR_CAPACITY, "chunk too long for the attention workspace");
+    if (!g.chunks.empty() &&
+        (g.frames + L > e->cfg.max_vocode_frames || g.s_elems + L * Lp > e->score_cap || (int)g.chunks.size() >= e->max_chunks)) {
+      out->push_back(g);
+      g = VocGroup();
+      g.R = ROW_PAD;
+      g.code0 = h_cu[i];
+    }
+    ChunkInfo ci;
+    ci.row0 = g.R;
+    ci.len = L;
+    ci.out0 = h_cu[i] - g.code0;
+    ci.s_off = (int)g.s_elems;
+    g.chunks.push_back(ci);
+    g.R += L + ROW_PAD;
+    g.frames += L;
+    g.s_elems += L * Lp;
+    g.max_len = std::max(g.max_len, L);
+  }
+  out->push_back(g);
+  return LVX_OK;
+}
+
+extern "C" int lvx_vocode(lvx_engine* e, const int32_t* d_codes, const int32_t* h_cu, int n_chunks, int bandwidth_id, float* d_pcm,
+                          void* stream) {
+  LVX_TRY(check_engine(e));
+  LVX_CHECK(d_codes && d_pcm, LVX_ERR_INVALID, "NULL argument");
+  LVX_CHECK(bandwidth_id >= 0 && bandwidth_id < e->cfg.voc_ada_rows, LVX_ERR_INVALID, "bandwidth_id out of range");
+  std::vector<VocGroup> groups;
+  LVX_TRY(plan_groups(e, h_cu, n_chunks, &groups));
+  for (const VocGroup& g : groups)
+    LVX_TRY(vocode_group(e, g, d_codes, nullptr, bandwidth_id, d_pcm, -1, nullptr, (cudaStream_t)stream));
+  return LVX_OK;
+}
+
+extern "C" int lvx_vocode_features(lvx_engine* e, const float* d_feats, const int32_t* h_cu, int n_chunks, int bandwidth_id,
+                                   float* d_pcm, void* stream) {
+  LVX_TRY(check_engine(e));
+  LVX_CHECK(d_feats && d_pcm, LVX_ERR_INVALID, "NULL argument");
+  LVX_CHECK(bandwidth_id >= 0 && bandwidth_id < e->cfg.voc_ada_rows, LVX_ERR_INVALID, "bandwidth_id out of range");
+  std::vector<VocGroup> groups;
+  LVX_TRY(plan_groups(e, h_cu, n_chunks, &groups));
+  for (const VocGroup& g : groups)
+    LVX_TRY(vocode_group(e, g, nullptr, d_feats, bandwidth_id, d_pcm, -1, nullptr, (cudaStream_t)stream));
+  return LVX_OK;
+}
+
+extern "C" int lvx_vocode_stage(lvx_engine* e, const int32_t* d_codes, int len, int bandwidth_id, int stage, float* d_out,
+                                void* stream) {
+  LVX_TRY(check_engine(e));
+  LVX_CHECK(d_codes && d_out, LVX_ERR_INVALID, "NULL argument");
+  LVX_CHECK(stage >= 0 && stage <= 5, LVX_ERR_INVALID, "stage out of range");
+  LVX_CHECK(bandwidth_id >= 0 && bandwidth_id < e->cfg.voc_ada_rows, LVX_ERR_INVALID, "bandwidth_id out of range");
+  const int32_t cu[2] = {0, len};
+  std::vector<VocGroup> groups;
+  LVX_TRY(plan_groups(e, cu, 1, &groups));
+  return vocode_group(e, groups[0], d_codes, nullptr, bandwidth_id, nullptr, stage, d_out, (cudaStream_t)stream);
+}
+
+extern "C" int lvx_test_gemm(lvx_engine* e, const float* d_A, const float* d_W, int M, int N, int K, int taps, float* d_C,
+                             void* stream) {
+  LVX_CHECK(e, LVX_ERR_INVALID, "engine is NULL");
+  LVX_CUDA(cudaSetDevice(e->device));
+  LVX_CHECK(d_A && d_W && d_C && M > 0 && N > 0 && K > 0 && taps >= 1 && K % taps == 0, LVX_ERR_INVALID, "bad argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int tap_K = K / taps;
+  LVX_CHECK(tap_K % 8 == 0, LVX_ERR_INVALID, "K / taps must be a multiple of 8");
+  GemmParams p;
+  p.C = d_C; p.M = M; p.lda = tap_K; p.ldc = N; p.a_rows = M; p.taps = taps; p.tap_K = tap_K; p.tap_pad = taps / 2;
+  GemmW w;
+  w.N = N; w.K = K; w.ld = K;
+  int status = LVX_OK;
+  if (e->adt() == F32) {
+    p.A = d_A;
+    p.a_cap = M;
+    w.f32 = const_cast<float*>(d_W);
+    status = run_gemm(e, p, w, F32, F32, st);
+  } else {
+    bf16 *a16 = nullptr, *w16 = nullptr;
+    const int Mp = ceil_div(M, 128) * 128;
+    LVX_CUDA(cudaMalloc(&a16, (size_t)Mp * tap_K * sizeof(bf16)));
+    LVX_CUDA(cudaMalloc(&w16, (size_t)N * K * sizeof(bf16)));
+    LVX_CUDA(cudaMemsetAsync(a16, 0, (size_t)Mp * tap_K * sizeof(bf16), st));
+    cast_bf16_kernel<<<1024, 256, 0, st>>>(d_A, a16, (size_t)M * tap_K);
+    cast_bf16_kernel<<<1024, 256, 0, st>>>(d_W, w16, (size_t)N * K);
+    p.A = a16;
+    p.a_cap = M;   // rows >= M must read as zero for the tap shifts: the tensor map ends at M
+    w.b16 = w16;
+    status = tc_make_desc(&w.tma, w16, N, K, K);
+    if (status == LVX_OK) status = run_gemm(e, p, w, B16, F32, st);
+    cudaStreamSynchronize(st);
+    e->tcw.act_maps.clear();   // the temporary operand is about to be freed
+    cudaFree(a16);
+    cudaFree(w16);
+  }
+  return status;
+}
+
+extern "C" int64_t lvx_kernel_launches(const lvx_engine* e) { return e ? e->launches : 0; }
+extern "C" int64_t lvx_device_bytes(const lvx_engine* e) { return e ? e->bytes : 0; }

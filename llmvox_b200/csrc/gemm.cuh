@@ -16,6 +16,7 @@ namespace lvx {
 struct GemmProblem {
   long long a_off, w_off, c_off;  // element offsets into A, W, C
   int M, N, K;
+  int lda, ldc;                   // per-problem leading dimensions (0 = GemmParams')
 };
 
 struct GemmParams {
@@ -31,6 +32,7 @@ struct GemmParams {
   int M = 0, N = 0, K = 0;
   int lda = 0, ldw = 0, ldc = 0, ldr = 0;
   int a_rows = 0;  // rows addressable in A (for tap shifts); 0 = M
+  int a_cap = 0;   // rows physically allocated behind A (tensor-map extent of the tcgen05 path); 0 = a_rows
   int taps = 1, tap_K = 0, tap_pad = 0;
   int act = ACT_NONE;
   float alpha = 1.0f;
@@ -83,6 +85,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmParams p) {
   const TW* W = reinterpret_cast<const TW*>(p.W);
   TC* C = reinterpret_cast<TC*>(p.C);
   int M = p.M, N = p.N, K = p.K;
+  int lda = p.lda, ldc = p.ldc;
   if (p.batch) {
     const GemmProblem pr = p.batch[blockIdx.z];
     A += pr.a_off;
@@ -91,6 +94,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmParams p) {
     M = pr.M;
     N = pr.N;
     K = pr.K;
+    if (pr.lda) lda = pr.lda;
+    if (pr.ldc) ldc = pr.ldc;
   }
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   if (m0 >= M || n0 >= N) return;
@@ -119,7 +124,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmParams p) {
       const int idx = tid + i * 256, r = idx >> 2, j = idx & 3;
       const int row = m0 + r + shift, kk = k0 + 4 * j;
       if (m0 + r < M && row >= 0 && row < a_rows && kk < K)
-        ra[i] = load4(A + (size_t)row * p.lda + c0 + 4 * j);
+        ra[i] = load4(A + (size_t)row * lda + c0 + 4 * j);
       else
         ra[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
@@ -221,7 +226,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmParams p) {
     for (int v4 = 0; v4 < NV; ++v4) {
       const int n = n0 + v4 * (BN / NV) + tx * 4;
       if (n >= N) continue;
-      gemm_epilogue_store4<TC>(p, C, p.ldc, N, m, n,
+      gemm_epilogue_store4<TC>(p, C, ldc, N, m, n,
                                make_float4(acc[i][4 * v4], acc[i][4 * v4 + 1], acc[i][4 * v4 + 2], acc[i][4 * v4 + 3]));
     }
   }

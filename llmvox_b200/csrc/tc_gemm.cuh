@@ -1,0 +1,418 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a (bf16 operands, fp32 accumulate in tensor memory).
+//
+//   D[i, j] = sum_k X[i, k] * Y[j, k]        X tile: 128 rows (UMMA M), Y tile: BN rows (UMMA N, 16..256)
+//
+// Both operands are K-major bf16 matrices read by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle) into a
+// multi-stage shared-memory ring; one elected thread issues tcgen05.mma (kind::f16, cta_group::1) into a TMEM
+// accumulator; four epilogue warps read it back with tcgen05.ld and apply the GemmParams epilogue.
+//
+//   normal mode : X = activations (rows m), Y = weight (rows n).  TMEM lane = m, column = n.  Multi-tap
+//                 (conv-as-GEMM) shifts the X row coordinate per tap; TMA zero-fills rows outside the tensor.
+//   swap mode   : X = weight (rows n), Y = activations (rows m, BN = M rounded up to 16).  TMEM lane = n,
+//                 column = m.  For the decode step, where M = sessions in flight is small: the 128-row UMMA M
+//                 dimension is filled by weight rows instead of padding, and C stores are coalesced along n.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
+// (TMEM lane quarter = warp_idx % 4).  One output tile per CTA; several CTAs are resident per SM so one CTA's
+// epilogue overlaps another's main loop.
+#pragma once
+#include <cuda.h>
+
+#include <map>
+#include <tuple>
+
+#include "common.cuh"
+#include "gemm.cuh"
+
+#ifndef LVX_OK
+#define LVX_OK 0
+#define LVX_ERR_INVALID 1
+#define LVX_ERR_CUDA 2
+#endif
+
+namespace lvx {
+
+constexpr int TC_BM = 128;  // UMMA M
+constexpr int TC_BK = 64;   // bf16 elements per k-block = one 128-byte swizzle row
+constexpr int TC_X_BYTES = TC_BM * TC_BK * 2;
+constexpr int TC_MAX_STAGES = 8;
+constexpr int TC_THREADS = 192;
+
+struct TmaDesc {
+  CUtensorMap map;  // box {64, 128}
+  bool valid = false;
+};
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct TcWorkspace {
+  int num_sms = 0;
+  PFN_encodeTiled encode = nullptr;
+  std::map<std::tuple<const void*, int, int, int, int>, CUtensorMap> act_maps;
+  int* d_err = nullptr;
+};
+
+static PFN_encodeTiled g_encode = nullptr;
+
+inline int tc_encode(CUtensorMap* m, const void* ptr, int rows, int cols, int ld, int box_rows) {
+  if (!g_encode) {
+    set_error("tensor-map encoder not initialised");
+    return LVX_ERR_CUDA;
+  }
+  if ((ld % 8) != 0 || (reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || box_rows < 1 || box_rows > 256) {
+    set_error("tensor map: leading dimension must be a multiple of 8 bf16 and the base 16-byte aligned");
+    return LVX_ERR_INVALID;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return LVX_ERR_CUDA;
+  }
+  return LVX_OK;
+}
+
+inline int tc_init(TcWorkspace* ws, int num_sms) {
+  ws->num_sms = num_sms;
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t err = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (err != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+      set_error("cudaGetDriverEntryPoint(cuTensorMapEncodeTiled) failed");
+      return LVX_ERR_CUDA;
+    }
+    g_encode = reinterpret_cast<PFN_encodeTiled>(fn);
+  }
+  ws->encode = g_encode;
+  return LVX_OK;
+}
+
+inline int tc_make_desc(TmaDesc* d, const bf16* ptr, int rows, int cols, int ld) {
+  int s = tc_encode(&d->map, ptr, rows, cols, ld, TC_BM);
+  d->valid = (s == LVX_OK);
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug must end in a trap (reported as a launch failure), never in a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]^T, bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns: thread t of the warp gets lane (quarter * 32 + t)
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte-swizzled operand tile (rows x 64 bf16, 8-row groups 1024 bytes apart)
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);  // start address
+  d |= (uint64_t)1 << 16;                    // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                    // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D = fp32, A = B = bf16, both K-major, M x N
+__host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct TcParams {
+  GemmParams g;
+  int BN;          // UMMA N = Y rows per tile
+  int stages;
+  int num_kb;      // K / 64 (rounded up; TMA zero-fills the tail)
+  int tmem_cols;   // power of two >= max(32, BN)
+};
+
+template <bool kSwap, typename TC>
+__global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const __grid_constant__ CUtensorMap mapX,
+                                                             const __grid_constant__ CUtensorMap mapY, const TcParams tp) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 1];
+  __shared__ uint32_t tmem_base_sh;
+
+  const GemmParams& p = tp.g;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int BN = tp.BN, stages = tp.stages, num_kb = tp.num_kb;
+  const uint32_t y_bytes = (uint32_t)BN * TC_BK * 2;
+  const uint32_t stage_bytes = TC_X_BYTES + y_bytes;
+  const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (TC_MAX_STAGES + s); };
+  const uint32_t tmem_full_bar = bar0 + 8u * (2 * TC_MAX_STAGES);
+
+  // tile origin: x0 = first X row, y0 = first Y row
+  const int x0 = (kSwap ? blockIdx.x : blockIdx.y) * TC_BM;
+  const int y0 = (kSwap ? blockIdx.y : blockIdx.x) * BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapX);
+    tma_prefetch_desc(&mapY);
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    __syncwarp();
+    tmem_alloc(smem_u32(&tmem_base_sh), (uint32_t)tp.tmem_cols);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_sh;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % stages;
+        const uint32_t ph = (uint32_t)(kb / stages) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), stage_bytes);
+        const int k0 = kb * TC_BK;
+        int xc = k0, xr = x0;
+        if (!kSwap && p.taps > 1) {
+          const int tap = k0 / p.tap_K;
+          xc = k0 - tap * p.tap_K;
+          xr = x0 + tap - p.tap_pad;
+        }
+        const uint32_t dst = tiles + (uint32_t)s * stage_bytes;
+        tma_load_2d(&mapX, full_bar(s), dst, xc, xr);
+        tma_load_2d(&mapY, full_bar(s), dst + TC_X_BYTES, k0, y0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int s = kb % stages;
+        const uint32_t ph = (uint32_t)(kb / stages) & 1u;
+        mbar_wait(full_bar(s), ph);
+        tc_fence_after();
+        const uint32_t xs = tiles + (uint32_t)s * stage_bytes;
+        const uint64_t adesc = umma_smem_desc(xs), bdesc = umma_smem_desc(xs + TC_X_BYTES);
+#pragma unroll
+        for (int k = 0; k < TC_BK / 16; ++k) {
+          // +32 bytes (16 bf16) along K inside the swizzle atom = +2 in the encoded start address
+          umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);   // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> registers -> global
+    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    TC* C = reinterpret_cast<TC*>(p.C);
+    const int i = x0 + q * 32 + lane;  // D row of this thread
+    const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16);
+    if (!kSwap) {
+      const int m = i;
+      const bool row_ok = m < p.M && (!p.row_chunk || p.row_chunk[m] >= 0);
+      for (int c = 0; c < BN; c += 16) {
+        float v[16];
+        tmem_ld16(trow + (uint32_t)c, v);
+        const int n = y0 + c;
+        if (!row_ok || n >= p.N) continue;
+        const bool full = (n + 16 <= p.N);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int nn = n + j;
+          if (full || nn < p.N) {
+            float xv = v[j] * p.alpha;
+            if (p.bias) xv += p.bias[nn];
+            xv = apply_act(xv, p.act);
+            if (p.col_scale) xv *= p.col_scale[nn];
+            if (p.residual) xv += p.residual[(size_t)m * p.ldr + nn];
+            v[j] = xv;
+          }
+        }
+        TC* dst = C + (size_t)m * p.ldc + n;
+        if (full && (p.ldc & 3) == 0) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) store4(dst + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (n + j < p.N) store1(dst + j, v[j]);
+        }
+      }
+    } else {
+      const int n = i;  // weight row = output column
+      const bool n_ok = n < p.N;
+      const float b = (p.bias && n_ok) ? p.bias[n] : 0.f;
+      const float cs = (p.col_scale && n_ok) ? p.col_scale[n] : 1.f;
+      for (int c = 0; c < BN; c += 16) {
+        float v[16];
+        tmem_ld16(trow + (uint32_t)c, v);
+        if (!n_ok) continue;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int m = y0 + c + j;
+          if (m >= p.M) break;
+          if (p.row_chunk && p.row_chunk[m] < 0) continue;
+          float xv = v[j] * p.alpha + b;
+          xv = apply_act(xv, p.act);
+          xv *= cs;
+          if (p.residual) xv += p.residual[(size_t)m * p.ldr + n];
+          store1(C + (size_t)m * p.ldc + n, xv);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_d, (uint32_t)tp.tmem_cols);
+  }
+}
+
+inline int tc_act_map(TcWorkspace* ws, const void* ptr, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+  auto key = std::make_tuple(ptr, rows, cols, ld, box_rows);
+  auto it = ws->act_maps.find(key);
+  if (it == ws->act_maps.end()) {
+    CUtensorMap m;
+    int s = tc_encode(&m, ptr, rows, cols, ld, box_rows);
+    if (s != LVX_OK) return s;
+    if (ws->act_maps.size() > 4096) ws->act_maps.clear();
+    it = ws->act_maps.emplace(key, m).first;
+  }
+  *out = it->second;
+  return LVX_OK;
+}
+
+template <bool kSwap, typename TC>
+inline int tc_launch(const CUtensorMap& mx, const CUtensorMap& my, const TcParams& tp, dim3 grid, cudaStream_t st) {
+  const size_t smem = (size_t)tp.stages * (TC_X_BYTES + (size_t)tp.BN * TC_BK * 2) + 1024;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t err = cudaFuncSetAttribute(tc_gemm_kernel<kSwap, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+    if (err != cudaSuccess) {
+      set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
+      return LVX_ERR_CUDA;
+    }
+    configured = 227 * 1024;
+  }
+  tc_gemm_kernel<kSwap, TC><<<grid, TC_THREADS, smem, st>>>(mx, my, tp);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    set_error(std::string("tc_gemm launch: ") + cudaGetErrorString(err));
+    return LVX_ERR_CUDA;
+  }
+  return LVX_OK;
+}
+
+// p.A: bf16 activations (M x K view, lda), p.a_cap rows addressable.  w: tensor map of the bf16 (N, K) weight.
+inline int tc_gemm(TcWorkspace* ws, const GemmParams& p, const TmaDesc& w, bool c_bf16, cudaStream_t st) {
+  if (!w.valid) {
+    set_error("tc_gemm: weight has no tensor map");
+    return LVX_ERR_INVALID;
+  }
+  if (p.M <= 0) return LVX_OK;
+  if (p.batch || p.w_kn || (p.taps > 1 && (p.tap_K % TC_BK) != 0)) {
+    set_error("tc_gemm: unsupported problem shape");
+    return LVX_ERR_INVALID;
+  }
+  const int a_cols = p.taps > 1 ? p.tap_K : p.K;
+  const int a_cap = p.a_cap ? p.a_cap : (p.a_rows ? p.a_rows : p.M);
+  const bool swap = p.taps == 1 && p.M <= 256;
+  TcParams tp;
+  tp.g = p;
+  tp.num_kb = ceil_div(p.K, TC_BK);
+  tp.BN = swap ? std::max(16, ceil_div(p.M, 16) * 16) : 128;
+  tp.tmem_cols = 32;
+  while (tp.tmem_cols < tp.BN) tp.tmem_cols *= 2;
+  const int stage_bytes = TC_X_BYTES + tp.BN * TC_BK * 2;
+  const int budget = tp.BN <= 128 ? 110 * 1024 : 220 * 1024;  // <= 128: two CTAs per SM
+  tp.stages = std::max(2, std::min(std::min(TC_MAX_STAGES, tp.num_kb), (budget - 1024) / stage_bytes));
+  CUtensorMap am;
+  int s = tc_act_map(ws, p.A, a_cap, a_cols, p.lda, swap ? tp.BN : TC_BM, &am);
+  if (s != LVX_OK) return s;
+  if (swap) {
+    dim3 grid(ceil_div(p.N, TC_BM), ceil_div(p.M, tp.BN));
+    return c_bf16 ? tc_launch<true, bf16>(w.map, am, tp, grid, st) : tc_launch<true, float>(w.map, am, tp, grid, st);
+  }
+  dim3 grid(ceil_div(p.N, tp.BN), ceil_div(p.M, TC_BM));
+  return c_bf16 ? tc_launch<false, bf16>(am, w.map, tp, grid, st) : tc_launch<false, float>(am, w.map, tp, grid, st);
+}
+
+}  // namespace lvx

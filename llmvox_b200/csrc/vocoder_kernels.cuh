@@ -60,7 +60,10 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float* __res
   const int row = (int)(i / (C / 4)), c = (int)(i % (C / 4)) * 4;
   if (row >= rows) return;
   const int ch = row_chunk[row];
-  if (ch < 0) return;
+  if (ch < 0) {  // padding row: the k=3 conv that follows must read zeros here
+    store4(out + (size_t)row * C + c, make_float4(0.f, 0.f, 0.f, 0.f));
+    return;
+  }
   const float2 st = stats[(size_t)ch * G + c / CPG];
   const float4 v = load4(x + (size_t)row * C + c), ww = load4(w + c), bb = load4(b + c);
   float r[4] = {(v.x - st.x) * st.y * ww.x + bb.x, (v.y - st.x) * st.y * ww.y + bb.y,

@@ -1,0 +1,216 @@
+"""Python face of the C-ABI engine (include/llmvox_b200.h).  torch is used for device memory and streams
+only; every computation happens in libllmvox_b200.so.  One Engine per GPU."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import LvxConfig, LvxSampling, PRECISION_BF16, PRECISION_FP32, check, i32_array
+from .weights import CODEBOOK_KEY, GPTArch, VocoderArch
+
+_UNUSED_PREFIXES = ("feature_extractor.",)   # SEANet encoder etc.: loaded by the reference, never executed
+
+
+@dataclass
+class Sampling:
+    """Sampler of GPT.generate (src/model.py:397-406); greedy = the hot loop's argmax (streaming_server.py:342-346)."""
+    greedy: bool = True
+    top_k: int = 0
+    temperature: float = 1.0
+    seed: int = 0
+
+    def to_c(self, d_uniform: Optional[torch.Tensor] = None) -> LvxSampling:
+        return LvxSampling(int(self.greedy), int(self.top_k), float(self.temperature), int(self.seed),
+                           d_uniform.data_ptr() if d_uniform is not None else None)
+
+
+class Engine:
+    def __init__(self, weights: Dict[str, torch.Tensor], device: int = 0, precision: str = "fp32",
+                 gpt_arch: Optional[GPTArch] = None, voc_arch: Optional[VocoderArch] = None,
+                 max_sessions: int = 256, max_context: int = 1024, max_batch: Optional[int] = None,
+                 max_vocode_frames: int = 32768, kv_page_tokens: int = 16, kv_pages: int = 0,
+                 pad_token_id: int = 384, eoa_token_id: int = 453):
+        if not torch.cuda.is_available():
+            raise RuntimeError("llmvox_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = _lib.load()
+        ga, va = gpt_arch or GPTArch(), voc_arch or VocoderArch()
+        cfg = LvxConfig()
+        check(self.lib.lvx_config_default(C.byref(cfg)))
+        cfg.n_layer, cfg.n_head, cfg.n_embd = ga.n_layer, ga.n_head, ga.n_embd
+        cfg.block_size, cfg.vocab_size, cfg.bias = ga.block_size, ga.vocab_size, int(ga.bias)
+        cfg.code_dim, cfg.n_codes = va.input_channels, va.vq_bins
+        cfg.voc_dim, cfg.voc_inter, cfg.voc_layers = va.dim, va.intermediate_dim, va.num_layers
+        cfg.voc_ada_rows, cfg.n_fft, cfg.hop = va.adanorm_num_embeddings, va.n_fft, va.hop_length
+        cfg.max_sessions, cfg.max_context = max_sessions, max_context
+        cfg.max_batch = max_batch or max_sessions
+        cfg.max_vocode_frames, cfg.kv_page_tokens, cfg.kv_pages = max_vocode_frames, kv_page_tokens, kv_pages
+        cfg.precision = {"fp32": PRECISION_FP32, "bf16": PRECISION_BF16}[precision]
+        cfg.pad_token_id, cfg.eoa_token_id = pad_token_id, eoa_token_id
+        self.cfg = cfg
+        self.precision = precision
+        self.device = torch.device("cuda", device)
+        self._h = C.c_void_p()
+        check(self.lib.lvx_engine_create(C.byref(cfg), device, C.byref(self._h)))
+        try:
+            self._load(weights)
+        except Exception:
+            self.close()
+            raise
+
+    # ------------------------------------------------------------------ lifecycle
+    def _load(self, weights: Dict[str, torch.Tensor]):
+        for name, t in weights.items():
+            if name != CODEBOOK_KEY and name.startswith(_UNUSED_PREFIXES):
+                continue
+            t = t.detach().to(device="cpu", dtype=torch.float32).contiguous()
+            if name == "transformer.wpe.weight" and t.shape[0] > self.cfg.max_context:
+                t = t[: self.cfg.max_context].contiguous()      # only positions < max_context are ever read
+            shape = (C.c_int64 * t.dim())(*t.shape)
+            check(self.lib.lvx_load_tensor(self._h, name.encode(), C.c_void_p(t.data_ptr()), shape, t.dim()))
+        check(self.lib.lvx_finalize_weights(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.lvx_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.lib.lvx_kernel_launches(self._h))
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self.lib.lvx_device_bytes(self._h))
+
+    def _stream(self, stream) -> C.c_void_p:
+        s = stream if stream is not None else torch.cuda.current_stream(self.device)
+        return C.c_void_p(s.cuda_stream)
+
+    # ------------------------------------------------------------------ sessions
+    def open(self, slots: Sequence[int], stream=None):
+        check(self.lib.lvx_session_open(self._h, i32_array(slots), len(slots), self._stream(stream)))
+
+    def release(self, slots: Sequence[int], stream=None):
+        check(self.lib.lvx_session_close(self._h, i32_array(slots), len(slots), self._stream(stream)))
+
+    def feed_text(self, slots: Sequence[int], ids: Sequence[Sequence[int]], stream=None):
+        offs, flat = [0], []
+        for seq in ids:
+            flat.extend(int(x) for x in seq)
+            offs.append(len(flat))
+        check(self.lib.lvx_feed_text(self._h, i32_array(slots), i32_array(offs), i32_array(flat or [0]), len(slots),
+                                     self._stream(stream)))
+
+    def session_length(self, slot: int) -> int:
+        out = C.c_int32()
+        check(self.lib.lvx_session_length(self._h, slot, C.byref(out)))
+        return out.value
+
+    # ------------------------------------------------------------------ decode
+    def decode_steps(self, slots: Sequence[int], n_steps: int, sampling: Optional[Sampling] = None, stream=None):
+        s = (sampling or Sampling()).to_c()
+        check(self.lib.lvx_decode_steps(self._h, i32_array(slots), len(slots), n_steps, C.byref(s), self._stream(stream)))
+
+    def decode_step_logits(self, slots: Sequence[int], forced: Optional[torch.Tensor] = None,
+                           sampling: Optional[Sampling] = None, uniform: Optional[torch.Tensor] = None,
+                           stream=None) -> Tuple[torch.Tensor, torch.Tensor]:
+        n = len(slots)
+        logits = torch.empty((n, self.cfg.vocab_size), dtype=torch.float32, device=self.device)
+        codes = torch.empty((n,), dtype=torch.int32, device=self.device)
+        s = (sampling or Sampling()).to_c(uniform)
+        fp = C.c_void_p(forced.data_ptr()) if forced is not None else None
+        if forced is not None:
+            assert forced.dtype == torch.int32 and forced.is_cuda and forced.numel() == n
+        check(self.lib.lvx_decode_step_logits(self._h, i32_array(slots), n, C.byref(s), fp, C.c_void_p(logits.data_ptr()),
+                                              C.c_void_p(codes.data_ptr()), self._stream(stream)))
+        return logits, codes
+
+    def decode_step_embeds(self, slots: Sequence[int], emb: torch.Tensor, positions: Sequence[int], stream=None) -> torch.Tensor:
+        n = len(slots)
+        emb = emb.to(device=self.device, dtype=torch.float32).contiguous()
+        assert emb.shape == (n, self.cfg.n_embd)
+        logits = torch.empty((n, self.cfg.vocab_size), dtype=torch.float32, device=self.device)
+        check(self.lib.lvx_decode_step_embeds(self._h, i32_array(slots), n, C.c_void_p(emb.data_ptr()), i32_array(positions),
+                                              C.c_void_p(logits.data_ptr()), self._stream(stream)))
+        return logits
+
+    def gather_codes(self, slots: Sequence[int], start: int, count: int, stream=None) -> torch.Tensor:
+        out = torch.empty((len(slots), count), dtype=torch.int32, device=self.device)
+        check(self.lib.lvx_gather_codes(self._h, i32_array(slots), len(slots), start, count, C.c_void_p(out.data_ptr()),
+                                        self._stream(stream)))
+        return out
+
+    def gather_code_ranges(self, slots: Sequence[int], starts: Sequence[int], counts: Sequence[int], stream=None) -> torch.Tensor:
+        out = torch.empty((max(1, int(sum(counts))),), dtype=torch.int32, device=self.device)
+        check(self.lib.lvx_gather_code_ranges(self._h, i32_array(slots), i32_array(starts), i32_array(counts), len(slots),
+                                              C.c_void_p(out.data_ptr()), self._stream(stream)))
+        return out[: int(sum(counts))]
+
+    # ------------------------------------------------------------------ embeddings
+    def codes_to_features(self, codes: torch.Tensor, stream=None) -> torch.Tensor:
+        codes = codes.to(device=self.device, dtype=torch.int32).contiguous().view(-1)
+        out = torch.empty((codes.numel(), self.cfg.code_dim), dtype=torch.float32, device=self.device)
+        check(self.lib.lvx_codes_to_features(self._h, C.c_void_p(codes.data_ptr()), codes.numel(), C.c_void_p(out.data_ptr()),
+                                             self._stream(stream)))
+        return out
+
+    def text_embed(self, ids: torch.Tensor, stream=None) -> torch.Tensor:
+        ids = ids.to(device=self.device, dtype=torch.int32).contiguous().view(-1)
+        out = torch.empty((ids.numel(), self.cfg.text_dim), dtype=torch.float32, device=self.device)
+        check(self.lib.lvx_text_embed(self._h, C.c_void_p(ids.data_ptr()), ids.numel(), C.c_void_p(out.data_ptr()),
+                                      self._stream(stream)))
+        return out
+
+    # ------------------------------------------------------------------ vocoder
+    def vocode(self, codes: torch.Tensor, cu: Sequence[int], bandwidth_id: int = 0, out: Optional[torch.Tensor] = None,
+               stream=None) -> torch.Tensor:
+        """codes: packed int32 device tensor; chunk i = codes[cu[i]:cu[i+1]].  -> packed PCM (hop * total,) fp32."""
+        assert codes.dtype == torch.int32 and codes.is_cuda and codes.is_contiguous()
+        total = int(cu[-1])
+        assert codes.numel() >= total
+        if out is None:
+            out = torch.empty((total * self.cfg.hop,), dtype=torch.float32, device=self.device)
+        check(self.lib.lvx_vocode(self._h, C.c_void_p(codes.data_ptr()), i32_array(cu), len(cu) - 1, bandwidth_id,
+                                  C.c_void_p(out.data_ptr()), self._stream(stream)))
+        return out
+
+    def vocode_features(self, feats: torch.Tensor, cu: Sequence[int], bandwidth_id: int = 0, stream=None) -> torch.Tensor:
+        """feats: packed channels-last (total, code_dim) fp32 device tensor."""
+        feats = feats.to(device=self.device, dtype=torch.float32).contiguous()
+        total = int(cu[-1])
+        assert feats.shape == (total, self.cfg.code_dim)
+        out = torch.empty((total * self.cfg.hop,), dtype=torch.float32, device=self.device)
+        check(self.lib.lvx_vocode_features(self._h, C.c_void_p(feats.data_ptr()), i32_array(cu), len(cu) - 1, bandwidth_id,
+                                           C.c_void_p(out.data_ptr()), self._stream(stream)))
+        return out
+
+    def test_gemm(self, A: torch.Tensor, Wt: torch.Tensor, taps: int = 1, stream=None) -> torch.Tensor:
+        """Test hook (lvx_test_gemm): A (M, K/taps) . Wt (N, K)^T -> (M, N) through the engine's GEMM path."""
+        A = A.to(device=self.device, dtype=torch.float32).contiguous()
+        Wt = Wt.to(device=self.device, dtype=torch.float32).contiguous()
+        M, N, K = A.shape[0], Wt.shape[0], Wt.shape[1]
+        assert A.shape[1] * taps == K
+        out = torch.empty((M, N), dtype=torch.float32, device=self.device)
+        check(self.lib.lvx_test_gemm(self._h, C.c_void_p(A.data_ptr()), C.c_void_p(Wt.data_ptr()), M, N, K, taps,
+                                     C.c_void_p(out.data_ptr()), self._stream(stream)))
+        return out
+
+    _STAGE_WIDTH = {0: "voc_dim", 1: "voc_dim", 2: "voc_dim", 3: "voc_dim", 4: "voc_dim", 5: "n_fft"}
+
+    def vocode_stage(self, codes: torch.Tensor, stage: int, bandwidth_id: int = 0, stream=None) -> torch.Tensor:
+        codes = codes.to(device=self.device, dtype=torch.int32).contiguous().view(-1)
+        width = getattr(self.cfg, self._STAGE_WIDTH[stage])
+        out = torch.empty((codes.numel(), width), dtype=torch.float32, device=self.device)
+        check(self.lib.lvx_vocode_stage(self._h, C.c_void_p(codes.data_ptr()), codes.numel(), bandwidth_id, stage,
+                                        C.c_void_p(out.data_ptr()), self._stream(stream)))
+        return out

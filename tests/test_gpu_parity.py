@@ -1,0 +1,361 @@
+"""GPU parity tests (run on the B200 box with -m gpu): the CUDA path, called through the C ABI, against the
+CPU oracle and against the fixtures the unmodified reference produced (tests/golden, oracle/make_golden.py).
+
+Tolerances (north_star): greedy tokens identical and logits within 1e-4 in fp32 mode; teacher-forced logits
+within 2e-2 in bf16 mode; waveforms >= 40 dB SNR versus the reference."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from llmvox_b200 import weights as W  # noqa: E402
+from oracle import llmvox_oracle as O  # noqa: E402
+
+SENT = ("the quick brown fox jumps over the lazy dog while seven small birds "
+        "sing a very old song near the river.")
+
+
+def snr_db(ref, x):
+    ref = np.asarray(ref, dtype=np.float64)
+    x = np.asarray(x, dtype=np.float64)
+    return 10 * np.log10((ref ** 2).sum() / max(((ref - x) ** 2).sum(), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def engines(weights):
+    from llmvox_b200.engine import Engine
+    cache = {}
+
+    def get(precision):
+        if precision not in cache:
+            cache[precision] = Engine(weights, device=0, precision=precision, max_sessions=72, max_context=256,
+                                      max_vocode_frames=4096)
+        return cache[precision]
+    yield get
+    for e in cache.values():
+        e.close()
+
+
+# ------------------------------------------------------------------------------------------------ GEMM kernels
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("M,N,K,taps", [(64, 768, 768, 1), (1, 2304, 768, 1), (37, 4096, 768, 1), (200, 768, 3072, 1),
+                                        (300, 2304, 768, 1), (1000, 1282, 2304, 1), (129, 768, 2304, 3),
+                                        (515, 768, 3584, 7), (16, 768, 2304, 3)])
+def test_gemm_against_torch(engines, precision, M, N, K, taps):
+    e = engines(precision)
+    g = torch.Generator().manual_seed(M * 7 + N + K + taps)
+    A = torch.randn(M, K // taps, generator=g)
+    Wt = torch.randn(N, K, generator=g) * 0.05
+    if precision == "bf16":
+        A, Wt = A.bfloat16().float(), Wt.bfloat16().float()
+    pad = taps // 2
+    Ap = torch.nn.functional.pad(A, (0, 0, pad, pad))
+    Acat = torch.cat([Ap[t:t + M] for t in range(taps)], dim=1)      # (M, K): tap-major columns
+    ref = (Acat.double() @ Wt.double().T).float()
+    out = e.test_gemm(A, Wt, taps).cpu()
+    tol = 2e-4 if precision == "fp32" else 2e-3
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max().item() < tol * max(1.0, ref.abs().max().item())
+
+
+# ------------------------------------------------------------------------------------------------ decode step
+def test_fp32_greedy_tokens_identical_to_reference_loop(engines, gold):
+    """config 0: the reference's own audio_generator_sync produced these codes (oracle/make_golden.py)."""
+    g = gold("config0_loop.npz")
+    e = engines("fp32")
+    n = int(g["n_steps"])
+    e.open([3])
+    e.feed_text([3], [g["text_ids"].tolist()])
+    e.decode_steps([3], n)
+    codes = e.gather_codes([3], 0, n).cpu().numpy()[0]
+    assert codes.tolist() == g["codes"].tolist()
+    assert e.session_length(3) == n
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_teacher_forced_logits(engines, gold, precision, tol):
+    g = gold("teacher_forced.npz")
+    e = engines(precision)
+    forced = torch.from_numpy(g["forced_codes"]).to("cuda", torch.int32)
+    e.open([0])
+    e.feed_text([0], [g["text_ids"].tolist()])
+    rows = []
+    for t in range(48):
+        logits, codes = e.decode_step_logits([0], forced=forced[t:t + 1])
+        rows.append(logits[0].cpu())
+        assert int(codes[0]) == int(logits[0].argmax())
+    got = torch.stack(rows).numpy()
+    err = np.abs(got - g["logits"]).max()
+    assert err < tol, err
+
+
+def test_fp32_logit_rows_of_the_greedy_loop(engines, gold):
+    g = gold("config0_loop.npz")
+    e = engines("fp32")
+    e.open([1])
+    e.feed_text([1], [g["text_ids"].tolist()])
+    want = dict(zip(g["logits_row_idx"].tolist(), g["logits_rows"]))
+    for t in range(int(g["n_steps"])):
+        logits, _ = e.decode_step_logits([1])
+        if t in want:
+            assert np.abs(logits[0].cpu().numpy() - want[t]).max() < 1e-4
+
+
+def test_batch_invariance_and_ragged_text(engines, weights):
+    """Sessions are independent: a session decodes the same codes alone and inside a batch of others with
+    different (and empty) texts; text ids beyond the text are PAD (streaming_server.py:316-320)."""
+    e = engines("fp32")
+    rng = np.random.RandomState(0)
+    texts = [rng.randint(3, 259, size=n).tolist() for n in (40, 0, 7, 25, 40)]
+    slots = [10, 11, 12, 13, 14]
+    e.open(slots)
+    e.feed_text(slots, texts)
+    e.decode_steps(slots, 30)
+    batch = e.gather_codes(slots, 0, 30).cpu().numpy()
+    for i, s in enumerate(slots):
+        e.open([20])
+        e.feed_text([20], [texts[i]])
+        e.decode_steps([20], 12)
+        e.decode_steps([20], 18)          # split calls continue the same sentence
+        alone = e.gather_codes([20], 0, 30).cpu().numpy()[0]
+        assert alone.tolist() == batch[i].tolist()
+    ref = O.decode_steps(weights, O.GPTArch(), texts[2], 30)
+    assert ref == batch[2].tolist()
+
+
+def test_bf16_decode_tracks_oracle_on_rounded_weights(engines, weights):
+    """bf16 mode: first divergence from the fp32 oracle run on the same bf16-rounded weights is reported; the
+    step-0 pick (no history) must agree and teacher-forced logits carry the 2e-2 bound (above)."""
+    e = engines("bf16")
+    ids = O.word_ids("hello", True)
+    e.open([0])
+    e.feed_text([0], [ids])
+    e.decode_steps([0], 24)
+    got = e.gather_codes([0], 0, 24).cpu().numpy()[0].tolist()
+    ref = O.decode_steps(W.round_weights_to_bf16(weights), O.GPTArch(), ids, 24)
+    assert got[0] == ref[0]
+    assert all(0 <= c < 4096 for c in got)
+
+
+def test_sampler_matches_generate_semantics(engines):
+    """src/model.py:397-406 restated in the oracle as inverse-CDF sampling against a supplied uniform."""
+    e = engines("fp32")
+    slots = list(range(30, 46))
+    rng = np.random.RandomState(5)
+    e.open(slots)
+    e.feed_text(slots, [rng.randint(3, 259, size=20).tolist() for _ in slots])
+    from llmvox_b200.engine import Sampling
+    g = torch.Generator().manual_seed(11)
+    for (temp, topk) in [(0.8, 5), (1.0, 50), (1.3, 0), (0.7, 1), (1.0, 4096)]:
+        u = torch.rand(len(slots), generator=g)
+        logits, codes = e.decode_step_logits(slots, sampling=Sampling(greedy=False, top_k=topk, temperature=temp),
+                                             uniform=u.cuda())
+        if topk == 1:
+            want = logits.argmax(dim=1).cpu()
+        else:
+            want = O.sample_from_logits(logits.cpu(), temp, topk if topk > 0 else None, u)
+        lg = logits.cpu() / temp
+        for b in range(len(slots)):
+            if int(codes[b]) != int(want[b]):
+                # fp32 vs fp64 CDF rounding may move a draw that sits on a bin edge to the neighbouring survivor
+                p = torch.softmax(lg[b].double(), dim=0)
+                assert abs(float(torch.cumsum(p, 0)[min(int(codes[b]), int(want[b]))]) - float(u[b])) < 1e-4
+    # seeded Philox path: reproducible and inside the top-k set
+    s = Sampling(greedy=False, top_k=3, temperature=1.0, seed=42)
+    logits, codes = e.decode_step_logits(slots, sampling=s)
+    top3 = torch.topk(logits, 3).indices
+    assert all(int(codes[b]) in top3[b].tolist() for b in range(len(slots)))
+
+
+# ------------------------------------------------------------------------------------------------ vocoder
+@pytest.mark.parametrize("precision,min_snr", [("fp32", 80.0), ("bf16", 40.0)])
+@pytest.mark.parametrize("L", [1, 2, 3, 5, 10, 30, 90, 160])
+def test_vocoder_chunks_against_reference(engines, gold, precision, min_snr, L):
+    g = gold("vocoder.npz")
+    e = engines(precision)
+    codes = torch.from_numpy(g[f"codes_{L}"]).to("cuda", torch.int32)
+    pcm = e.vocode(codes, [0, L]).cpu().numpy()
+    assert pcm.shape == (320 * L,)
+    assert snr_db(g[f"pcm_{L}"], pcm) > min_snr, snr_db(g[f"pcm_{L}"], pcm)
+
+
+@pytest.mark.parametrize("precision,min_snr", [("fp32", 80.0), ("bf16", 40.0)])
+@pytest.mark.parametrize("L", [270, 480, 810, 1280])
+def test_vocoder_long_chunks_sliced(engines, gold, precision, min_snr, L):
+    g = gold("vocoder.npz")
+    e = engines(precision)
+    codes = torch.from_numpy(g[f"codes_{L}"]).to("cuda", torch.int32)
+    pcm = e.vocode(codes, [0, L]).cpu().numpy()
+    n, m = len(pcm), len(pcm) // 2
+    sl = np.concatenate([pcm[:2560], pcm[m - 1280:m + 1280], pcm[-2560:]])
+    assert snr_db(g[f"pcm_{L}"], sl) > min_snr, snr_db(g[f"pcm_{L}"], sl)
+    rms = float(np.sqrt((pcm.astype(np.float64) ** 2).mean()))
+    assert abs(rms - float(g[f"rms_{L}"])) < 0.02 * float(g[f"rms_{L}"])
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("bf16", 6e-2)])
+def test_vocoder_stage_activations(engines, gold, precision, tol):
+    g = gold("vocoder.npz")
+    e = engines(precision)
+    codes = torch.from_numpy(g["codes_30"]).to("cuda", torch.int32)
+    for stage, key in [(0, "act30_embed"), (1, "act30_res0"), (2, "act30_attn"), (3, "act30_posnet"), (4, "act30_backbone")]:
+        got = e.vocode_stage(codes, stage).cpu().numpy()
+        ref = g[key]
+        err = np.abs(got - ref).max() / max(1.0, np.abs(ref).max())
+        assert err < tol, (key, err)
+
+
+def test_vocoder_bandwidth_id_selects_adanorm_row(engines, gold):
+    g = gold("vocoder.npz")
+    e = engines("fp32")
+    codes = torch.from_numpy(g["codes_bw2"]).to("cuda", torch.int32)
+    pcm2 = e.vocode(codes, [0, len(codes)], bandwidth_id=2).cpu().numpy()
+    pcm0 = e.vocode(codes, [0, len(codes)], bandwidth_id=0).cpu().numpy()
+    assert snr_db(g["pcm_bw2"], pcm2) > 80
+    assert snr_db(g["pcm_bw2"], pcm0) < 30
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_ragged_batch_equals_independent_chunks(engines, precision):
+    """Quirk 3 of the reference: every chunk is decoded independently, so a ragged batch
+    must reproduce each chunk's own decode (conv padding, GroupNorm statistics, attention and iSTFT edges are
+    per chunk)."""
+    e = engines(precision)
+    g = torch.Generator().manual_seed(3)
+    lens = [10, 1, 30, 7, 90, 2, 33]
+    cu = np.concatenate([[0], np.cumsum(lens)]).tolist()
+    codes = torch.randint(0, 4096, (cu[-1],), generator=g).to("cuda", torch.int32)
+    batch = e.vocode(codes, cu).cpu().numpy()
+    for i, L in enumerate(lens):
+        alone = e.vocode(codes[cu[i]:cu[i + 1]].contiguous(), [0, L]).cpu().numpy()
+        seg = batch[320 * cu[i]:320 * cu[i + 1]]
+        if precision == "fp32":
+            assert np.abs(seg - alone).max() < 1e-5 * max(1.0, np.abs(alone).max())
+        else:
+            assert snr_db(alone, seg) > 60
+
+
+def test_vocoder_groups_split_transparently(weights):
+    """More frames than max_vocode_frames: the call is cut into launch groups without changing results."""
+    from llmvox_b200.engine import Engine
+    small = Engine(weights, device=0, precision="fp32", max_sessions=2, max_context=32, max_vocode_frames=64)
+    g = torch.Generator().manual_seed(4)
+    lens = [40, 30, 20, 50, 10]
+    cu = np.concatenate([[0], np.cumsum(lens)]).tolist()
+    codes = torch.randint(0, 4096, (cu[-1],), generator=g).to("cuda", torch.int32)
+    got = small.vocode(codes, cu).cpu().numpy()
+    for i, L in enumerate(lens):
+        alone = small.vocode(codes[cu[i]:cu[i + 1]].contiguous(), [0, L]).cpu().numpy()
+        assert np.abs(got[320 * cu[i]:320 * cu[i + 1]] - alone).max() < 1e-5 * max(1.0, np.abs(alone).max())
+    from llmvox_b200._lib import LvxError
+    with pytest.raises(LvxError):
+        small.vocode(codes[:100].contiguous(), [0, 100])        # one chunk longer than the workspace
+    with pytest.raises(LvxError):
+        small.vocode(codes, [0, 10, 10])                          # empty chunk
+    small.close()
+
+
+# ------------------------------------------------------------------------------------------------ whole path
+def test_streaming_chunks_match_reference_loop(engines, gold):
+    """config 0 end to end through the batched host loop: chunk schedule 10/30/90 and the PCM of each chunk
+    against what the reference put on its audio queue."""
+    from llmvox_b200.streaming import synthesize
+    g = gold("config0_loop.npz")
+    e = engines("fp32")
+    n = int(g["n_steps"])
+    codes, per = synthesize(e, [g["text_ids"].tolist()], n, initial_dump_size=10, stop_on_eoa=True, flush_tail=False)
+    assert codes[0].tolist() == g["codes"].tolist()
+    assert [c.length for c in per[0]] == g["chunk_lens"].tolist()
+    for i, ch in enumerate(per[0]):
+        assert snr_db(g[f"pcm{i}"], ch.pcm) > 80
+
+
+def test_replica1_schedule(engines, gold):
+    from llmvox_b200.streaming import synthesize
+    from llmvox_b200.tokenizer import sentence_ids
+    g = gold("replica1_loop.npz")
+    e = engines("fp32")
+    codes, per = synthesize(e, [sentence_ids(SENT)], 200, initial_dump_size=160, stop_on_eoa=True, flush_tail=False)
+    assert codes[0].tolist() == g["codes"].tolist()
+    assert [c.length for c in per[0]] == g["chunk_lens"].tolist()
+    assert snr_db(g["pcm0_head"], per[0][0].pcm[:3200]) > 80
+    assert snr_db(g["pcm0_tail"], per[0][0].pcm[-3200:]) > 80
+
+
+def test_model_handler_drop_in_protocol(gold):
+    """The reference call sites of streaming_server.py:306-365 against the mirror: tokenizer, llm_model,
+    codes_to_features, model(emb, kvcache), decode."""
+    import torch.nn.functional as F
+    from llmvox_b200.model_handler import ModelHandler
+    g = gold("config0_loop.npz")
+    mh = ModelHandler({"random_init_seed": 1234, "max_sessions": 8, "max_context": 160, "max_vocode_frames": 512}, 0)
+    assert mh.tokenizer("fox")["input_ids"] == [105, 114, 123, 1]
+    ids = g["text_ids"].tolist()
+    kv, prev, cur, codes = None, None, None, []
+    want = dict(zip(g["logits_row_idx"].tolist(), g["logits_rows"]))
+    for t in range(40):
+        te = mh.llm_model(torch.tensor([[ids[t]]]).to(mh.device))
+        assert te.shape == (1, 1, 256)
+        if t == 0:
+            se = torch.zeros((1, 1, 512), device=mh.device)
+        else:
+            se = mh.wavtokenizer.codes_to_features(torch.tensor([[cur]]).to(mh.device)).permute(0, 2, 1)
+        x = F.normalize(torch.cat([te, se], dim=2), p=2, dim=2, eps=1e-8)
+        inp = x if t == 0 else torch.cat([prev, x], dim=1)
+        out, _, kv = mh.model(inp, kvcache=kv)
+        assert out.shape == (1, 1, 4096)
+        if t in want:
+            assert np.abs(out[0, -1].cpu().numpy() - want[t]).max() < 1e-4
+        cur = out[:, -1, :].softmax(-1).argmax(-1).item()
+        codes.append(cur)
+        prev = inp
+    assert codes == g["codes"].tolist()[:40]
+    feats = mh.wavtokenizer.codes_to_features(torch.tensor([codes[:10]]).to(mh.device))
+    assert feats.shape == (1, 512, 10)
+    audio = mh.wavtokenizer.decode(feats, bandwidth_id=torch.tensor([0]).to(mh.device)).squeeze(0)
+    assert audio.shape == (3200,)
+    assert snr_db(g["pcm0"], audio.cpu().numpy()) > 80
+    # batched API on the same handler
+    wavs = mh.synthesize([SENT, "hello there."], max_steps=45, stop_on_eoa=False)
+    assert wavs[0].shape == (45 * 320,) and wavs[1].shape == (45 * 320,)
+    assert snr_db(g["pcm0"], wavs[0][:3200]) > 80
+    mh.engine.close()
+
+
+# ------------------------------------------------------------------------------------------------ full size
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_config1_full_size_properties(engines, weights, precision):
+    """BASELINE config 1 shape: 64 streams x 200 codes, chunks 10/30/90/70.  Size-independent properties:
+    session 0 equals its own solo run (fp32), every chunk equals its independent decode, PCM is finite."""
+    from llmvox_b200.streaming import synthesize
+    e = engines(precision)
+    rng = np.random.RandomState(9)
+    texts = [rng.randint(3, 259, size=rng.randint(20, 200)).tolist() for _ in range(64)]
+    codes, per = synthesize(e, texts, 200, initial_dump_size=10, stop_on_eoa=False, flush_tail=True)
+    assert codes.shape == (64, 200) and codes.min() >= 0 and codes.max() < 4096
+    for chs in per:
+        assert [c.length for c in chs] == [10, 30, 90, 70]
+        assert all(np.isfinite(c.pcm).all() for c in chs)
+    if precision == "fp32":
+        ref = O.decode_steps(weights, O.GPTArch(), texts[5], 60)
+        assert ref == codes[5, :60].tolist()
+    ch = per[17][2]
+    alone = e.vocode(torch.from_numpy(codes[17, 40:130].astype(np.int32)).cuda(), [0, 90]).cpu().numpy()
+    assert snr_db(alone, ch.pcm) > (100 if precision == "fp32" else 60)
+
+
+def test_error_behaviour(engines):
+    from llmvox_b200._lib import LvxError
+    e = engines("fp32")
+    with pytest.raises(LvxError):
+        e.decode_steps([50], 1)                      # slot never opened
+    e.open([50])
+    with pytest.raises(LvxError):
+        e.decode_steps([50, 50], 1)                  # duplicate slot
+    with pytest.raises(LvxError):
+        e.decode_steps([50], 10_000)                 # beyond max_context (the reference asserts t <= block_size)
+    with pytest.raises(LvxError):
+        e.feed_text([50], [[999]])                   # text id outside the 386-row table
+    with pytest.raises(LvxError):
+        e.gather_codes([50], 0, 5)                   # nothing decoded yet

@@ -1,0 +1,122 @@
+"""CPU-only tests of the host-side logic and of the C-ABI surface (no compute calls)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from llmvox_b200 import _lib
+from llmvox_b200 import weights as W
+from llmvox_b200.scheduler import ChunkScheduler
+from llmvox_b200.tokenizer import ByT5Tokenizer, sentence_ids
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_tokenizer_matches_reference_byt5(gold):
+    g = gold("tokenizer.npz")
+    tok = ByT5Tokenizer()
+    for text, ids in zip(g["texts"], g["ids"]):
+        assert tok(str(text).strip())["input_ids"] == list(ids), text
+    assert len(tok) == 386
+
+
+def test_sentence_ids_match_config0_fixture(gold):
+    g = gold("config0_loop.npz")
+    sent = ("the quick brown fox jumps over the lazy dog while seven small birds "
+            "sing a very old song near the river.")
+    assert sentence_ids(sent) == g["text_ids"].tolist()
+
+
+@pytest.mark.parametrize("name", ["no_eoa_r0", "no_eoa_r1", "eoa_mid", "eoa_on_boundary", "eoa_first"])
+def test_chunk_scheduler_matches_reference_loop(gold, name):
+    """The scripted token streams went through the reference's own audio_generator_sync (oracle/make_golden.py):
+    positive event = chunk of that many codes, -2 = end of sentence."""
+    g = gold("scheduler.npz")
+    script = g[name + "_script"].tolist()
+    sc = ChunkScheduler(dump_size=int(g[name + "_dump"]))
+    events = []
+    for code in script:
+        for (_, length) in sc.push(code):
+            events.append(length)
+        if sc.done:
+            events.append(-2)
+            sc.new_sentence()
+    assert events == g[name + "_events"].tolist()
+
+
+def test_chunk_scheduler_ranges_are_contiguous_and_flush():
+    sc = ChunkScheduler(dump_size=10, stop_on_eoa=False)
+    out = []
+    for _ in range(200):
+        out += sc.push(None)
+    assert out == [(0, 10), (10, 30), (40, 90)]
+    assert sc.steps_to_next_event() == 270 - 70
+    assert sc.flush() == [(130, 70)]
+    assert sc.flush() == []
+
+
+def test_c_abi_library_exports_every_declared_symbol():
+    """Every function include/llmvox_b200.h declares must be exported by the built library, and the ctypes
+    table must cover the header."""
+    hdr = open(os.path.join(ROOT, "include", "llmvox_b200.h")).read()
+    declared = set(re.findall(r"\b(lvx_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"lvx_engine", "lvx_config", "lvx_sampling"}
+    assert len(declared) >= 20
+    lib = _lib.load()
+    bound = {n for n, _, _ in _lib.SYMBOLS}
+    assert declared == bound, declared ^ bound
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.lvx_version() >= 100
+    cfg = _lib.LvxConfig()
+    assert lib.lvx_config_default(ctypes.byref(cfg)) == 0
+    assert (cfg.n_layer, cfg.n_head, cfg.n_embd, cfg.vocab_size) == (4, 8, 768, 4096)
+    assert (cfg.n_fft, cfg.hop, cfg.pad_token_id, cfg.eoa_token_id) == (1280, 320, 384, 453)
+    assert lib.lvx_config_default(None) != 0
+    assert b"NULL" in lib.lvx_last_error()
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "llmvox_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle|import_module\(.oracle|oracle/", src, re.M), f
+
+
+def test_engine_refuses_to_run_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("needs a CPU-only box")
+    from llmvox_b200.engine import Engine
+    from llmvox_b200.model_handler import ModelHandler
+    with pytest.raises(RuntimeError):
+        Engine({}, device=0)
+    with pytest.raises(RuntimeError):
+        ModelHandler({"random_init_seed": 1}, None)
+
+
+def test_checkpoint_formats_roundtrip(tmp_path):
+    arch = W.GPTArch()
+    sd = W.make_random_weights(7, wpe_rows=64)
+    W.save_llmvox_checkpoint(str(tmp_path / "gpt.pt"), arch, sd, compiled_prefix=True)
+    W.save_wavtokenizer_checkpoint(str(tmp_path / "wav.ckpt"), sd)
+    arch2, g = W.load_llmvox_checkpoint(str(tmp_path / "gpt.pt"))
+    v = W.load_wavtokenizer_checkpoint(str(tmp_path / "wav.ckpt"))
+    assert arch2 == arch
+    assert all(not k.startswith("_orig_mod.") for k in g)
+    assert torch.equal(g["lm_head.weight"], sd["lm_head.weight"])
+    assert torch.equal(v[W.CODEBOOK_KEY], sd[W.CODEBOOK_KEY])
+    assert set(v) == {k for k in sd if k.startswith(("backbone.", "head.")) or k == W.CODEBOOK_KEY}
+
+
+def test_seeded_weights_are_reproducible():
+    a = W.make_random_weights(1234, wpe_rows=16)
+    b = W.make_random_weights(1234, wpe_rows=16)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    r = W.round_weights_to_bf16(a)
+    k = "transformer.h.0.attn.c_attn.weight"
+    assert torch.equal(r[k], a[k].bfloat16().float()) and not torch.equal(r[k], a[k])

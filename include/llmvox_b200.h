@@ -160,6 +160,14 @@ int lvx_vocode_stage(lvx_engine* e, const int32_t* d_codes, int len, int bandwid
 int lvx_test_gemm(lvx_engine* e, const float* d_A, const float* d_W, int M, int N, int K, int taps, float* d_C,
                   void* stream);
 
+/* Per-kernel timing for bench.py's roofline: while enabled, every launch is bracketed by a pair of CUDA events
+ * on the launching stream (this serialises nothing but adds ~2 us of host work per launch, so the profiled pass
+ * is run beside the timed region, never inside it).  lvx_profile_report synchronises the device and writes one
+ * JSON object {"<kernel>": {"launches": n, "ms": t, "flops": f, "bytes": b}, ...} (algorithmic flops / bytes,
+ * GEMMs only) into buf, then clears the records. */
+int lvx_profile_enable(lvx_engine* e, int on);
+int lvx_profile_report(lvx_engine* e, char* buf, int64_t buf_size);
+
 /* Counters for bench.py's "gpu_launches": kernels launched by this engine since creation. */
 int64_t lvx_kernel_launches(const lvx_engine* e);
 /* Bytes of device memory the engine allocated. */

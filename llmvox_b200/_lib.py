@@ -52,6 +52,8 @@ SYMBOLS = [
     ("lvx_vocode_features", C.c_int, [_VP, _VP, _I32P, C.c_int, C.c_int, _VP, _VP]),
     ("lvx_vocode_stage", C.c_int, [_VP, _VP, C.c_int, C.c_int, C.c_int, _VP, _VP]),
     ("lvx_test_gemm", C.c_int, [_VP, _VP, _VP, C.c_int, C.c_int, C.c_int, C.c_int, _VP, _VP]),
+    ("lvx_profile_enable", C.c_int, [_VP, C.c_int]),
+    ("lvx_profile_report", C.c_int, [_VP, C.c_char_p, C.c_int64]),
     ("lvx_kernel_launches", C.c_int64, [_VP]),
     ("lvx_device_bytes", C.c_int64, [_VP]),
 ]

@@ -167,13 +167,15 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const float* __re
 #pragma unroll
   for (int i = 0; i < DPL; ++i) acc[i] = 0.f;
 
+  // the 8-lane groups of a warp run different trip counts: shuffles are confined to the group's own lanes
+  const unsigned gmask = 0xFFu << (lane & 24);
   auto absorb = [&](const float* kk, const float* vv) {
     float d = 0.f;
 #pragma unroll
     for (int i = 0; i < DPL; ++i) d = fmaf(q[i], kk[i], d);
-    d += __shfl_xor_sync(0xffffffffu, d, 4);
-    d += __shfl_xor_sync(0xffffffffu, d, 2);
-    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    d += __shfl_xor_sync(gmask, d, 4);
+    d += __shfl_xor_sync(gmask, d, 2);
+    d += __shfl_xor_sync(gmask, d, 1);
     d *= scale;
     const float mn = fmaxf(m, d);
     const float corr = expf(m - mn), pr = expf(d - mn);

@@ -193,8 +193,45 @@ struct lvx_engine {
   float2* v_stats = nullptr;
   TcWorkspace tcw;
 
+  // ---- optional per-launch profiler (lvx_profile_enable)
+  struct ProfRec {
+    const char* name;
+    cudaEvent_t a, b;
+    double flops, bytes;
+  };
+  bool prof_on = false;
+  std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  cudaEvent_t get_event() {
+    if (!ev_pool.empty()) {
+      cudaEvent_t ev = ev_pool.back();
+      ev_pool.pop_back();
+      return ev;
+    }
+    cudaEvent_t ev;
+    cudaEventCreate(&ev);
+    return ev;
+  }
+
   DT adt() const { return cfg.precision == LVX_PRECISION_BF16 ? B16 : F32; }
 };
+
+struct ProfScope {
+  lvx_engine* e;
+  cudaStream_t st;
+  size_t idx = (size_t)-1;
+  ProfScope(lvx_engine* e_, const char* name, cudaStream_t st_, double flops = 0, double bytes = 0) : e(e_), st(st_) {
+    if (!e->prof_on) return;
+    lvx_engine::ProfRec r{name, e->get_event(), e->get_event(), flops, bytes};
+    cudaEventRecord(r.a, st);
+    idx = e->prof.size();
+    e->prof.push_back(r);
+  }
+  ~ProfScope() {
+    if (idx != (size_t)-1) cudaEventRecord(e->prof[idx].b, st);
+  }
+};
+#define PROF(e, name, st) ProfScope _prof_scope_##__LINE__((e), (name), (st))
 
 #define LAUNCHED(e)                                                                                  \
   do {                                                                                               \
@@ -641,6 +678,12 @@ static int run_gemm(lvx_engine* e, GemmParams p, const GemmW& w, DT ta, DT tc, c
   p.N = w.N;
   p.K = w.K;
   p.ldw = w.ld;
+  const double el = (double)dt_size(e->adt());
+  const int a_cols = p.taps > 1 ? p.tap_K : p.K;
+  const bool swap = e->adt() == B16 && p.taps == 1 && p.M <= 256;
+  ProfScope prof(e, e->adt() == F32 ? "gemm_simt" : (swap ? "tc_gemm_swap" : "tc_gemm"), st, 2.0 * p.M * (double)w.N * w.K,
+                 (double)p.M * a_cols * el + (double)w.N * w.K * el + (double)p.M * w.N * (double)dt_size(tc) +
+                     (p.residual ? (double)p.M * w.N * 4.0 : 0.0));
   if (e->adt() == F32) {
     p.W = w.f32;
     cudaError_t err = launch_gemm_simt<float, float, float>(p, st);
@@ -656,6 +699,7 @@ static int run_gemm(lvx_engine* e, GemmParams p, const GemmW& w, DT ta, DT tc, c
 }
 
 static int run_gemm_batched(lvx_engine* e, GemmParams p, DT ta, DT tw, DT tc, cudaStream_t st) {
+  ProfScope prof(e, "gemm_simt_batched", st);
   cudaError_t err;
   if (ta == F32)
     err = launch_gemm_simt<float, float, float>(p, st);
@@ -673,6 +717,7 @@ template <int C>
 static int run_layernorm(lvx_engine* e, const float* x, int rows, const float* w, const float* b, float eps,
                          const int* row_chunk, void* out, cudaStream_t st) {
   if (rows <= 0) return LVX_OK;
+  PROF(e, "layernorm", st);
   if (e->adt() == F32)
     layernorm_kernel<float, C><<<ceil_div(rows, 8), 256, 0, st>>>(x, rows, w, b, eps, row_chunk, (float*)out);
   else
@@ -804,6 +849,7 @@ static int gpt_body(lvx_engine* e, int n, const int* pos_override, cudaStream_t 
     p.A = e->h; p.C = e->qkv; p.M = n; p.lda = C; p.ldc = 3 * C; p.bias = L.attn_b;
     LVX_TRY(run_gemm(e, p, L.attn, a, F32, st));
     dim3 grid(n, c.n_head);
+    PROF(e, "decode_attention", st);
     if (a == F32)
       decode_attention_kernel<float, float, 96><<<grid, 128, 0, st>>>(e->qkv, (float*)e->kv, e->d_slots, e->st, pos_override, l,
                                                                        c.n_head, c.kv_page_tokens, e->pool_pages, 0, (float*)e->y);
@@ -845,12 +891,16 @@ static SamplerArgs sampler_args(const lvx_sampling* s) {
 
 static int decode_one_step(lvx_engine* e, int n, const SamplerArgs& sa, float* d_logits, cudaStream_t st) {
   const lvx_config& c = e->cfg;
+  {
+  PROF(e, "assemble_input", st);
   assemble_input_kernel<<<n, c.n_embd / 4, 0, st>>>(e->d_slots, e->st, W(e, "text_table"),
                                                     W(e, "feature_extractor.encodec.quantizer.vq.layers.0._codebook.embed"),
                                                     W(e, "transformer.wpe.weight"), c.text_dim, c.code_dim, c.pad_token_id, 0, e->x);
   LAUNCHED(e);
+  }
   LVX_TRY(gpt_body(e, n, nullptr, st));
   LVX_TRY(lm_head_logits(e, n, d_logits, st));
+  PROF(e, "sampler", st);
   sampler_kernel<4096><<<n, 256, 0, st>>>(d_logits, c.vocab_size, e->d_slots, e->st, sa);
   LAUNCHED(e);
   return LVX_OK;
@@ -995,6 +1045,7 @@ struct VocGroup {
 
 static int groupnorm(lvx_engine* e, const VocGroup& g, const float* x, const float* w, const float* b, int swish, void* out,
                      cudaStream_t st) {
+  PROF(e, "groupnorm", st);
   dim3 grid(32, (unsigned)g.chunks.size());
   groupnorm_stats_kernel<768><<<grid, 256, 0, st>>>(x, e->d_chunks, 1e-6f, e->v_stats);
   LAUNCHED(e);
@@ -1117,6 +1168,8 @@ static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes
   // 12 x ConvNeXtBlock (modules.py:43-60)
   for (int i = 0; i < c.voc_layers; ++i) {
     auto& X = e->cnx[i];
+    {
+    PROF(e, "dwconv_adaln", st);
     if (a == F32)
       dwconv_adaln_kernel<float, 768><<<ceil_div(g.R, 8), 256, 0, st>>>(e->v_x, g.R, e->row_chunk, e->d_chunks, X.dw_w, X.dw_b,
                                                                          X.scale + (size_t)bw * D, X.shift + (size_t)bw * D, 1e-6f,
@@ -1126,6 +1179,7 @@ static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes
                                                                         X.scale + (size_t)bw * D, X.shift + (size_t)bw * D, 1e-6f,
                                                                         (bf16*)e->v_h);
     LAUNCHED(e);
+    }
     GemmParams p;
     p.A = e->v_h; p.C = e->v_big; p.M = g.R; p.lda = D; p.ldc = I; p.bias = X.b1; p.act = ACT_GELU_ERF; p.row_chunk = e->row_chunk;
     LVX_TRY(run_gemm(e, p, X.pw1, a, a, st));
@@ -1173,6 +1227,7 @@ static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes
   }
   if (stage == 5) return dump(e->v_frames, NF, NF);
   // overlap-add + trim + envelope (spectral_ops.py:59-73)
+  PROF(e, "overlap_add", st);
   dim3 grid(ceil_div(g.max_len * c.hop, 256), nch);
   overlap_add_kernel<<<grid, 256, 0, st>>>(e->v_frames, NF, e->d_chunks, e->window, NF, c.hop, d_pcm + (size_t)g.code0 * c.hop);
   LAUNCHED(e);
@@ -1286,6 +1341,42 @@ extern "C" int lvx_test_gemm(lvx_engine* e, const float* d_A, const float* d_W, 
     cudaFree(w16);
   }
   return status;
+}
+
+extern "C" int lvx_profile_enable(lvx_engine* e, int on) {
+  LVX_CHECK(e, LVX_ERR_INVALID, "engine is NULL");
+  e->prof_on = on != 0;
+  return LVX_OK;
+}
+
+extern "C" int lvx_profile_report(lvx_engine* e, char* buf, int64_t buf_size) {
+  LVX_CHECK(e && buf && buf_size > 2, LVX_ERR_INVALID, "bad argument");
+  LVX_CUDA(cudaSetDevice(e->device));
+  LVX_CUDA(cudaDeviceSynchronize());
+  struct Agg { long long n = 0; double ms = 0, flops = 0, bytes = 0; };
+  std::map<std::string, Agg> agg;
+  for (auto& r : e->prof) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    Agg& a = agg[r.name];
+    a.n++; a.ms += ms; a.flops += r.flops; a.bytes += r.bytes;
+    e->ev_pool.push_back(r.a);
+    e->ev_pool.push_back(r.b);
+  }
+  e->prof.clear();
+  std::string out = "{";
+  bool first = true;
+  for (auto& kv : agg) {
+    char line[512];
+    snprintf(line, sizeof(line), "%s\"%s\": {\"launches\": %lld, \"ms\": %.6f, \"flops\": %.6e, \"bytes\": %.6e}", first ? "" : ", ",
+             kv.first.c_str(), kv.second.n, kv.second.ms, kv.second.flops, kv.second.bytes);
+    out += line;
+    first = false;
+  }
+  out += "}";
+  LVX_CHECK((int64_t)out.size() + 1 <= buf_size, LVX_ERR_CAPACITY, "report buffer too small");
+  memcpy(buf, out.c_str(), out.size() + 1);
+  return LVX_OK;
 }
 
 extern "C" int64_t lvx_kernel_launches(const lvx_engine* e) { return e ? e->launches : 0; }

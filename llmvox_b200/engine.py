@@ -92,6 +92,15 @@ class Engine:
     def device_bytes(self) -> int:
         return int(self.lib.lvx_device_bytes(self._h))
 
+    def profile(self, on: bool):
+        check(self.lib.lvx_profile_enable(self._h, int(on)))
+
+    def profile_report(self) -> dict:
+        import json
+        buf = C.create_string_buffer(1 << 16)
+        check(self.lib.lvx_profile_report(self._h, buf, len(buf)))
+        return json.loads(buf.value.decode())
+
     def _stream(self, stream) -> C.c_void_p:
         s = stream if stream is not None else torch.cuda.current_stream(self.device)
         return C.c_void_p(s.cuda_stream)

@@ -149,7 +149,7 @@ class ModelHandler:
         self.device = torch.device(f"cuda:{device_id}")
         gpt_arch = W.GPTArch()
         if cfg.get("random_init_seed") is not None:
-            sd = W.make_random_weights(int(cfg["random_init_seed"]), wpe_rows=cfg["max_context"])
+            sd = W.make_random_weights(int(cfg["random_init_seed"]))
         else:
             gpt_arch, sd = W.load_llmvox_checkpoint(cfg["llmvox_checkpoint_path"])
             sd.update(W.load_wavtokenizer_checkpoint(cfg["wav_model_path"]))

@@ -74,7 +74,11 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def mark(self):
+        """Start of the timed region: earlier samples (warm-up) are dropped."""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
@@ -86,7 +90,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t_mark = getattr(self, "t_mark", 0.0)
+        rows = [r for (t, r) in self.rows if t >= t_mark] or [r for (_, r) in self.rows[-3:]]
+        for r in rows:
             f = [x.strip() for x in r.split(",")]
             if len(f) < 6:
                 continue
@@ -207,10 +213,11 @@ def run_gpu(args):
     for g in groups[:n_groups]:
         e.open(g)
         e.feed_text(g, texts)
+    clocks = ClockSampler(local)
     for g in groups[:Wm]:
         device_step(e, g, pcm)
     barrier()
-    clocks = ClockSampler(local)
+    clocks.mark()
     l0 = e.kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -220,6 +227,7 @@ def run_gpu(args):
     barrier()
     launches = e.kernel_launches - l0
     ms = ev0.elapsed_time(ev1)
+    time.sleep(0.15)      # let nvidia-smi emit the sample that covers the end of the region
     clk = clocks.stop()
     assert torch.isfinite(pcm[:: 4099]).all()
 
@@ -281,7 +289,7 @@ def run_gpu(args):
         line = {"metric": "audio-sec generated/sec", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": K,
                 "warmup": Wm, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": args.precision, "data": "synthetic",
-                "config": {"workload": "config1: 64 streams x 200 codes per GPU, KV-cached greedy decode + chunked vocoder (10/30/90/70)",
+                "config": {"workload": f"config1: {STREAMS} streams x {TOKENS} codes per GPU, KV-cached greedy decode + chunked vocoder ({'/'.join(map(str, SCHEDULE))})",
                            "weights": "random-init english-tiny GPT + frame75 WavTokenizer decoder, seed 1234",
                            "l2": "no flush: per-step working set (189 MB bf16 weights + KV + activations) exceeds the 126 MB L2"},
                 "x_realtime_per_gpu": value / world,
@@ -305,7 +313,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="llmvox_b200", choices=["llmvox_b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--short", action="store_true", help="40-code utterances (chunks 10/30): a short run for ncu captures")
     args = ap.parse_args()
+    if args.short:
+        global TOKENS, SCHEDULE
+        TOKENS, SCHEDULE = 40, [10, 30]
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -193,6 +193,16 @@ struct lvx_engine {
   float2* v_stats = nullptr;
   TcWorkspace tcw;
 
+  // ---- CUDA graphs of one decode iteration, keyed by (sessions, sampler); replayed on an engine-owned stream
+  struct StepGraph {
+    cudaGraphExec_t exec = nullptr;
+    int64_t launches = 0;
+  };
+  std::map<std::string, StepGraph> graphs;
+  cudaStream_t gstream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  bool use_graphs = true;
+
   // ---- optional per-launch profiler (lvx_profile_enable)
   struct ProfRec {
     const char* name;
@@ -455,6 +465,16 @@ extern "C" int lvx_engine_create(const lvx_config* cfg, int device, lvx_engine**
   declare_tensors(e);
   int s = engine_alloc(e);
   if (s == LVX_OK && c.precision == LVX_PRECISION_BF16) s = tc_init(&e->tcw, prop.multiProcessorCount);
+  if (s == LVX_OK) {
+    const char* env = getenv("LLMVOX_B200_NO_GRAPH");
+    e->use_graphs = !(env && env[0] == '1');
+    if (cudaStreamCreateWithFlags(&e->gstream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess) {
+      set_error("could not create the engine's stream / events");
+      s = LVX_ERR_CUDA;
+    }
+  }
   if (s != LVX_OK) {
     lvx_engine_destroy(e);
     return s;
@@ -467,6 +487,16 @@ extern "C" int lvx_engine_destroy(lvx_engine* e) {
   if (!e) return LVX_OK;
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
+  for (auto& g : e->graphs)
+    if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+  if (e->gstream) cudaStreamDestroy(e->gstream);
+  if (e->ev_in) cudaEventDestroy(e->ev_in);
+  if (e->ev_out) cudaEventDestroy(e->ev_out);
+  for (auto& r : e->prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
   for (void* p : e->allocs) cudaFree(p);
   for (auto& kv : e->w)
     if (kv.second.d) cudaFree(kv.second.d);
@@ -849,14 +879,16 @@ static int gpt_body(lvx_engine* e, int n, const int* pos_override, cudaStream_t 
     p.A = e->h; p.C = e->qkv; p.M = n; p.lda = C; p.ldc = 3 * C; p.bias = L.attn_b;
     LVX_TRY(run_gemm(e, p, L.attn, a, F32, st));
     dim3 grid(n, c.n_head);
-    PROF(e, "decode_attention", st);
-    if (a == F32)
-      decode_attention_kernel<float, float, 96><<<grid, 128, 0, st>>>(e->qkv, (float*)e->kv, e->d_slots, e->st, pos_override, l,
-                                                                       c.n_head, c.kv_page_tokens, e->pool_pages, 0, (float*)e->y);
-    else
-      decode_attention_kernel<bf16, bf16, 96><<<grid, 128, 0, st>>>(e->qkv, (bf16*)e->kv, e->d_slots, e->st, pos_override, l,
-                                                                     c.n_head, c.kv_page_tokens, e->pool_pages, 0, (bf16*)e->y);
-    LAUNCHED(e);
+    {
+      PROF(e, "decode_attention", st);
+      if (a == F32)
+        decode_attention_kernel<float, float, 96><<<grid, 128, 0, st>>>(e->qkv, (float*)e->kv, e->d_slots, e->st, pos_override, l,
+                                                                         c.n_head, c.kv_page_tokens, e->pool_pages, 0, (float*)e->y);
+      else
+        decode_attention_kernel<bf16, bf16, 96><<<grid, 128, 0, st>>>(e->qkv, (bf16*)e->kv, e->d_slots, e->st, pos_override, l,
+                                                                       c.n_head, c.kv_page_tokens, e->pool_pages, 0, (bf16*)e->y);
+      LAUNCHED(e);
+    }
     GemmParams q;
     q.A = e->y; q.C = e->x; q.M = n; q.lda = C; q.ldc = C; q.bias = L.proj_b; q.residual = e->x; q.ldr = C;
     LVX_TRY(run_gemm(e, q, L.proj, a, F32, st));
@@ -926,7 +958,45 @@ extern "C" int lvx_decode_steps(lvx_engine* e, const int32_t* h_slots, int n, in
   SamplerArgs sa = sampler_args(s);
   LVX_CHECK(sa.greedy || sa.temperature > 0.f, LVX_ERR_INVALID, "temperature must be positive");
   LVX_CHECK(!(sa.uniform && n_steps > 1), LVX_ERR_INVALID, "d_uniform supplies one draw per session: use n_steps == 1");
-  for (int t = 0; t < n_steps; ++t) LVX_TRY(decode_one_step(e, n, sa, e->logits, st));
+  if (e->use_graphs && !e->prof_on && !sa.uniform) {
+    // every iteration launches the same kernels with the same arguments (all per-session state lives on the
+    // device), so one captured iteration is replayed n_steps times
+    char key[96];
+    snprintf(key, sizeof(key), "%d|%d|%d|%.9g|%llu", n, sa.greedy, sa.top_k, (double)sa.temperature, (unsigned long long)sa.seed);
+    auto it = e->graphs.find(key);
+    if (it == e->graphs.end()) {
+      cudaGraph_t graph = nullptr;
+      const int64_t l0 = e->launches;
+      LVX_CUDA(cudaStreamBeginCapture(e->gstream, cudaStreamCaptureModeThreadLocal));
+      int s2 = decode_one_step(e, n, sa, e->logits, e->gstream);
+      cudaError_t ce = cudaStreamEndCapture(e->gstream, &graph);
+      const int64_t per = e->launches - l0;
+      e->launches = l0;
+      if (s2 != LVX_OK) {
+        if (graph) cudaGraphDestroy(graph);
+        return s2;
+      }
+      LVX_CHECK(ce == cudaSuccess && graph, LVX_ERR_CUDA, std::string("stream capture failed: ") + cudaGetErrorString(ce));
+      lvx_engine::StepGraph sg;
+      ce = cudaGraphInstantiate(&sg.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      LVX_CHECK(ce == cudaSuccess, LVX_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+      sg.launches = per;
+      if (e->graphs.size() > 64) {
+        for (auto& g : e->graphs) cudaGraphExecDestroy(g.second.exec);
+        e->graphs.clear();
+      }
+      it = e->graphs.emplace(key, sg).first;
+    }
+    LVX_CUDA(cudaEventRecord(e->ev_in, st));
+    LVX_CUDA(cudaStreamWaitEvent(e->gstream, e->ev_in, 0));
+    for (int t = 0; t < n_steps; ++t) LVX_CUDA(cudaGraphLaunch(it->second.exec, e->gstream));
+    LVX_CUDA(cudaEventRecord(e->ev_out, e->gstream));
+    LVX_CUDA(cudaStreamWaitEvent(st, e->ev_out, 0));
+    e->launches += it->second.launches * n_steps;
+  } else {
+    for (int t = 0; t < n_steps; ++t) LVX_TRY(decode_one_step(e, n, sa, e->logits, st));
+  }
   for (int i = 0; i < n; ++i) e->h_len[h_slots[i]] += n_steps;
   return LVX_OK;
 }

@@ -79,8 +79,13 @@ inline int tc_encode(CUtensorMap* m, const void* ptr, int rows, int cols, int ld
   return LVX_OK;
 }
 
+inline int tc_configure();
 inline int tc_init(TcWorkspace* ws, int num_sms) {
   ws->num_sms = num_sms;
+  {
+    int s = tc_configure();
+    if (s != LVX_OK) return s;
+  }
   if (!g_encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -194,7 +199,86 @@ struct TcParams {
   int stages;
   int num_kb;      // K / 64 (rounded up; TMA zero-fills the tail)
   int tmem_cols;   // power of two >= max(32, BN)
+  int splits;      // split-K factor = cluster size along z (1, 2, 4 or 8)
 };
+
+// ---- thread-block cluster helpers (split-K partial sums are exchanged through distributed shared memory)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ float4 ld_dsmem_v4(uint32_t local_addr, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_addr), "r"(rank));
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
+  return v;
+}
+
+// Epilogue of `ncols` (multiple of 4, <= 16) accumulator columns j0.. of D row i.  Order as GemmParams states:
+// alpha, + bias, activation, * col_scale, + residual.  All loads of a chunk are issued before its stores
+// (C may alias residual: every thread reads and writes only its own elements).
+template <bool kSwap, typename TC>
+__device__ __forceinline__ void tc_epilogue_chunk(const GemmParams& p, int i, int j0, const float* v, int ncols) {
+  TC* C = reinterpret_cast<TC*>(p.C);
+  if (!kSwap) {
+    const int m = i;
+    if (m >= p.M || (p.row_chunk && p.row_chunk[m] < 0)) return;
+    const bool vec = (p.ldc & 3) == 0 && (!p.residual || (p.ldr & 3) == 0);
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      if (j >= ncols) break;
+      const int n = j0 + j;
+      if (n >= p.N) break;
+      if (n + 4 <= p.N && vec) {
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f), cs = make_float4(1.f, 1.f, 1.f, 1.f), r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) b = load4(p.bias + n);
+        if (p.col_scale) cs = load4(p.col_scale + n);
+        if (p.residual) r = load4(p.residual + (size_t)m * p.ldr + n);
+        float4 o;
+        o.x = apply_act(v[j] * p.alpha + b.x, p.act) * cs.x + r.x;
+        o.y = apply_act(v[j + 1] * p.alpha + b.y, p.act) * cs.y + r.y;
+        o.z = apply_act(v[j + 2] * p.alpha + b.z, p.act) * cs.z + r.z;
+        o.w = apply_act(v[j + 3] * p.alpha + b.w, p.act) * cs.w + r.w;
+        store4(C + (size_t)m * p.ldc + n, o);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int nn = n + t;
+          if (nn < p.N) {
+            float xv = v[j + t] * p.alpha;
+            if (p.bias) xv += p.bias[nn];
+            xv = apply_act(xv, p.act);
+            if (p.col_scale) xv *= p.col_scale[nn];
+            if (p.residual) xv += p.residual[(size_t)m * p.ldr + nn];
+            store1(C + (size_t)m * p.ldc + nn, xv);
+          }
+        }
+      }
+    }
+  } else {
+    const int n = i;  // weight row = output column; the 32 lanes of a warp cover 32 consecutive n
+    if (n >= p.N) return;
+    const float b = p.bias ? p.bias[n] : 0.f;
+    const float cs = p.col_scale ? p.col_scale[n] : 1.f;
+    float r[16];
+    bool ok[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int m = j0 + j;
+      ok[j] = j < ncols && m < p.M && (!p.row_chunk || p.row_chunk[m] >= 0);
+      r[j] = (ok[j] && p.residual) ? p.residual[(size_t)m * p.ldr + n] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      if (ok[j]) store1(C + (size_t)(j0 + j) * p.ldc + n, apply_act(v[j] * p.alpha + b, p.act) * cs + r[j]);
+    }
+  }
+}
 
 template <bool kSwap, typename TC>
 __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const __grid_constant__ CUtensorMap mapX,
@@ -205,7 +289,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const __grid_consta
 
   const GemmParams& p = tp.g;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int BN = tp.BN, stages = tp.stages, num_kb = tp.num_kb;
+  const int BN = tp.BN, stages = tp.stages, S = tp.splits;
   const uint32_t y_bytes = (uint32_t)BN * TC_BK * 2;
   const uint32_t stage_bytes = TC_X_BYTES + y_bytes;
   const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -214,9 +298,12 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const __grid_consta
   auto empty_bar = [&](int s) { return bar0 + 8u * (TC_MAX_STAGES + s); };
   const uint32_t tmem_full_bar = bar0 + 8u * (2 * TC_MAX_STAGES);
 
-  // tile origin: x0 = first X row, y0 = first Y row
+  // tile origin: x0 = first X row, y0 = first Y row; this CTA's share of the K loop
   const int x0 = (kSwap ? blockIdx.x : blockIdx.y) * TC_BM;
   const int y0 = (kSwap ? blockIdx.y : blockIdx.x) * BN;
+  const int rank = S > 1 ? (int)cluster_ctarank() : 0;
+  const int kb0 = (int)((long long)tp.num_kb * rank / S), kb1 = (int)((long long)tp.num_kb * (rank + 1) / S);
+  const int nk = kb1 - kb0;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapX);
@@ -237,14 +324,20 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const __grid_consta
   tc_fence_after();
   const uint32_t tmem_d = tmem_base_sh;
 
+  // split-K partial tile in shared memory (reuses the operand ring once the MMAs are done): [128][BN + 4] fp32
+  const int RS = BN + 4;
+  const int q = warp & 3;              // TMEM lane quarter an epilogue warp may read
+  const int drow = q * 32 + lane;      // D row (TMEM lane) of an epilogue thread
+  const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16);
+
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % stages;
-        const uint32_t ph = (uint32_t)(kb / stages) & 1u;
+      for (int it = 0; it < nk; ++it) {
+        const int s = it % stages;
+        const uint32_t ph = (uint32_t)(it / stages) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);
         mbar_expect_tx(full_bar(s), stage_bytes);
-        const int k0 = kb * TC_BK;
+        const int k0 = (kb0 + it) * TC_BK;
         int xc = k0, xr = x0;
         if (!kSwap && p.taps > 1) {
           const int tap = k0 / p.tap_K;
@@ -259,9 +352,9 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const __grid_consta
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(TC_BM, BN);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % stages;
-        const uint32_t ph = (uint32_t)(kb / stages) & 1u;
+      for (int it = 0; it < nk; ++it) {
+        const int s = it % stages;
+        const uint32_t ph = (uint32_t)(it / stages) & 1u;
         mbar_wait(full_bar(s), ph);
         tc_fence_after();
         const uint32_t xs = tiles + (uint32_t)s * stage_bytes;
@@ -269,73 +362,62 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const __grid_consta
 #pragma unroll
         for (int k = 0; k < TC_BK / 16; ++k) {
           // +32 bytes (16 bf16) along K inside the swizzle atom = +2 in the encoded start address
-          umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_bf16(tmem_d, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
         }
         umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
       }
       umma_commit(tmem_full_bar);   // accumulator complete
     }
   } else {
-    // ---------------- epilogue: TMEM -> registers -> global
-    const int q = warp & 3;  // TMEM lane quarter this warp may read
+    // ---------------- epilogue warps: TMEM -> registers -> (global | partial tile in smem)
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    TC* C = reinterpret_cast<TC*>(p.C);
-    const int i = x0 + q * 32 + lane;  // D row of this thread
-    const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16);
-    if (!kSwap) {
-      const int m = i;
-      const bool row_ok = m < p.M && (!p.row_chunk || p.row_chunk[m] >= 0);
+    if (S == 1) {
       for (int c = 0; c < BN; c += 16) {
         float v[16];
         tmem_ld16(trow + (uint32_t)c, v);
-        const int n = y0 + c;
-        if (!row_ok || n >= p.N) continue;
-        const bool full = (n + 16 <= p.N);
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int nn = n + j;
-          if (full || nn < p.N) {
-            float xv = v[j] * p.alpha;
-            if (p.bias) xv += p.bias[nn];
-            xv = apply_act(xv, p.act);
-            if (p.col_scale) xv *= p.col_scale[nn];
-            if (p.residual) xv += p.residual[(size_t)m * p.ldr + nn];
-            v[j] = xv;
-          }
-        }
-        TC* dst = C + (size_t)m * p.ldc + n;
-        if (full && (p.ldc & 3) == 0) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) store4(dst + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
-        } else {
-#pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if (n + j < p.N) store1(dst + j, v[j]);
-        }
+        tc_epilogue_chunk<kSwap, TC>(p, x0 + drow, y0 + c, v, 16);
       }
     } else {
-      const int n = i;  // weight row = output column
-      const bool n_ok = n < p.N;
-      const float b = (p.bias && n_ok) ? p.bias[n] : 0.f;
-      const float cs = (p.col_scale && n_ok) ? p.col_scale[n] : 1.f;
+      float* red = reinterpret_cast<float*>(smem_raw + (tiles - smem_u32(smem_raw)));
       for (int c = 0; c < BN; c += 16) {
         float v[16];
         tmem_ld16(trow + (uint32_t)c, v);
-        if (!n_ok) continue;
+        float* dst = red + (size_t)drow * RS + c;
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          const int m = y0 + c + j;
-          if (m >= p.M) break;
-          if (p.row_chunk && p.row_chunk[m] < 0) continue;
-          float xv = v[j] * p.alpha + b;
-          xv = apply_act(xv, p.act);
-          xv *= cs;
-          if (p.residual) xv += p.residual[(size_t)m * p.ldr + n];
-          store1(C + (size_t)m * p.ldc + n, xv);
-        }
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
     }
+  }
+  if (S > 1) {
+    // every CTA of the cluster now holds its K-slice partial; rank r reduces and finishes columns
+    // [r * BN / S, (r + 1) * BN / S) in fixed rank order (deterministic), reading peers through DSMEM
+    tc_fence_before();
+    __syncwarp();
+    cluster_sync_all();
+    if (warp >= 2) {
+      const int cw = BN / S;
+      const uint32_t red0 = tiles;
+      for (int c = rank * cw; c < (rank + 1) * cw; c += 16) {
+        const int ncols = min(16, (rank + 1) * cw - c);
+        float v[16];
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (j < ncols) {
+            const uint32_t off = red0 + (uint32_t)(((size_t)drow * RS + c + j) * 4);
+            for (int r = 0; r < S; ++r) {
+              const float4 t = ld_dsmem_v4(off, (uint32_t)r);
+              a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+            }
+          }
+          v[j] = a.x; v[j + 1] = a.y; v[j + 2] = a.z; v[j + 3] = a.w;
+        }
+        tc_epilogue_chunk<kSwap, TC>(p, x0 + drow, y0 + c, v, ncols);
+      }
+    }
+    __syncwarp();
+    cluster_sync_all();   // peers may still be reading this CTA's partial
   }
   tc_fence_before();
   __syncthreads();
@@ -360,25 +442,79 @@ inline int tc_act_map(TcWorkspace* ws, const void* ptr, int rows, int cols, int 
   return LVX_OK;
 }
 
-template <bool kSwap, typename TC>
-inline int tc_launch(const CUtensorMap& mx, const CUtensorMap& my, const TcParams& tp, dim3 grid, cudaStream_t st) {
-  const size_t smem = (size_t)tp.stages * (TC_X_BYTES + (size_t)tp.BN * TC_BK * 2) + 1024;
-  static size_t configured = 0;
-  if (smem > configured) {
-    cudaError_t err = cudaFuncSetAttribute(tc_gemm_kernel<kSwap, TC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
-    if (err != cudaSuccess) {
-      set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
-      return LVX_ERR_CUDA;
-    }
-    configured = 227 * 1024;
+// opt every instantiation into the large dynamic shared-memory carve-out (done once per device at engine creation,
+// never inside a stream capture)
+inline int tc_configure() {
+  cudaError_t err = cudaFuncSetAttribute(tc_gemm_kernel<true, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+  if (err == cudaSuccess)
+    err = cudaFuncSetAttribute(tc_gemm_kernel<true, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+  if (err == cudaSuccess)
+    err = cudaFuncSetAttribute(tc_gemm_kernel<false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+  if (err == cudaSuccess)
+    err = cudaFuncSetAttribute(tc_gemm_kernel<false, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+  if (err != cudaSuccess) {
+    set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
+    return LVX_ERR_CUDA;
   }
-  tc_gemm_kernel<kSwap, TC><<<grid, TC_THREADS, smem, st>>>(mx, my, tp);
-  cudaError_t err = cudaGetLastError();
+  return LVX_OK;
+}
+
+template <bool kSwap, typename TC>
+inline int tc_launch(const CUtensorMap& mx, const CUtensorMap& my, const TcParams& tp, dim3 grid, size_t smem, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = (unsigned)tp.splits;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t err = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<kSwap, TC>, mx, my, tp);
   if (err != cudaSuccess) {
     set_error(std::string("tc_gemm launch: ") + cudaGetErrorString(err));
     return LVX_ERR_CUDA;
   }
   return LVX_OK;
+}
+
+// Launch plan: tile shape, split-K factor and pipeline depth for one problem.
+struct TcPlan {
+  bool swap;
+  int BN, splits, stages, tmem_cols;
+  dim3 grid;
+  size_t smem;
+};
+
+inline TcPlan tc_plan(const TcWorkspace* ws, const GemmParams& p) {
+  TcPlan pl;
+  const int num_kb = ceil_div(p.K, TC_BK);
+  pl.swap = p.taps == 1 && p.M <= 256;
+  pl.BN = pl.swap ? std::max(16, ceil_div(p.M, 16) * 16) : 128;
+  const int gx = pl.swap ? ceil_div(p.N, TC_BM) : ceil_div(p.N, pl.BN);
+  const int gy = pl.swap ? ceil_div(p.M, pl.BN) : ceil_div(p.M, TC_BM);
+  const int tiles = gx * gy;
+  const int sms = ws->num_sms > 0 ? ws->num_sms : 148;
+  // few tiles: split K across a cluster so that about 1.5 CTAs per SM pull operands concurrently
+  int S = 1;
+  while (S < 8 && tiles * (S * 2) <= sms + sms / 2 && num_kb >= S * 2 && (pl.BN / (S * 2)) % 4 == 0 && pl.BN / (S * 2) >= 4) S *= 2;
+  pl.splits = S;
+  pl.tmem_cols = 32;
+  while (pl.tmem_cols < pl.BN) pl.tmem_cols *= 2;
+  const int stage_bytes = TC_X_BYTES + pl.BN * TC_BK * 2;
+  const int nk = ceil_div(num_kb, S);
+  const bool one_per_sm = tiles * S <= sms || pl.BN > 128;
+  const int budget = one_per_sm ? 200 * 1024 : 110 * 1024;
+  int stages = std::max(2, std::min(std::min(TC_MAX_STAGES, nk), (budget - 1024) / stage_bytes));
+  const size_t red_bytes = S > 1 ? (size_t)TC_BM * (pl.BN + 4) * 4 : 0;
+  while ((size_t)stages * stage_bytes < red_bytes) ++stages;
+  pl.stages = stages;
+  pl.smem = (size_t)stages * stage_bytes + 1024;
+  pl.grid = dim3(gx, gy, S);
+  return pl;
 }
 
 // p.A: bf16 activations (M x K view, lda), p.a_cap rows addressable.  w: tensor map of the bf16 (N, K) weight.
@@ -394,25 +530,20 @@ inline int tc_gemm(TcWorkspace* ws, const GemmParams& p, const TmaDesc& w, bool 
   }
   const int a_cols = p.taps > 1 ? p.tap_K : p.K;
   const int a_cap = p.a_cap ? p.a_cap : (p.a_rows ? p.a_rows : p.M);
-  const bool swap = p.taps == 1 && p.M <= 256;
+  const TcPlan pl = tc_plan(ws, p);
   TcParams tp;
   tp.g = p;
   tp.num_kb = ceil_div(p.K, TC_BK);
-  tp.BN = swap ? std::max(16, ceil_div(p.M, 16) * 16) : 128;
-  tp.tmem_cols = 32;
-  while (tp.tmem_cols < tp.BN) tp.tmem_cols *= 2;
-  const int stage_bytes = TC_X_BYTES + tp.BN * TC_BK * 2;
-  const int budget = tp.BN <= 128 ? 110 * 1024 : 220 * 1024;  // <= 128: two CTAs per SM
-  tp.stages = std::max(2, std::min(std::min(TC_MAX_STAGES, tp.num_kb), (budget - 1024) / stage_bytes));
+  tp.BN = pl.BN;
+  tp.tmem_cols = pl.tmem_cols;
+  tp.stages = pl.stages;
+  tp.splits = pl.splits;
   CUtensorMap am;
-  int s = tc_act_map(ws, p.A, a_cap, a_cols, p.lda, swap ? tp.BN : TC_BM, &am);
+  int s = tc_act_map(ws, p.A, a_cap, a_cols, p.lda, pl.swap ? pl.BN : TC_BM, &am);
   if (s != LVX_OK) return s;
-  if (swap) {
-    dim3 grid(ceil_div(p.N, TC_BM), ceil_div(p.M, tp.BN));
-    return c_bf16 ? tc_launch<true, bf16>(w.map, am, tp, grid, st) : tc_launch<true, float>(w.map, am, tp, grid, st);
-  }
-  dim3 grid(ceil_div(p.N, tp.BN), ceil_div(p.M, TC_BM));
-  return c_bf16 ? tc_launch<false, bf16>(am, w.map, tp, grid, st) : tc_launch<false, float>(am, w.map, tp, grid, st);
+  if (pl.swap)
+    return c_bf16 ? tc_launch<true, bf16>(w.map, am, tp, pl.grid, pl.smem, st) : tc_launch<true, float>(w.map, am, tp, pl.grid, pl.smem, st);
+  return c_bf16 ? tc_launch<false, bf16>(am, w.map, tp, pl.grid, pl.smem, st) : tc_launch<false, float>(am, w.map, tp, pl.grid, pl.smem, st);
 }
 
 }  // namespace lvx

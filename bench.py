@@ -168,12 +168,13 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
-def device_step(e, slots, pcm_out):
-    """One pass over one batch whose text already sits on the device: decode to each chunk boundary, vocode the
-    64 chunks that became ready as one ragged batch.  No host synchronisation."""
+def device_step(e, runner, slots, pcm_out):
+    """One pass over one batch whose text already sits on the device: decode to each chunk boundary (on the decode
+    lanes), vocode the 64 chunks that became ready as one ragged batch (control stream; overlaps the lanes' next
+    iterations).  No host synchronisation."""
     pos = 0
     for L in SCHEDULE:
-        e.decode_steps(slots, L)
+        runner.decode(slots, L)
         codes = e.gather_codes(slots, pos, L)                       # (64, L) int32 on the device
         cu = list(range(0, (len(slots) + 1) * L, L))
         e.vocode(codes.view(-1), cu, 0, out=pcm_out[pos * len(slots) * 320:(pos + L) * len(slots) * 320])
@@ -185,7 +186,7 @@ def run_gpu(args):
     from llmvox_b200 import build as B
     from llmvox_b200 import weights as W
     from llmvox_b200.engine import Engine
-    from llmvox_b200.streaming import BatchSynthesizer
+    from llmvox_b200.streaming import BatchSynthesizer, LaneRunner
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -198,7 +199,8 @@ def run_gpu(args):
     sd = W.make_random_weights(SEED, wpe_rows=256)
     n_groups = Wm + K
     e = Engine(sd, device=local, precision=args.precision, max_sessions=STREAMS * (n_groups + 1), max_batch=STREAMS,
-               max_context=208, max_vocode_frames=STREAMS * 96)
+               max_context=208, max_vocode_frames=STREAMS * 96, decode_lanes=args.lanes)
+    runner = LaneRunner(e, args.lanes)
     texts = synthetic_text(STREAMS, 1000 + rank)
     groups = [list(range(g * STREAMS, (g + 1) * STREAMS)) for g in range(n_groups + 1)]
     pcm = torch.empty((STREAMS * TOKENS * 320,), dtype=torch.float32, device=e.device)
@@ -213,16 +215,17 @@ def run_gpu(args):
     for g in groups[:n_groups]:
         e.open(g)
         e.feed_text(g, texts)
+    runner.sync_from_control()
     clocks = ClockSampler(local)
     for g in groups[:Wm]:
-        device_step(e, g, pcm)
+        device_step(e, runner, g, pcm)
     barrier()
     clocks.mark()
     l0 = e.kernel_launches
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for g in groups[Wm:Wm + K]:
-        device_step(e, g, pcm)
+        device_step(e, runner, g, pcm)
     ev1.record()
     barrier()
     launches = e.kernel_launches - l0
@@ -232,7 +235,7 @@ def run_gpu(args):
     assert torch.isfinite(pcm[:: 4099]).all()
 
     # ---- e2e: host text ids in, PCM out to pinned host memory, through the public batched API
-    bs = BatchSynthesizer(e, STREAMS, SCHEDULE[0], stop_on_eoa=False, slots=groups[n_groups])
+    bs = BatchSynthesizer(e, STREAMS, SCHEDULE[0], stop_on_eoa=False, slots=groups[n_groups], lanes=args.lanes)
     e2e_steps = max(3, min(K, 10))
 
     def e2e_step():
@@ -253,8 +256,10 @@ def run_gpu(args):
     # ---- per-kernel profile of one step (events around every launch), beside the timed region
     e.open(groups[0])
     e.feed_text(groups[0], texts)
+    runner.sync_from_control()
+    torch.cuda.synchronize()
     e.profile(True)
-    device_step(e, groups[0], pcm)
+    device_step(e, LaneRunner(e, 1), groups[0], pcm)
     prof = e.profile_report()
     e.profile(False)
 
@@ -291,6 +296,7 @@ def run_gpu(args):
                 "dtype": args.precision, "data": "synthetic",
                 "config": {"workload": f"config1: {STREAMS} streams x {TOKENS} codes per GPU, KV-cached greedy decode + chunked vocoder ({'/'.join(map(str, SCHEDULE))})",
                            "weights": "random-init english-tiny GPT + frame75 WavTokenizer decoder, seed 1234",
+                           "decode_lanes": args.lanes,
                            "l2": "no flush: per-step working set (189 MB bf16 weights + KV + activations) exceeds the 126 MB L2"},
                 "x_realtime_per_gpu": value / world,
                 "roofline": roof,
@@ -313,6 +319,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="llmvox_b200", choices=["llmvox_b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--lanes", type=int, default=4, help="decode lanes: groups of sessions whose dependent chains run concurrently")
     ap.add_argument("--short", action="store_true", help="40-code utterances (chunks 10/30): a short run for ncu captures")
     args = ap.parse_args()
     if args.short:

@@ -48,6 +48,7 @@ typedef struct lvx_config {
   int32_t precision;        /* LVX_PRECISION_*                                                         */
   int32_t pad_token_id;     /* 384: text id fed once a session's text is exhausted (:316-320)          */
   int32_t eoa_token_id;     /* 453                                                                     */
+  int32_t decode_lanes;     /* independent decode workspaces (lvx_decode_steps_lane); 0 or 1 = one     */
 } lvx_config;
 
 /* Sampler.  greedy != 0 (or top_k == 1): argmax with lowest-index tie break = the hot loop's
@@ -102,6 +103,14 @@ int lvx_feed_text(lvx_engine* e, const int32_t* h_slots, const int32_t* h_offset
  * t = 0) and position t; the new code is appended to the session's device-side code history. */
 int lvx_decode_steps(lvx_engine* e, const int32_t* h_slots, int n, int n_steps, const lvx_sampling* s,
                      void* stream);
+
+/* Same on decode lane `lane` (0 <= lane < decode_lanes).  A decode iteration is a chain of ~35 dependent,
+ * latency-bound kernels; sessions are independent, so disjoint groups of sessions can run their chains
+ * CONCURRENTLY: each lane owns its own workspace and CUDA graphs, and calls on different lanes may be enqueued
+ * on different streams without any ordering between them.  lvx_decode_steps == lane 0.  All other entry points
+ * (open / feed / gather / vocode) share one staging area and must be issued on one stream at a time. */
+int lvx_decode_steps_lane(lvx_engine* e, int lane, const int32_t* h_slots, int n, int n_steps, const lvx_sampling* s,
+                          void* stream);
 
 /* Test hook: ONE step that also returns the logits (n x vocab fp32, device) and the picked codes (n,
  * device, may be NULL).  With d_forced_codes != NULL the code stored in the history (and therefore fed

@@ -18,7 +18,7 @@ class LvxConfig(C.Structure):
         "text_vocab", "text_dim", "code_dim", "n_codes",
         "voc_dim", "voc_inter", "voc_layers", "voc_ada_rows", "n_fft", "hop",
         "max_sessions", "max_context", "kv_page_tokens", "kv_pages", "max_batch", "max_vocode_frames",
-        "precision", "pad_token_id", "eoa_token_id")]
+        "precision", "pad_token_id", "eoa_token_id", "decode_lanes")]
 
 
 class LvxSampling(C.Structure):
@@ -41,6 +41,7 @@ SYMBOLS = [
     ("lvx_session_close", C.c_int, [_VP, _I32P, C.c_int, _VP]),
     ("lvx_feed_text", C.c_int, [_VP, _I32P, _I32P, _I32P, C.c_int, _VP]),
     ("lvx_decode_steps", C.c_int, [_VP, _I32P, C.c_int, C.c_int, C.POINTER(LvxSampling), _VP]),
+    ("lvx_decode_steps_lane", C.c_int, [_VP, C.c_int, _I32P, C.c_int, C.c_int, C.POINTER(LvxSampling), _VP]),
     ("lvx_decode_step_logits", C.c_int, [_VP, _I32P, C.c_int, C.POINTER(LvxSampling), _VP, _VP, _VP, _VP]),
     ("lvx_decode_step_embeds", C.c_int, [_VP, _I32P, C.c_int, _VP, _I32P, _VP, _VP]),
     ("lvx_gather_codes", C.c_int, [_VP, _I32P, C.c_int, C.c_int, C.c_int, _VP, _VP]),

@@ -176,11 +176,8 @@ struct lvx_engine {
   std::vector<int> h_len, h_text_len, h_open, h_npages, free_pages, stamp;
   std::vector<std::vector<int>> h_pages;
   int stamp_ctr = 0;
-  int *d_slots = nullptr, *d_aux = nullptr, *d_ids = nullptr, *d_upd = nullptr;
-  // ---- decode workspace
-  int Bp = 0;
-  float *x = nullptr, *qkv = nullptr, *logits = nullptr;
-  void *h = nullptr, *y = nullptr, *g = nullptr;
+  int *d_slots = nullptr, *d_aux = nullptr, *d_ids = nullptr;   // staging of the control calls (open / feed / gather)
+  int Bp = 0;   // decode workspace rows (max_batch padded to the tensor-core tile)
   // ---- vocoder workspace
   int R_max = 0;
   long long score_cap = 0;
@@ -193,14 +190,21 @@ struct lvx_engine {
   float2* v_stats = nullptr;
   TcWorkspace tcw;
 
-  // ---- CUDA graphs of one decode iteration, keyed by (sessions, sampler); replayed on an engine-owned stream
+  // ---- decode lanes: independent workspaces so that groups of sessions can run their (latency-bound) dependent
+  // chains concurrently on different streams; each lane caches CUDA graphs of its decode iteration
   struct StepGraph {
     cudaGraphExec_t exec = nullptr;
     int64_t launches = 0;
   };
-  std::map<std::string, StepGraph> graphs;
-  cudaStream_t gstream = nullptr;
-  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  struct Lane {
+    int *d_slots = nullptr, *d_upd = nullptr, *d_pos = nullptr;
+    float *x = nullptr, *qkv = nullptr, *logits = nullptr;
+    void *h = nullptr, *y = nullptr, *g = nullptr;
+    std::map<std::string, StepGraph> graphs;
+  };
+  std::vector<Lane> lanes;
+  int lane_cta_budget = 0;
+  cudaStream_t gstream = nullptr;   // capture only: graphs are launched on the caller's stream
   bool use_graphs = true;
 
   // ---- optional per-launch profiler (lvx_profile_enable)
@@ -364,6 +368,7 @@ extern "C" int lvx_config_default(lvx_config* cfg) {
   cfg->precision = LVX_PRECISION_FP32;
   cfg->pad_token_id = 384;
   cfg->eoa_token_id = 453;
+  cfg->decode_lanes = 1;
   return LVX_OK;
 }
 
@@ -393,16 +398,21 @@ static int engine_alloc(lvx_engine* e) {
   LVX_TRY(dev_alloc(e, &e->d_slots, B));
   LVX_TRY(dev_alloc(e, &e->d_aux, 2 * B + 2));
   LVX_TRY(dev_alloc(e, &e->d_ids, (size_t)B * c.max_context));
-  LVX_TRY(dev_alloc(e, &e->d_upd, (size_t)3 * B * e->max_pages));
-  // decode workspace (rows padded to the tensor-core tile so TMA boxes stay in bounds)
+  // decode workspaces, one per lane (rows padded to the tensor-core tile so TMA boxes stay in bounds)
   const int Bp = ceil_div(B, 128) * 128;
   e->Bp = Bp;
-  LVX_TRY(dev_alloc(e, &e->x, (size_t)Bp * C));
-  LVX_TRY(dev_alloc(e, &e->qkv, (size_t)Bp * 3 * C));
-  LVX_TRY(dev_alloc(e, &e->logits, (size_t)Bp * c.vocab_size));
-  LVX_TRY(dev_alloc_bytes(e, &e->h, (size_t)Bp * C * dt_size(a)));
-  LVX_TRY(dev_alloc_bytes(e, &e->y, (size_t)Bp * C * dt_size(a)));
-  LVX_TRY(dev_alloc_bytes(e, &e->g, (size_t)Bp * 4 * C * dt_size(a)));
+  e->lanes.resize(std::max(1, c.decode_lanes));
+  for (auto& ln : e->lanes) {
+    LVX_TRY(dev_alloc(e, &ln.d_slots, B));
+    LVX_TRY(dev_alloc(e, &ln.d_pos, B));
+    LVX_TRY(dev_alloc(e, &ln.d_upd, (size_t)3 * B * e->max_pages));
+    LVX_TRY(dev_alloc(e, &ln.x, (size_t)Bp * C));
+    LVX_TRY(dev_alloc(e, &ln.qkv, (size_t)Bp * 3 * C));
+    LVX_TRY(dev_alloc(e, &ln.logits, (size_t)Bp * c.vocab_size));
+    LVX_TRY(dev_alloc_bytes(e, &ln.h, (size_t)Bp * C * dt_size(a)));
+    LVX_TRY(dev_alloc_bytes(e, &ln.y, (size_t)Bp * C * dt_size(a)));
+    LVX_TRY(dev_alloc_bytes(e, &ln.g, (size_t)Bp * 4 * C * dt_size(a)));
+  }
   // vocoder workspace
   const int D = c.voc_dim, I = c.voc_inter;
   e->R_max = ceil_div(c.max_vocode_frames + 2 * ROW_PAD, 128) * 128 + 128;
@@ -450,6 +460,7 @@ extern "C" int lvx_engine_create(const lvx_config* cfg, int device, lvx_engine**
   LVX_CHECK(c.kv_page_tokens > 0 && c.max_vocode_frames > 0, LVX_ERR_INVALID, "bad capacity");
   LVX_CHECK(c.voc_inter % 64 == 0 && c.code_dim % 64 == 0, LVX_ERR_INVALID, "voc_inter / code_dim must be multiples of 64");
   LVX_CHECK(c.precision == LVX_PRECISION_FP32 || c.precision == LVX_PRECISION_BF16, LVX_ERR_INVALID, "bad precision");
+  LVX_CHECK(c.decode_lanes >= 0 && c.decode_lanes <= 16, LVX_ERR_INVALID, "decode_lanes must be in [0, 16]");
   int ndev = 0;
   LVX_CUDA(cudaGetDeviceCount(&ndev));
   LVX_CHECK(device >= 0 && device < ndev, LVX_ERR_INVALID, "no such CUDA device");
@@ -468,12 +479,11 @@ extern "C" int lvx_engine_create(const lvx_config* cfg, int device, lvx_engine**
   if (s == LVX_OK) {
     const char* env = getenv("LLMVOX_B200_NO_GRAPH");
     e->use_graphs = !(env && env[0] == '1');
-    if (cudaStreamCreateWithFlags(&e->gstream, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming) != cudaSuccess) {
-      set_error("could not create the engine's stream / events");
+    if (cudaStreamCreateWithFlags(&e->gstream, cudaStreamNonBlocking) != cudaSuccess) {
+      set_error("could not create the engine's capture stream");
       s = LVX_ERR_CUDA;
     }
+    e->lane_cta_budget = std::max(24, prop.multiProcessorCount / (int)e->lanes.size());
   }
   if (s != LVX_OK) {
     lvx_engine_destroy(e);
@@ -487,11 +497,10 @@ extern "C" int lvx_engine_destroy(lvx_engine* e) {
   if (!e) return LVX_OK;
   cudaSetDevice(e->device);
   cudaDeviceSynchronize();
-  for (auto& g : e->graphs)
-    if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
+  for (auto& ln : e->lanes)
+    for (auto& g : ln.graphs)
+      if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
   if (e->gstream) cudaStreamDestroy(e->gstream);
-  if (e->ev_in) cudaEventDestroy(e->ev_in);
-  if (e->ev_out) cudaEventDestroy(e->ev_out);
   for (auto& r : e->prof) {
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
@@ -789,7 +798,7 @@ static void release_pages(lvx_engine* e, int slot) {
 }
 
 // makes sure every slot owns pages for `tokens[i]` KV tokens; patches the device page table
-static int ensure_pages(lvx_engine* e, const int32_t* h_slots, int n, const std::vector<int>& tokens, cudaStream_t st) {
+static int ensure_pages(lvx_engine* e, const int32_t* h_slots, int n, const std::vector<int>& tokens, int* d_upd, cudaStream_t st) {
   std::vector<int> upd;
   for (int i = 0; i < n; ++i) {
     const int s = h_slots[i];
@@ -806,8 +815,8 @@ static int ensure_pages(lvx_engine* e, const int32_t* h_slots, int n, const std:
   }
   if (!upd.empty()) {
     const int m = (int)upd.size() / 3;
-    LVX_CUDA(cudaMemcpyAsync(e->d_upd, upd.data(), upd.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-    patch_pages_kernel<<<ceil_div(m, 256), 256, 0, st>>>(e->d_upd, m, e->st);
+    LVX_CUDA(cudaMemcpyAsync(d_upd, upd.data(), upd.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+    patch_pages_kernel<<<ceil_div(m, 256), 256, 0, st>>>(d_upd, m, e->st);
     LAUNCHED(e);
   }
   return LVX_OK;
@@ -868,45 +877,46 @@ extern "C" int lvx_feed_text(lvx_engine* e, const int32_t* h_slots, const int32_
 
 // ------------------------------------------------------------------------------------------------ decode
 // One GPT.forward over n session rows whose residual stream x is already assembled (src/model.py:220-234).
-static int gpt_body(lvx_engine* e, int n, const int* pos_override, cudaStream_t st) {
+static int gpt_body(lvx_engine* e, lvx_engine::Lane& ln, int n, const int* pos_override, cudaStream_t st) {
   const lvx_config& c = e->cfg;
   const int C = c.n_embd;
   const DT a = e->adt();
+  const int budget = e->lane_cta_budget;
   for (int l = 0; l < c.n_layer; ++l) {
     auto& L = e->layers[l];
-    LVX_TRY(run_layernorm<768>(e, e->x, n, L.ln1_w, L.ln1_b, 1e-5f, nullptr, e->h, st));
+    LVX_TRY(run_layernorm<768>(e, ln.x, n, L.ln1_w, L.ln1_b, 1e-5f, nullptr, ln.h, st));
     GemmParams p;
-    p.A = e->h; p.C = e->qkv; p.M = n; p.lda = C; p.ldc = 3 * C; p.bias = L.attn_b;
+    p.A = ln.h; p.C = ln.qkv; p.M = n; p.lda = C; p.ldc = 3 * C; p.bias = L.attn_b; p.cta_budget = budget;
     LVX_TRY(run_gemm(e, p, L.attn, a, F32, st));
     dim3 grid(n, c.n_head);
     {
       PROF(e, "decode_attention", st);
       if (a == F32)
-        decode_attention_kernel<float, float, 96><<<grid, 128, 0, st>>>(e->qkv, (float*)e->kv, e->d_slots, e->st, pos_override, l,
-                                                                         c.n_head, c.kv_page_tokens, e->pool_pages, 0, (float*)e->y);
+        decode_attention_kernel<float, float, 96><<<grid, 128, 0, st>>>(ln.qkv, (float*)e->kv, ln.d_slots, e->st, pos_override, l,
+                                                                         c.n_head, c.kv_page_tokens, e->pool_pages, 0, (float*)ln.y);
       else
-        decode_attention_kernel<bf16, bf16, 96><<<grid, 128, 0, st>>>(e->qkv, (bf16*)e->kv, e->d_slots, e->st, pos_override, l,
-                                                                       c.n_head, c.kv_page_tokens, e->pool_pages, 0, (bf16*)e->y);
+        decode_attention_kernel<bf16, bf16, 96><<<grid, 128, 0, st>>>(ln.qkv, (bf16*)e->kv, ln.d_slots, e->st, pos_override, l,
+                                                                       c.n_head, c.kv_page_tokens, e->pool_pages, 0, (bf16*)ln.y);
       LAUNCHED(e);
     }
     GemmParams q;
-    q.A = e->y; q.C = e->x; q.M = n; q.lda = C; q.ldc = C; q.bias = L.proj_b; q.residual = e->x; q.ldr = C;
+    q.A = ln.y; q.C = ln.x; q.M = n; q.lda = C; q.ldc = C; q.bias = L.proj_b; q.residual = ln.x; q.ldr = C; q.cta_budget = budget;
     LVX_TRY(run_gemm(e, q, L.proj, a, F32, st));
-    LVX_TRY(run_layernorm<768>(e, e->x, n, L.ln2_w, L.ln2_b, 1e-5f, nullptr, e->h, st));
+    LVX_TRY(run_layernorm<768>(e, ln.x, n, L.ln2_w, L.ln2_b, 1e-5f, nullptr, ln.h, st));
     GemmParams f;
-    f.A = e->h; f.C = e->g; f.M = n; f.lda = C; f.ldc = 4 * C; f.bias = L.fc_b; f.act = ACT_GELU_TANH;
+    f.A = ln.h; f.C = ln.g; f.M = n; f.lda = C; f.ldc = 4 * C; f.bias = L.fc_b; f.act = ACT_GELU_TANH; f.cta_budget = budget;
     LVX_TRY(run_gemm(e, f, L.fc, a, a, st));
     GemmParams r;
-    r.A = e->g; r.C = e->x; r.M = n; r.lda = 4 * C; r.ldc = C; r.bias = L.proj2_b; r.residual = e->x; r.ldr = C;
+    r.A = ln.g; r.C = ln.x; r.M = n; r.lda = 4 * C; r.ldc = C; r.bias = L.proj2_b; r.residual = ln.x; r.ldr = C; r.cta_budget = budget;
     LVX_TRY(run_gemm(e, r, L.proj2, a, F32, st));
   }
-  LVX_TRY(run_layernorm<768>(e, e->x, n, e->lnf_w, e->lnf_b, 1e-5f, nullptr, e->h, st));
+  LVX_TRY(run_layernorm<768>(e, ln.x, n, e->lnf_w, e->lnf_b, 1e-5f, nullptr, ln.h, st));
   return LVX_OK;
 }
 
-static int lm_head_logits(lvx_engine* e, int n, float* d_logits, cudaStream_t st) {
+static int lm_head_logits(lvx_engine* e, lvx_engine::Lane& ln, int n, float* d_logits, cudaStream_t st) {
   GemmParams p;
-  p.A = e->h; p.C = d_logits; p.M = n; p.lda = e->cfg.n_embd; p.ldc = e->cfg.vocab_size;
+  p.A = ln.h; p.C = d_logits; p.M = n; p.lda = e->cfg.n_embd; p.ldc = e->cfg.vocab_size; p.cta_budget = e->lane_cta_budget;
   return run_gemm(e, p, e->lm_head, e->adt(), F32, st);
 }
 
@@ -921,84 +931,102 @@ static SamplerArgs sampler_args(const lvx_sampling* s) {
   return a;
 }
 
-static int decode_one_step(lvx_engine* e, int n, const SamplerArgs& sa, float* d_logits, cudaStream_t st) {
+static int decode_one_step(lvx_engine* e, lvx_engine::Lane& ln, int n, const SamplerArgs& sa, float* d_logits, cudaStream_t st) {
   const lvx_config& c = e->cfg;
   {
-  PROF(e, "assemble_input", st);
-  assemble_input_kernel<<<n, c.n_embd / 4, 0, st>>>(e->d_slots, e->st, W(e, "text_table"),
-                                                    W(e, "feature_extractor.encodec.quantizer.vq.layers.0._codebook.embed"),
-                                                    W(e, "transformer.wpe.weight"), c.text_dim, c.code_dim, c.pad_token_id, 0, e->x);
-  LAUNCHED(e);
+    PROF(e, "assemble_input", st);
+    assemble_input_kernel<<<n, c.n_embd / 4, 0, st>>>(ln.d_slots, e->st, W(e, "text_table"),
+                                                      W(e, "feature_extractor.encodec.quantizer.vq.layers.0._codebook.embed"),
+                                                      W(e, "transformer.wpe.weight"), c.text_dim, c.code_dim, c.pad_token_id, 0, ln.x);
+    LAUNCHED(e);
   }
-  LVX_TRY(gpt_body(e, n, nullptr, st));
-  LVX_TRY(lm_head_logits(e, n, d_logits, st));
+  LVX_TRY(gpt_body(e, ln, n, nullptr, st));
+  LVX_TRY(lm_head_logits(e, ln, n, d_logits, st));
   PROF(e, "sampler", st);
-  sampler_kernel<4096><<<n, 256, 0, st>>>(d_logits, c.vocab_size, e->d_slots, e->st, sa);
+  sampler_kernel<4096><<<n, 256, 0, st>>>(d_logits, c.vocab_size, ln.d_slots, e->st, sa);
   LAUNCHED(e);
   return LVX_OK;
 }
 
-static int prepare_decode(lvx_engine* e, const int32_t* h_slots, int n, int n_steps, cudaStream_t st) {
-  LVX_TRY(check_slots(e, h_slots, n, true));
-  std::vector<int> need(n);
-  for (int i = 0; i < n; ++i) {
-    need[i] = e->h_len[h_slots[i]] + n_steps;
-    LVX_CHECK(need[i] <= e->cfg.max_context, LVX_ERR_CAPACITY, "session would exceed max_context");
-  }
-  LVX_TRY(upload_slots(e, h_slots, n, st));
-  LVX_TRY(ensure_pages(e, h_slots, n, need, st));
+// slot checks, page allocation and the lane's slot list / page-table patches on `st`
+static int prepare_decode(lvx_engine* e, lvx_engine::Lane& ln, const int32_t* h_slots, int n, const std::vector<int>& need,
+                          cudaStream_t st) {
+  for (int i = 0; i < n; ++i) LVX_CHECK(need[i] <= e->cfg.max_context, LVX_ERR_CAPACITY, "session would exceed max_context");
+  LVX_CUDA(cudaMemcpyAsync(ln.d_slots, h_slots, n * sizeof(int), cudaMemcpyHostToDevice, st));
+  LVX_TRY(ensure_pages(e, h_slots, n, need, ln.d_upd, st));
   return LVX_OK;
 }
 
-extern "C" int lvx_decode_steps(lvx_engine* e, const int32_t* h_slots, int n, int n_steps, const lvx_sampling* s, void* stream) {
+// Graph of `iters` decode iterations for (n sessions, sampler) on this lane: every iteration launches the same
+// kernels with the same arguments (all per-session state lives on the device), so it is captured once.
+static int lane_graph(lvx_engine* e, lvx_engine::Lane& ln, int n, int iters, const SamplerArgs& sa, lvx_engine::StepGraph** out) {
+  char key[112];
+  snprintf(key, sizeof(key), "%d|%d|%d|%d|%.9g|%llu", n, iters, sa.greedy, sa.top_k, (double)sa.temperature,
+           (unsigned long long)sa.seed);
+  auto it = ln.graphs.find(key);
+  if (it == ln.graphs.end()) {
+    cudaGraph_t graph = nullptr;
+    const int64_t l0 = e->launches;
+    LVX_CUDA(cudaStreamBeginCapture(e->gstream, cudaStreamCaptureModeThreadLocal));
+    int s2 = LVX_OK;
+    for (int t = 0; t < iters && s2 == LVX_OK; ++t) s2 = decode_one_step(e, ln, n, sa, ln.logits, e->gstream);
+    cudaError_t ce = cudaStreamEndCapture(e->gstream, &graph);
+    const int64_t per = e->launches - l0;
+    e->launches = l0;
+    if (s2 != LVX_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return s2;
+    }
+    LVX_CHECK(ce == cudaSuccess && graph, LVX_ERR_CUDA, std::string("stream capture failed: ") + cudaGetErrorString(ce));
+    lvx_engine::StepGraph sg;
+    ce = cudaGraphInstantiate(&sg.exec, graph, 0);
+    cudaGraphDestroy(graph);
+    LVX_CHECK(ce == cudaSuccess, LVX_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
+    sg.launches = per;
+    if (ln.graphs.size() > 64) {
+      for (auto& g : ln.graphs) cudaGraphExecDestroy(g.second.exec);
+      ln.graphs.clear();
+    }
+    it = ln.graphs.emplace(key, sg).first;
+  }
+  *out = &it->second;
+  return LVX_OK;
+}
+
+extern "C" int lvx_decode_steps_lane(lvx_engine* e, int lane, const int32_t* h_slots, int n, int n_steps, const lvx_sampling* s,
+                                     void* stream) {
   LVX_TRY(check_engine(e));
+  LVX_CHECK(lane >= 0 && lane < (int)e->lanes.size(), LVX_ERR_INVALID, "decode lane out of range");
   LVX_CHECK(n_steps > 0, LVX_ERR_INVALID, "n_steps must be positive");
   cudaStream_t st = (cudaStream_t)stream;
-  LVX_TRY(prepare_decode(e, h_slots, n, n_steps, st));
+  lvx_engine::Lane& ln = e->lanes[lane];
+  LVX_TRY(check_slots(e, h_slots, n, true));
+  std::vector<int> need(n);
+  for (int i = 0; i < n; ++i) need[i] = e->h_len[h_slots[i]] + n_steps;
+  LVX_TRY(prepare_decode(e, ln, h_slots, n, need, st));
   SamplerArgs sa = sampler_args(s);
   LVX_CHECK(sa.greedy || sa.temperature > 0.f, LVX_ERR_INVALID, "temperature must be positive");
   LVX_CHECK(!(sa.uniform && n_steps > 1), LVX_ERR_INVALID, "d_uniform supplies one draw per session: use n_steps == 1");
   if (e->use_graphs && !e->prof_on && !sa.uniform) {
-    // every iteration launches the same kernels with the same arguments (all per-session state lives on the
-    // device), so one captured iteration is replayed n_steps times
-    char key[96];
-    snprintf(key, sizeof(key), "%d|%d|%d|%.9g|%llu", n, sa.greedy, sa.top_k, (double)sa.temperature, (unsigned long long)sa.seed);
-    auto it = e->graphs.find(key);
-    if (it == e->graphs.end()) {
-      cudaGraph_t graph = nullptr;
-      const int64_t l0 = e->launches;
-      LVX_CUDA(cudaStreamBeginCapture(e->gstream, cudaStreamCaptureModeThreadLocal));
-      int s2 = decode_one_step(e, n, sa, e->logits, e->gstream);
-      cudaError_t ce = cudaStreamEndCapture(e->gstream, &graph);
-      const int64_t per = e->launches - l0;
-      e->launches = l0;
-      if (s2 != LVX_OK) {
-        if (graph) cudaGraphDestroy(graph);
-        return s2;
-      }
-      LVX_CHECK(ce == cudaSuccess && graph, LVX_ERR_CUDA, std::string("stream capture failed: ") + cudaGetErrorString(ce));
-      lvx_engine::StepGraph sg;
-      ce = cudaGraphInstantiate(&sg.exec, graph, 0);
-      cudaGraphDestroy(graph);
-      LVX_CHECK(ce == cudaSuccess, LVX_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(ce));
-      sg.launches = per;
-      if (e->graphs.size() > 64) {
-        for (auto& g : e->graphs) cudaGraphExecDestroy(g.second.exec);
-        e->graphs.clear();
-      }
-      it = e->graphs.emplace(key, sg).first;
+    const int unroll = 10;   // iterations per graph launch for long runs
+    int left = n_steps;
+    while (left > 0) {
+      const int iters = left >= unroll ? unroll : 1;
+      lvx_engine::StepGraph* g = nullptr;
+      LVX_TRY(lane_graph(e, ln, n, iters, sa, &g));
+      LVX_CUDA(cudaGraphLaunch(g->exec, st));
+      e->launches += g->launches;
+      left -= iters;
     }
-    LVX_CUDA(cudaEventRecord(e->ev_in, st));
-    LVX_CUDA(cudaStreamWaitEvent(e->gstream, e->ev_in, 0));
-    for (int t = 0; t < n_steps; ++t) LVX_CUDA(cudaGraphLaunch(it->second.exec, e->gstream));
-    LVX_CUDA(cudaEventRecord(e->ev_out, e->gstream));
-    LVX_CUDA(cudaStreamWaitEvent(st, e->ev_out, 0));
-    e->launches += it->second.launches * n_steps;
   } else {
-    for (int t = 0; t < n_steps; ++t) LVX_TRY(decode_one_step(e, n, sa, e->logits, st));
+    for (int t = 0; t < n_steps; ++t) LVX_TRY(decode_one_step(e, ln, n, sa, ln.logits, st));
   }
   for (int i = 0; i < n; ++i) e->h_len[h_slots[i]] += n_steps;
   return LVX_OK;
+}
+
+extern "C" int lvx_decode_steps(lvx_engine* e, const int32_t* h_slots, int n, int n_steps, const lvx_sampling* s, void* stream) {
+  return lvx_decode_steps_lane(e, 0, h_slots, n, n_steps, s, stream);
 }
 
 extern "C" int lvx_decode_step_logits(lvx_engine* e, const int32_t* h_slots, int n, const lvx_sampling* s,
@@ -1006,12 +1034,16 @@ extern "C" int lvx_decode_step_logits(lvx_engine* e, const int32_t* h_slots, int
   LVX_TRY(check_engine(e));
   LVX_CHECK(d_logits, LVX_ERR_INVALID, "d_logits is NULL");
   cudaStream_t st = (cudaStream_t)stream;
-  LVX_TRY(prepare_decode(e, h_slots, n, 1, st));
+  lvx_engine::Lane& ln = e->lanes[0];
+  LVX_TRY(check_slots(e, h_slots, n, true));
+  std::vector<int> need(n);
+  for (int i = 0; i < n; ++i) need[i] = e->h_len[h_slots[i]] + 1;
+  LVX_TRY(prepare_decode(e, ln, h_slots, n, need, st));
   SamplerArgs sa = sampler_args(s);
   LVX_CHECK(sa.greedy || sa.temperature > 0.f, LVX_ERR_INVALID, "temperature must be positive");
   sa.forced = d_forced_codes;
   sa.out_codes = d_codes;
-  LVX_TRY(decode_one_step(e, n, sa, d_logits, st));
+  LVX_TRY(decode_one_step(e, ln, n, sa, d_logits, st));
   for (int i = 0; i < n; ++i) e->h_len[h_slots[i]] += 1;
   return LVX_OK;
 }
@@ -1021,23 +1053,22 @@ extern "C" int lvx_decode_step_embeds(lvx_engine* e, const int32_t* h_slots, int
   LVX_TRY(check_engine(e));
   LVX_CHECK(d_emb && h_positions && d_logits, LVX_ERR_INVALID, "NULL argument");
   cudaStream_t st = (cudaStream_t)stream;
+  lvx_engine::Lane& ln = e->lanes[0];
   LVX_TRY(check_slots(e, h_slots, n, true));
   std::vector<int> need(n);
   for (int i = 0; i < n; ++i) {
     // the reference's cache holds exactly T-1 tokens when the caller feeds T rows (src/model.py:74-79)
     LVX_CHECK(h_positions[i] == e->h_len[h_slots[i]], LVX_ERR_STATE, "position != tokens held by the session's cache");
     need[i] = h_positions[i] + 1;
-    LVX_CHECK(need[i] <= e->cfg.max_context, LVX_ERR_CAPACITY, "session would exceed max_context");
   }
-  LVX_TRY(upload_slots(e, h_slots, n, st));
-  LVX_TRY(ensure_pages(e, h_slots, n, need, st));
-  int* d_pos = e->d_aux;
+  LVX_TRY(prepare_decode(e, ln, h_slots, n, need, st));
+  int* d_pos = ln.d_pos;
   LVX_CUDA(cudaMemcpyAsync(d_pos, h_positions, n * sizeof(int), cudaMemcpyHostToDevice, st));
-  add_wpe_kernel<<<n, 192, 0, st>>>(d_emb, d_pos, W(e, "transformer.wpe.weight"), e->cfg.n_embd, e->x);
+  add_wpe_kernel<<<n, 192, 0, st>>>(d_emb, d_pos, W(e, "transformer.wpe.weight"), e->cfg.n_embd, ln.x);
   LAUNCHED(e);
-  LVX_TRY(gpt_body(e, n, d_pos, st));
-  LVX_TRY(lm_head_logits(e, n, d_logits, st));
-  set_ctx_kernel<<<ceil_div(n, 256), 256, 0, st>>>(e->d_slots, d_pos, n, e->st);
+  LVX_TRY(gpt_body(e, ln, n, d_pos, st));
+  LVX_TRY(lm_head_logits(e, ln, n, d_logits, st));
+  set_ctx_kernel<<<ceil_div(n, 256), 256, 0, st>>>(ln.d_slots, d_pos, n, e->st);
   LAUNCHED(e);
   for (int i = 0; i < n; ++i) e->h_len[h_slots[i]] += 1;
   return LVX_OK;

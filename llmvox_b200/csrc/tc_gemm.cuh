@@ -497,7 +497,8 @@ inline TcPlan tc_plan(const TcWorkspace* ws, const GemmParams& p) {
   const int gx = pl.swap ? ceil_div(p.N, TC_BM) : ceil_div(p.N, pl.BN);
   const int gy = pl.swap ? ceil_div(p.M, pl.BN) : ceil_div(p.M, TC_BM);
   const int tiles = gx * gy;
-  const int sms = ws->num_sms > 0 ? ws->num_sms : 148;
+  const int all_sms = ws->num_sms > 0 ? ws->num_sms : 148;
+  const int sms = p.cta_budget > 0 ? std::min(p.cta_budget, all_sms) : all_sms;
   // few tiles: split K across a cluster so that about 1.5 CTAs per SM pull operands concurrently
   int S = 1;
   while (S < 8 && tiles * (S * 2) <= sms + sms / 2 && num_kb >= S * 2 && (pl.BN / (S * 2)) % 4 == 0 && pl.BN / (S * 2) >= 4) S *= 2;
@@ -506,7 +507,7 @@ inline TcPlan tc_plan(const TcWorkspace* ws, const GemmParams& p) {
   while (pl.tmem_cols < pl.BN) pl.tmem_cols *= 2;
   const int stage_bytes = TC_X_BYTES + pl.BN * TC_BK * 2;
   const int nk = ceil_div(num_kb, S);
-  const bool one_per_sm = tiles * S <= sms || pl.BN > 128;
+  const bool one_per_sm = tiles * S <= all_sms || pl.BN > 128;
   const int budget = one_per_sm ? 200 * 1024 : 110 * 1024;
   int stages = std::max(2, std::min(std::min(TC_MAX_STAGES, nk), (budget - 1024) / stage_bytes));
   const size_t red_bytes = S > 1 ? (size_t)TC_BM * (pl.BN + 4) * 4 : 0;

@@ -33,7 +33,7 @@ class Engine:
                  gpt_arch: Optional[GPTArch] = None, voc_arch: Optional[VocoderArch] = None,
                  max_sessions: int = 256, max_context: int = 1024, max_batch: Optional[int] = None,
                  max_vocode_frames: int = 32768, kv_page_tokens: int = 16, kv_pages: int = 0,
-                 pad_token_id: int = 384, eoa_token_id: int = 453):
+                 pad_token_id: int = 384, eoa_token_id: int = 453, decode_lanes: int = 1):
         if not torch.cuda.is_available():
             raise RuntimeError("llmvox_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.load()
@@ -50,6 +50,8 @@ class Engine:
         cfg.max_vocode_frames, cfg.kv_page_tokens, cfg.kv_pages = max_vocode_frames, kv_page_tokens, kv_pages
         cfg.precision = {"fp32": PRECISION_FP32, "bf16": PRECISION_BF16}[precision]
         cfg.pad_token_id, cfg.eoa_token_id = pad_token_id, eoa_token_id
+        cfg.decode_lanes = decode_lanes
+        self.decode_lanes = max(1, decode_lanes)
         self.cfg = cfg
         self.precision = precision
         self.device = torch.device("cuda", device)
@@ -126,9 +128,12 @@ class Engine:
         return out.value
 
     # ------------------------------------------------------------------ decode
-    def decode_steps(self, slots: Sequence[int], n_steps: int, sampling: Optional[Sampling] = None, stream=None):
+    def decode_steps(self, slots: Sequence[int], n_steps: int, sampling: Optional[Sampling] = None, stream=None, lane: int = 0):
+        """n_steps decode iterations for `slots` on decode lane `lane`.  Calls on different lanes may be enqueued on
+        different streams and run concurrently (sessions are independent)."""
         s = (sampling or Sampling()).to_c()
-        check(self.lib.lvx_decode_steps(self._h, i32_array(slots), len(slots), n_steps, C.byref(s), self._stream(stream)))
+        check(self.lib.lvx_decode_steps_lane(self._h, lane, i32_array(slots), len(slots), n_steps, C.byref(s),
+                                             self._stream(stream)))
 
     def decode_step_logits(self, slots: Sequence[int], forced: Optional[torch.Tensor] = None,
                            sampling: Optional[Sampling] = None, uniform: Optional[torch.Tensor] = None,

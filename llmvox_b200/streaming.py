@@ -18,6 +18,51 @@ from .engine import Engine, Sampling
 from .scheduler import ChunkScheduler, INITIAL_DUMP_SIZE_1, MAX_DUMP_SIZE
 
 
+class LaneRunner:
+    """Runs the decode iterations of a batch as `lanes` independent groups on their own CUDA streams.
+
+    A decode iteration is a chain of dependent, latency-bound kernels that leaves most of the GPU idle; sessions
+    never interact, so disjoint groups advance concurrently (engine decode lanes), and the control stream (gather /
+    vocode / copies) overlaps with the lanes' next iterations.  Lanes only ever wait for the event recorded by
+    `sync_from_control()` (after open / feed), never for vocoder work."""
+
+    def __init__(self, engine: Engine, lanes: Optional[int] = None):
+        self.e = engine
+        self.G = max(1, min(engine.decode_lanes, lanes or engine.decode_lanes))
+        self.streams = [torch.cuda.Stream(device=engine.device) for _ in range(self.G)] if self.G > 1 else [None]
+
+    def split(self, slots: Sequence[int]) -> List[List[int]]:
+        n, G = len(slots), min(self.G, len(slots))
+        base, rem = divmod(n, G)
+        out, pos = [], 0
+        for g in range(G):
+            k = base + (1 if g < rem else 0)
+            out.append(list(slots[pos:pos + k]))
+            pos += k
+        return out
+
+    def sync_from_control(self):
+        """Lanes wait for everything enqueued so far on the current (control) stream."""
+        if self.G == 1:
+            return
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.e.device))
+        for st in self.streams:
+            st.wait_event(ev)
+
+    def decode(self, slots: Sequence[int], n_steps: int, sampling: Optional[Sampling] = None):
+        """Enqueues n_steps iterations for every group; the control stream then waits for all lanes."""
+        if self.G == 1:
+            self.e.decode_steps(slots, n_steps, sampling)
+            return
+        main = torch.cuda.current_stream(self.e.device)
+        for g, grp in enumerate(self.split(slots)):
+            self.e.decode_steps(grp, n_steps, sampling, stream=self.streams[g], lane=g)
+            ev = torch.cuda.Event()
+            ev.record(self.streams[g])
+            main.wait_event(ev)
+
+
 @dataclass
 class Chunk:
     session: int          # index into the batch
@@ -34,7 +79,7 @@ class BatchSynthesizer:
 
     def __init__(self, engine: Engine, n_sessions: int, initial_dump_size: int = INITIAL_DUMP_SIZE_1,
                  max_dump_size: int = MAX_DUMP_SIZE, stop_on_eoa: bool = True, sampling: Optional[Sampling] = None,
-                 slots: Optional[Sequence[int]] = None, bandwidth_id: int = 0):
+                 slots: Optional[Sequence[int]] = None, bandwidth_id: int = 0, lanes: Optional[int] = None):
         self.e = engine
         self.n = n_sessions
         self.slots = list(slots) if slots is not None else list(range(n_sessions))
@@ -45,7 +90,7 @@ class BatchSynthesizer:
         self.sampling = sampling or Sampling()
         self.bw = bandwidth_id
         self.steps_done = 0
-        self._pinned: Optional[torch.Tensor] = None
+        self.runner = LaneRunner(engine, lanes)
 
     def start(self, text_ids: Sequence[Sequence[int]]):
         """Opens the sessions (the per-sentence reset of :404-416) and hands them their text ids."""
@@ -55,16 +100,13 @@ class BatchSynthesizer:
         for s in self.sched:
             s.new_sentence()
         self.steps_done = 0
+        self.runner.sync_from_control()
 
-    def _pinned_buf(self, n: int) -> torch.Tensor:
-        if self._pinned is None or self._pinned.numel() < n:
-            self._pinned = torch.empty((max(n, 1 << 20),), dtype=torch.float32, pin_memory=True)
-        return self._pinned
-
-    def _emit(self, ready: List[Tuple[int, int, int]], copy: bool = True) -> List[Chunk]:
-        """ready: (session index, start, length).  One ragged vocoder batch + one async D2H."""
+    def _enqueue_emit(self, ready: List[Tuple[int, int, int]]):
+        """ready: (session index, start, length).  Enqueues one ragged vocoder batch + one async D2H into pinned
+        memory on the control stream; returns a ticket for `_finish_emit`."""
         if not ready:
-            return []
+            return None
         slots = [self.slots[i] for i, _, _ in ready]
         starts = [s for _, s, _ in ready]
         counts = [c for _, _, c in ready]
@@ -85,10 +127,18 @@ class BatchSynthesizer:
         for j in order:
             cu.append(cu[-1] + counts[j])
         pcm = self.e.vocode(codes, cu, self.bw)
-        hop = self.e.cfg.hop
-        host = self._pinned_buf(pcm.numel())[: pcm.numel()]
+        host = self._pinned_pair(pcm.numel())[: pcm.numel()]
         host.copy_(pcm, non_blocking=True)
-        torch.cuda.current_stream(self.e.device).synchronize()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.e.device))
+        return (ready, order, cu, host, ev, pcm)
+
+    def _finish_emit(self, ticket, copy: bool = True) -> List[Chunk]:
+        if ticket is None:
+            return []
+        ready, order, cu, host, ev, _pcm = ticket
+        ev.synchronize()
+        hop = self.e.cfg.hop
         out = []
         arr = host.numpy()
         for k, j in enumerate(order):
@@ -98,13 +148,33 @@ class BatchSynthesizer:
         out.sort(key=lambda ch: (ch.session, ch.start))
         return out
 
+    def _pinned_pair(self, n: int):
+        """Two pinned buffers used alternately: round r's PCM is read by the host while round r+1's is written
+        (with copy=False a yielded chunk aliases its buffer and is valid until two rounds later)."""
+        if not hasattr(self, "_pp") or self._pp[0].numel() < n:
+            self._pp = [torch.empty((max(n, 1 << 20),), dtype=torch.float32, pin_memory=True) for _ in range(2)]
+            self._pp_i = 0
+        self._pp_i ^= 1
+        return self._pp[self._pp_i]
+
     def run(self, max_steps: int, flush_tail: bool = False, copy: bool = True) -> Iterator[List[Chunk]]:
-        """Decodes up to `max_steps` codes per session, yielding the chunks of each round as they are ready."""
+        """Decodes up to `max_steps` codes per session, yielding the chunks of each round as they are ready.
+
+        Software-pipelined: round r+1's decode iterations are enqueued on the lanes BEFORE the host waits for round
+        r's PCM, so the vocoder and the copies of round r overlap the decode of round r+1.  With stop_on_eoa the
+        codes of round r are read back first (they decide which sessions are still active); codes a session decodes
+        past its EOA are discarded, as the reference resets there."""
         active = list(range(self.n))
+        pending = None                      # ticket of the previous round
         while active and self.steps_done < max_steps:
             k = min(min(self.sched[i].steps_to_next_event() for i in active), max_steps - self.steps_done)
             slots = [self.slots[i] for i in active]
-            self.e.decode_steps(slots, k, self.sampling)
+            self.runner.decode(slots, k, self.sampling)
+            if pending is not None:         # round r-1's PCM is surely done by now or soon: hand it out
+                chunks = self._finish_emit(pending, copy)
+                pending = None
+                if chunks:
+                    yield chunks
             new_codes = None
             if self.stop_on_eoa:   # the EOA test is the only reason a code value visits the host
                 new_codes = self.e.gather_codes(slots, self.steps_done, k).cpu().numpy()
@@ -113,12 +183,14 @@ class BatchSynthesizer:
                 sc = self.sched[i]
                 for t in range(k):
                     if sc.done:
-                        break          # codes decoded past the EOA are discarded, as the reference resets there
+                        break
                     for (s, c) in sc.push(int(new_codes[a, t]) if new_codes is not None else None):
                         ready.append((i, s, c))
             self.steps_done += k
-            chunks = self._emit(ready, copy)
+            pending = self._enqueue_emit(ready)
             active = [i for i in active if not self.sched[i].done]
+        if pending is not None:
+            chunks = self._finish_emit(pending, copy)
             if chunks:
                 yield chunks
         if flush_tail:
@@ -126,7 +198,7 @@ class BatchSynthesizer:
             for i in range(self.n):
                 if not self.sched[i].done:
                     ready.extend((i, s, c) for (s, c) in self.sched[i].flush())
-            chunks = self._emit(ready, copy)
+            chunks = self._finish_emit(self._enqueue_emit(ready), copy)
             if chunks:
                 yield chunks
 
@@ -138,10 +210,10 @@ class BatchSynthesizer:
 
 def synthesize(engine: Engine, text_ids: Sequence[Sequence[int]], max_steps: int, initial_dump_size: int = INITIAL_DUMP_SIZE_1,
                stop_on_eoa: bool = True, flush_tail: bool = True, sampling: Optional[Sampling] = None,
-               bandwidth_id: int = 0) -> Tuple[np.ndarray, List[List[Chunk]]]:
+               bandwidth_id: int = 0, lanes: Optional[int] = None) -> Tuple[np.ndarray, List[List[Chunk]]]:
     """Text ids -> (codes, per-session chunk lists)."""
     bs = BatchSynthesizer(engine, len(text_ids), initial_dump_size, stop_on_eoa=stop_on_eoa, sampling=sampling,
-                          bandwidth_id=bandwidth_id)
+                          bandwidth_id=bandwidth_id, lanes=lanes)
     bs.start(text_ids)
     per: List[List[Chunk]] = [[] for _ in text_ids]
     for chunks in bs.run(max_steps, flush_tail=flush_tail):

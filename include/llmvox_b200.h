@@ -118,6 +118,9 @@ int lvx_decode_steps_lane(lvx_engine* e, int lane, const int32_t* h_slots, int n
 int lvx_decode_step_logits(lvx_engine* e, const int32_t* h_slots, int n, const lvx_sampling* s,
                            const int32_t* d_forced_codes, float* d_logits, int32_t* d_codes, void* stream);
 
+/* Test hook: copies the logits of the LAST decode iteration run on `lane` (n x vocab fp32) to d_out. */
+int lvx_peek_logits(lvx_engine* e, int lane, int n, float* d_out, void* stream);
+
 /* Drop-in for `model(emb, kvcache)` (streaming_server.py:341 -> src/model.py:201-237): the caller supplies
  * the assembled, normalised input row of each session (n x n_embd fp32, device) and its position (the
  * reference's T-1); returns logits (n x vocab fp32, device) and appends K/V.  No code is recorded. */

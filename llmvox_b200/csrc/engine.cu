@@ -18,6 +18,7 @@
 #include "decode_kernels.cuh"
 #include "gemm.cuh"
 #include "tc_gemm.cuh"
+#include "fused_decode.cuh"
 #include "vocoder_kernels.cuh"
 
 namespace lvx {
@@ -196,7 +197,14 @@ struct lvx_engine {
     cudaGraphExec_t exec = nullptr;
     int64_t launches = 0;
   };
+  struct FusedCtx {
+    FusedParams P;
+    FusedPlan plan;
+    CUtensorMap* d_maps = nullptr;
+  };
   struct Lane {
+    std::map<int, FusedCtx> fused;   // persistent fused decode kernel, keyed by the number of sessions
+    unsigned* d_bar = nullptr;
     int *d_slots = nullptr, *d_upd = nullptr, *d_pos = nullptr;
     float *x = nullptr, *qkv = nullptr, *logits = nullptr;
     void *h = nullptr, *y = nullptr, *g = nullptr;
@@ -206,6 +214,7 @@ struct lvx_engine {
   int lane_cta_budget = 0;
   cudaStream_t gstream = nullptr;   // capture only: graphs are launched on the caller's stream
   bool use_graphs = true;
+  bool use_fused = true;
 
   // ---- optional per-launch profiler (lvx_profile_enable)
   struct ProfRec {
@@ -404,6 +413,7 @@ static int engine_alloc(lvx_engine* e) {
   e->lanes.resize(std::max(1, c.decode_lanes));
   for (auto& ln : e->lanes) {
     LVX_TRY(dev_alloc(e, &ln.d_slots, B));
+    LVX_TRY(dev_alloc(e, &ln.d_bar, 64));
     LVX_TRY(dev_alloc(e, &ln.d_pos, B));
     LVX_TRY(dev_alloc(e, &ln.d_upd, (size_t)3 * B * e->max_pages));
     LVX_TRY(dev_alloc(e, &ln.x, (size_t)Bp * C));
@@ -479,6 +489,8 @@ extern "C" int lvx_engine_create(const lvx_config* cfg, int device, lvx_engine**
   if (s == LVX_OK) {
     const char* env = getenv("LLMVOX_B200_NO_GRAPH");
     e->use_graphs = !(env && env[0] == '1');
+    const char* env2 = getenv("LLMVOX_B200_NO_FUSED");
+    e->use_fused = !(env2 && env2[0] == '1');
     if (cudaStreamCreateWithFlags(&e->gstream, cudaStreamNonBlocking) != cudaSuccess) {
       set_error("could not create the engine's capture stream");
       s = LVX_ERR_CUDA;
@@ -993,6 +1005,68 @@ static int lane_graph(lvx_engine* e, lvx_engine::Lane& ln, int n, int iters, con
   return LVX_OK;
 }
 
+// Persistent fused decode kernel (fused_decode.cuh): context for (lane, n sessions), built on first use.
+static int fused_ctx(lvx_engine* e, lvx_engine::Lane& ln, int n, lvx_engine::FusedCtx** out) {
+  auto it = ln.fused.find(n);
+  if (it == ln.fused.end()) {
+    const lvx_config& c = e->cfg;
+    const int C = c.n_embd, L = c.n_layer;
+    lvx_engine::FusedCtx fc;
+    LVX_TRY(fused_plan(n, &fc.plan));
+    const int n_maps = 4 * L + 1 + 3;
+    std::vector<CUtensorMap> maps(n_maps);
+    for (int l = 0; l < L; ++l) {
+      maps[4 * l + 0] = e->layers[l].attn.tma.map;
+      maps[4 * l + 1] = e->layers[l].proj.tma.map;
+      maps[4 * l + 2] = e->layers[l].fc.tma.map;
+      maps[4 * l + 3] = e->layers[l].proj2.tma.map;
+    }
+    maps[4 * L] = e->lm_head.tma.map;
+    const int ih = 4 * L + 1, iy = ih + 1, ig = ih + 2;
+    LVX_TRY(tc_encode(&maps[ih], ln.h, e->Bp, C, C, fc.plan.BN));
+    LVX_TRY(tc_encode(&maps[iy], ln.y, e->Bp, C, C, fc.plan.BN));
+    LVX_TRY(tc_encode(&maps[ig], ln.g, e->Bp, 4 * C, 4 * C, fc.plan.BN));
+    LVX_TRY(dev_alloc(e, &fc.d_maps, n_maps));
+    LVX_CUDA(cudaMemcpy(fc.d_maps, maps.data(), n_maps * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
+    FusedParams& P = fc.P;
+    memset(&P, 0, sizeof(P));
+    P.n = n; P.BN = fc.plan.BN; P.stages = fc.plan.stages; P.tmem_cols = fc.plan.tmem_cols; P.n_clusters = fc.plan.n_clusters;
+    P.n_layer = L; P.n_head = c.n_head; P.C = C; P.vocab = c.vocab_size;
+    P.maps = fc.d_maps;
+    P.slots = ln.d_slots;
+    P.st = e->st;
+    P.text_table = W(e, "text_table");
+    P.codebook = W(e, "feature_extractor.encodec.quantizer.vq.layers.0._codebook.embed");
+    P.wpe = W(e, "transformer.wpe.weight");
+    P.text_dim = c.text_dim; P.code_dim = c.code_dim; P.pad_id = c.pad_token_id;
+    auto gemm = [&](int map_a, int map_w, const GemmW& w, const float* bias, const float* residual, void* Cout, int ldc, int c_bf16,
+                    int act) {
+      FusedGemm g;
+      g.map_a = map_a; g.map_w = map_w; g.N = w.N; g.K = w.K; g.bias = bias; g.residual = residual; g.C = Cout; g.ldc = ldc;
+      g.c_bf16 = c_bf16; g.act = act;
+      return g;
+    };
+    for (int l = 0; l < L; ++l) {
+      auto& Ly = e->layers[l];
+      FusedLayer& F = P.layer[l];
+      F.ln1_w = Ly.ln1_w; F.ln1_b = Ly.ln1_b; F.ln2_w = Ly.ln2_w; F.ln2_b = Ly.ln2_b;
+      F.qkv = gemm(ih, 4 * l + 0, Ly.attn, Ly.attn_b, nullptr, ln.qkv, 3 * C, 0, ACT_NONE);
+      F.proj = gemm(iy, 4 * l + 1, Ly.proj, Ly.proj_b, ln.x, ln.x, C, 0, ACT_NONE);
+      F.fc = gemm(ih, 4 * l + 2, Ly.fc, Ly.fc_b, nullptr, ln.g, 4 * C, 1, ACT_GELU_TANH);
+      F.proj2 = gemm(ig, 4 * l + 3, Ly.proj2, Ly.proj2_b, ln.x, ln.x, C, 0, ACT_NONE);
+    }
+    P.lnf_w = e->lnf_w; P.lnf_b = e->lnf_b;
+    P.lm_head = gemm(ih, 4 * L, e->lm_head, nullptr, nullptr, ln.logits, c.vocab_size, 0, ACT_NONE);
+    P.x = ln.x; P.qkv = ln.qkv; P.logits = ln.logits;
+    P.h = (bf16*)ln.h; P.y = (bf16*)ln.y;
+    P.kv = (bf16*)e->kv; P.page_tokens = c.kv_page_tokens; P.pool_pages = e->pool_pages;
+    P.bar = ln.d_bar;
+    it = ln.fused.emplace(n, fc).first;
+  }
+  *out = &it->second;
+  return LVX_OK;
+}
+
 extern "C" int lvx_decode_steps_lane(lvx_engine* e, int lane, const int32_t* h_slots, int n, int n_steps, const lvx_sampling* s,
                                      void* stream) {
   LVX_TRY(check_engine(e));
@@ -1007,7 +1081,17 @@ extern "C" int lvx_decode_steps_lane(lvx_engine* e, int lane, const int32_t* h_s
   SamplerArgs sa = sampler_args(s);
   LVX_CHECK(sa.greedy || sa.temperature > 0.f, LVX_ERR_INVALID, "temperature must be positive");
   LVX_CHECK(!(sa.uniform && n_steps > 1), LVX_ERR_INVALID, "d_uniform supplies one draw per session: use n_steps == 1");
-  if (e->use_graphs && !e->prof_on && !sa.uniform) {
+  const lvx_config& c = e->cfg;
+  if (e->use_fused && e->adt() == B16 && sa.greedy && !e->prof_on && n <= 128 && c.n_layer <= FD_MAX_LAYERS && c.n_embd == 768 &&
+      c.vocab_size % 4 == 0) {
+    // one persistent launch runs all n_steps iterations (fused_decode.cuh)
+    lvx_engine::FusedCtx* fc = nullptr;
+    LVX_TRY(fused_ctx(e, ln, n, &fc));
+    fc->P.n_iters = n_steps;
+    LVX_CUDA(cudaMemsetAsync(ln.d_bar, 0, sizeof(unsigned), st));
+    LVX_TRY(fused_launch(fc->P, fc->plan, st));
+    e->launches += 1;
+  } else if (e->use_graphs && !e->prof_on && !sa.uniform) {
     const int unroll = 10;   // iterations per graph launch for long runs
     int left = n_steps;
     while (left > 0) {
@@ -1027,6 +1111,14 @@ extern "C" int lvx_decode_steps_lane(lvx_engine* e, int lane, const int32_t* h_s
 
 extern "C" int lvx_decode_steps(lvx_engine* e, const int32_t* h_slots, int n, int n_steps, const lvx_sampling* s, void* stream) {
   return lvx_decode_steps_lane(e, 0, h_slots, n, n_steps, s, stream);
+}
+
+extern "C" int lvx_peek_logits(lvx_engine* e, int lane, int n, float* d_out, void* stream) {
+  LVX_TRY(check_engine(e));
+  LVX_CHECK(lane >= 0 && lane < (int)e->lanes.size() && n > 0 && n <= e->cfg.max_batch && d_out, LVX_ERR_INVALID, "bad argument");
+  LVX_CUDA(cudaMemcpyAsync(d_out, e->lanes[lane].logits, (size_t)n * e->cfg.vocab_size * sizeof(float), cudaMemcpyDeviceToDevice,
+                           (cudaStream_t)stream));
+  return LVX_OK;
 }
 
 extern "C" int lvx_decode_step_logits(lvx_engine* e, const int32_t* h_slots, int n, const lvx_sampling* s,

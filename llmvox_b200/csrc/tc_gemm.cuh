@@ -238,7 +238,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const GemmParams& p, int i, in
         float4 b = make_float4(0.f, 0.f, 0.f, 0.f), cs = make_float4(1.f, 1.f, 1.f, 1.f), r = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias) b = load4(p.bias + n);
         if (p.col_scale) cs = load4(p.col_scale + n);
-        if (p.residual) r = load4(p.residual + (size_t)m * p.ldr + n);
+        if (p.residual) r = __ldcg(reinterpret_cast<const float4*>(p.residual + (size_t)m * p.ldr + n));
         float4 o;
         o.x = apply_act(v[j] * p.alpha + b.x, p.act) * cs.x + r.x;
         o.y = apply_act(v[j + 1] * p.alpha + b.y, p.act) * cs.y + r.y;
@@ -254,7 +254,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const GemmParams& p, int i, in
             if (p.bias) xv += p.bias[nn];
             xv = apply_act(xv, p.act);
             if (p.col_scale) xv *= p.col_scale[nn];
-            if (p.residual) xv += p.residual[(size_t)m * p.ldr + nn];
+            if (p.residual) xv += __ldcg(p.residual + (size_t)m * p.ldr + nn);
             store1(C + (size_t)m * p.ldc + nn, xv);
           }
         }
@@ -271,7 +271,7 @@ __device__ __forceinline__ void tc_epilogue_chunk(const GemmParams& p, int i, in
     for (int j = 0; j < 16; ++j) {
       const int m = j0 + j;
       ok[j] = j < ncols && m < p.M && (!p.row_chunk || p.row_chunk[m] >= 0);
-      r[j] = (ok[j] && p.residual) ? p.residual[(size_t)m * p.ldr + n] : 0.f;
+      r[j] = (ok[j] && p.residual) ? __ldcg(p.residual + (size_t)m * p.ldr + n) : 0.f;
     }
 #pragma unroll
     for (int j = 0; j < 16; ++j) {

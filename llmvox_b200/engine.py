@@ -149,6 +149,12 @@ class Engine:
                                               C.c_void_p(codes.data_ptr()), self._stream(stream)))
         return logits, codes
 
+    def peek_logits(self, n: int, lane: int = 0, stream=None) -> torch.Tensor:
+        """Test hook: logits of the last decode iteration run on `lane`."""
+        out = torch.empty((n, self.cfg.vocab_size), dtype=torch.float32, device=self.device)
+        check(self.lib.lvx_peek_logits(self._h, lane, n, C.c_void_p(out.data_ptr()), self._stream(stream)))
+        return out
+
     def decode_step_embeds(self, slots: Sequence[int], emb: torch.Tensor, positions: Sequence[int], stream=None) -> torch.Tensor:
         n = len(slots)
         emb = emb.to(device=self.device, dtype=torch.float32).contiguous()

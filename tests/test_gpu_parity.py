@@ -375,6 +375,48 @@ def test_decode_lanes_do_not_change_results(weights, precision):
     e.close()
 
 
+@pytest.mark.parametrize("n", [1, 5, 64, 100])
+def test_fused_decode_kernel_matches_the_multi_kernel_path(weights, n):
+    """The persistent fused decode kernel (bf16, greedy) against the kernel-per-op path on a twin engine: at every
+    step the twin is teacher-forced with the fused kernel's pick, so both see identical histories; logits must agree
+    within the bf16 bound and every fused pick must be the argmax of its own logits."""
+    import os
+    from llmvox_b200.engine import Engine
+    kw = dict(device=0, precision="bf16", max_sessions=n, max_context=48, max_vocode_frames=256)
+    fused = Engine(weights, **kw)
+    os.environ["LLMVOX_B200_NO_FUSED"] = "1"
+    try:
+        plain = Engine(weights, **kw)
+    finally:
+        del os.environ["LLMVOX_B200_NO_FUSED"]
+    rng = np.random.RandomState(n)
+    texts = [rng.randint(3, 259, size=rng.randint(0, 40)).tolist() for _ in range(n)]
+    slots = list(range(n))
+    for e in (fused, plain):
+        e.open(slots)
+        e.feed_text(slots, texts)
+    worst = 0.0
+    for t in range(20):
+        fused.decode_steps(slots, 1)
+        codes = fused.gather_codes(slots, t, 1).view(-1).contiguous()
+        lf = fused.peek_logits(n)
+        lp, _ = plain.decode_step_logits(slots, forced=codes)
+        assert (lf.argmax(dim=1).to(torch.int32) == codes).all()
+        worst = max(worst, float((lf - lp).abs().max()))
+    assert worst < 2e-2, worst
+    # several iterations inside one launch == the same iterations one launch at a time
+    fused.open(slots)
+    fused.feed_text(slots, texts)
+    fused.decode_steps(slots, 20)
+    again = fused.gather_codes(slots, 0, 20).cpu()
+    step = torch.stack([fused.gather_codes(slots, t, 1).view(-1).cpu() for t in range(20)], dim=1)
+    assert fused.session_length(0) == 20
+    plain_codes = plain.gather_codes(slots, 0, 20).cpu()
+    assert (again == plain_codes).all() and (step == again).all()
+    fused.close()
+    plain.close()
+
+
 def test_error_behaviour(engines):
     from llmvox_b200._lib import LvxError
     e = engines("fp32")

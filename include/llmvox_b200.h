@@ -121,6 +121,13 @@ int lvx_decode_step_logits(lvx_engine* e, const int32_t* h_slots, int n, const l
 /* Test hook: copies the logits of the LAST decode iteration run on `lane` (n x vocab fp32) to d_out. */
 int lvx_peek_logits(lvx_engine* e, int lane, int n, float* d_out, void* stream);
 
+/* Test hook: raw host copy of a decode-lane workspace buffer (which: 0 x, 1 qkv (fp32); 2 h, 3 y, 4 g (activation type)). */
+int lvx_peek_buffer(lvx_engine* e, int lane, int which, void* h_out, int64_t bytes);
+
+/* Test hook: with LLMVOX_B200_TRACE set at engine creation, CTA 0 of the fused decode kernel stamps clock64() at every
+ * phase boundary of the last iteration of a launch; this copies the first `count` (<= 256) stamps to h_out. */
+int lvx_peek_trace(lvx_engine* e, int lane, long long* h_out, int count);
+
 /* Drop-in for `model(emb, kvcache)` (streaming_server.py:341 -> src/model.py:201-237): the caller supplies
  * the assembled, normalised input row of each session (n x n_embd fp32, device) and its position (the
  * reference's T-1); returns logits (n x vocab fp32, device) and appends K/V.  No code is recorded. */

@@ -205,6 +205,7 @@ struct lvx_engine {
   struct Lane {
     std::map<int, FusedCtx> fused;   // persistent fused decode kernel, keyed by the number of sessions
     unsigned* d_bar = nullptr;
+    long long* d_trace = nullptr;
     int *d_slots = nullptr, *d_upd = nullptr, *d_pos = nullptr;
     float *x = nullptr, *qkv = nullptr, *logits = nullptr;
     void *h = nullptr, *y = nullptr, *g = nullptr;
@@ -414,6 +415,7 @@ static int engine_alloc(lvx_engine* e) {
   for (auto& ln : e->lanes) {
     LVX_TRY(dev_alloc(e, &ln.d_slots, B));
     LVX_TRY(dev_alloc(e, &ln.d_bar, 64));
+    LVX_TRY(dev_alloc(e, &ln.d_trace, 256));
     LVX_TRY(dev_alloc(e, &ln.d_pos, B));
     LVX_TRY(dev_alloc(e, &ln.d_upd, (size_t)3 * B * e->max_pages));
     LVX_TRY(dev_alloc(e, &ln.x, (size_t)Bp * C));
@@ -1061,6 +1063,7 @@ static int fused_ctx(lvx_engine* e, lvx_engine::Lane& ln, int n, lvx_engine::Fus
     P.h = (bf16*)ln.h; P.y = (bf16*)ln.y;
     P.kv = (bf16*)e->kv; P.page_tokens = c.kv_page_tokens; P.pool_pages = e->pool_pages;
     P.bar = ln.d_bar;
+    P.trace = getenv("LLMVOX_B200_TRACE") ? ln.d_trace : nullptr;
     it = ln.fused.emplace(n, fc).first;
   }
   *out = &it->second;
@@ -1087,6 +1090,7 @@ extern "C" int lvx_decode_steps_lane(lvx_engine* e, int lane, const int32_t* h_s
     // one persistent launch runs all n_steps iterations (fused_decode.cuh)
     lvx_engine::FusedCtx* fc = nullptr;
     LVX_TRY(fused_ctx(e, ln, n, &fc));
+    LVX_CHECK(n <= fc->plan.n_clusters * FD_CLUSTER, LVX_ERR_CAPACITY, "fused decode: fewer co-resident CTAs than sessions");
     fc->P.n_iters = n_steps;
     LVX_CUDA(cudaMemsetAsync(ln.d_bar, 0, sizeof(unsigned), st));
     LVX_TRY(fused_launch(fc->P, fc->plan, st));
@@ -1111,6 +1115,26 @@ extern "C" int lvx_decode_steps_lane(lvx_engine* e, int lane, const int32_t* h_s
 
 extern "C" int lvx_decode_steps(lvx_engine* e, const int32_t* h_slots, int n, int n_steps, const lvx_sampling* s, void* stream) {
   return lvx_decode_steps_lane(e, 0, h_slots, n, n_steps, s, stream);
+}
+
+extern "C" int lvx_peek_trace(lvx_engine* e, int lane, long long* h_out, int count) {
+  LVX_TRY(check_engine(e));
+  LVX_CHECK(lane >= 0 && lane < (int)e->lanes.size() && h_out && count > 0 && count <= 256, LVX_ERR_INVALID, "bad argument");
+  LVX_CUDA(cudaDeviceSynchronize());
+  LVX_CUDA(cudaMemcpy(h_out, e->lanes[lane].d_trace, count * sizeof(long long), cudaMemcpyDeviceToHost));
+  return LVX_OK;
+}
+
+// Test hook: raw copy of a lane workspace buffer (0 x fp32, 1 qkv fp32, 2 h, 3 y, 4 g; h/y/g in the activation type)
+extern "C" int lvx_peek_buffer(lvx_engine* e, int lane, int which, void* h_out, int64_t bytes) {
+  LVX_TRY(check_engine(e));
+  LVX_CHECK(lane >= 0 && lane < (int)e->lanes.size() && h_out && bytes > 0, LVX_ERR_INVALID, "bad argument");
+  auto& ln = e->lanes[lane];
+  const void* src = which == 0 ? (void*)ln.x : which == 1 ? (void*)ln.qkv : which == 2 ? ln.h : which == 3 ? ln.y : which == 4 ? ln.g : nullptr;
+  LVX_CHECK(src, LVX_ERR_INVALID, "bad buffer id");
+  LVX_CUDA(cudaDeviceSynchronize());
+  LVX_CUDA(cudaMemcpy(h_out, src, bytes, cudaMemcpyDeviceToHost));
+  return LVX_OK;
 }
 
 extern "C" int lvx_peek_logits(lvx_engine* e, int lane, int n, float* d_out, void* stream) {

@@ -149,6 +149,25 @@ class Engine:
                                               C.c_void_p(codes.data_ptr()), self._stream(stream)))
         return logits, codes
 
+    def peek_buffer(self, which: str, rows: int, lane: int = 0):
+        """Test hook: host copy of a decode-lane workspace buffer ('x', 'qkv', 'h', 'y', 'g') as float32 (rows, width)."""
+        import numpy as np
+        C_ = self.cfg.n_embd
+        idx, width, f32 = {"x": (0, C_, True), "qkv": (1, 3 * C_, True), "h": (2, C_, False), "y": (3, C_, False),
+                           "g": (4, 4 * C_, False)}[which]
+        f32 = f32 or self.precision == "fp32"
+        buf = np.empty((rows, width), dtype=np.float32 if f32 else np.uint16)
+        check(self.lib.lvx_peek_buffer(self._h, lane, idx, C.c_void_p(buf.ctypes.data), buf.nbytes))
+        if not f32:
+            buf = (buf.astype(np.uint32) << 16).view(np.float32)
+        return buf
+
+    def peek_trace(self, count: int = 128, lane: int = 0):
+        """Test hook: clock64 stamps of the fused decode kernel's phase boundaries (LLMVOX_B200_TRACE=1)."""
+        buf = (C.c_int64 * count)()
+        check(self.lib.lvx_peek_trace(self._h, lane, buf, count))
+        return list(buf)
+
     def peek_logits(self, n: int, lane: int = 0, stream=None) -> torch.Tensor:
         """Test hook: logits of the last decode iteration run on `lane`."""
         out = torch.empty((n, self.cfg.vocab_size), dtype=torch.float32, device=self.device)

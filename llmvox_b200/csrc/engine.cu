@@ -162,7 +162,7 @@ struct lvx_engine {
   float* embed_b = nullptr;
   Res res[4];
   float *at_nw = nullptr, *at_nb = nullptr, *at_qkv_b = nullptr, *at_proj_b = nullptr;
-  GemmW at_qkv, at_proj;
+  GemmW at_qkv, at_proj, at_v;   // at_v: the v rows of at_qkv (bf16 mode, transposed-V GEMM of the tensor-core attention)
   float *pn5_w = nullptr, *pn5_b = nullptr, *norm_scale = nullptr, *norm_shift = nullptr;
   std::vector<CNX> cnx;
   float *fln_w = nullptr, *fln_b = nullptr, *head_b = nullptr, *window = nullptr;
@@ -186,6 +186,7 @@ struct lvx_engine {
   GemmProblem *d_prob_s = nullptr, *d_prob_pv = nullptr;
   int *row_chunk = nullptr, *code_rows = nullptr;
   int max_chunks = 0;
+  bf16* v_vt = nullptr;   // V^T of the pos_net attention: [voc_dim][R_max] bf16
   void *v_feats = nullptr, *v_h = nullptr, *v_big = nullptr, *v_spec = nullptr, *v_P = nullptr, *v_h3 = nullptr;
   float *v_x = nullptr, *v_t = nullptr, *v_raw = nullptr, *v_frames = nullptr, *v_S = nullptr;
   float2* v_stats = nullptr;
@@ -224,6 +225,7 @@ struct lvx_engine {
     double flops, bytes;
   };
   bool prof_on = false;
+  bool prof_detail = false;   // lvx_profile_enable(2): label vocoder GEMMs by role
   std::vector<ProfRec> prof;
   std::vector<cudaEvent_t> ev_pool;
   cudaEvent_t get_event() {
@@ -427,7 +429,9 @@ static int engine_alloc(lvx_engine* e) {
   }
   // vocoder workspace
   const int D = c.voc_dim, I = c.voc_inter;
-  e->R_max = ceil_div(c.max_vocode_frames + 2 * ROW_PAD, 128) * 128 + 128;
+  // padded rows of one launch group: frames + (alignment to 8 + ROW_PAD) per chunk; plan_groups also closes a group
+  // when its padded rows would exceed this capacity (batches of very many tiny chunks)
+  e->R_max = ceil_div(c.max_vocode_frames + c.max_vocode_frames / 4 + 4096, 128) * 128 + 128;
   e->max_chunks = c.max_vocode_frames;
   e->raw_ld = (c.n_fft + 2 + 3) & ~3;
   e->spec_ld = ceil_div(c.n_fft + 2, 64) * 64;
@@ -449,6 +453,7 @@ static int engine_alloc(lvx_engine* e) {
   LVX_TRY(dev_alloc_bytes(e, &e->v_P, (size_t)e->score_cap * dt_size(a)));
   LVX_TRY(dev_alloc(e, &e->v_stats, (size_t)e->max_chunks * 32));
   if (a == B16) {
+    LVX_TRY(dev_alloc(e, &e->v_vt, (size_t)D * R));
     LVX_TRY(dev_alloc_bytes(e, &e->v_spec, R * 3 * e->spec_ld * sizeof(bf16)));
     LVX_TRY(dev_alloc_bytes(e, &e->v_h3, R * 3 * D * sizeof(bf16)));
   } else {
@@ -491,8 +496,10 @@ extern "C" int lvx_engine_create(const lvx_config* cfg, int device, lvx_engine**
   if (s == LVX_OK) {
     const char* env = getenv("LLMVOX_B200_NO_GRAPH");
     e->use_graphs = !(env && env[0] == '1');
-    const char* env2 = getenv("LLMVOX_B200_NO_FUSED");
-    e->use_fused = !(env2 && env2[0] == '1');
+    // the persistent fused decode kernel is opt-in: it wins on the decode chain alone (270 vs 290 us / iteration at 64
+    // sessions) but, being a whole-GPU cooperative launch, it cannot overlap with the vocoder or another lane
+    const char* env2 = getenv("LLMVOX_B200_FUSED");
+    e->use_fused = env2 && env2[0] == '1';
     if (cudaStreamCreateWithFlags(&e->gstream, cudaStreamNonBlocking) != cudaSuccess) {
       set_error("could not create the engine's capture stream");
       s = LVX_ERR_CUDA;
@@ -640,6 +647,11 @@ extern "C" int lvx_finalize_weights(lvx_engine* e) {
     }
     e->at_qkv_b = bq;
     LVX_TRY(make_gemm_w(e, &e->at_qkv, wq, 3 * D, D, D));
+    if (e->adt() == B16) {
+      e->at_v.b16 = e->at_qkv.b16 + (size_t)2 * D * D;
+      e->at_v.N = D; e->at_v.K = D; e->at_v.ld = D;
+      LVX_TRY(tc_make_desc(&e->at_v.tma, e->at_v.b16, D, D, D));
+    }
     LVX_TRY(make_gemm_w(e, &e->at_proj, W(e, p + "proj_out.weight"), D, D, D));
     e->at_proj_b = W(e, p + "proj_out.bias");
   }
@@ -734,7 +746,7 @@ static int run_gemm(lvx_engine* e, GemmParams p, const GemmW& w, DT ta, DT tc, c
   const double el = (double)dt_size(e->adt());
   const int a_cols = p.taps > 1 ? p.tap_K : p.K;
   const bool swap = e->adt() == B16 && p.taps == 1 && p.M <= 256;
-  ProfScope prof(e, e->adt() == F32 ? "gemm_simt" : (swap ? "tc_gemm_swap" : "tc_gemm"), st, 2.0 * p.M * (double)w.N * w.K,
+  ProfScope prof(e, p.tag ? p.tag : (e->adt() == F32 ? "gemm_simt" : (swap ? "tc_gemm_swap" : "tc_gemm")), st, 2.0 * p.M * (double)w.N * w.K,
                  (double)p.M * a_cols * el + (double)w.N * w.K * el + (double)p.M * w.N * (double)dt_size(tc) +
                      (p.residual ? (double)p.M * w.N * 4.0 : 0.0));
   if (e->adt() == F32) {
@@ -1283,6 +1295,7 @@ static int conv_gemm(lvx_engine* e, const VocGroup& g, const void* A, int Cin, i
   p.A = A; p.C = out; p.M = g.R; p.lda = Cin; p.ldc = e->cfg.voc_dim; p.a_rows = g.R;
   p.taps = taps; p.tap_K = Cin; p.tap_pad = taps / 2;
   p.bias = bias; p.residual = residual; p.ldr = e->cfg.voc_dim; p.row_chunk = e->row_chunk;
+  if (e->prof_detail) p.tag = taps == 7 ? "tc_gemm:embed_k7" : "tc_gemm:resnet_k3";
   return run_gemm(e, p, w, e->adt(), F32, st);
 }
 
@@ -1340,32 +1353,84 @@ static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes
     LVX_TRY(groupnorm(e, g, e->v_x, e->at_nw, e->at_nb, 0, e->v_h, st));
     GemmParams p;
     p.A = e->v_h; p.C = e->v_big; p.M = g.R; p.lda = D; p.ldc = 3 * D; p.bias = e->at_qkv_b; p.row_chunk = e->row_chunk;
+    if (e->prof_detail) p.tag = "tc_gemm:attn_qkv";
     LVX_TRY(run_gemm(e, p, e->at_qkv, a, a, st));
-    std::vector<GemmProblem> ps(nch), pv(nch);
-    for (int i = 0; i < nch; ++i) {
-      const ChunkInfo& ci = g.chunks[i];
-      const int L = ci.len, Lp = (L + 3) & ~3;
-      ps[i] = GemmProblem{(long long)ci.row0 * 3 * D, (long long)ci.row0 * 3 * D + D, (long long)ci.s_off, L, L, D, 0, Lp};
-      pv[i] = GemmProblem{(long long)ci.s_off, (long long)ci.row0 * 3 * D + 2 * D, (long long)ci.row0 * D, L, D, L, Lp, 0};
+    // chunks longer than 256 frames (bf16 mode): QK^T and PV as tcgen05 GEMMs with per-chunk tensor maps; the rest
+    // as one ragged batch on the FMA-pipe kernel (a tensor-core launch per tiny chunk would cost more than it saves)
+    std::vector<int> small, large;
+    for (int i = 0; i < nch; ++i) ((a == B16 && g.chunks[i].len > 256) ? large : small).push_back(i);
+    const int ns = (int)small.size();
+    std::vector<GemmProblem> ps(std::max(ns, 1)), pv(std::max(ns, 1));
+    int small_max = 0;
+    for (int j = 0; j < ns; ++j) {
+      const ChunkInfo& ci = g.chunks[small[j]];
+      const int L = ci.len, Lp = (L + 7) & ~7;
+      ps[j] = GemmProblem{(long long)ci.row0 * 3 * D, (long long)ci.row0 * 3 * D + D, (long long)ci.s_off, L, L, D, 0, Lp};
+      pv[j] = GemmProblem{(long long)ci.s_off, (long long)ci.row0 * 3 * D + 2 * D, (long long)ci.row0 * D, L, D, L, Lp, 0};
+      small_max = std::max(small_max, L);
     }
-    LVX_CUDA(cudaMemcpyAsync(e->d_prob_s, ps.data(), nch * sizeof(GemmProblem), cudaMemcpyHostToDevice, st));
-    LVX_CUDA(cudaMemcpyAsync(e->d_prob_pv, pv.data(), nch * sizeof(GemmProblem), cudaMemcpyHostToDevice, st));
-    GemmParams s;
-    s.A = e->v_big; s.W = e->v_big; s.C = e->v_S; s.batch = e->d_prob_s; s.n_batch = nch; s.lda = 3 * D; s.ldw = 3 * D;
-    s.max_M = g.max_len; s.max_N = g.max_len; s.alpha = 1.0f / sqrtf((float)D);
-    LVX_TRY(run_gemm_batched(e, s, a, a, F32, st));
+    const float att_scale = 1.0f / sqrtf((float)D);
+    if (ns) {
+      LVX_CUDA(cudaMemcpyAsync(e->d_prob_s, ps.data(), ns * sizeof(GemmProblem), cudaMemcpyHostToDevice, st));
+      LVX_CUDA(cudaMemcpyAsync(e->d_prob_pv, pv.data(), ns * sizeof(GemmProblem), cudaMemcpyHostToDevice, st));
+      GemmParams s;
+      s.A = e->v_big; s.W = e->v_big; s.C = e->v_S; s.batch = e->d_prob_s; s.n_batch = ns; s.lda = 3 * D; s.ldw = 3 * D;
+      s.max_M = small_max; s.max_N = small_max; s.alpha = att_scale;
+      LVX_TRY(run_gemm_batched(e, s, a, a, F32, st));
+    }
+    if (!large.empty()) {
+      // V^T for the whole group: Vt[c, r] = (Wv . h^T)[c, r] + bv[c]  (swap-mode tiles, transposed store)
+      GemmParams t;
+      t.A = e->v_h; t.C = e->v_vt; t.M = g.R; t.lda = D; t.ldc = e->R_max; t.bias = e->at_qkv_b + 2 * D; t.c_transposed = 1;
+      t.a_cap = e->R_max;
+      if (e->prof_detail) t.tag = "tc_gemm:attn_vt";
+      LVX_TRY(run_gemm(e, t, e->at_v, a, a, st));
+      for (int i : large) {
+        const ChunkInfo& ci = g.chunks[i];
+        const int L = ci.len, Lp = (L + 7) & ~7;
+        const bf16* qk = (const bf16*)e->v_big + (size_t)ci.row0 * 3 * D;
+        CUtensorMap qm;
+        TmaDesc km;
+        LVX_TRY(tc_encode(&qm, qk, L, D, 3 * D, TC_BM));
+        LVX_TRY(tc_encode(&km.map, qk + D, L, D, 3 * D, TC_BM));
+        km.valid = true;
+        GemmParams s;
+        s.A = qk; s.C = e->v_S + ci.s_off; s.M = L; s.N = L; s.K = D; s.lda = 3 * D; s.ldw = 3 * D; s.ldc = Lp; s.alpha = att_scale;
+        ProfScope prof(e, "tc_gemm:attn_qk", st, 2.0 * L * (double)L * D, 0);
+        LVX_TRY(tc_gemm(&e->tcw, s, km, false, st, &qm));
+        e->launches++;
+      }
+    }
     if (a == F32)
       attn_softmax_kernel<float><<<ceil_div(g.R, 8), 256, 0, st>>>(e->v_S, e->v_S, e->d_chunks, e->row_chunk, g.R);
     else
       attn_softmax_kernel<bf16><<<ceil_div(g.R, 8), 256, 0, st>>>(e->v_S, (bf16*)e->v_P, e->d_chunks, e->row_chunk, g.R);
     LAUNCHED(e);
-    GemmParams o;
-    o.A = (a == F32) ? (void*)e->v_S : e->v_P; o.W = e->v_big; o.C = e->v_h; o.batch = e->d_prob_pv; o.n_batch = nch;
-    o.ldw = 3 * D; o.ldc = D; o.w_kn = 1; o.max_M = g.max_len; o.max_N = D;
-    LVX_TRY(run_gemm_batched(e, o, a, a, a, st));
+    if (ns) {
+      GemmParams o;
+      o.A = (a == F32) ? (void*)e->v_S : e->v_P; o.W = e->v_big; o.C = e->v_h; o.batch = e->d_prob_pv; o.n_batch = ns;
+      o.ldw = 3 * D; o.ldc = D; o.w_kn = 1; o.max_M = small_max; o.max_N = D;
+      LVX_TRY(run_gemm_batched(e, o, a, a, a, st));
+    }
+    for (int i : large) {
+      const ChunkInfo& ci = g.chunks[i];
+      const int L = ci.len, Lp = (L + 7) & ~7;
+      const bf16* P = (const bf16*)e->v_P + ci.s_off;
+      CUtensorMap pm;
+      TmaDesc vm;
+      LVX_TRY(tc_encode(&pm, P, L, L, Lp, TC_BM));
+      LVX_TRY(tc_encode(&vm.map, e->v_vt + ci.row0, D, L, e->R_max, TC_BM));
+      vm.valid = true;
+      GemmParams o;
+      o.A = P; o.C = (bf16*)e->v_h + (size_t)ci.row0 * D; o.M = L; o.N = D; o.K = L; o.lda = Lp; o.ldw = e->R_max; o.ldc = D;
+      ProfScope prof(e, "tc_gemm:attn_pv", st, 2.0 * L * (double)L * D, 0);
+      LVX_TRY(tc_gemm(&e->tcw, o, vm, true, st, &pm));
+      e->launches++;
+    }
     GemmParams q;
     q.A = e->v_h; q.C = e->v_x; q.M = g.R; q.lda = D; q.ldc = D; q.bias = e->at_proj_b; q.residual = e->v_x; q.ldr = D;
     q.row_chunk = e->row_chunk;
+    if (e->prof_detail) q.tag = "tc_gemm:attn_proj";
     LVX_TRY(run_gemm(e, q, e->at_proj, a, F32, st));
   }
   if (stage == 2) return dump(e->v_x, D, D);
@@ -1399,10 +1464,12 @@ static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes
     }
     GemmParams p;
     p.A = e->v_h; p.C = e->v_big; p.M = g.R; p.lda = D; p.ldc = I; p.bias = X.b1; p.act = ACT_GELU_ERF; p.row_chunk = e->row_chunk;
+    if (e->prof_detail) p.tag = "tc_gemm:pw1_gelu";
     LVX_TRY(run_gemm(e, p, X.pw1, a, a, st));
     GemmParams q;
     q.A = e->v_big; q.C = e->v_x; q.M = g.R; q.lda = I; q.ldc = D; q.bias = X.b2; q.col_scale = X.gamma; q.residual = e->v_x;
     q.ldr = D; q.row_chunk = e->row_chunk;
+    if (e->prof_detail) q.tag = "tc_gemm:pw2_res";
     LVX_TRY(run_gemm(e, q, X.pw2, a, F32, st));
   }
   // final_layer_norm (models.py:234) + head.out (heads.py:53)
@@ -1429,6 +1496,7 @@ static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes
     LAUNCHED(e);
     GemmParams p;
     p.A = e->v_h3; p.C = e->v_raw; p.M = g.R; p.lda = 3 * D; p.ldc = e->raw_ld; p.bias = e->head_b; p.row_chunk = e->row_chunk;
+    if (e->prof_detail) p.tag = "tc_gemm:head_x3";
     LVX_TRY(run_gemm(e, p, e->head, a, F32, st));
     dim3 grid(ceil_div(e->spec_ld, 256), g.R);
     // fp32 spectrum into v_frames' storage is not possible (needed later); reuse v_big as fp32 scratch
@@ -1440,6 +1508,7 @@ static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes
     LAUNCHED(e);
     GemmParams q;
     q.A = e->v_spec; q.C = e->v_frames; q.M = g.R; q.lda = 3 * e->spec_ld; q.ldc = NF; q.row_chunk = e->row_chunk;
+    if (e->prof_detail) q.tag = "tc_gemm:idft_x3";
     LVX_TRY(run_gemm(e, q, e->idft, a, F32, st));
   }
   if (stage == 5) return dump(e->v_frames, NF, NF);
@@ -1461,22 +1530,24 @@ static int plan_groups(lvx_engine* e, const int32_t* h_cu, int n_chunks, std::ve
     const int L = h_cu[i + 1] - h_cu[i];
     LVX_CHECK(L > 0, LVX_ERR_INVALID, "empty chunk (the reference never decodes zero codes)");
     LVX_CHECK(L <= e->cfg.max_vocode_frames, LVX_ERR_CAPACITY, "chunk longer than max_vocode_frames");
-    const long long Lp = (L + 3) & ~3;
+    const long long Lp = (L + 7) & ~7;
     LVX_CHECK((long long)L * Lp <= e->score_cap, LVX_ERR_CAPACITY, "chunk too long for the attention workspace");
+    const int row0_next = (g.R + 7) & ~7;
     if (!g.chunks.empty() &&
-        (g.frames + L > e->cfg.max_vocode_frames || g.s_elems + L * Lp > e->score_cap || (int)g.chunks.size() >= e->max_chunks)) {
+        (g.frames + L > e->cfg.max_vocode_frames || g.s_elems + L * Lp > e->score_cap || (int)g.chunks.size() >= e->max_chunks ||
+         row0_next + L + ROW_PAD > e->R_max - 128)) {
       out->push_back(g);
       g = VocGroup();
       g.R = ROW_PAD;
       g.code0 = h_cu[i];
     }
     ChunkInfo ci;
-    ci.row0 = g.R;
+    ci.row0 = (g.R + 7) & ~7;   // 16-byte aligned bf16 column offset for the transposed-V tensor maps
     ci.len = L;
     ci.out0 = h_cu[i] - g.code0;
     ci.s_off = (int)g.s_elems;
     g.chunks.push_back(ci);
-    g.R += L + ROW_PAD;
+    g.R = ci.row0 + L + ROW_PAD;
     g.frames += L;
     g.s_elems += L * Lp;
     g.max_len = std::max(g.max_len, L);
@@ -1563,6 +1634,7 @@ extern "C" int lvx_test_gemm(lvx_engine* e, const float* d_A, const float* d_W, 
 extern "C" int lvx_profile_enable(lvx_engine* e, int on) {
   LVX_CHECK(e, LVX_ERR_INVALID, "engine is NULL");
   e->prof_on = on != 0;
+  e->prof_detail = on == 2;
   return LVX_OK;
 }
 

@@ -219,44 +219,76 @@ __device__ __forceinline__ float4 ld_dsmem_v4(uint32_t local_addr, uint32_t rank
   return v;
 }
 
+// exact-erf GELU (torch.nn.GELU(), WavTokenizer/decoder/modules.py:35) with erf by Abramowitz-Stegun 7.1.26
+// (|error| <= 1.5e-7, i.e. fp32-exact for this purpose) on MUFU.RCP / MUFU.EX2: ~16 instructions instead of erff's ~40.
+// The epilogue of the ConvNeXt pw1 GEMM (K = 768) is instruction-bound, so this is what sets its tensor utilisation.
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float z = fabsf(x) * 0.7071067811865476f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
+  const float erf_abs = 1.0f - poly * __expf(-z * z);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
+template <int ACT>
+__device__ __forceinline__ float tc_act(float v) {
+  if (ACT == ACT_GELU_TANH) return gelu_tanh(v);
+  if (ACT == ACT_GELU_ERF) return gelu_erf_fast(v);
+  return v;
+}
+
 // Epilogue of `ncols` (multiple of 4, <= 16) accumulator columns j0.. of D row i.  Order as GemmParams states:
 // alpha, + bias, activation, * col_scale, + residual.  All loads of a chunk are issued before its stores
-// (C may alias residual: every thread reads and writes only its own elements).
-template <bool kSwap, typename TC>
+// (C may alias residual: every thread reads and writes only its own elements).  ACT is a compile-time switch so the
+// per-element path carries no activation branch.
+template <bool kSwap, typename TC, int ACT>
 __device__ __forceinline__ void tc_epilogue_chunk(const GemmParams& p, int i, int j0, const float* v, int ncols) {
   TC* C = reinterpret_cast<TC*>(p.C);
   if (!kSwap) {
     const int m = i;
     if (m >= p.M || (p.row_chunk && p.row_chunk[m] < 0)) return;
-    const bool vec = (p.ldc & 3) == 0 && (!p.residual || (p.ldr & 3) == 0);
+    const bool vec = (p.ldc & (sizeof(TC) == 2 ? 7 : 3)) == 0 && (!p.residual || (p.ldr & 3) == 0) && j0 + ncols <= p.N && (ncols & 7) == 0;
+    if (vec) {
+      TC* dst = C + (size_t)m * p.ldc + j0;
+      const float* res = p.residual ? p.residual + (size_t)m * p.ldr + j0 : nullptr;
 #pragma unroll
-    for (int j = 0; j < 16; j += 4) {
-      if (j >= ncols) break;
-      const int n = j0 + j;
-      if (n >= p.N) break;
-      if (n + 4 <= p.N && vec) {
-        float4 b = make_float4(0.f, 0.f, 0.f, 0.f), cs = make_float4(1.f, 1.f, 1.f, 1.f), r = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias) b = load4(p.bias + n);
-        if (p.col_scale) cs = load4(p.col_scale + n);
-        if (p.residual) r = __ldcg(reinterpret_cast<const float4*>(p.residual + (size_t)m * p.ldr + n));
-        float4 o;
-        o.x = apply_act(v[j] * p.alpha + b.x, p.act) * cs.x + r.x;
-        o.y = apply_act(v[j + 1] * p.alpha + b.y, p.act) * cs.y + r.y;
-        o.z = apply_act(v[j + 2] * p.alpha + b.z, p.act) * cs.z + r.z;
-        o.w = apply_act(v[j + 3] * p.alpha + b.w, p.act) * cs.w + r.w;
-        store4(C + (size_t)m * p.ldc + n, o);
-      } else {
+      for (int j = 0; j < 16; j += 8) {
+        if (j < ncols) {
+          float o[8];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int nn = n + t;
-          if (nn < p.N) {
-            float xv = v[j + t] * p.alpha;
-            if (p.bias) xv += p.bias[nn];
-            xv = apply_act(xv, p.act);
-            if (p.col_scale) xv *= p.col_scale[nn];
-            if (p.residual) xv += __ldcg(p.residual + (size_t)m * p.ldr + nn);
-            store1(C + (size_t)m * p.ldc + nn, xv);
+          for (int h = 0; h < 8; h += 4) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f), cs = make_float4(1.f, 1.f, 1.f, 1.f), r = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) b = load4(p.bias + j0 + j + h);
+            if (p.col_scale) cs = load4(p.col_scale + j0 + j + h);
+            if (res) r = __ldcg(reinterpret_cast<const float4*>(res + j + h));
+            o[h] = tc_act<ACT>(v[j + h] * p.alpha + b.x) * cs.x + r.x;
+            o[h + 1] = tc_act<ACT>(v[j + h + 1] * p.alpha + b.y) * cs.y + r.y;
+            o[h + 2] = tc_act<ACT>(v[j + h + 2] * p.alpha + b.z) * cs.z + r.z;
+            o[h + 3] = tc_act<ACT>(v[j + h + 3] * p.alpha + b.w) * cs.w + r.w;
           }
+          if (sizeof(TC) == 2) {   // 8 bf16 = one 16-byte store
+            uint4 u;
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(o[0], o[1]), h1 = __floats2bfloat162_rn(o[2], o[3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(o[4], o[5]), h3 = __floats2bfloat162_rn(o[6], o[7]);
+            u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+            u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(dst) + j) = u;
+          } else {
+            store4(dst + j, make_float4(o[0], o[1], o[2], o[3]));
+            store4(dst + j + 4, make_float4(o[4], o[5], o[6], o[7]));
+          }
+        }
+      }
+    } else {
+#pragma unroll 4
+      for (int j = 0; j < ncols; ++j) {
+        const int nn = j0 + j;
+        if (nn < p.N) {
+          float xv = v[j] * p.alpha;
+          if (p.bias) xv += p.bias[nn];
+          xv = tc_act<ACT>(xv);
+          if (p.col_scale) xv *= p.col_scale[nn];
+          if (p.residual) xv += __ldcg(p.residual + (size_t)m * p.ldr + nn);
+          store1(C + (size_t)m * p.ldc + nn, xv);
         }
       }
     }
@@ -265,24 +297,57 @@ __device__ __forceinline__ void tc_epilogue_chunk(const GemmParams& p, int i, in
     if (n >= p.N) return;
     const float b = p.bias ? p.bias[n] : 0.f;
     const float cs = p.col_scale ? p.col_scale[n] : 1.f;
-    float r[16];
-    bool ok[16];
+    if (p.c_transposed) {
+      // C[n, m]: the thread's 16 columns are contiguous (the vocoder attention's V^T operand)
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const int m = j0 + j;
-      ok[j] = j < ncols && m < p.M && (!p.row_chunk || p.row_chunk[m] >= 0);
-      r[j] = (ok[j] && p.residual) ? __ldcg(p.residual + (size_t)m * p.ldr + n) : 0.f;
+      for (int j = 0; j < 16; ++j) {
+        const int m = j0 + j;
+        if (j < ncols && m < p.M) store1(C + (size_t)n * p.ldc + m, tc_act<ACT>(v[j] * p.alpha + b) * cs);
+      }
+      return;
     }
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      if (ok[j]) store1(C + (size_t)(j0 + j) * p.ldc + n, apply_act(v[j] * p.alpha + b, p.act) * cs + r[j]);
+    for (int j4 = 0; j4 < 16; j4 += 4) {
+      if (j4 >= ncols) break;
+      float r[4];
+      bool ok[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const int m = j0 + j4 + t;
+        ok[t] = m < p.M && (!p.row_chunk || p.row_chunk[m] >= 0);
+        r[t] = (ok[t] && p.residual) ? __ldcg(p.residual + (size_t)m * p.ldr + n) : 0.f;
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (ok[t]) store1(C + (size_t)(j0 + j4 + t) * p.ldc + n, tc_act<ACT>(v[j4 + t] * p.alpha + b) * cs + r[t]);
     }
   }
 }
 
 template <bool kSwap, typename TC>
-__global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const __grid_constant__ CUtensorMap mapX,
-                                                             const __grid_constant__ CUtensorMap mapY, const TcParams tp) {
+__device__ __forceinline__ void tc_epilogue_dispatch(const GemmParams& p, int i, int j0, const float* v, int ncols) {
+  if (p.act == ACT_GELU_ERF)
+    tc_epilogue_chunk<kSwap, TC, ACT_GELU_ERF>(p, i, j0, v, ncols);
+  else if (p.act == ACT_GELU_TANH)
+    tc_epilogue_chunk<kSwap, TC, ACT_GELU_TANH>(p, i, j0, v, ncols);
+  else
+    tc_epilogue_chunk<kSwap, TC, ACT_NONE>(p, i, j0, v, ncols);
+}
+
+// warps: 0 = TMA producer, 1 = MMA issuer, 2.. = epilogue.  Swap mode (small N tile) keeps 4 epilogue warps; normal
+// mode uses 8 (two per TMEM lane quarter, each taking half of the tile's columns): its epilogues (GELU, gamma,
+// residual) are instruction-bound at K = 768.
+template <bool kSwap>
+struct TcShape {
+  static constexpr int kEpiWarps = kSwap ? 4 : 8;
+  static constexpr int kThreads = 64 + 32 * kEpiWarps;
+};
+
+template <bool kSwap, typename TC>
+__global__ void __launch_bounds__(TcShape<kSwap>::kThreads, kSwap ? 1 : 2) tc_gemm_kernel(const __grid_constant__ CUtensorMap mapX,
+                                                                          const __grid_constant__ CUtensorMap mapY,
+                                                                          const TcParams tp) {
+  constexpr int kHalves = TcShape<kSwap>::kEpiWarps / 4;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 1];
   __shared__ uint32_t tmem_base_sh;
@@ -327,6 +392,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const __grid_consta
   // split-K partial tile in shared memory (reuses the operand ring once the MMAs are done): [128][BN + 4] fp32
   const int RS = BN + 4;
   const int q = warp & 3;              // TMEM lane quarter an epilogue warp may read
+  const int half = (warp - 2) >> 2;    // which share of the columns this epilogue warp takes (0 .. kHalves-1)
   const int drow = q * 32 + lane;      // D row (TMEM lane) of an epilogue thread
   const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16);
 
@@ -372,20 +438,22 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const __grid_consta
     // ---------------- epilogue warps: TMEM -> registers -> (global | partial tile in smem)
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    const int c_lo = half * (BN / kHalves), c_hi = (half + 1) * (BN / kHalves);   // multiples of 8 (BN % 16 == 0)
     if (S == 1) {
-      for (int c = 0; c < BN; c += 16) {
+      for (int c = c_lo; c < c_hi; c += 16) {
         float v[16];
         tmem_ld16(trow + (uint32_t)c, v);
-        tc_epilogue_chunk<kSwap, TC>(p, x0 + drow, y0 + c, v, 16);
+        tc_epilogue_dispatch<kSwap, TC>(p, x0 + drow, y0 + c, v, min(16, c_hi - c));
       }
     } else {
       float* red = reinterpret_cast<float*>(smem_raw + (tiles - smem_u32(smem_raw)));
-      for (int c = 0; c < BN; c += 16) {
+      for (int c = c_lo; c < c_hi; c += 16) {
         float v[16];
         tmem_ld16(trow + (uint32_t)c, v);
         float* dst = red + (size_t)drow * RS + c;
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        for (int j = 0; j < 16; j += 4)
+          if (c + j < c_hi) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       }
     }
   }
@@ -396,10 +464,12 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const __grid_consta
     __syncwarp();
     cluster_sync_all();
     if (warp >= 2) {
-      const int cw = BN / S;
+      const int cw = BN / S;                       // multiple of 4 (launch plan)
+      const int cwh = (cw / kHalves + 3) & ~3;     // this warp's share of the rank's columns
+      const int c_lo = rank * cw + half * cwh, c_hi = min((rank + 1) * cw, c_lo + cwh);
       const uint32_t red0 = tiles;
-      for (int c = rank * cw; c < (rank + 1) * cw; c += 16) {
-        const int ncols = min(16, (rank + 1) * cw - c);
+      for (int c = c_lo; c < c_hi; c += 16) {
+        const int ncols = min(16, c_hi - c);
         float v[16];
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
@@ -413,7 +483,7 @@ __global__ void __launch_bounds__(TC_THREADS) tc_gemm_kernel(const __grid_consta
           }
           v[j] = a.x; v[j + 1] = a.y; v[j + 2] = a.z; v[j + 3] = a.w;
         }
-        tc_epilogue_chunk<kSwap, TC>(p, x0 + drow, y0 + c, v, ncols);
+        tc_epilogue_dispatch<kSwap, TC>(p, x0 + drow, y0 + c, v, ncols);
       }
     }
     __syncwarp();
@@ -463,7 +533,7 @@ template <bool kSwap, typename TC>
 inline int tc_launch(const CUtensorMap& mx, const CUtensorMap& my, const TcParams& tp, dim3 grid, size_t smem, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
-  cfg.blockDim = dim3(TC_THREADS);
+  cfg.blockDim = dim3(TcShape<kSwap>::kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -492,8 +562,8 @@ struct TcPlan {
 inline TcPlan tc_plan(const TcWorkspace* ws, const GemmParams& p) {
   TcPlan pl;
   const int num_kb = ceil_div(p.K, TC_BK);
-  pl.swap = p.taps == 1 && p.M <= 256;
-  pl.BN = pl.swap ? std::max(16, ceil_div(p.M, 16) * 16) : 128;
+  pl.swap = p.c_transposed || (p.taps == 1 && p.M <= 256);
+  pl.BN = pl.swap ? std::min(256, std::max(16, ceil_div(p.M, 16) * 16)) : 128;
   const int gx = pl.swap ? ceil_div(p.N, TC_BM) : ceil_div(p.N, pl.BN);
   const int gy = pl.swap ? ceil_div(p.M, pl.BN) : ceil_div(p.M, TC_BM);
   const int tiles = gx * gy;
@@ -519,7 +589,8 @@ inline TcPlan tc_plan(const TcWorkspace* ws, const GemmParams& p) {
 }
 
 // p.A: bf16 activations (M x K view, lda), p.a_cap rows addressable.  w: tensor map of the bf16 (N, K) weight.
-inline int tc_gemm(TcWorkspace* ws, const GemmParams& p, const TmaDesc& w, bool c_bf16, cudaStream_t st) {
+inline int tc_gemm(TcWorkspace* ws, const GemmParams& p, const TmaDesc& w, bool c_bf16, cudaStream_t st,
+                   const CUtensorMap* a_map = nullptr) {
   if (!w.valid) {
     set_error("tc_gemm: weight has no tensor map");
     return LVX_ERR_INVALID;
@@ -540,7 +611,11 @@ inline int tc_gemm(TcWorkspace* ws, const GemmParams& p, const TmaDesc& w, bool 
   tp.stages = pl.stages;
   tp.splits = pl.splits;
   CUtensorMap am;
-  int s = tc_act_map(ws, p.A, a_cap, a_cols, p.lda, pl.swap ? pl.BN : TC_BM, &am);
+  int s = LVX_OK;
+  if (a_map)
+    am = *a_map;   // caller-built (per-chunk attention operands): box rows must be 128
+  else
+    s = tc_act_map(ws, p.A, a_cap, a_cols, p.lda, pl.swap ? pl.BN : TC_BM, &am);
   if (s != LVX_OK) return s;
   if (pl.swap)
     return c_bf16 ? tc_launch<true, bf16>(w.map, am, tp, pl.grid, pl.smem, st) : tc_launch<true, float>(w.map, am, tp, pl.grid, pl.smem, st);

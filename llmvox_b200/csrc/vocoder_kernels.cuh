@@ -1,6 +1,7 @@
 // WavTokenizer-decoder kernels other than the GEMMs (a3, a11-a13).  Activations are channels-last
 // (rows = frames, 768 contiguous channels) in a PADDED RAGGED layout: chunk i owns rows
-// [row0_i, row0_i + L_i); ROW_PAD zero rows precede the first chunk and follow every chunk, so the k=3 / k=7
+// [row0_i, row0_i + L_i) with row0_i a multiple of 8; at least ROW_PAD zero rows precede the first chunk and follow every
+// chunk, so the k=3 / k=7
 // convolutions (as multi-tap GEMMs) read zeros at chunk edges exactly like the reference's per-chunk
 // zero padding.  row_chunk[r] = chunk index of row r, or -1 for a padding row.
 #pragma once
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(256) dwconv_adaln_kernel(const float* __restri
 
 // ---------------------------------------------------------------------------------------------------
 // Row softmax of the pos_net attention scores (models.py:117-118; the C^-0.5 scale is the GEMM's alpha).
-// Scores of chunk i: L x Lp fp32 at s_off (Lp = L rounded up to 4; pad columns are written as zeros so the
+// Scores of chunk i: L x Lp fp32 at s_off (Lp = L rounded up to 8; pad columns are written as zeros so the
 // P.V GEMM may read them).  One warp per row.  Output type = GEMM operand type, in place for fp32.
 // ---------------------------------------------------------------------------------------------------
 template <typename TOut>
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(256) attn_softmax_kernel(const float* __restri
   const int ch = row_chunk[row];
   if (ch < 0) return;
   const ChunkInfo ci = chunks[ch];
-  const int L = ci.len, Lp = (L + 3) & ~3;
+  const int L = ci.len, Lp = (L + 7) & ~7;
   const size_t off = (size_t)ci.s_off + (size_t)(row - ci.row0) * Lp;
   const float* s = S + off;
   float mx = -INFINITY;

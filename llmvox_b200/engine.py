@@ -94,7 +94,8 @@ class Engine:
     def device_bytes(self) -> int:
         return int(self.lib.lvx_device_bytes(self._h))
 
-    def profile(self, on: bool):
+    def profile(self, on):
+        """True / 1: per kernel class; 2: vocoder GEMMs labelled by role as well."""
         check(self.lib.lvx_profile_enable(self._h, int(on)))
 
     def profile_report(self) -> dict:

@@ -11,7 +11,7 @@ from llmvox_b200 import weights as W
 from llmvox_b200.engine import Engine
 from llmvox_b200.streaming import LaneRunner
 
-ITERS = int(os.environ.get("PROBE_ITERS", "100"))
+ITERS = int(os.environ.get("PROBE_ITERS", "100"))   # LLMVOX_B200_FUSED=1 probes the fused kernel
 sd = W.make_random_weights(1234, wpe_rows=256)
 e = Engine(sd, device=0, precision=os.environ.get("PROBE_PRECISION", "bf16"), max_sessions=256, max_batch=256, max_context=256,
            max_vocode_frames=1024, decode_lanes=8)

@@ -1,4 +1,5 @@
 import os, sys
+os.environ["LLMVOX_B200_FUSED"] = "1"
 import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from llmvox_b200 import weights as W

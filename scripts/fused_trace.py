@@ -1,6 +1,7 @@
 """Phase-by-phase clock trace of the fused decode kernel (CTA 0, last iteration)."""
 import os
 import sys
+os.environ["LLMVOX_B200_FUSED"] = "1"
 
 os.environ["LLMVOX_B200_TRACE"] = "1"
 import numpy as np

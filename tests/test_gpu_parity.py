@@ -383,12 +383,12 @@ def test_fused_decode_kernel_matches_the_multi_kernel_path(weights, n):
     import os
     from llmvox_b200.engine import Engine
     kw = dict(device=0, precision="bf16", max_sessions=n, max_context=48, max_vocode_frames=256)
-    fused = Engine(weights, **kw)
-    os.environ["LLMVOX_B200_NO_FUSED"] = "1"
+    os.environ["LLMVOX_B200_FUSED"] = "1"          # opt-in path, read at engine creation
     try:
-        plain = Engine(weights, **kw)
+        fused = Engine(weights, **kw)
     finally:
-        del os.environ["LLMVOX_B200_NO_FUSED"]
+        del os.environ["LLMVOX_B200_FUSED"]
+    plain = Engine(weights, **kw)
     rng = np.random.RandomState(n)
     texts = [rng.randint(3, 259, size=rng.randint(0, 40)).tolist() for _ in range(n)]
     slots = list(range(n))

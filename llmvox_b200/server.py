@@ -1,0 +1,62 @@
+"""Wire-format shim: a `/tts` endpoint with the reference's request / response format
+(streaming_server.py:494-540; consumer client/endpoints.py:30-55) on top of the engine.
+
+Response = `application/octet-stream`, chunked: the raw float32 little-endian mono 24 kHz PCM of each vocoder chunk, in
+the order the two-replica protocol (replicas.py) plays them; nothing else is framed on the wire (the reference yields
+`None` at end of answer, which the HTTP layer drops).  The upstream LLM / ASR / VLM of the reference's other endpoints
+stay out of scope: the text to speak is the request's `text`, split into words like an LLM token stream would be."""
+from __future__ import annotations
+
+from typing import Iterator, List, Optional
+
+import numpy as np
+
+from .replicas import DEFAULT_EOS, ReplicaPipeline, mux_audio_queues
+
+SAMPLE_RATE = 24000
+
+
+def pcm_to_wire(pcm: np.ndarray) -> bytes:
+    """`audio.cpu().numpy().astype('float32').tobytes()` (streaming_server.py:368): float32, native = little endian."""
+    return np.ascontiguousarray(pcm, dtype="<f4").tobytes()
+
+
+def wire_to_pcm(data: bytes) -> np.ndarray:
+    return np.frombuffer(data, dtype="<f4")
+
+
+def text_to_word_stream(text: str, eos_token: str = DEFAULT_EOS) -> List[str]:
+    """A whole text as the word stream an LLM streamer would have produced: words keep their leading space and the
+    last one carries the EOS token (text_streamer_producer sees exactly such items, streaming_server.py:226-244)."""
+    words = [w for w in text.strip().split(" ") if w]
+    out = [(" " if i else "") + w for i, w in enumerate(words)]
+    if out:
+        out[-1] = out[-1] + eos_token
+    return out
+
+
+def tts_stream(pipeline: ReplicaPipeline, text: str, eos_token: str = DEFAULT_EOS) -> Iterator[bytes]:
+    q0, q1 = pipeline.run(text_to_word_stream(text, eos_token), eos_token)
+    for item in mux_audio_queues(q0, q1):
+        if item is not None:
+            yield item
+
+
+def create_app(model_handler, eos_token: str = DEFAULT_EOS):
+    """FastAPI app with POST /tts {"text": ...} -> StreamingResponse, as the reference's endpoint."""
+    from fastapi import FastAPI
+    from fastapi.responses import StreamingResponse
+    from pydantic import BaseModel
+
+    class TTSRequest(BaseModel):
+        text: str
+
+    app = FastAPI()
+    cfg = model_handler.config
+    pipeline = ReplicaPipeline(model_handler.engine, (cfg["initial_dump_size_1"], cfg["initial_dump_size_2"]), cfg["max_dump_size"])
+
+    @app.post("/tts")
+    def tts(request: TTSRequest):
+        return StreamingResponse(tts_stream(pipeline, request.text, eos_token), media_type="application/octet-stream")
+
+    return app

@@ -312,5 +312,95 @@ def main():
         print(f, os.path.getsize(os.path.join(GOLD, f)) // 1024, "KiB")
 
 
+def _extract(src, tree, name):
+    fn = next(n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.AsyncFunctionDef)) and n.name == name)
+    return ast.get_source_segment(src, fn)
+
+
+def protocol_golden():
+    """Queue-protocol fixtures from the reference's own clean_text,
+    text_streamer_producer and audio_generator_async (streaming_server.py:106-149, :184-248, :428-469)."""
+    import asyncio
+    import json
+    import re
+    import importlib.util
+    from queue import Empty
+    src = open(os.path.join(REF, "streaming_server.py")).read()
+    tree = ast.parse(src)
+    spec = importlib.util.spec_from_file_location("refcfg", os.path.join(REF, "configs/inference_config.py"))
+    refcfg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(refcfg)
+    cfg = dict(refcfg.config)
+    cfg["chat_type"] = "text"
+    ns = dict(torch=torch, re=re, config=cfg, Queue=queue.Queue, StreamModel=object, asyncio=asyncio, Empty=Empty, asr_model=None)
+    for name in ("clean_text", "text_streamer_producer", "audio_generator_async"):
+        exec(compile(_extract(src, tree, name), f"streaming_server.py::{name}", "exec"), ns)
+    out = {"eos": cfg["eos_token"]}
+    texts = ["  Hello **world** - it's 5. #1 & co @home ... 1,000/2 \\ ", "plain words", "a--b", "3. 4.5 x", "wait.... what", "###",
+             "C:\\dir//file", "tabs\tand\nnewlines", "1,234,567 and 1, 2"]
+    out["clean_text"] = [[t, ns["clean_text"](t)] for t in texts]
+
+    class Req:
+        def __init__(self, text):
+            self.text = text
+
+        def __contains__(self, k):
+            return k == "text"
+
+    class Stream:
+        def __init__(self, outs):
+            self.outs = outs
+
+        def predict(self, _):
+            return iter(self.outs)
+    streams = [
+        ["Hello", " there.", "", "-", " How", " are", " you.", " Fine", " thanks." + cfg["eos_token"]],
+        ["One.", "Two.", "Three.", cfg["eos_token"]],
+        ["**bold**", " a-b", " 5.", " #tag", " x & y.", " ", "tail"],
+    ]
+    out["router"] = []
+    for outs in streams:
+        q1, q2 = queue.Queue(), queue.Queue()
+        with contextlib.redirect_stdout(io.StringIO()):
+            ns["text_streamer_producer"](Req("prompt"), Stream(outs), q1, q2)
+        out["router"].append({"outputs": outs, "q0": list(q1.queue), "q1": list(q2.queue)})
+
+    def enc(x):
+        return {"b": x.decode()} if isinstance(x, bytes) else x
+
+    async def drain(a, b):
+        qa, qb = queue.Queue(), queue.Queue()
+        for x in a:
+            qa.put(x)
+        for x in b:
+            qb.put(x)
+        gen = ns["audio_generator_async"](qa, qb)
+        got = []
+        try:
+            while True:
+                got.append(await asyncio.wait_for(gen.__anext__(), timeout=2.5))
+        except (asyncio.TimeoutError, StopAsyncIteration):
+            pass
+        return got
+    mux_cases = [
+        ([b"a", b"b", 1, b"e", "end", None], [b"c", b"d", 0, None]),
+        ([1, b"x"], [b"y", "end", b"z", 0, b"never"]),
+        ([b"p", None, b"q", "end"], []),
+    ]
+    out["mux"] = []
+    for a, b in mux_cases:
+        with contextlib.redirect_stdout(io.StringIO()):
+            got = asyncio.run(drain(a, b))
+        out["mux"].append({"q0": [enc(x) for x in a], "q1": [enc(x) for x in b], "yield": [enc(x) for x in got]})
+    with open(os.path.join(GOLD, "protocol.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    print("protocol.json written:", len(out["clean_text"]), "clean_text,", len(out["router"]), "router,", len(out["mux"]), "mux cases")
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "protocol":
+        sys.path[:0] = [REF]
+        protocol_golden()
+    else:
+        main()
+        protocol_golden()

@@ -263,6 +263,39 @@ def run_gpu(args):
     prof = e.profile_report()
     e.profile(False)
 
+    # ---- vocoder bulk leg (BASELINE config 3 shape, scaled to one launch group): tensor-pipe roofline of the GEMM-bound half
+    voc = None
+    if rank == 0 and not args.short:
+        vb_streams, vb_len = 48, 1280
+        g = torch.Generator().manual_seed(3)
+        vcodes = torch.randint(0, 4096, (vb_streams * vb_len,), generator=g).to(e.device, torch.int32)
+        from llmvox_b200.engine import Engine as _E
+        ve = _E(sd, device=local, precision=args.precision, max_sessions=2, max_context=32, max_vocode_frames=vb_streams * vb_len + 64)
+        vcu = list(range(0, (vb_streams + 1) * vb_len, vb_len))
+        vout = torch.empty((vb_streams * vb_len * 320,), dtype=torch.float32, device=e.device)
+        for _ in range(2):
+            ve.vocode(vcodes, vcu, out=vout)
+        torch.cuda.synchronize()
+        v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        v0.record()
+        for _ in range(3):
+            ve.vocode(vcodes, vcu, out=vout)
+        v1.record()
+        torch.cuda.synchronize()
+        vms = v0.elapsed_time(v1) / 3
+        vfl = vb_streams * vb_len * 132.78e6          # algorithmic FLOPs per frame at L = 1280
+        ve.profile(2)
+        ve.vocode(vcodes, vcu, out=vout)
+        vrep = ve.profile_report()
+        ve.profile(False)
+        ve.close()
+        pk = measured_peaks()
+        voc = {"workload": f"{vb_streams} streams x {vb_len} codes, one chunk each (config 3 shape)", "ms": vms,
+               "audio_s_per_s": vb_streams * vb_len / CODES_PER_SEC / (vms / 1e3), "tflops": vfl / (vms / 1e3) / 1e12,
+               "frac_of_sustained_peak": vfl / (vms / 1e3) / 1e12 / pk["bf16_tflops_sustained"],
+               "gemm_tflops": {k: round(v["flops"] / (v["ms"] / 1e3) / 1e12, 1) for k, v in vrep.items() if v["flops"] > 0},
+               "share_ms": {k: round(v["ms"], 3) for k, v in sorted(vrep.items(), key=lambda kv: -kv[1]["ms"])}}
+
     t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=e.device)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -305,6 +338,7 @@ def run_gpu(args):
                                  "sample": f"{cpu_streams} of the {STREAMS} streams, sequential batch-1: {TOKENS} codes + chunks {SCHEDULE} each"},
                 "e2e": {"value": e2e_value, "unit": "audio-s/s", "steps": e2e_steps, "h2d_bytes_per_step": bytes_in,
                         "d2h_bytes_per_step": STREAMS * TOKENS * 320 * 4},
+                "vocoder_bulk": voc,
                 "gpu_launches": int(launches), "clocks": clk}
         print(json.dumps(line))
     e.close()

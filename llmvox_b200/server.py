@@ -5,8 +5,6 @@ Response = `application/octet-stream`, chunked: the raw float32 little-endian mo
 the order the two-replica protocol (replicas.py) plays them; nothing else is framed on the wire (the reference yields
 `None` at end of answer, which the HTTP layer drops).  The upstream LLM / ASR / VLM of the reference's other endpoints
 stay out of scope: the text to speak is the request's `text`, split into words like an LLM token stream would be."""
-from __future__ import annotations
-
 from typing import Iterator, List, Optional
 
 import numpy as np

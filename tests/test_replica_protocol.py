@@ -119,3 +119,19 @@ def test_tts_endpoint_streams_float32_pcm():
     pcm = wire_to_pcm(r.content)
     assert pcm.size % 320 == 0 and pcm.size > 0 and np.isfinite(pcm).all()
     mh.engine.close()
+
+
+def test_tts_endpoint_wiring_on_cpu(monkeypatch):
+    """The ASGI layer alone (stub chunk source): POST /tts -> 200, octet-stream, chunks concatenated untouched."""
+    from fastapi.testclient import TestClient
+    import llmvox_b200.server as S
+
+    class StubHandler:
+        config = {"initial_dump_size_1": 10, "initial_dump_size_2": 160, "max_dump_size": 1280}
+        engine = None
+    chunks = [np.arange(320, dtype=np.float32).tobytes(), np.zeros(640, dtype=np.float32).tobytes()]
+    monkeypatch.setattr(S, "tts_stream", lambda pipeline, text, eos=S.DEFAULT_EOS: iter(chunks))
+    r = TestClient(S.create_app(StubHandler())).post("/tts", json={"text": "hi."})
+    assert r.status_code == 200 and r.headers["content-type"].startswith("application/octet-stream")
+    assert r.content == b"".join(chunks)
+    assert TestClient(S.create_app(StubHandler())).post("/tts", json={}).status_code == 422

@@ -315,8 +315,11 @@ def run_gpu(args):
                     "frac": ach / peaks["bf16_tflops_sustained"], "traffic": None}
         else:
             ach = r["bytes"] / (r["ms"] / 1e3) / 1e9 if r["bytes"] else 0.0
+            # traffic: dram__bytes_read+write per launch from the committed `ncu --set full` capture of the decode GEMMs
+            # (profiles/r01c_*: 68.8 MB over the 17 GEMMs of one iteration, cold cache) -- 1.09x the algorithmic bytes
             roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / peaks["hbm_gbs"], "traffic": None}
+                    "frac": ach / peaks["hbm_gbs"], "traffic": 4.05e6 if name == "tc_gemm_swap" else None,
+                    "algorithmic_bytes_per_launch": r["bytes"] / max(1, r["launches"])}
         roof.update({"launches_per_step": r["launches"], "avg_launch_us": 1e3 * r["ms"] / max(1, r["launches"]),
                      "share_of_step": r["ms"] / total_ms, "peak_source": peaks["source"] + " (MEASURED_PEAKS.json)"})
         threads = os.cpu_count() or 1

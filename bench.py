@@ -245,6 +245,19 @@ def run_gpu(args):
             n += sum(c.length for c in chunks)
         return n
     e2e_step()
+    # p50 first-chunk latency (the metric's second half): host text ids -> first 10-code chunk's PCM in host memory
+    fc = []
+    for _ in range(9):
+        torch.cuda.synchronize()
+        tf = time.perf_counter()
+        bs.start(texts)
+        gen = bs.run(SCHEDULE[0], flush_tail=False, copy=False)
+        first = next(gen)
+        fc.append(1e3 * (time.perf_counter() - tf))
+        assert len(first) == STREAMS
+        for _ in gen:
+            pass
+    first_chunk_ms = float(np.median(fc[2:]))
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
@@ -341,6 +354,8 @@ def run_gpu(args):
                                  "sample": f"{cpu_streams} of the {STREAMS} streams, sequential batch-1: {TOKENS} codes + chunks {SCHEDULE} each"},
                 "e2e": {"value": e2e_value, "unit": "audio-s/s", "steps": e2e_steps, "h2d_bytes_per_step": bytes_in,
                         "d2h_bytes_per_step": STREAMS * TOKENS * 320 * 4},
+                "first_chunk_latency": {"p50_ms": first_chunk_ms, "streams": STREAMS, "codes": SCHEDULE[0],
+                                        "what": "host text ids -> PCM of every stream's first chunk in pinned host memory"},
                 "vocoder_bulk": voc,
                 "gpu_launches": int(launches), "clocks": clk}
         print(json.dumps(line))
@@ -357,10 +372,12 @@ def main():
     ap.add_argument("--impl", default="llmvox_b200", choices=["llmvox_b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--lanes", type=int, default=2, help="decode lanes: groups of sessions whose dependent chains run concurrently")
+    ap.add_argument("--streams", type=int, default=64, help="concurrent streams per GPU (BASELINE config 1: 64)")
     ap.add_argument("--short", action="store_true", help="40-code utterances (chunks 10/30): a short run for ncu captures")
     args = ap.parse_args()
+    global TOKENS, SCHEDULE, STREAMS
+    STREAMS = args.streams
     if args.short:
-        global TOKENS, SCHEDULE
         TOKENS, SCHEDULE = 40, [10, 30]
     if args.impl == "reference":
         run_reference(args)

@@ -178,7 +178,7 @@ class ReplicaPipeline:
             bs.sched[i] = ChunkScheduler(dump_size=start_dump.get(i, self.dump[sentences[i].replica]), max_dump=self.max_dump,
                                          eoa=self.e.cfg.eoa_token_id)
         max_steps = max(len(s.ids) for s in sentences) + self.pad_tail
-        bs.start([s.ids for s in sentences])
+        bs.start([s.ids for s in sentences], keep_schedule=True)
         per: List[List] = [[] for _ in sentences]
         for chunks in bs.run(max_steps, flush_tail=False):
             for ch in chunks:

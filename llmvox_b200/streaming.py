@@ -86,19 +86,24 @@ class BatchSynthesizer:
         assert len(self.slots) == n_sessions
         self.sched = [ChunkScheduler(dump_size=initial_dump_size, max_dump=max_dump_size, stop_on_eoa=stop_on_eoa,
                                      eoa=engine.cfg.eoa_token_id) for _ in range(n_sessions)]
+        self.initial_dump_size = initial_dump_size
         self.stop_on_eoa = stop_on_eoa
         self.sampling = sampling or Sampling()
         self.bw = bandwidth_id
         self.steps_done = 0
         self.runner = LaneRunner(engine, lanes)
 
-    def start(self, text_ids: Sequence[Sequence[int]]):
-        """Opens the sessions (the per-sentence reset of :404-416) and hands them their text ids."""
+    def start(self, text_ids: Sequence[Sequence[int]], keep_schedule: bool = False):
+        """Opens the sessions (the per-sentence reset of :404-416) and hands them their text ids.  A new call is a new
+        request (fresh generator threads in the reference, so the dump size starts at its initial value again);
+        `keep_schedule=True` continues the same request, where the dump size only ever grows (:373-375)."""
         assert len(text_ids) == self.n
         self.e.open(self.slots)
         self.e.feed_text(self.slots, text_ids)
         for s in self.sched:
             s.new_sentence()
+            if not keep_schedule:
+                s.dump_size = self.initial_dump_size
         self.steps_done = 0
         self.runner.sync_from_control()
 

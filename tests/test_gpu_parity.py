@@ -271,6 +271,21 @@ def test_streaming_chunks_match_reference_loop(engines, gold):
         assert snr_db(g[f"pcm{i}"], ch.pcm) > 80
 
 
+def test_batch_synthesizer_restart_resets_the_schedule(engines):
+    """start() = a new request: chunks 10/30/... again; keep_schedule=True = next sentence of the same request."""
+    from llmvox_b200.streaming import BatchSynthesizer
+    e = engines("fp32")
+    bs = BatchSynthesizer(e, 2, 10, stop_on_eoa=False, slots=[60, 61])
+    ids = [[5, 6, 7], [8]]
+    for keep, want in ((False, [10, 30, 5]), (False, [10, 30, 5]), (True, [45])):
+        bs.start(ids, keep_schedule=keep)
+        got = [[], []]
+        for chunks in bs.run(45, flush_tail=True):
+            for ch in chunks:
+                got[ch.session].append(ch.length)
+        assert got == [want, want]
+
+
 def test_replica1_schedule(engines, gold):
     from llmvox_b200.streaming import synthesize
     from llmvox_b200.tokenizer import sentence_ids

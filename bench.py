@@ -371,7 +371,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="llmvox_b200", choices=["llmvox_b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--lanes", type=int, default=2, help="decode lanes: groups of sessions whose dependent chains run concurrently")
+    ap.add_argument("--lanes", type=int, default=4, help="decode lanes: groups of sessions whose dependent chains run concurrently")
     ap.add_argument("--streams", type=int, default=64, help="concurrent streams per GPU (BASELINE config 1: 64)")
     ap.add_argument("--short", action="store_true", help="40-code utterances (chunks 10/30): a short run for ncu captures")
     args = ap.parse_args()

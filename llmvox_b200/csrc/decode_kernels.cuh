@@ -26,6 +26,8 @@ __global__ void assemble_input_kernel(const int* __restrict__ slots, SessionStat
                                                              const float* __restrict__ wpe, int text_dim, int code_dim,
                                                              int pad_id, int step_offset, float* __restrict__ x) {
   __shared__ float red[32];
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x, slot = slots[b];
   const int t = st.ctx_len[slot] + step_offset;
   const int C = text_dim + code_dim;
@@ -72,6 +74,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
                                                         float eps, const int* __restrict__ row_chunk,
                                                         TOut* __restrict__ out) {
   constexpr int V = C / 128;  // float4 per lane
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   if (row_chunk && row_chunk[row] < 0) return;
@@ -129,6 +133,8 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const float* __re
   constexpr int NG = 16;       // token groups per CTA
   __shared__ float sm_m[NG], sm_l[NG];
   __shared__ __align__(16) float sm_acc[NG][HD];
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x, h = blockIdx.y, slot = slots[b];
   const int C = n_head * HD;
   const int T = pos_override ? pos_override[b] : st.ctx_len[slot] + step_offset;  // cached tokens; new token index
@@ -271,6 +277,8 @@ __global__ void __launch_bounds__(256) sampler_kernel(const float* __restrict__ 
   __shared__ unsigned int sel_prefix, sel_remaining;
   __shared__ float seg_sum[256];
   __shared__ int pick_sh;
+  pdl_launch_dependents();
+  pdl_wait();
   const int b = blockIdx.x, slot = slots[b], tid = threadIdx.x;
   const float* lg = logits + (size_t)b * V;
   const bool greedy = a.greedy != 0;

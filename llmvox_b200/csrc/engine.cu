@@ -217,6 +217,7 @@ struct lvx_engine {
   cudaStream_t gstream = nullptr;   // capture only: graphs are launched on the caller's stream
   bool use_graphs = true;
   bool use_fused = true;
+  bool use_pdl = true;      // programmatic dependent launch along the decode chain (LLMVOX_B200_NO_PDL=1 disables)
 
   // ---- optional per-launch profiler (lvx_profile_enable)
   struct ProfRec {
@@ -498,6 +499,8 @@ extern "C" int lvx_engine_create(const lvx_config* cfg, int device, lvx_engine**
     e->use_graphs = !(env && env[0] == '1');
     // the persistent fused decode kernel is opt-in: it wins on the decode chain alone (270 vs 290 us / iteration at 64
     // sessions) but, being a whole-GPU cooperative launch, it cannot overlap with the vocoder or another lane
+    const char* env3 = getenv("LLMVOX_B200_NO_PDL");
+    e->use_pdl = !(env3 && env3[0] == '1');
     const char* env2 = getenv("LLMVOX_B200_FUSED");
     e->use_fused = env2 && env2[0] == '1';
     if (cudaStreamCreateWithFlags(&e->gstream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -780,13 +783,15 @@ static int run_gemm_batched(lvx_engine* e, GemmParams p, DT ta, DT tw, DT tc, cu
 
 template <int C>
 static int run_layernorm(lvx_engine* e, const float* x, int rows, const float* w, const float* b, float eps,
-                         const int* row_chunk, void* out, cudaStream_t st) {
+                         const int* row_chunk, void* out, cudaStream_t st, bool pdl = false) {
   if (rows <= 0) return LVX_OK;
   PROF(e, "layernorm", st);
+  cudaError_t err;
   if (e->adt() == F32)
-    layernorm_kernel<float, C><<<ceil_div(rows, 8), 256, 0, st>>>(x, rows, w, b, eps, row_chunk, (float*)out);
+    err = launch_pdl(layernorm_kernel<float, C>, dim3(ceil_div(rows, 8)), dim3(256), 0, st, pdl, x, rows, w, b, eps, row_chunk, (float*)out);
   else
-    layernorm_kernel<bf16, C><<<ceil_div(rows, 8), 256, 0, st>>>(x, rows, w, b, eps, row_chunk, (bf16*)out);
+    err = launch_pdl(layernorm_kernel<bf16, C>, dim3(ceil_div(rows, 8)), dim3(256), 0, st, pdl, x, rows, w, b, eps, row_chunk, (bf16*)out);
+  LVX_CHECK(err == cudaSuccess, LVX_ERR_CUDA, std::string("layernorm launch: ") + cudaGetErrorString(err));
   LAUNCHED(e);
   return LVX_OK;
 }
@@ -908,41 +913,45 @@ static int gpt_body(lvx_engine* e, lvx_engine::Lane& ln, int n, const int* pos_o
   const int C = c.n_embd;
   const DT a = e->adt();
   const int budget = e->lane_cta_budget;
+  const bool pdl = e->use_pdl && !e->prof_on;
   for (int l = 0; l < c.n_layer; ++l) {
     auto& L = e->layers[l];
-    LVX_TRY(run_layernorm<768>(e, ln.x, n, L.ln1_w, L.ln1_b, 1e-5f, nullptr, ln.h, st));
+    LVX_TRY(run_layernorm<768>(e, ln.x, n, L.ln1_w, L.ln1_b, 1e-5f, nullptr, ln.h, st, pdl));
     GemmParams p;
-    p.A = ln.h; p.C = ln.qkv; p.M = n; p.lda = C; p.ldc = 3 * C; p.bias = L.attn_b; p.cta_budget = budget;
+    p.A = ln.h; p.C = ln.qkv; p.M = n; p.lda = C; p.ldc = 3 * C; p.bias = L.attn_b; p.cta_budget = budget; p.pdl = pdl;
     LVX_TRY(run_gemm(e, p, L.attn, a, F32, st));
     dim3 grid(n, c.n_head);
     {
       PROF(e, "decode_attention", st);
+      cudaError_t err;
       if (a == F32)
-        decode_attention_kernel<float, float, 96><<<grid, 128, 0, st>>>(ln.qkv, (float*)e->kv, ln.d_slots, e->st, pos_override, l,
-                                                                         c.n_head, c.kv_page_tokens, e->pool_pages, 0, (float*)ln.y);
+        err = launch_pdl(decode_attention_kernel<float, float, 96>, grid, dim3(128), 0, st, pdl, (const float*)ln.qkv, (float*)e->kv,
+                         (const int*)ln.d_slots, e->st, pos_override, l, c.n_head, c.kv_page_tokens, e->pool_pages, 0, (float*)ln.y);
       else
-        decode_attention_kernel<bf16, bf16, 96><<<grid, 128, 0, st>>>(ln.qkv, (bf16*)e->kv, ln.d_slots, e->st, pos_override, l,
-                                                                       c.n_head, c.kv_page_tokens, e->pool_pages, 0, (bf16*)ln.y);
+        err = launch_pdl(decode_attention_kernel<bf16, bf16, 96>, grid, dim3(128), 0, st, pdl, (const float*)ln.qkv, (bf16*)e->kv,
+                         (const int*)ln.d_slots, e->st, pos_override, l, c.n_head, c.kv_page_tokens, e->pool_pages, 0, (bf16*)ln.y);
+      LVX_CHECK(err == cudaSuccess, LVX_ERR_CUDA, std::string("attention launch: ") + cudaGetErrorString(err));
       LAUNCHED(e);
     }
     GemmParams q;
-    q.A = ln.y; q.C = ln.x; q.M = n; q.lda = C; q.ldc = C; q.bias = L.proj_b; q.residual = ln.x; q.ldr = C; q.cta_budget = budget;
+    q.A = ln.y; q.C = ln.x; q.M = n; q.lda = C; q.ldc = C; q.bias = L.proj_b; q.residual = ln.x; q.ldr = C; q.cta_budget = budget; q.pdl = pdl;
     LVX_TRY(run_gemm(e, q, L.proj, a, F32, st));
-    LVX_TRY(run_layernorm<768>(e, ln.x, n, L.ln2_w, L.ln2_b, 1e-5f, nullptr, ln.h, st));
+    LVX_TRY(run_layernorm<768>(e, ln.x, n, L.ln2_w, L.ln2_b, 1e-5f, nullptr, ln.h, st, pdl));
     GemmParams f;
-    f.A = ln.h; f.C = ln.g; f.M = n; f.lda = C; f.ldc = 4 * C; f.bias = L.fc_b; f.act = ACT_GELU_TANH; f.cta_budget = budget;
+    f.A = ln.h; f.C = ln.g; f.M = n; f.lda = C; f.ldc = 4 * C; f.bias = L.fc_b; f.act = ACT_GELU_TANH; f.cta_budget = budget; f.pdl = pdl;
     LVX_TRY(run_gemm(e, f, L.fc, a, a, st));
     GemmParams r;
-    r.A = ln.g; r.C = ln.x; r.M = n; r.lda = 4 * C; r.ldc = C; r.bias = L.proj2_b; r.residual = ln.x; r.ldr = C; r.cta_budget = budget;
+    r.A = ln.g; r.C = ln.x; r.M = n; r.lda = 4 * C; r.ldc = C; r.bias = L.proj2_b; r.residual = ln.x; r.ldr = C; r.cta_budget = budget; r.pdl = pdl;
     LVX_TRY(run_gemm(e, r, L.proj2, a, F32, st));
   }
-  LVX_TRY(run_layernorm<768>(e, ln.x, n, e->lnf_w, e->lnf_b, 1e-5f, nullptr, ln.h, st));
+  LVX_TRY(run_layernorm<768>(e, ln.x, n, e->lnf_w, e->lnf_b, 1e-5f, nullptr, ln.h, st, pdl));
   return LVX_OK;
 }
 
 static int lm_head_logits(lvx_engine* e, lvx_engine::Lane& ln, int n, float* d_logits, cudaStream_t st) {
   GemmParams p;
   p.A = ln.h; p.C = d_logits; p.M = n; p.lda = e->cfg.n_embd; p.ldc = e->cfg.vocab_size; p.cta_budget = e->lane_cta_budget;
+  p.pdl = e->use_pdl && !e->prof_on;
   return run_gemm(e, p, e->lm_head, e->adt(), F32, st);
 }
 
@@ -961,15 +970,21 @@ static int decode_one_step(lvx_engine* e, lvx_engine::Lane& ln, int n, const Sam
   const lvx_config& c = e->cfg;
   {
     PROF(e, "assemble_input", st);
-    assemble_input_kernel<<<n, c.n_embd / 4, 0, st>>>(ln.d_slots, e->st, W(e, "text_table"),
-                                                      W(e, "feature_extractor.encodec.quantizer.vq.layers.0._codebook.embed"),
-                                                      W(e, "transformer.wpe.weight"), c.text_dim, c.code_dim, c.pad_token_id, 0, ln.x);
+    cudaError_t err = launch_pdl(assemble_input_kernel, dim3(n), dim3(c.n_embd / 4), 0, st, e->use_pdl && !e->prof_on,
+                                 (const int*)ln.d_slots, e->st, (const float*)W(e, "text_table"),
+                                 (const float*)W(e, "feature_extractor.encodec.quantizer.vq.layers.0._codebook.embed"),
+                                 (const float*)W(e, "transformer.wpe.weight"), c.text_dim, c.code_dim, c.pad_token_id, 0, ln.x);
+    LVX_CHECK(err == cudaSuccess, LVX_ERR_CUDA, std::string("assemble launch: ") + cudaGetErrorString(err));
     LAUNCHED(e);
   }
   LVX_TRY(gpt_body(e, ln, n, nullptr, st));
   LVX_TRY(lm_head_logits(e, ln, n, d_logits, st));
   PROF(e, "sampler", st);
-  sampler_kernel<4096><<<n, 256, 0, st>>>(d_logits, c.vocab_size, ln.d_slots, e->st, sa);
+  {
+    cudaError_t err = launch_pdl(sampler_kernel<4096>, dim3(n), dim3(256), 0, st, e->use_pdl && !e->prof_on, (const float*)d_logits,
+                                 c.vocab_size, (const int*)ln.d_slots, e->st, sa);
+    LVX_CHECK(err == cudaSuccess, LVX_ERR_CUDA, std::string("sampler launch: ") + cudaGetErrorString(err));
+  }
   LAUNCHED(e);
   return LVX_OK;
 }

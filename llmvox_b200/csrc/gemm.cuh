@@ -38,6 +38,7 @@ struct GemmParams {
   float alpha = 1.0f;
   int w_kn = 0;
   int max_M = 0, max_N = 0;  // batch mode: largest problem (grid sizing)
+  int pdl = 0;                // launch with programmatic dependent launch (decode chain)
   int c_transposed = 0;       // tcgen05 swap mode only: store C[n, m] instead of C[m, n]
   const char* tag = nullptr;  // profiler label (host only)
   int cta_budget = 0;        // tcgen05 path: SMs this launch should aim to fill (0 = all); see decode lanes

@@ -352,6 +352,7 @@ __global__ void __launch_bounds__(TcShape<kSwap>::kThreads, kSwap ? 1 : 2) tc_ge
   __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 1];
   __shared__ uint32_t tmem_base_sh;
 
+  pdl_launch_dependents();   // the successor may be scheduled as soon as every CTA of this grid is running
   const GemmParams& p = tp.g;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int BN = tp.BN, stages = tp.stages, S = tp.splits;
@@ -398,7 +399,17 @@ __global__ void __launch_bounds__(TcShape<kSwap>::kThreads, kSwap ? 1 : 2) tc_ge
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int it = 0; it < nk; ++it) {
+      // swap mode: X tiles are WEIGHTS, which do not depend on the predecessor kernel -- their loads for the first ring
+      // pass are issued before waiting for it (PDL); the activation (Y) tiles follow after the wait
+      const int pre = kSwap ? min(nk, stages) : 0;
+      for (int it = 0; it < pre; ++it) {
+        mbar_expect_tx(full_bar(it), stage_bytes);
+        tma_load_2d(&mapX, full_bar(it), tiles + (uint32_t)it * stage_bytes, (kb0 + it) * TC_BK, x0);
+      }
+      pdl_wait();
+      for (int it = 0; it < pre; ++it)
+        tma_load_2d(&mapY, full_bar(it), tiles + (uint32_t)it * stage_bytes + TC_X_BYTES, (kb0 + it) * TC_BK, y0);
+      for (int it = pre; it < nk; ++it) {
         const int s = it % stages;
         const uint32_t ph = (uint32_t)(it / stages) & 1u;
         mbar_wait(empty_bar(s), ph ^ 1u);
@@ -438,6 +449,7 @@ __global__ void __launch_bounds__(TcShape<kSwap>::kThreads, kSwap ? 1 : 2) tc_ge
     // ---------------- epilogue warps: TMEM -> registers -> (global | partial tile in smem)
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
+    pdl_wait();   // residual reads and output writes must follow the predecessor's completion
     const int c_lo = half * (BN / kHalves), c_hi = (half + 1) * (BN / kHalves);   // multiples of 8 (BN % 16 == 0)
     if (S == 1) {
       for (int c = c_lo; c < c_hi; c += 16) {
@@ -536,13 +548,15 @@ inline int tc_launch(const CUtensorMap& mx, const CUtensorMap& my, const TcParam
   cfg.blockDim = dim3(TcShape<kSwap>::kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = (unsigned)tp.splits;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = tp.g.pdl ? 2 : 1;
   cudaError_t err = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<kSwap, TC>, mx, my, tp);
   if (err != cudaSuccess) {
     set_error(std::string("tc_gemm launch: ") + cudaGetErrorString(err));

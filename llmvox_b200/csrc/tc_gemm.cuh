@@ -193,6 +193,11 @@ __host__ __device__ __forceinline__ uint32_t umma_idesc_bf16(int M, int N) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+inline bool tc_no_persistent() {
+  static const bool off = [] { const char* e = getenv("LLMVOX_B200_NO_PERSISTENT"); return e && e[0] == '1'; }();
+  return off;
+}
+
 struct TcParams {
   GemmParams g;
   int BN;          // UMMA N = Y rows per tile
@@ -224,10 +229,13 @@ __device__ __forceinline__ float4 ld_dsmem_v4(uint32_t local_addr, uint32_t rank
 // The epilogue of the ConvNeXt pw1 GEMM (K = 768) is instruction-bound, so this is what sets its tensor utilisation.
 __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float z = fabsf(x) * 0.7071067811865476f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
   const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
-  const float erf_abs = 1.0f - poly * __expf(-z * z);
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+  const float erfv = copysignf(fmaf(-poly, e, 1.0f), x);
+  const float hx = 0.5f * x;
+  return fmaf(hx, erfv, hx);
 }
 template <int ACT>
 __device__ __forceinline__ float tc_act(float v) {
@@ -524,6 +532,10 @@ inline int tc_act_map(TcWorkspace* ws, const void* ptr, int rows, int cols, int 
   return LVX_OK;
 }
 
+template <typename TC>
+__global__ void tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
+                                          const TcParams tp);
+
 // opt every instantiation into the large dynamic shared-memory carve-out (done once per device at engine creation,
 // never inside a stream capture)
 inline int tc_configure() {
@@ -534,6 +546,10 @@ inline int tc_configure() {
     err = cudaFuncSetAttribute(tc_gemm_kernel<false, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
   if (err == cudaSuccess)
     err = cudaFuncSetAttribute(tc_gemm_kernel<false, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+  if (err == cudaSuccess)
+    err = cudaFuncSetAttribute(tc_gemm_persistent_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+  if (err == cudaSuccess)
+    err = cudaFuncSetAttribute(tc_gemm_persistent_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
   if (err != cudaSuccess) {
     set_error(std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(err));
     return LVX_ERR_CUDA;
@@ -560,6 +576,151 @@ inline int tc_launch(const CUtensorMap& mx, const CUtensorMap& my, const TcParam
   cudaError_t err = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<kSwap, TC>, mx, my, tp);
   if (err != cudaSuccess) {
     set_error(std::string("tc_gemm launch: ") + cudaGetErrorString(err));
+    return LVX_ERR_CUDA;
+  }
+  return LVX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Persistent normal-mode GEMM for large M (the vocoder's bulk shapes): 128 x 256 tiles, one CTA per SM looping over
+// tiles, TWO TMEM accumulators (2 x 256 columns = all 512) so that the epilogue of tile i overlaps the MMAs of tile
+// i + 1 inside the same CTA, 4-stage operand ring (48 KB per stage).  Warps: 0 TMA producer, 1 MMA issuer, 2..9 epilogue
+// (two per TMEM lane quarter, 128 columns each).  Against the 128 x 128 kernel: half the L2 bytes per flop for the weight
+// operand and no serialisation of epilogue and main loop when K is short (K = 768: the epilogue of 32K elements is as long
+// as the MMAs).
+constexpr int TCP_BN = 256;
+constexpr int TCP_STAGES = 4;
+constexpr int TCP_THREADS = 320;
+constexpr int TCP_STAGE_BYTES = TC_X_BYTES + TCP_BN * TC_BK * 2;   // 48 KB
+
+template <typename TC>
+__global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapX,
+                                                                            const __grid_constant__ CUtensorMap mapY,
+                                                                            const TcParams tp) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * TCP_STAGES + 4];
+  __shared__ uint32_t tmem_base_sh;
+
+  const GemmParams& p = tp.g;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (TCP_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * TCP_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * TCP_STAGES + 2 + a); };
+  const int num_kb = tp.num_kb;
+  const int n_tiles_n = ceil_div(p.N, TCP_BN), n_tiles_m = ceil_div(p.M, TC_BM);
+  const int n_tiles = n_tiles_n * n_tiles_m;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapX);
+    tma_prefetch_desc(&mapY);
+    for (int s = 0; s < TCP_STAGES; ++s) {
+      mbar_init(full_bar(s), 1);
+      mbar_init(empty_bar(s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(tfull_bar(a), 1);
+      mbar_init(tempty_bar(a), 8);   // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    __syncwarp();
+    tmem_alloc(smem_u32(&tmem_base_sh), 512u);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_sh;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int gi = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int x0 = (t / n_tiles_n) * TC_BM, y0 = (t % n_tiles_n) * TCP_BN;   // n fastest: neighbours share the A tile in L2
+        for (int kb = 0; kb < num_kb; ++kb, ++gi) {
+          const int s = gi % TCP_STAGES;
+          const uint32_t ph = (uint32_t)(gi / TCP_STAGES) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_expect_tx(full_bar(s), TCP_STAGE_BYTES);
+          const int k0 = kb * TC_BK;
+          int xc = k0, xr = x0;
+          if (p.taps > 1) {
+            const int tap = k0 / p.tap_K;
+            xc = k0 - tap * p.tap_K;
+            xr = x0 + tap - p.tap_pad;
+          }
+          const uint32_t dst = tiles + (uint32_t)s * TCP_STAGE_BYTES;
+          tma_load_2d(&mapX, full_bar(s), dst, xc, xr);
+          tma_load_2d(&mapY, full_bar(s), dst + TC_X_BYTES, k0, y0);                       // weight rows y0 .. y0 + 127
+          tma_load_2d(&mapY, full_bar(s), dst + TC_X_BYTES + TC_X_BYTES, k0, y0 + TC_BM);  // and y0 + 128 .. y0 + 255
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_bf16(TC_BM, TCP_BN);
+      int gi = 0, i = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+        const int acc = i & 1;
+        mbar_wait(tempty_bar(acc), ((uint32_t)(i >> 1) & 1u) ^ 1u);   // the epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t dcol = tmem_d + (uint32_t)(acc * TCP_BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++gi) {
+          const int s = gi % TCP_STAGES;
+          const uint32_t ph = (uint32_t)(gi / TCP_STAGES) & 1u;
+          mbar_wait(full_bar(s), ph);
+          tc_fence_after();
+          const uint32_t xs = tiles + (uint32_t)s * TCP_STAGE_BYTES;
+          const uint64_t adesc = umma_smem_desc(xs), bdesc = umma_smem_desc(xs + TC_X_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / 16; ++k)
+            umma_bf16(dcol, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit(empty_bar(s));
+        }
+        umma_commit(tfull_bar(acc));
+      }
+    }
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int drow = q * 32 + lane;
+    int i = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+      const int acc = i & 1;
+      const int x0 = (t / n_tiles_n) * TC_BM, y0 = (t % n_tiles_n) * TCP_BN;
+      mbar_wait(tfull_bar(acc), (uint32_t)(i >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TCP_BN);
+      const int c_lo = half * (TCP_BN / 2), c_hi = c_lo + TCP_BN / 2;
+      for (int c = c_lo; c < c_hi; c += 16) {
+        if (y0 + c >= p.N) break;   // warp-uniform: columns past N (last N tile)
+        float v[16];
+        tmem_ld16(trow + (uint32_t)c, v);
+        tc_epilogue_dispatch<false, TC>(p, x0 + drow, y0 + c, v, 16);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tempty_bar(acc)) : "memory");
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    tmem_dealloc(tmem_d, 512u);
+  }
+}
+
+template <typename TC>
+inline int tc_launch_persistent(const CUtensorMap& mx, const CUtensorMap& my, const TcParams& tp, int grid, cudaStream_t st) {
+  const size_t smem = (size_t)TCP_STAGES * TCP_STAGE_BYTES + 1024;
+  tc_gemm_persistent_kernel<TC><<<grid, TCP_THREADS, smem, st>>>(mx, my, tp);
+  cudaError_t err = cudaGetLastError();
+  if (err != cudaSuccess) {
+    set_error(std::string("tc_gemm_persistent launch: ") + cudaGetErrorString(err));
     return LVX_ERR_CUDA;
   }
   return LVX_OK;
@@ -624,6 +785,25 @@ inline int tc_gemm(TcWorkspace* ws, const GemmParams& p, const TmaDesc& w, bool 
   tp.tmem_cols = pl.tmem_cols;
   tp.stages = pl.stages;
   tp.splits = pl.splits;
+  // large-M normal-mode problems: persistent 128 x 256 tiles (at least ~1.3 tiles per SM, N wide enough to fill them)
+  if (!pl.swap && !tc_no_persistent() && p.N >= 192) {
+    const int n_tiles = ceil_div(p.M, TC_BM) * ceil_div(p.N, TCP_BN);
+    const int sms = ws->num_sms > 0 ? ws->num_sms : 148;
+    if (n_tiles >= sms + sms / 3) {
+      CUtensorMap pam;
+      int ps = LVX_OK;
+      if (a_map)
+        pam = *a_map;
+      else
+        ps = tc_act_map(ws, p.A, a_cap, a_cols, p.lda, TC_BM, &pam);
+      if (ps != LVX_OK) return ps;
+      TcParams pp = tp;
+      pp.BN = TCP_BN;
+      pp.splits = 1;
+      const int grid = std::min(n_tiles, sms);
+      return c_bf16 ? tc_launch_persistent<bf16>(pam, w.map, pp, grid, st) : tc_launch_persistent<float>(pam, w.map, pp, grid, st);
+    }
+  }
   CUtensorMap am;
   int s = LVX_OK;
   if (a_map)

@@ -41,7 +41,9 @@ def engines(weights):
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("M,N,K,taps", [(64, 768, 768, 1), (1, 2304, 768, 1), (37, 4096, 768, 1), (200, 768, 3072, 1),
                                         (300, 2304, 768, 1), (1000, 1282, 2304, 1), (129, 768, 2304, 3),
-                                        (515, 768, 3584, 7), (16, 768, 2304, 3)])
+                                        (515, 768, 3584, 7), (16, 768, 2304, 3),
+                                        # large M: the persistent 128 x 256 double-buffered kernel (bf16 mode)
+                                        (9000, 768, 768, 1), (4100, 2304, 768, 1), (9001, 768, 2304, 3), (6000, 1282, 768, 1)])
 def test_gemm_against_torch(engines, precision, M, N, K, taps):
     e = engines(precision)
     g = torch.Generator().manual_seed(M * 7 + N + K + taps)

@@ -348,6 +348,11 @@ def run_gpu(args):
                            "decode_lanes": args.lanes,
                            "l2": "no flush: per-step working set (189 MB bf16 weights + KV + activations) exceeds the 126 MB L2"},
                 "x_realtime_per_gpu": value / world,
+                # whole-step view: bf16 weights once per iteration + KV read/append, against measured HBM peak
+                "roofline_step": (lambda by: {"bound": "hbm", "algorithmic_bytes": by, "achieved": by / (ms / K / 1e3) / 1e9,
+                                              "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": by / (ms / K / 1e3) / 1e9 / peaks["hbm_gbs"],
+                                              "note": "decode bytes of one step per GPU / step time; the step is latency-bound (DESIGN.md 5)"})(
+                    TOKENS * 62914560.0 + STREAMS * 12288.0 * (TOKENS * (TOKENS + 1) / 2)),
                 "roofline": roof,
                 "kernels": {k: {"launches": v["launches"], "ms": round(v["ms"], 4)} for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
                 "cpu_baseline": {"value": ca / cdt, "unit": "audio-s/s", "cores": threads, "kind": "port",

@@ -115,8 +115,8 @@ template <int C>
 __global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x, int rows, int width, int ld_in,
                                                      bf16* __restrict__ out, int seg, int ld_out) {
   // out[r, 0:seg) = hi, [seg, 2seg) = lo, [2seg, 3seg) = hi; columns >= width are zero
-  const int r = blockIdx.y;
-  const int j = blockIdx.x * 256 + threadIdx.x;
+  const int r = blockIdx.x;   // rows on grid.x: a launch group may hold more than 65535 rows
+  const int j = blockIdx.y * 256 + threadIdx.x;
   if (r >= rows || j >= seg) return;
   float v = j < width ? x[(size_t)r * ld_in + j] : 0.f;
   const bf16 hi = __float2bfloat16_rn(v);
@@ -1496,7 +1496,7 @@ static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes
     GemmParams p;
     p.A = e->v_h; p.C = e->v_raw; p.M = g.R; p.lda = D; p.ldc = e->raw_ld; p.bias = e->head_b; p.row_chunk = e->row_chunk;
     LVX_TRY(run_gemm(e, p, e->head, a, F32, st));
-    dim3 grid(ceil_div(e->spec_ld, 256), g.R);
+    dim3 grid(g.R, ceil_div(e->spec_ld, 256));
     head_activation_kernel<float><<<grid, 256, 0, st>>>(e->v_raw, e->raw_ld, g.R, e->row_chunk, bins, (float*)e->v_spec, e->spec_ld);
     LAUNCHED(e);
     GemmParams q;
@@ -1506,19 +1506,19 @@ static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes
     layernorm_kernel<float, 768><<<ceil_div(g.R, 8), 256, 0, st>>>(e->v_x, g.R, e->fln_w, e->fln_b, 1e-6f, e->row_chunk, e->v_t);
     LAUNCHED(e);
     if (stage == 4) return dump(e->v_t, D, D);
-    dim3 g3(ceil_div(D, 256), g.R);
+    dim3 g3(g.R, ceil_div(D, 256));
     split3_kernel<768><<<g3, 256, 0, st>>>(e->v_t, g.R, D, D, (bf16*)e->v_h3, D, 3 * D);
     LAUNCHED(e);
     GemmParams p;
     p.A = e->v_h3; p.C = e->v_raw; p.M = g.R; p.lda = 3 * D; p.ldc = e->raw_ld; p.bias = e->head_b; p.row_chunk = e->row_chunk;
     if (e->prof_detail) p.tag = "tc_gemm:head_x3";
     LVX_TRY(run_gemm(e, p, e->head, a, F32, st));
-    dim3 grid(ceil_div(e->spec_ld, 256), g.R);
+    dim3 grid(g.R, ceil_div(e->spec_ld, 256));
     // fp32 spectrum into v_frames' storage is not possible (needed later); reuse v_big as fp32 scratch
     float* spec32 = (float*)e->v_big;
     head_activation_kernel<float><<<grid, 256, 0, st>>>(e->v_raw, e->raw_ld, g.R, e->row_chunk, bins, spec32, e->spec_ld);
     LAUNCHED(e);
-    dim3 g4(ceil_div(e->spec_ld, 256), g.R);
+    dim3 g4(g.R, ceil_div(e->spec_ld, 256));
     split3_kernel<768><<<g4, 256, 0, st>>>(spec32, g.R, e->spec_ld, e->spec_ld, (bf16*)e->v_spec, e->spec_ld, 3 * e->spec_ld);
     LAUNCHED(e);
     GemmParams q;

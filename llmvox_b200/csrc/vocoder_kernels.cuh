@@ -218,9 +218,9 @@ template <typename TOut>
 __global__ void __launch_bounds__(256) head_activation_kernel(const float* __restrict__ raw, int ld_raw, int rows,
                                                               const int* __restrict__ row_chunk, int bins,
                                                               TOut* __restrict__ out, int ldo) {
-  const int row = blockIdx.y;
+  const int row = blockIdx.x;   // rows on grid.x: a launch group may hold more than 65535 rows
   if (row >= rows || row_chunk[row] < 0) return;
-  const int j = blockIdx.x * 256 + threadIdx.x;
+  const int j = blockIdx.y * 256 + threadIdx.x;
   if (j >= ldo) return;
   const float* r = raw + (size_t)row * ld_raw;
   float v = 0.f;

@@ -215,6 +215,10 @@ struct lvx_engine {
   std::vector<Lane> lanes;
   int lane_cta_budget = 0;
   cudaStream_t gstream = nullptr;   // capture only: graphs are launched on the caller's stream
+  // helper streams: the per-chunk attention GEMMs of long vocoder chunks are independent and run side by side
+  static constexpr int kAux = 4;
+  cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {nullptr, nullptr, nullptr, nullptr};
   bool use_graphs = true;
   bool use_fused = true;
   bool use_pdl = true;      // programmatic dependent launch along the decode chain (LLMVOX_B200_NO_PDL=1 disables)
@@ -508,6 +512,14 @@ extern "C" int lvx_engine_create(const lvx_config* cfg, int device, lvx_engine**
       s = LVX_ERR_CUDA;
     }
     e->lane_cta_budget = std::max(24, prop.multiProcessorCount / (int)e->lanes.size());
+    bool ok = cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    for (int a = 0; a < lvx_engine::kAux && ok; ++a)
+      ok = cudaStreamCreateWithFlags(&e->aux[a], cudaStreamNonBlocking) == cudaSuccess &&
+           cudaEventCreateWithFlags(&e->ev_join[a], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok && s == LVX_OK) {
+      set_error("could not create the engine's helper streams");
+      s = LVX_ERR_CUDA;
+    }
   }
   if (s != LVX_OK) {
     lvx_engine_destroy(e);
@@ -525,6 +537,11 @@ extern "C" int lvx_engine_destroy(lvx_engine* e) {
     for (auto& g : ln.graphs)
       if (g.second.exec) cudaGraphExecDestroy(g.second.exec);
   if (e->gstream) cudaStreamDestroy(e->gstream);
+  for (int a = 0; a < lvx_engine::kAux; ++a) {
+    if (e->aux[a]) cudaStreamDestroy(e->aux[a]);
+    if (e->ev_join[a]) cudaEventDestroy(e->ev_join[a]);
+  }
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   for (auto& r : e->prof) {
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
@@ -1323,6 +1340,19 @@ static int resnet_block(lvx_engine* e, const VocGroup& g, const lvx_engine::Res&
   return LVX_OK;
 }
 
+static int aux_fork(lvx_engine* e, cudaStream_t st) {
+  LVX_CUDA(cudaEventRecord(e->ev_fork, st));
+  for (int a = 0; a < lvx_engine::kAux; ++a) LVX_CUDA(cudaStreamWaitEvent(e->aux[a], e->ev_fork, 0));
+  return LVX_OK;
+}
+static int aux_join(lvx_engine* e, cudaStream_t st) {
+  for (int a = 0; a < lvx_engine::kAux; ++a) {
+    LVX_CUDA(cudaEventRecord(e->ev_join[a], e->aux[a]));
+    LVX_CUDA(cudaStreamWaitEvent(st, e->ev_join[a], 0));
+  }
+  return LVX_OK;
+}
+
 // stage: -1 = full pipeline; otherwise stop after that stage and copy the activation to d_stage_out
 static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes, const float* d_feats, int bw, float* d_pcm,
                         int stage, float* d_stage_out, cudaStream_t st) {
@@ -1400,7 +1430,10 @@ static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes
       t.a_cap = e->R_max;
       if (e->prof_detail) t.tag = "tc_gemm:attn_vt";
       LVX_TRY(run_gemm(e, t, e->at_v, a, a, st));
+      LVX_TRY(aux_fork(e, st));
+      int rr = 0;
       for (int i : large) {
+        cudaStream_t cs = e->aux[rr++ % lvx_engine::kAux];
         const ChunkInfo& ci = g.chunks[i];
         const int L = ci.len, Lp = (L + 7) & ~7;
         const bf16* qk = (const bf16*)e->v_big + (size_t)ci.row0 * 3 * D;
@@ -1411,10 +1444,11 @@ static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes
         km.valid = true;
         GemmParams s;
         s.A = qk; s.C = e->v_S + ci.s_off; s.M = L; s.N = L; s.K = D; s.lda = 3 * D; s.ldw = 3 * D; s.ldc = Lp; s.alpha = att_scale;
-        ProfScope prof(e, "tc_gemm:attn_qk", st, 2.0 * L * (double)L * D, 0);
-        LVX_TRY(tc_gemm(&e->tcw, s, km, false, st, &qm));
+        ProfScope prof(e, "tc_gemm:attn_qk", cs, 2.0 * L * (double)L * D, 0);
+        LVX_TRY(tc_gemm(&e->tcw, s, km, false, cs, &qm));
         e->launches++;
       }
+      LVX_TRY(aux_join(e, st));
     }
     if (a == F32)
       attn_softmax_kernel<float><<<ceil_div(g.R, 8), 256, 0, st>>>(e->v_S, e->v_S, e->d_chunks, e->row_chunk, g.R);
@@ -1427,7 +1461,10 @@ static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes
       o.ldw = 3 * D; o.ldc = D; o.w_kn = 1; o.max_M = small_max; o.max_N = D;
       LVX_TRY(run_gemm_batched(e, o, a, a, a, st));
     }
+    if (!large.empty()) LVX_TRY(aux_fork(e, st));
+    int rr2 = 0;
     for (int i : large) {
+      cudaStream_t cs = e->aux[rr2++ % lvx_engine::kAux];
       const ChunkInfo& ci = g.chunks[i];
       const int L = ci.len, Lp = (L + 7) & ~7;
       const bf16* P = (const bf16*)e->v_P + ci.s_off;
@@ -1438,10 +1475,11 @@ static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes
       vm.valid = true;
       GemmParams o;
       o.A = P; o.C = (bf16*)e->v_h + (size_t)ci.row0 * D; o.M = L; o.N = D; o.K = L; o.lda = Lp; o.ldw = e->R_max; o.ldc = D;
-      ProfScope prof(e, "tc_gemm:attn_pv", st, 2.0 * L * (double)L * D, 0);
-      LVX_TRY(tc_gemm(&e->tcw, o, vm, true, st, &pm));
+      ProfScope prof(e, "tc_gemm:attn_pv", cs, 2.0 * L * (double)L * D, 0);
+      LVX_TRY(tc_gemm(&e->tcw, o, vm, true, cs, &pm));
       e->launches++;
     }
+    if (!large.empty()) LVX_TRY(aux_join(e, st));
     GemmParams q;
     q.A = e->v_h; q.C = e->v_x; q.M = g.R; q.lda = D; q.ldc = D; q.bias = e->at_proj_b; q.residual = e->v_x; q.ldr = D;
     q.row_chunk = e->row_chunk;

@@ -238,6 +238,22 @@ def test_ragged_batch_equals_independent_chunks(engines, precision):
             assert snr_db(alone, seg) > 45    # split-K plan differs with the row count (see full-size test)
 
 
+def test_vocoder_launch_group_above_65535_rows(weights):
+    """One launch group with more padded rows than a CUDA grid's y limit (rows ride on grid.x), through the persistent
+    128 x 256 GEMM; a chunk inside the big batch equals its solo decode."""
+    from llmvox_b200.engine import Engine
+    big = Engine(weights, device=0, precision="bf16", max_sessions=2, max_context=32, max_vocode_frames=70000)
+    g = torch.Generator().manual_seed(8)
+    n, L = 52, 1280
+    codes = torch.randint(0, 4096, (n * L,), generator=g).to("cuda", torch.int32)
+    pcm = big.vocode(codes, list(range(0, (n + 1) * L, L)))
+    assert torch.isfinite(pcm).all()
+    k = 37
+    alone = big.vocode(codes[k * L:(k + 1) * L].contiguous(), [0, L]).cpu().numpy()
+    assert snr_db(alone, pcm[k * L * 320:(k + 1) * L * 320].cpu().numpy()) > 45
+    big.close()
+
+
 def test_vocoder_groups_split_transparently(weights):
     """More frames than max_vocode_frames: the call is cut into launch groups without changing results."""
     from llmvox_b200.engine import Engine

@@ -120,3 +120,39 @@ def test_seeded_weights_are_reproducible():
     r = W.round_weights_to_bf16(a)
     k = "transformer.h.0.attn.c_attn.weight"
     assert torch.equal(r[k], a[k].bfloat16().float()) and not torch.equal(r[k], a[k])
+
+
+def test_chunk_scheduler_properties_against_the_oracle_schedule():
+    """Random code streams (with and without EOA codes): the incremental scheduler must cut exactly the chunks the
+    oracle's replay of streaming_server.py:357-422 cuts, ranges must tile the sentence without gaps, and the dump
+    size may only grow up to max_dump."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import llmvox_oracle as O
+
+    @settings(max_examples=150, deadline=None)
+    @given(st.lists(st.sampled_from([453, 7, 8, 9, 1000]), min_size=1, max_size=400), st.sampled_from([10, 160]),
+           st.sampled_from([1280, 90]))
+    def check(codes, dump, max_dump):
+        sc = ChunkScheduler(dump_size=dump, max_dump=max_dump)
+        pos, got = 0, []
+        last_dump = dump
+        while pos < len(codes):
+            chunks, used, new_dump = O.chunk_schedule(codes[pos:], sc.dump_size, max_dump=max_dump)
+            mine = []
+            for k in range(used):
+                mine += sc.push(codes[pos + k])
+                assert last_dump <= sc.dump_size <= max(max_dump, dump)
+                last_dump = sc.dump_size
+            assert [c for (_, c) in mine] == [len(c) for c in chunks]
+            start = 0
+            for (s, c) in mine:
+                assert s == start and c > 0
+                start += c
+            assert sc.dump_size == new_dump
+            got.append(mine)
+            pos += used
+            if sc.done:
+                sc.new_sentence()
+            else:
+                assert pos == len(codes)
+    check()

@@ -178,6 +178,20 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// TMA load multicast to the CTAs of `mask`: the tile lands at the same shared-memory offset in each of them and each CTA's
+// mbarrier (same offset) receives the byte count
+__device__ __forceinline__ void tma_load_2d_mcast(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+// tcgen05.commit that arrives on the mbarrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void umma_commit_mcast(uint32_t bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+               : "memory");
+}
+
 // K-major, 128-byte-swizzled operand tile (rows x 64 bf16, 8-row groups 1024 bytes apart)
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
   uint64_t d = 0;
@@ -584,10 +598,12 @@ inline int tc_launch(const CUtensorMap& mx, const CUtensorMap& my, const TcParam
 // ---------------------------------------------------------------------------------------------------------------------
 // Persistent normal-mode GEMM for large M (the vocoder's bulk shapes): 128 x 256 tiles, one CTA per SM looping over
 // tiles, TWO TMEM accumulators (2 x 256 columns = all 512) so that the epilogue of tile i overlaps the MMAs of tile
-// i + 1 inside the same CTA, 4-stage operand ring (48 KB per stage).  Warps: 0 TMA producer, 1 MMA issuer, 2..9 epilogue
-// (two per TMEM lane quarter, 128 columns each).  Against the 128 x 128 kernel: half the L2 bytes per flop for the weight
-// operand and no serialisation of epilogue and main loop when K is short (K = 768: the epilogue of 32K elements is as long
-// as the MMAs).
+// i + 1 inside the same CTA, 4-stage operand ring (48 KB per stage).  CTAs work in CLUSTERS OF TWO on vertically adjacent
+// tiles (same weight columns): each CTA loads its own activation tile and HALF of the weight tile, the latter with TMA
+// multicast into both CTAs, so the weight operand crosses L2 -> SM once per pair (operand bytes per flop drop by a third;
+// these GEMMs run against the L2 bandwidth ceiling).  A ring stage is reused only after BOTH CTAs' MMAs have read it: the
+// tcgen05.commit that frees a stage arrives on the empty barrier of both CTAs.
+// Warps: 0 TMA producer, 1 MMA issuer, 2..9 epilogue (two per TMEM lane quarter, 128 columns each).
 constexpr int TCP_BN = 256;
 constexpr int TCP_STAGES = 4;
 constexpr int TCP_THREADS = 320;
@@ -610,15 +626,17 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
   auto tfull_bar = [&](int a) { return bar0 + 8u * (2 * TCP_STAGES + a); };
   auto tempty_bar = [&](int a) { return bar0 + 8u * (2 * TCP_STAGES + 2 + a); };
   const int num_kb = tp.num_kb;
-  const int n_tiles_n = ceil_div(p.N, TCP_BN), n_tiles_m = ceil_div(p.M, TC_BM);
-  const int n_tiles = n_tiles_n * n_tiles_m;
+  const int n_tiles_n = ceil_div(p.N, TCP_BN), n_pairs_m = ceil_div(ceil_div(p.M, TC_BM), 2);
+  const int n_items = n_tiles_n * n_pairs_m;           // one item = two vertically adjacent tiles
+  const int rank = (int)cluster_ctarank();             // 0 / 1 inside the pair
+  const int cluster_id = (int)blockIdx.x >> 1, n_clusters = (int)gridDim.x >> 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapX);
     tma_prefetch_desc(&mapY);
     for (int s = 0; s < TCP_STAGES; ++s) {
       mbar_init(full_bar(s), 1);
-      mbar_init(empty_bar(s), 1);
+      mbar_init(empty_bar(s), 2);    // both CTAs of the pair have consumed the stage
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(tfull_bar(a), 1);
@@ -634,12 +652,14 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_d = tmem_base_sh;
+  cluster_sync_all();   // the peer's barriers exist before any multicast reaches them
 
   if (warp == 0) {
     if (lane == 0) {
       int gi = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int x0 = (t / n_tiles_n) * TC_BM, y0 = (t % n_tiles_n) * TCP_BN;   // n fastest: neighbours share the A tile in L2
+      for (int w = cluster_id; w < n_items; w += n_clusters) {
+        // n fastest: neighbouring clusters share the activation tiles in L2
+        const int x0 = ((w / n_tiles_n) * 2 + rank) * TC_BM, y0 = (w % n_tiles_n) * TCP_BN;
         for (int kb = 0; kb < num_kb; ++kb, ++gi) {
           const int s = gi % TCP_STAGES;
           const uint32_t ph = (uint32_t)(gi / TCP_STAGES) & 1u;
@@ -654,8 +674,8 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
           }
           const uint32_t dst = tiles + (uint32_t)s * TCP_STAGE_BYTES;
           tma_load_2d(&mapX, full_bar(s), dst, xc, xr);
-          tma_load_2d(&mapY, full_bar(s), dst + TC_X_BYTES, k0, y0);                       // weight rows y0 .. y0 + 127
-          tma_load_2d(&mapY, full_bar(s), dst + TC_X_BYTES + TC_X_BYTES, k0, y0 + TC_BM);  // and y0 + 128 .. y0 + 255
+          // this CTA's half of the weight tile (rows y0 + 128 * rank ..), delivered to both CTAs
+          tma_load_2d_mcast(&mapY, full_bar(s), dst + TC_X_BYTES + (uint32_t)rank * TC_X_BYTES, k0, y0 + rank * TC_BM, (uint16_t)3);
         }
       }
     }
@@ -663,7 +683,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_bf16(TC_BM, TCP_BN);
       int gi = 0, i = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+      for (int w = cluster_id; w < n_items; w += n_clusters, ++i) {
         const int acc = i & 1;
         mbar_wait(tempty_bar(acc), ((uint32_t)(i >> 1) & 1u) ^ 1u);   // the epilogue has drained this accumulator
         tc_fence_after();
@@ -678,7 +698,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k)
             umma_bf16(dcol, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          umma_commit(empty_bar(s));
+          umma_commit_mcast(empty_bar(s), (uint16_t)3);   // frees the stage in BOTH CTAs once these MMAs have read it
         }
         umma_commit(tfull_bar(acc));
       }
@@ -687,9 +707,9 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int drow = q * 32 + lane;
     int i = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++i) {
+    for (int w = cluster_id; w < n_items; w += n_clusters, ++i) {
       const int acc = i & 1;
-      const int x0 = (t / n_tiles_n) * TC_BM, y0 = (t % n_tiles_n) * TCP_BN;
+      const int x0 = ((w / n_tiles_n) * 2 + rank) * TC_BM, y0 = (w % n_tiles_n) * TCP_BN;
       mbar_wait(tfull_bar(acc), (uint32_t)(i >> 1) & 1u);
       tc_fence_after();
       const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TCP_BN);
@@ -698,7 +718,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
         if (y0 + c >= p.N) break;   // warp-uniform: columns past N (last N tile)
         float v[16];
         tmem_ld16(trow + (uint32_t)c, v);
-        tc_epilogue_dispatch<false, TC>(p, x0 + drow, y0 + c, v, 16);
+        tc_epilogue_dispatch<false, TC>(p, x0 + drow, y0 + c, v, 16);   // rows >= M (odd tile count: the pair's second tile) store nothing
       }
       tc_fence_before();
       __syncwarp();
@@ -707,6 +727,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
   }
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();   // the peer may still multicast into this CTA's smem / arrive on its barriers
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
@@ -717,8 +738,19 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
 template <typename TC>
 inline int tc_launch_persistent(const CUtensorMap& mx, const CUtensorMap& my, const TcParams& tp, int grid, cudaStream_t st) {
   const size_t smem = (size_t)TCP_STAGES * TCP_STAGE_BYTES + 1024;
-  tc_gemm_persistent_kernel<TC><<<grid, TCP_THREADS, smem, st>>>(mx, my, tp);
-  cudaError_t err = cudaGetLastError();
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(grid & ~1));
+  cfg.blockDim = dim3(TCP_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t err = cudaLaunchKernelEx(&cfg, tc_gemm_persistent_kernel<TC>, mx, my, tp);
   if (err != cudaSuccess) {
     set_error(std::string("tc_gemm_persistent launch: ") + cudaGetErrorString(err));
     return LVX_ERR_CUDA;
@@ -800,7 +832,7 @@ inline int tc_gemm(TcWorkspace* ws, const GemmParams& p, const TmaDesc& w, bool 
       TcParams pp = tp;
       pp.BN = TCP_BN;
       pp.splits = 1;
-      const int grid = std::min(n_tiles, sms);
+      const int grid = std::max(2, std::min(2 * ceil_div(ceil_div(p.M, TC_BM), 2) * ceil_div(p.N, TCP_BN), sms));
       return c_bf16 ? tc_launch_persistent<bf16>(pam, w.map, pp, grid, st) : tc_launch_persistent<float>(pam, w.map, pp, grid, st);
     }
   }

@@ -19,6 +19,7 @@
 #include "gemm.cuh"
 #include "tc_gemm.cuh"
 #include "fused_decode.cuh"
+#include "cluster_decode.cuh"
 #include "vocoder_kernels.cuh"
 
 namespace lvx {
@@ -222,6 +223,13 @@ struct lvx_engine {
   bool use_graphs = true;
   bool use_fused = true;
   bool use_pdl = true;      // programmatic dependent launch along the decode chain (LLMVOX_B200_NO_PDL=1 disables)
+  // cluster-resident decode kernel (cluster_decode.cuh): per-rank weight streams + table norms, built on first use
+  bool use_cluster = false;
+  bool cd_ready = false;
+  uint8_t* cd_stream = nullptr;
+  long long cd_stream_bytes = 0;
+  float *cd_text_ss = nullptr, *cd_code_ss = nullptr;
+  int cd_max_clusters = 0;
 
   // ---- optional per-launch profiler (lvx_profile_enable)
   struct ProfRec {
@@ -507,6 +515,8 @@ extern "C" int lvx_engine_create(const lvx_config* cfg, int device, lvx_engine**
     e->use_pdl = !(env3 && env3[0] == '1');
     const char* env2 = getenv("LLMVOX_B200_FUSED");
     e->use_fused = env2 && env2[0] == '1';
+    const char* env4 = getenv("LLMVOX_B200_CLUSTER");
+    e->use_cluster = env4 && env4[0] == '1';
     if (cudaStreamCreateWithFlags(&e->gstream, cudaStreamNonBlocking) != cudaSuccess) {
       set_error("could not create the engine's capture stream");
       s = LVX_ERR_CUDA;
@@ -1114,6 +1124,72 @@ static int fused_ctx(lvx_engine* e, lvx_engine::Lane& ln, int n, lvx_engine::Fus
   return LVX_OK;
 }
 
+// Cluster-resident decode kernel (cluster_decode.cuh): the per-rank weight streams and the table row norms, built once.
+static int cluster_init(lvx_engine* e) {
+  if (e->cd_ready) return LVX_OK;
+  const lvx_config& c = e->cfg;
+  LVX_TRY(cluster_decode_configure(&e->cd_max_clusters));
+  LVX_CHECK(e->cd_max_clusters >= 1, LVX_ERR_CUDA, "cluster decode: no 16-CTA cluster fits on this device");
+  if (getenv("LLMVOX_B200_TRACE")) fprintf(stderr, "[llmvox_b200] cluster decode: %d co-resident clusters of %d CTAs\n", e->cd_max_clusters, CD_CLUSTER);
+  std::vector<CdLayerW> lw(c.n_layer);
+  for (int l = 0; l < c.n_layer; ++l) {
+    auto& L = e->layers[l];
+    lw[l] = CdLayerW{L.attn.f32, L.proj.f32, L.fc.f32, L.proj2.f32, L.attn.ld, L.proj.ld, L.fc.ld, L.proj2.ld, L.ln1_w, L.ln2_w};
+  }
+  std::vector<CdPackDesc> descs;
+  e->cd_stream_bytes = cd_build_descs(lw.data(), c.n_layer, e->lm_head.f32, e->lm_head.ld, e->lnf_w, &descs);
+  LVX_TRY(dev_alloc_bytes(e, (void**)&e->cd_stream, (size_t)e->cd_stream_bytes * CD_CLUSTER));
+  CdPackDesc* d_descs = nullptr;
+  LVX_CUDA(cudaMalloc(&d_descs, descs.size() * sizeof(CdPackDesc)));
+  LVX_CUDA(cudaMemcpy(d_descs, descs.data(), descs.size() * sizeof(CdPackDesc), cudaMemcpyHostToDevice));
+  cd_pack_kernel<<<(unsigned)descs.size(), 256>>>(d_descs, e->cd_stream);
+  LAUNCHED(e);
+  LVX_TRY(dev_alloc(e, &e->cd_text_ss, (size_t)c.text_vocab));
+  LVX_TRY(dev_alloc(e, &e->cd_code_ss, (size_t)c.vocab_size));
+  cd_row_ss_kernel<<<ceil_div(c.text_vocab, 8), 256>>>(W(e, "text_table"), c.text_vocab, c.text_dim, e->cd_text_ss);
+  LAUNCHED(e);
+  cd_row_ss_kernel<<<ceil_div(c.vocab_size, 8), 256>>>(W(e, "feature_extractor.encodec.quantizer.vq.layers.0._codebook.embed"),
+                                                      c.vocab_size, c.code_dim, e->cd_code_ss);
+  LAUNCHED(e);
+  LVX_CUDA(cudaDeviceSynchronize());
+  cudaFree(d_descs);
+  e->cd_ready = true;
+  return LVX_OK;
+}
+
+static bool cluster_applicable(const lvx_engine* e, const SamplerArgs& sa) {
+  const lvx_config& c = e->cfg;
+  return e->use_cluster && e->adt() == B16 && sa.greedy && !sa.forced && !sa.out_codes && !e->prof_on && c.n_embd == CD_C &&
+         c.n_head == CD_H && c.vocab_size == CD_V && c.n_layer <= CD_MAX_LAYERS && c.text_dim + c.code_dim == CD_C && !c.bias &&
+         (c.kv_page_tokens & (c.kv_page_tokens - 1)) == 0 && e->max_pages <= 64 &&
+         (long long)e->pool_pages * c.kv_page_tokens * c.n_embd < (1LL << 31);
+}
+
+static int cluster_launch(lvx_engine* e, lvx_engine::Lane& ln, int n, int n_steps, cudaStream_t st) {
+  LVX_TRY(cluster_init(e));
+  const lvx_config& c = e->cfg;
+  ClusterParams P;
+  memset(&P, 0, sizeof(P));
+  P.n = n; P.n_iters = n_steps; P.n_layer = c.n_layer;
+  P.slots = ln.d_slots;
+  P.st = e->st;
+  P.text_table = W(e, "text_table");
+  P.codebook = W(e, "feature_extractor.encodec.quantizer.vq.layers.0._codebook.embed");
+  P.wpe = W(e, "transformer.wpe.weight");
+  P.text_ss = e->cd_text_ss; P.code_ss = e->cd_code_ss;
+  P.text_dim = c.text_dim; P.code_dim = c.code_dim; P.pad_id = c.pad_token_id;
+  P.wstream = e->cd_stream; P.stream_bytes = e->cd_stream_bytes;
+  P.kv = (bf16*)e->kv; P.pool_pages = e->pool_pages;
+  P.page_shift = 0;
+  while ((1 << P.page_shift) < c.kv_page_tokens) P.page_shift += 1;
+  P.logits = ln.logits;
+  P.trace = getenv("LLMVOX_B200_TRACE") ? ln.d_trace : nullptr;
+  P.dbg = getenv("LLMVOX_B200_CD_DBG") ? atoi(getenv("LLMVOX_B200_CD_DBG")) : 0;
+  LVX_TRY(cluster_decode_launch(P, st));
+  e->launches += 1;
+  return LVX_OK;
+}
+
 extern "C" int lvx_decode_steps_lane(lvx_engine* e, int lane, const int32_t* h_slots, int n, int n_steps, const lvx_sampling* s,
                                      void* stream) {
   LVX_TRY(check_engine(e));
@@ -1129,7 +1205,9 @@ extern "C" int lvx_decode_steps_lane(lvx_engine* e, int lane, const int32_t* h_s
   LVX_CHECK(sa.greedy || sa.temperature > 0.f, LVX_ERR_INVALID, "temperature must be positive");
   LVX_CHECK(!(sa.uniform && n_steps > 1), LVX_ERR_INVALID, "d_uniform supplies one draw per session: use n_steps == 1");
   const lvx_config& c = e->cfg;
-  if (e->use_fused && e->adt() == B16 && sa.greedy && !e->prof_on && n <= 128 && c.n_layer <= FD_MAX_LAYERS && c.n_embd == 768 &&
+  if (cluster_applicable(e, sa)) {
+    LVX_TRY(cluster_launch(e, ln, n, n_steps, st));
+  } else if (e->use_fused && e->adt() == B16 && sa.greedy && !e->prof_on && n <= 128 && c.n_layer <= FD_MAX_LAYERS && c.n_embd == 768 &&
       c.vocab_size % 4 == 0) {
     // one persistent launch runs all n_steps iterations (fused_decode.cuh)
     lvx_engine::FusedCtx* fc = nullptr;

@@ -450,6 +450,48 @@ def test_fused_decode_kernel_matches_the_multi_kernel_path(weights, n):
     plain.close()
 
 
+@pytest.mark.parametrize("n", [1, 5, 16, 17, 64])
+def test_cluster_decode_kernel_matches_the_multi_kernel_path(weights, n):
+    """The cluster-resident decode kernel (cluster_decode.cuh; bf16, greedy) against the kernel-per-op path on a twin
+    engine: the twin is teacher-forced with the cluster kernel's pick at every step, so both see identical histories;
+    logits must agree within the bf16 bound, every pick must be the argmax of its own logits, and n iterations inside
+    one launch must equal n launches of one iteration (fixed reduction order: bit-identical)."""
+    import os
+    from llmvox_b200.engine import Engine
+    kw = dict(device=0, precision="bf16", max_sessions=n, max_context=48, max_vocode_frames=256)
+    os.environ["LLMVOX_B200_CLUSTER"] = "1"          # read at engine creation
+    try:
+        clus = Engine(weights, **kw)
+    finally:
+        del os.environ["LLMVOX_B200_CLUSTER"]
+    plain = Engine(weights, **kw)
+    rng = np.random.RandomState(n)
+    texts = [rng.randint(3, 259, size=rng.randint(0, 40)).tolist() for _ in range(n)]
+    slots = list(range(n))
+    for e in (clus, plain):
+        e.open(slots)
+        e.feed_text(slots, texts)
+    worst = 0.0
+    for t in range(36):                               # crosses two KV page boundaries (16 tokens per page)
+        clus.decode_steps(slots, 1)
+        codes = clus.gather_codes(slots, t, 1).view(-1).contiguous()
+        lf = clus.peek_logits(n)
+        lp, _ = plain.decode_step_logits(slots, forced=codes)
+        assert (lf.argmax(dim=1).to(torch.int32) == codes).all()
+        worst = max(worst, float((lf - lp).abs().max()))
+    assert worst < 2e-2, worst
+    first = clus.gather_codes(slots, 0, 36).cpu()
+    clus.open(slots)
+    clus.feed_text(slots, texts)
+    clus.decode_steps(slots, 36)
+    again = clus.gather_codes(slots, 0, 36).cpu()
+    assert clus.session_length(0) == 36
+    assert (again == first).all()
+    assert (again == plain.gather_codes(slots, 0, 36).cpu()).all()
+    clus.close()
+    plain.close()
+
+
 def test_error_behaviour(engines):
     from llmvox_b200._lib import LvxError
     e = engines("fp32")

@@ -39,6 +39,9 @@ TOKENS = 200
 SCHEDULE = [10, 30, 90, 70]          # reference chunk schedule for 200 codes (replica 0) + flushed tail
 CODES_PER_SEC = 75.0                 # 24 kHz / hop 320
 SEED = 1234
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of cluster_decode_kernel, from the committed `ncu --set full`
+# capture of this command's launches (profiles/README.md); None until a capture of the current kernel is committed
+CLUSTER_TRAFFIC = None
 
 
 def synthetic_text(n_streams: int, seed: int):
@@ -331,7 +334,7 @@ def run_gpu(args):
             # traffic: dram__bytes_read+write per launch from the committed `ncu --set full` capture of the decode GEMMs
             # (profiles/r01c_*: 68.8 MB over the 17 GEMMs of one iteration, cold cache) -- 1.09x the algorithmic bytes
             roof = {"kernel": name, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                    "frac": ach / peaks["hbm_gbs"], "traffic": 4.05e6 if name == "tc_gemm_swap" else None,
+                    "frac": ach / peaks["hbm_gbs"], "traffic": CLUSTER_TRAFFIC if name == "cluster_decode" else 4.05e6 if name == "tc_gemm_swap" else None,
                     "algorithmic_bytes_per_launch": r["bytes"] / max(1, r["launches"])}
         roof.update({"launches_per_step": r["launches"], "avg_launch_us": 1e3 * r["ms"] / max(1, r["launches"]),
                      "share_of_step": r["ms"] / total_ms, "peak_source": peaks["source"] + " (MEASURED_PEAKS.json)"})

@@ -49,16 +49,17 @@ constexpr int CD_VR = CD_V / CD_CLUSTER;       // 256
 constexpr int CD_MAX_LAYERS = 8;
 constexpr int CD_STAGES = 8;
 constexpr int CD_SLOT = 16384;                 // bytes per ring slot (one 128-row x 64-column tile)
-constexpr int CD_THREADS = 352;                // warp 0 producer, warps 1-2 MMA issuers, warps 3..10 workers
-constexpr int CD_WORKER0 = 96;                 // first worker thread
+constexpr int CD_NI = 3;                       // MMA issuer warps
+constexpr int CD_THREADS = 384;                // warp 0 producer, warps 1-3 MMA issuers, warps 4..11 workers
+constexpr int CD_WORKER0 = 128;                // first worker thread
 constexpr int CD_WORKERS = 256;
 constexpr int CD_ABLK = CD_NB * 128;           // one 64-wide k-block of an activation operand (16 rows x 128 B)
 // Weight stream items (one bulk copy + one ring slot each, <= 16 KB so that 8 are in flight).  Per layer:
-//   qkv  : 12 x [128 rows x 64 k] (rows 0..127), then the 16-row tail as [8 k-blocks x 2 KB] + [4 k-blocks x 2 KB]
+//   qkv  : 12 x [128 rows x 64 k] (rows 0..127), then the 16-row tail as 3 x [4 k-blocks x 2 KB]
 //   proj : 6 x [2 k-blocks x 48 rows]
 //   fc   : 12 x [128 rows x 64 k], then the 64-row tail as 6 x [2 k-blocks x 8 KB]
 //   proj2: 18 x [128 rows x 64 k]  (row tile m = s / 3, k-block s % 3 of this CTA's k-slice)
-// then lm_head: 24 x [128 rows x 64 k] (k-block major; item j = row tile (j ^ (j >> 1)) & 1)
+// then lm_head: 24 x [128 rows x 64 k] (k-block major; item j = row tile j & 1)
 constexpr int CD_TILE = 16384;
 constexpr int CD_QT = (CD_QR - 128) * 128;     // one k-block of the qkv tail (16 rows)
 constexpr int CD_PT = CD_XR * 128;             // one k-block of proj (48 rows)
@@ -67,11 +68,11 @@ constexpr long long CD_LAYER_BYTES = (long long)CD_QR * CD_C * 2 + (long long)CD
                                      (long long)CD_C * CD_FR * 2;
 constexpr long long CD_LM_BYTES = (long long)CD_VR * CD_C * 2;
 // TMEM accumulator columns
-// Two copies of every accumulator, 128 columns apart, one per MMA issuer warp: the issuers take the ring items
-// alternately (even / odd ring position), each accumulating into its own copy, and the epilogue adds the two.  With
+// Three copies of every accumulator, 128 columns apart, one per MMA issuer warp: issuer w takes the ring items at
+// positions = w (mod 3), accumulating into its own copy, and the epilogue adds the three.  With
 // N = 16 a GEMM phase is bound by the issuing warp's serial per-item latency (barrier poll, fence, 4 MMAs, commit:
 // ~300 cycles per 16 KB item, measured; M = 64 instead of 128 changed it by only 13 %), not by the tensor pipe.
-constexpr int CD_TM_QKV = 0, CD_TM_PROJ = 32, CD_TM_FC = 96, CD_TM_PROJ2 = 0, CD_TM_LM = 96, CD_TM_BANK = 128, CD_TM_COLS = 256;
+constexpr int CD_TM_QKV = 0, CD_TM_PROJ = 32, CD_TM_FC = 96, CD_TM_PROJ2 = 0, CD_TM_LM = 96, CD_TM_BANK = 128, CD_TM_COLS = 512;
 // shared-memory carve (offsets from the 1024-aligned base)
 constexpr int CD_OFF_RING = 0;
 constexpr int CD_OFF_A1 = CD_OFF_RING + CD_STAGES * CD_SLOT;          // [12 k-blocks][16 x 128 B]: LN(x) / y operand
@@ -152,20 +153,30 @@ __device__ __noinline__ void cd_spin_cluster(uint32_t bar, uint32_t parity) {
     if (clock64() - t0 > 4000000000LL) __trap();
   }
 }
-__device__ __forceinline__ void cd_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
-               "r"(bytes), "r"(bar)
+__device__ __forceinline__ void cd_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar), "l"(policy)
                : "memory");
+}
+__device__ __forceinline__ uint64_t cd_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t cd_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
 }
 __device__ __forceinline__ void cd_workers_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 // generic-proxy stores into shared memory (own CTA / a peer's) before the tensor core (async proxy) reads them
 __device__ __forceinline__ void cd_proxy_fence_cta() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void cd_proxy_fence_cluster() { asm volatile("fence.proxy.async.shared::cluster;" ::: "memory"); }
-// 32 lanes x 8 consecutive fp32 columns of the two accumulator copies, summed
+// 32 lanes x 8 consecutive fp32 columns of the three accumulator copies, summed
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
-  uint32_t r[2][8];
+  uint32_t r[CD_NI][8];
 #pragma unroll
-  for (int j = 0; j < 2; ++j)
+  for (int j = 0; j < CD_NI; ++j)
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=r"(r[j][0]), "=r"(r[j][1]), "=r"(r[j][2]), "=r"(r[j][3]), "=r"(r[j][4]), "=r"(r[j][5]), "=r"(r[j][6]), "=r"(r[j][7])
                  : "r"(taddr + (uint32_t)(128 * j))
@@ -173,7 +184,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 8; ++i)
-    v[i] = __uint_as_float(r[0][i]) + __uint_as_float(r[1][i]);
+    v[i] = (__uint_as_float(r[0][i]) + __uint_as_float(r[1][i])) + __uint_as_float(r[2][i]);
 }
 __device__ __forceinline__ uint4 cd_pack8(const float* f) {
   uint4 u;
@@ -207,6 +218,13 @@ __device__ __forceinline__ void cd_unpack8_h(uint4 u, float* f) {
 // byte offset of the 16-byte chunk holding elements [k, k+8) of session row n inside a K-major SW128 activation operand
 __device__ __forceinline__ uint32_t cd_act_chunk(int n, int k) {
   return (uint32_t)((k >> 6) * CD_ABLK + n * 128 + ((((k & 63) >> 3) ^ (n & 7)) << 4));
+}
+// streaming 16-byte load of the KV cache: weak (the rows were written iterations ago, with cluster-scope acquires in
+// between, which also drop L1), no L1 allocation (no reuse)
+__device__ __forceinline__ uint4 cd_ld_stream(const bf16* p) {
+  uint4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
 }
 // order-preserving float -> uint key (argmax through redux.sync)
 __device__ __forceinline__ uint32_t cd_fkey(float v) {
@@ -242,28 +260,28 @@ __device__ __forceinline__ uint32_t cd_stage_wait(uint32_t sbase, uint32_t bars,
   return sbase + CD_OFF_RING + (gi % CD_STAGES) * CD_SLOT;
 }
 // `128 + tail`-row weight slice against the K = 768 operand `act`: 12 full tiles into `d`, then the tail rows
-// (tail_bytes per k-block, `per` k-blocks per item) into d + 16.  This warp takes the items at ring positions of parity
-// `par` (d already points at its accumulator copy).  Returns the advanced ring position.
+// (tail_bytes per k-block, `per` k-blocks per item) into d + 16.  This warp takes the items at ring positions = par
+// (mod 3) (d already points at its accumulator copy).  Returns the advanced ring position.
 __device__ __forceinline__ unsigned cd_mma_rowsplit(uint32_t sbase, uint32_t bars, uint32_t idesc, unsigned gi, unsigned par, uint32_t act,
                                                     uint32_t d, int tail_bytes, int per) {
 #pragma unroll 1
   for (int kb = 0; kb < CD_C / 64; ++kb, ++gi) {
-    if ((gi & 1u) != par) continue;
+    if (gi % CD_NI != par) continue;
     const uint32_t a = cd_stage_wait(sbase, bars, gi);
     if (cd_elect()) {
-      cd_kblock(d, a, act + kb * CD_ABLK, idesc, kb >= 2 ? 1u : 0u);   // each warp's first item of the tile starts its copy
+      cd_kblock(d, a, act + kb * CD_ABLK, idesc, kb >= CD_NI ? 1u : 0u);   // each warp's first item of the tile starts its copy
       umma_commit(cd_bar_empty(bars, gi % CD_STAGES));
     }
     __syncwarp();
   }
 #pragma unroll 1
   for (int kb = 0, it = 0; kb < CD_C / 64; kb += per, ++it, ++gi) {
-    if ((gi & 1u) != par) continue;
+    if (gi % CD_NI != par) continue;
     const uint32_t a = cd_stage_wait(sbase, bars, gi);
     if (cd_elect()) {
 #pragma unroll 1
       for (int kk = 0; kk < per && kb + kk < CD_C / 64; ++kk)
-        cd_kblock(d + CD_NB, a + kk * tail_bytes, act + (kb + kk) * CD_ABLK, idesc, (it >= 2 || kk) ? 1u : 0u);
+        cd_kblock(d + CD_NB, a + kk * tail_bytes, act + (kb + kk) * CD_ABLK, idesc, (it >= CD_NI || kk) ? 1u : 0u);
       umma_commit(cd_bar_empty(bars, gi % CD_STAGES));
     }
     __syncwarp();
@@ -275,148 +293,143 @@ __device__ __forceinline__ unsigned cd_mma_rowsplit(uint32_t sbase, uint32_t bar
 
 // ---- attention of one (session, head) by one warp: src/model.py:68-98, one query row against [cache ; new row].
 // q / k / v of the new token come from shared memory (fp32), the cache from the paged pool (layout of
-// decode_attention_kernel).  4 token groups x 8 lanes (12 dims each); a batch = 4 tokens per group whose K / V loads are
-// issued one batch ahead; ONE online-softmax rescale per batch.  Output row -> `yst` (bf16, 96 values).
-// Requirements checked on the host: page_tokens = 1 << page_shift, at most 64 pages per session (page table in
-// registers), every plane of the pool addressable with 32-bit element offsets.
-__device__ __noinline__ void cd_attention_warp(bf16* kv, const int* pt, int page_shift, long long pool_pages, int layer, int T, int h,
-                                               const float* qkv, bf16* yst) {
-  constexpr int HD = CD_HD, DPL = HD / 8, NV = DPL / 4, UN = 4;
+// decode_attention_kernel: [layer][k|v][page][head][16 tokens][96] bf16, i.e. one page of one head = 3 KB contiguous).
+// Every global load is a fully coalesced 512-byte warp access (the L1 request rate, not latency or bandwidth, is what
+// bounded the versions that read one row per lane or 8 bytes per lane: measured 0.13-0.18 us per cached token).
+//   scores : a block = 32 tokens = 2 pages = 12 warp loads; lane i of load k holds chunk 32k + i of the block (token
+//            (32k + i) / 12, dims 8 ((8k + i) % 12) ..+8): its partial dot product goes to a per-warp scratch row, and
+//            lane t then adds the 12 partials of token base + t.  A lane only ever meets 3 of the 12 q chunks (registers).
+//            One warp max / sum per 32 tokens (online softmax).
+//   P V    : lanes 0-11 / 12-23 = the twelve 16-byte chunks of the V rows of tokens 2j / 2j+1; 8 output dims per lane,
+//            the probability arrives by shuffle; the two token halves are merged once at the end.
+// The V loads of block b and the K loads of block b+1 are in flight while block b is computed.
+// Returns (lanes 0-11 and, duplicated, 12-23) chunk c = lane % 12 of the bf16 output row: y[8c .. 8c+8).
+// Requirements checked on the host: 16 tokens per page, at most 64 pages per session (page table in registers), every
+// plane of the pool addressable with 32-bit element offsets.
+__device__ __noinline__ uint4 cd_attention_warp(bf16* kv, const int* pt, long long pool_pages, int layer, int T, int h, const float* qkv,
+                                                float* scratch) {
+  constexpr int HD = CD_HD, NC = HD / 8;   // 12 chunks of 8 dims
+  constexpr uint32_t head_stride = 16 * HD, page_stride = CD_H * head_stride;
   const int lane = threadIdx.x & 31;
-  const int g = lane >> 3, sub = lane & 7;
-  float q[DPL], kn[DPL], vn[DPL];
-#pragma unroll
-  for (int i = 0; i < DPL; i += 4) {
-    const float4 a = *reinterpret_cast<const float4*>(qkv + sub * DPL + i);
-    const float4 k4 = *reinterpret_cast<const float4*>(qkv + HD + sub * DPL + i);
-    const float4 v4 = *reinterpret_cast<const float4*>(qkv + 2 * HD + sub * DPL + i);
-    const float scale = 0.10206207261596577f;   // 96^-0.5
-    q[i] = a.x * scale; q[i + 1] = a.y * scale; q[i + 2] = a.z * scale; q[i + 3] = a.w * scale;
-    kn[i] = round_to<bf16>(k4.x); kn[i + 1] = round_to<bf16>(k4.y); kn[i + 2] = round_to<bf16>(k4.z); kn[i + 3] = round_to<bf16>(k4.w);
-    vn[i] = round_to<bf16>(v4.x); vn[i + 1] = round_to<bf16>(v4.y); vn[i + 2] = round_to<bf16>(v4.z); vn[i + 3] = round_to<bf16>(v4.w);
-  }
-  const uint32_t page_mask = (1u << page_shift) - 1u;
-  const uint32_t head_stride = (uint32_t)HD << page_shift;
-  const uint32_t page_stride = CD_H * head_stride;
+  const int gsel = (lane >= NC && lane < 2 * NC) ? 1 : 0, cc = lane % NC;
   const size_t plane = (size_t)pool_pages * page_stride;
-  bf16* const kbase = kv + (size_t)(layer * 2) * plane + h * head_stride + sub * DPL;
-  bf16* const vbase = kbase + plane;
-  // the page table lives in registers (lane i: entries i and i + 32): token -> page is a shuffle
-  const int n_pages = (T >> page_shift) + 1;
+  const bf16* const kbase = kv + (size_t)(layer * 2) * plane + h * head_stride + 8 * lane;
+  const bf16* const vbase = kv + (size_t)(layer * 2 + 1) * plane + h * head_stride + 8 * cc;
+  const int n_pages = (T >> 4) + 1;
   const int pt0 = (lane < n_pages) ? __ldg(pt + lane) : 0, pt1 = (lane + 32 < n_pages) ? __ldg(pt + lane + 32) : 0;
-  auto token_off = [&](int tk) -> uint32_t {   // every lane calls (shuffles); tokens may differ per lane
-    const int pidx = tk >> page_shift;
+  auto page_at = [&](int pidx) -> uint32_t {   // warp-uniform argument
     const int a = __shfl_sync(0xffffffffu, pt0, pidx & 31), c = __shfl_sync(0xffffffffu, pt1, pidx & 31);
-    return (uint32_t)((pidx & 32) ? c : a) * page_stride + ((uint32_t)tk & page_mask) * HD;
+    return (uint32_t)((pidx & 32) ? c : a);
   };
-  {   // append the new token (O(1); the reference torch.cat's the whole cache, src/model.py:74-77)
-    const uint32_t o = token_off(T);
-    if (g == 0) {
-#pragma unroll
-      for (int i = 0; i < DPL; i += 4) {
-        store4(kbase + o + i, make_float4(kn[i], kn[i + 1], kn[i + 2], kn[i + 3]));
-        store4(vbase + o + i, make_float4(vn[i], vn[i + 1], vn[i + 2], vn[i + 3]));
-      }
+  // new token: bf16-rounded like every cached row; lanes 0-11 append chunk cc of k and v (O(1): the reference
+  // torch.cat's the whole cache, src/model.py:74-77)
+  uint4 kn, vn;
+  {
+    const float4 k0 = *reinterpret_cast<const float4*>(qkv + HD + 8 * cc), k1 = *reinterpret_cast<const float4*>(qkv + HD + 8 * cc + 4);
+    const float4 v0 = *reinterpret_cast<const float4*>(qkv + 2 * HD + 8 * cc), v1 = *reinterpret_cast<const float4*>(qkv + 2 * HD + 8 * cc + 4);
+    const float kf[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w}, vf[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    kn = cd_pack8(kf);
+    vn = cd_pack8(vf);
+    const uint32_t o = page_at(T >> 4) * page_stride + (uint32_t)(T & 15) * HD;
+    if (lane < NC) {
+      *reinterpret_cast<uint4*>(const_cast<bf16*>(kbase) - 8 * lane + o + 8 * cc) = kn;
+      *reinterpret_cast<uint4*>(const_cast<bf16*>(vbase) + o) = vn;
     }
   }
-  float m = -INFINITY, l = 0.f, acc[DPL];
+  // the three q chunks this lane meets: (lane + {0, 8, 4}) % 12 for loads k % 3 = 0, 1, 2
+  float q3[3][8];
 #pragma unroll
-  for (int i = 0; i < DPL; ++i) acc[i] = 0.f;
-  uint2 kA[UN][NV], vA[UN][NV], kB[UN][NV], vB[UN][NV];
-  auto issue = [&](int base, uint2 (&kr)[UN][NV], uint2 (&vr)[UN][NV]) {
+  for (int r = 0; r < 3; ++r) {
+    const int c = (lane + ((8 * r) % NC)) % NC;
+    const float4 a = *reinterpret_cast<const float4*>(qkv + 8 * c), b = *reinterpret_cast<const float4*>(qkv + 8 * c + 4);
+    q3[r][0] = a.x; q3[r][1] = a.y; q3[r][2] = a.z; q3[r][3] = a.w; q3[r][4] = b.x; q3[r][5] = b.y; q3[r][6] = b.z; q3[r][7] = b.w;
+  }
+  const float scale = 0.10206207261596577f;   // 96^-0.5
+  float m = -INFINITY, l = 0.f, acc[8];
 #pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      const uint32_t o = token_off(max(min(base + 4 * u + g, T - 1), 0));   // clamped: always a valid, written token (T > 0)
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  uint4 kr[NC], vr[16];
+  uint32_t pg0 = page_at(0) * page_stride, pg1 = page_at(1) * page_stride;   // pages of the block (entry 1 may be unallocated = 0)
 #pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        kr[u][i] = __ldcg(reinterpret_cast<const uint2*>(kbase + o) + i);
-        vr[u][i] = __ldcg(reinterpret_cast<const uint2*>(vbase + o) + i);
-      }
-    }
-  };
-  issue(0, kA, vA);   // unconditional (no divergent shuffles): with T == 0 the values are never consumed
+  for (int k = 0; k < NC; ++k) kr[k] = cd_ld_stream(kbase + (k < 6 ? pg0 : pg1) + 256 * (k % 6));
 #pragma unroll 1
-  for (int base = 0; base < T; base += 4 * UN) {
-    issue(base + 4 * UN, kB, vB);   // past the end: clamped to token T - 1, never consumed
-    float d[UN];
+  for (int base = 0; base < T; base += 32) {
 #pragma unroll
-    for (int u = 0; u < UN; ++u) {
-      float s = 0.f;
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        float k0, k1, k2, k3;
-        cd_unpack2(kA[u][i].x, k0, k1);
-        cd_unpack2(kA[u][i].y, k2, k3);
-        s = fmaf(q[4 * i], k0, s); s = fmaf(q[4 * i + 1], k1, s); s = fmaf(q[4 * i + 2], k2, s); s = fmaf(q[4 * i + 3], k3, s);
-      }
-      s += __shfl_xor_sync(0xffffffffu, s, 4);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      d[u] = (base + 4 * u + g < T) ? s : -INFINITY;
+    for (int j = 0; j < 16; ++j) {   // V rows of tokens base + 2j (+1), clamped to a written token
+      const int tk = min(2 * j + gsel, T - 1 - base);
+      vr[j] = cd_ld_stream(vbase + ((tk & 16) ? pg1 : pg0) + (uint32_t)(tk & 15) * HD);   // lanes 24-31 repeat lanes 0-7 (same sectors)
     }
-    const float mn = fmaxf(fmaxf(fmaxf(d[0], d[1]), fmaxf(d[2], d[3])), m);
-    const float mref = (mn == -INFINITY) ? 0.f : mn;   // a group with no token yet: every exp below is exp(-inf) = 0
-    const float corr = __expf(m - mref);
-    float pr[UN];
 #pragma unroll
-    for (int u = 0; u < UN; ++u) pr[u] = __expf(d[u] - mref);
-    l = l * corr + ((pr[0] + pr[1]) + (pr[2] + pr[3]));
+    for (int k = 0; k < NC; ++k) {
+      float f[8], sc = 0.f;
+      cd_unpack8(kr[k], f);
 #pragma unroll
-    for (int i = 0; i < DPL; ++i) acc[i] *= corr;
-#pragma unroll
-    for (int u = 0; u < UN; ++u) {
-#pragma unroll
-      for (int i = 0; i < NV; ++i) {
-        float v0, v1, v2, v3;
-        cd_unpack2(vA[u][i].x, v0, v1);
-        cd_unpack2(vA[u][i].y, v2, v3);
-        acc[4 * i] = fmaf(pr[u], v0, acc[4 * i]); acc[4 * i + 1] = fmaf(pr[u], v1, acc[4 * i + 1]);
-        acc[4 * i + 2] = fmaf(pr[u], v2, acc[4 * i + 2]); acc[4 * i + 3] = fmaf(pr[u], v3, acc[4 * i + 3]);
-      }
+      for (int i = 0; i < 8; ++i) sc = fmaf(q3[k % 3][i], f[i], sc);
+      scratch[32 * k + lane] = sc;
     }
+    __syncwarp();
+    float sc;
+    {
+      const float4 a = *reinterpret_cast<const float4*>(scratch + NC * lane), b = *reinterpret_cast<const float4*>(scratch + NC * lane + 4),
+                   c = *reinterpret_cast<const float4*>(scratch + NC * lane + 8);
+      sc = ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w)) + ((c.x + c.y) + (c.z + c.w));
+    }
+    __syncwarp();
+    const bool valid = base + lane < T;
+    sc = valid ? sc * scale : -INFINITY;   // select, not arithmetic: rows past T may hold anything
+    const float mn = fmaxf(m, warp_max(sc));   // finite: token `base` is valid
+    const float corr = __expf(m - mn), pr = valid ? __expf(sc - mn) : 0.f;
+    l = l * corr + warp_sum(pr);
     m = mn;
+    // K pages of the next block (past the end: page-table entries are 0 = a mapped page, never consumed)
+    pg0 = page_at((base >> 4) + 2) * page_stride;
+    pg1 = page_at((base >> 4) + 3) * page_stride;
 #pragma unroll
-    for (int u = 0; u < UN; ++u) {
+    for (int k = 0; k < NC; ++k) kr[k] = cd_ld_stream(kbase + (k < 6 ? pg0 : pg1) + 256 * (k % 6));
 #pragma unroll
-      for (int i = 0; i < NV; ++i) { kA[u][i] = kB[u][i]; vA[u][i] = vB[u][i]; }
+    for (int i = 0; i < 8; ++i) acc[i] *= corr;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float pj = __shfl_sync(0xffffffffu, pr, 2 * j + gsel);
+      float f[8];
+      cd_unpack8(vr[j], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(pj, f[i], acc[i]);
     }
   }
-  {   // the new token: taken by group T % 4 (the group that would own index T)
-    float s = 0.f;
+  {   // the new token (every lane computes its score; only the first token half adds its value row)
+    float sc = 0.f;
 #pragma unroll
-    for (int i = 0; i < DPL; ++i) s = fmaf(q[i], kn[i], s);
-    s += __shfl_xor_sync(0xffffffffu, s, 4);
-    s += __shfl_xor_sync(0xffffffffu, s, 2);
-    s += __shfl_xor_sync(0xffffffffu, s, 1);
-    const float dn = (g == (T & 3)) ? s : -INFINITY;
-    const float mn = fmaxf(m, dn);
-    const float mref = (mn == -INFINITY) ? 0.f : mn;
-    const float corr = __expf(m - mref), pn = __expf(dn - mref);
+    for (int c = 0; c < NC; ++c) {
+      const float4 q0 = *reinterpret_cast<const float4*>(qkv + 8 * c), q1 = *reinterpret_cast<const float4*>(qkv + 8 * c + 4);
+      const uint4 kc = make_uint4(__shfl_sync(0xffffffffu, kn.x, c), __shfl_sync(0xffffffffu, kn.y, c), __shfl_sync(0xffffffffu, kn.z, c),
+                                  __shfl_sync(0xffffffffu, kn.w, c));
+      float f[8];
+      cd_unpack8(kc, f);
+      sc = fmaf(q0.x, f[0], sc); sc = fmaf(q0.y, f[1], sc); sc = fmaf(q0.z, f[2], sc); sc = fmaf(q0.w, f[3], sc);
+      sc = fmaf(q1.x, f[4], sc); sc = fmaf(q1.y, f[5], sc); sc = fmaf(q1.z, f[6], sc); sc = fmaf(q1.w, f[7], sc);
+    }
+    sc *= scale;
+    const float mn = fmaxf(m, sc);
+    const float corr = __expf(m - mn), pn = __expf(sc - mn);
     l = l * corr + pn;
+    float f[8];
+    cd_unpack8(vn, f);
+    const float pv = gsel ? 0.f : pn;
 #pragma unroll
-    for (int i = 0; i < DPL; ++i) acc[i] = fmaf(pn, vn[i], acc[i] * corr);
-    m = mn;
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(pv, f[i], acc[i] * corr);
   }
-  // merge the 4 groups (lanes with equal `sub` hold the same dims)
+  // merge the two token halves (lane c += lane c + 12), normalise, pack; lanes 12-23 get a copy
+  const float inv = 1.0f / l;
+  float o[8];
 #pragma unroll
-  for (int o = 8; o <= 16; o <<= 1) {
-    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), l2 = __shfl_xor_sync(0xffffffffu, l, o);
-    const float M = fmaxf(m, m2);
-    const float mref = (M == -INFINITY) ? 0.f : M;
-    const float w1 = __expf(m - mref), w2 = __expf(m2 - mref);
-    l = l * w1 + l2 * w2;
-#pragma unroll
-    for (int i = 0; i < DPL; ++i) {
-      const float a2 = __shfl_xor_sync(0xffffffffu, acc[i], o);
-      acc[i] = acc[i] * w1 + a2 * w2;
-    }
-    m = M;
-  }
-  if (g == 0) {
-    const float inv = 1.0f / l;
-#pragma unroll
-    for (int i = 0; i < DPL; i += 4) store4(yst + sub * DPL + i, make_float4(acc[i] * inv, acc[i + 1] * inv, acc[i + 2] * inv, acc[i + 3] * inv));
-  }
+  for (int i = 0; i < 8; ++i) o[i] = (acc[i] + __shfl_down_sync(0xffffffffu, acc[i], NC)) * inv;
+  uint4 out = cd_pack8(o);
+  out.x = __shfl_sync(0xffffffffu, out.x, cc);
+  out.y = __shfl_sync(0xffffffffu, out.y, cc);
+  out.z = __shfl_sync(0xffffffffu, out.z, cc);
+  out.w = __shfl_sync(0xffffffffu, out.w, cc);
+  return out;
 }
 
 #define CD_T() do { if (trp) *trp++ = clock64(); } while (0)
@@ -442,7 +455,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
       mbar_init(cd_bar_empty(bars, s), 1);
     }
     mbar_init(cd_bar_act(bars), 1);
-    mbar_init(cd_bar_tmem(bars), 2);   // one commit per MMA issuer warp
+    mbar_init(cd_bar_tmem(bars), CD_NI);   // one commit per MMA issuer warp
     mbar_init(cd_bar_x(bars, 0), CD_CLUSTER);
     mbar_init(cd_bar_x(bars, 1), CD_CLUSTER);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -451,7 +464,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
     __syncwarp();
     tmem_alloc(smem_u32(&tmem_base_sh), CD_TM_COLS);
   }
-  if (warp >= 3) {   // session scalars of this cluster
+  if (warp > CD_NI) {   // session scalars of this cluster
     const int wt = tid - CD_WORKER0;
     int* sm_slot = reinterpret_cast<int*>(sgen + CD_OFF_SMALL);
     if (wt < CD_NB) {
@@ -471,9 +484,11 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
     // ------------------------------------------------------------------ weight producer: free-running bulk copies
     {
       // (items, bytes) runs of the stream: 7 per layer, then lm_head
-      const int run_count[8] = {12, 1, 1, 6, 12, 6, 18, 24};
-      const int run_bytes[8] = {CD_TILE, 8 * CD_QT, 4 * CD_QT, 2 * CD_PT, CD_TILE, 2 * CD_FT, CD_TILE, CD_TILE};
+      const int run_count[8] = {12, 3, 0, 6, 12, 6, 18, 24};
+      const int run_bytes[8] = {CD_TILE, 4 * CD_QT, 0, 2 * CD_PT, CD_TILE, 2 * CD_FT, CD_TILE, CD_TILE};
       const uint8_t* const src0 = P.wstream + (size_t)rank * (size_t)P.stream_bytes;
+      // the stream is re-read every iteration by every cluster: keep it in L2 (measured: evict_first is 3 % slower)
+      const uint64_t policy = (P.dbg & 4) ? cd_policy_evict_first() : cd_policy_evict_last();
       unsigned gi = 0;
 #pragma unroll 1
       for (int iter = 0; iter < n_iters; ++iter) {
@@ -490,7 +505,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
               cd_spin(cd_bar_empty(bars, s), ((gi / CD_STAGES) & 1u) ^ 1u);
               if (cd_elect()) {
                 mbar_expect_tx(cd_bar_full(bars, s), bytes);
-                cd_bulk_g2s(sbase + CD_OFF_RING + s * CD_SLOT, src, bytes, cd_bar_full(bars, s));
+                cd_bulk_g2s(sbase + CD_OFF_RING + s * CD_SLOT, src, bytes, cd_bar_full(bars, s), policy);
               }
               __syncwarp();
               src += bytes;
@@ -500,10 +515,10 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
         }
       }
     }
-  } else if (warp <= 2) {
-    // ------------------------------------------------------------------ MMA issuers (two warps, alternate ring items)
+  } else if (warp <= CD_NI) {
+    // ------------------------------------------------------------------ MMA issuers (three warps, ring items round-robin)
     {
-      const unsigned par = (unsigned)(warp - 1);
+      const unsigned par = (unsigned)(warp - 1);   // this issuer takes ring positions = par (mod CD_NI)
       const uint32_t idesc = umma_idesc_bf16((P.dbg & 1) ? 64 : 128, CD_NB);
       const uint32_t a1 = sbase + CD_OFF_A1, a2 = sbase + CD_OFF_A2, ay = sbase + CD_OFF_AY;
       const uint32_t tm = tmem + CD_TM_BANK * par;   // this warp's accumulator copy
@@ -517,11 +532,11 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
           tc_fence_after();
           if (sl == 2 * n_layer) {
 #pragma unroll 1
-            for (int j = 0; j < 24; ++j, ++gi) {   // lm_head: k-block j / 2, row tile (j ^ (j >> 1)) & 1 (tiles alternate issuers)
-              if ((gi & 1u) != par) continue;
+            for (int j = 0; j < 24; ++j, ++gi) {   // lm_head: k-block j / 2, row tile j & 1 (a tile's items cycle through the issuers)
+              if (gi % CD_NI != par) continue;
               const uint32_t a = cd_stage_wait(sbase, bars, gi);
               if (cd_elect()) {
-                cd_kblock(tm + CD_TM_LM + CD_NB * ((j ^ (j >> 1)) & 1), a, a1 + (j >> 1) * CD_ABLK, idesc, j >= 4 ? 1u : 0u);
+                cd_kblock(tm + CD_TM_LM + CD_NB * (j & 1), a, a1 + (j >> 1) * CD_ABLK, idesc, j >= 2 * CD_NI ? 1u : 0u);
                 umma_commit(cd_bar_empty(bars, gi % CD_STAGES));
               }
               __syncwarp();
@@ -529,16 +544,16 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
             if (cd_elect()) umma_commit(cd_bar_tmem(bars));
             __syncwarp();
           } else if (!(sl & 1)) {
-            gi = cd_mma_rowsplit(sbase, bars, idesc, gi, par, a1, tm + CD_TM_QKV, CD_QT, 8);
+            gi = cd_mma_rowsplit(sbase, bars, idesc, gi, par, a1, tm + CD_TM_QKV, CD_QT, 4);
             cd_spin(cd_bar_act(bars), g & 1u);   // attention output operand ready
             g += 1;
             tc_fence_after();
 #pragma unroll 1
             for (int j = 0; j < 6; ++j, ++gi) {   // proj: 2 k-blocks of 48 rows per item
-              if ((gi & 1u) != par) continue;
+              if (gi % CD_NI != par) continue;
               const uint32_t a = cd_stage_wait(sbase, bars, gi);
               if (cd_elect()) {
-                cd_kblock(tm + CD_TM_PROJ, a, ay + (2 * j) * CD_ABLK, idesc, j >= 2 ? 1u : 0u);
+                cd_kblock(tm + CD_TM_PROJ, a, ay + (2 * j) * CD_ABLK, idesc, j >= CD_NI ? 1u : 0u);
                 cd_kblock(tm + CD_TM_PROJ, a + CD_PT, ay + (2 * j + 1) * CD_ABLK, idesc, 1u);
                 umma_commit(cd_bar_empty(bars, gi % CD_STAGES));
               }
@@ -553,11 +568,11 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
             tc_fence_after();
 #pragma unroll 1
             for (int s2 = 0; s2 < 18; ++s2, ++gi) {   // proj2: row tile m, k-block kb of this CTA's k-slice
-              if ((gi & 1u) != par) continue;
+              if (gi % CD_NI != par) continue;
               const int m = s2 / 3, kb = s2 - 3 * m;
               const uint32_t a = cd_stage_wait(sbase, bars, gi);
               if (cd_elect()) {
-                cd_kblock(tm + CD_TM_PROJ2 + CD_NB * m, a, a2 + kb * CD_ABLK, idesc, kb >= 2 ? 1u : 0u);
+                cd_kblock(tm + CD_TM_PROJ2 + CD_NB * m, a, a2 + kb * CD_ABLK, idesc, 0u);   // one k-block per issuer
                 umma_commit(cd_bar_empty(bars, gi % CD_STAGES));
               }
               __syncwarp();
@@ -723,22 +738,19 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
           // ================= attention: warp ww = session 8 * odd + ww of the group, head = rank / 2
           {
             const int n = 8 * odd + ww;
-            bf16* yst = reinterpret_cast<bf16*>(sgen + CD_OFF_YST) + ww * CD_HD;
-            if (n < nloc) {
+            uint4 val = make_uint4(0u, 0u, 0u, 0u);
+            if (n < nloc) {   // warp-uniform
               const int slot = sm_slot[n];
-              cd_attention_warp(P.kv, P.st.page_table + (size_t)slot * P.st.max_pages, P.page_shift, P.pool_pages, l, (P.dbg & 2) ? 0 : sm_t[n], head,
-                                qkvb + ww * 288, yst);
-            } else {
-              for (int i = lane; i < CD_HD / 2; i += 32) reinterpret_cast<uint32_t*>(yst)[i] = 0u;
+              // scratch: 384 floats per warp inside A1 (LN1(x) has been consumed by the qkv MMAs; the LN2 gather comes later)
+              val = cd_attention_warp(P.kv, P.st.page_table + (size_t)slot * P.st.max_pages, P.pool_pages, l, (P.dbg & 2) ? 0 : sm_t[n],
+                                      head, qkvb + ww * 288, reinterpret_cast<float*>(sgen + CD_OFF_A1) + ww * 384);
             }
-            __syncwarp();
-            // output row to every peer's y operand: 12 chunks x 16 peers, two peers per store instruction
-            const int ch = lane % 12, dsel = lane / 12;
-            if (dsel < 2) {
-              const uint4 val = *reinterpret_cast<const uint4*>(yst + 8 * ch);
+            // output row to every peer's y operand: lanes 0-11 / 12-23 hold the 12 chunks, 8 peers each
+            if (lane < 24) {
+              const int ch = lane % 12, d0 = (lane / 12) * 8;
               const uint32_t off = sbase + CD_OFF_AY + cd_act_chunk(n, CD_HD * head + 8 * ch);
 #pragma unroll 1
-              for (int d2 = 0; d2 < CD_CLUSTER; d2 += 2) cd_st_remote_v4(cd_mapa(off, (uint32_t)(d2 + dsel)), val);
+              for (int d2 = 0; d2 < 8; ++d2) cd_st_remote_v4(cd_mapa(off, (uint32_t)(d0 + d2)), val);
             }
           }
           CD_T();
@@ -960,8 +972,8 @@ inline long long cd_build_descs(const CdLayerW* layers, int n_layer, const float
         o += CD_TILE;
       }
     }
-    for (int j = 0; j < 24; ++j) {   // k-block j / 2, row tile (j ^ (j >> 1)) & 1: a tile's items alternate between the issuers
-      seg(lm_head, lnf_w, ld_lm, CD_VR * r + 128 * ((j ^ (j >> 1)) & 1), 128, 64 * (j >> 1), o, 0);
+    for (int j = 0; j < 24; ++j) {   // k-block j / 2, row tile j & 1
+      seg(lm_head, lnf_w, ld_lm, CD_VR * r + 128 * (j & 1), 128, 64 * (j >> 1), o, 0);
       o += CD_TILE;
     }
   }

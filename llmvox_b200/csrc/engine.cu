@@ -515,8 +515,10 @@ extern "C" int lvx_engine_create(const lvx_config* cfg, int device, lvx_engine**
     e->use_pdl = !(env3 && env3[0] == '1');
     const char* env2 = getenv("LLMVOX_B200_FUSED");
     e->use_fused = env2 && env2[0] == '1';
+    // cluster-resident decode kernel (cluster_decode.cuh): the default greedy bf16 path; LLMVOX_B200_CLUSTER=0 selects the
+    // kernel-per-op path (CUDA graphs + programmatic dependent launch) instead
     const char* env4 = getenv("LLMVOX_B200_CLUSTER");
-    e->use_cluster = env4 && env4[0] == '1';
+    e->use_cluster = !(env4 && env4[0] == '0');
     if (cudaStreamCreateWithFlags(&e->gstream, cudaStreamNonBlocking) != cudaSuccess) {
       set_error("could not create the engine's capture stream");
       s = LVX_ERR_CUDA;
@@ -1159,13 +1161,13 @@ static int cluster_init(lvx_engine* e) {
 
 static bool cluster_applicable(const lvx_engine* e, const SamplerArgs& sa) {
   const lvx_config& c = e->cfg;
-  return e->use_cluster && e->adt() == B16 && sa.greedy && !sa.forced && !sa.out_codes && !e->prof_on && c.n_embd == CD_C &&
+  return e->use_cluster && e->adt() == B16 && sa.greedy && !sa.forced && !sa.out_codes && c.n_embd == CD_C &&
          c.n_head == CD_H && c.vocab_size == CD_V && c.n_layer <= CD_MAX_LAYERS && c.text_dim + c.code_dim == CD_C && !c.bias &&
-         (c.kv_page_tokens & (c.kv_page_tokens - 1)) == 0 && e->max_pages <= 64 &&
+         c.kv_page_tokens == 16 && e->max_pages <= 64 &&
          (long long)e->pool_pages * c.kv_page_tokens * c.n_embd < (1LL << 31);
 }
 
-static int cluster_launch(lvx_engine* e, lvx_engine::Lane& ln, int n, int n_steps, cudaStream_t st) {
+static int cluster_launch(lvx_engine* e, lvx_engine::Lane& ln, const int32_t* h_slots, int n, int n_steps, cudaStream_t st) {
   LVX_TRY(cluster_init(e));
   const lvx_config& c = e->cfg;
   ClusterParams P;
@@ -1185,6 +1187,13 @@ static int cluster_launch(lvx_engine* e, lvx_engine::Lane& ln, int n, int n_step
   P.logits = ln.logits;
   P.trace = getenv("LLMVOX_B200_TRACE") ? ln.d_trace : nullptr;
   P.dbg = getenv("LLMVOX_B200_CD_DBG") ? atoi(getenv("LLMVOX_B200_CD_DBG")) : 0;
+  // algorithmic bytes of this launch: the bf16 GEMM weights once per iteration + KV read and append
+  double bytes = (double)n_steps * 2.0 * ((double)c.n_layer * 12.0 * CD_C * CD_C + (double)CD_C * CD_V);
+  for (int i = 0; i < n; ++i) {
+    const double t0 = e->h_len[h_slots[i]];
+    bytes += (double)c.n_layer * 2.0 * CD_C * 2.0 * ((double)n_steps * (t0 + 1.0) + 0.5 * n_steps * (n_steps - 1.0));
+  }
+  ProfScope prof_scope(e, "cluster_decode", st, 0.0, bytes);
   LVX_TRY(cluster_decode_launch(P, st));
   e->launches += 1;
   return LVX_OK;
@@ -1206,7 +1215,7 @@ extern "C" int lvx_decode_steps_lane(lvx_engine* e, int lane, const int32_t* h_s
   LVX_CHECK(!(sa.uniform && n_steps > 1), LVX_ERR_INVALID, "d_uniform supplies one draw per session: use n_steps == 1");
   const lvx_config& c = e->cfg;
   if (cluster_applicable(e, sa)) {
-    LVX_TRY(cluster_launch(e, ln, n, n_steps, st));
+    LVX_TRY(cluster_launch(e, ln, h_slots, n, n_steps, st));
   } else if (e->use_fused && e->adt() == B16 && sa.greedy && !e->prof_on && n <= 128 && c.n_layer <= FD_MAX_LAYERS && c.n_embd == 768 &&
       c.vocab_size % 4 == 0) {
     // one persistent launch runs all n_steps iterations (fused_decode.cuh)

@@ -101,7 +101,7 @@ struct ClusterParams {
   bf16* kv;
   int page_shift;     // KV page = 1 << page_shift tokens
   long long pool_pages;
-  float* logits;      // [n, V] fp32 or null: every iteration's logits (test hook / lvx_peek_logits)
+  float* logits;      // [n, V] fp32 or null: logits of the launch's last iteration (test hook / lvx_peek_logits)
   long long* trace;   // optional clock64 stamps of cluster 0 / rank 0, last iteration
   int dbg;            // timing experiments only (wrong results): bit 0 = M=64 MMAs, bit 1 = attention over an empty cache
 };
@@ -605,7 +605,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
       cd_workers_sync();
       const uint32_t bar = cd_bar_x(bars, xphase & 1u);
       if (wt < CD_CLUSTER) cd_mbar_arrive_remote(cd_mapa(bar, (uint32_t)wt));
-      cd_spin_cluster(bar, (xphase >> 1) & 1u);
+      cd_spin_cluster(bar, (xphase >> 1) & 1u);   // (a cta-scope acquire here is no faster and failed the parity test: measured)
       xphase += 1;
     };
     // the activation operand of the next GEMM is complete in this CTA's shared memory
@@ -831,7 +831,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
         const int row = CD_VR * rank + 32 * q + lane;
 #pragma unroll 1
         for (int i = 0; i < 8; ++i) {
-          if (P.logits && 8 * hh + i < nloc) {
+          if (P.logits && iter == n_iters - 1 && 8 * hh + i < nloc) {   // only the launch's last iteration is ever read back
             float* lg = P.logits + (size_t)(n0 + 8 * hh + i) * CD_V + row;
             lg[0] = v0[i];
             lg[128] = v1[i];

@@ -112,6 +112,13 @@ int lvx_decode_steps(lvx_engine* e, const int32_t* h_slots, int n, int n_steps, 
 int lvx_decode_steps_lane(lvx_engine* e, int lane, const int32_t* h_slots, int n, int n_steps, const lvx_sampling* s,
                           void* stream);
 
+/* Greedy bf16 decode path of lvx_decode_steps[_lane]: on != 0 (default) = the cluster-resident kernel (one 16-CTA
+ * cluster per 16 sessions runs whole iterations; at most 7 clusters in flight per engine), 0 = the kernel-per-op chain
+ * (CUDA graphs + programmatic dependent launch), which is the better choice for batches far above 112 sessions.  Both
+ * compute src/model.py:201-237 with the same numerics class; fp32 mode and sampled decoding always
+ * use the kernel-per-op chain.  Host-side flag: takes effect for the calls that follow. */
+int lvx_set_cluster_decode(lvx_engine* e, int on);
+
 /* Test hook: ONE step that also returns the logits (n x vocab fp32, device) and the picked codes (n,
  * device, may be NULL).  With d_forced_codes != NULL the code stored in the history (and therefore fed
  * back at the next step) is d_forced_codes[i] instead of the pick: teacher forcing. */

@@ -42,6 +42,7 @@ SYMBOLS = [
     ("lvx_feed_text", C.c_int, [_VP, _I32P, _I32P, _I32P, C.c_int, _VP]),
     ("lvx_decode_steps", C.c_int, [_VP, _I32P, C.c_int, C.c_int, C.POINTER(LvxSampling), _VP]),
     ("lvx_decode_steps_lane", C.c_int, [_VP, C.c_int, _I32P, C.c_int, C.c_int, C.POINTER(LvxSampling), _VP]),
+    ("lvx_set_cluster_decode", C.c_int, [_VP, C.c_int]),
     ("lvx_decode_step_logits", C.c_int, [_VP, _I32P, C.c_int, C.POINTER(LvxSampling), _VP, _VP, _VP, _VP]),
     ("lvx_peek_buffer", C.c_int, [_VP, C.c_int, C.c_int, _VP, C.c_int64]),
     ("lvx_peek_trace", C.c_int, [_VP, C.c_int, C.POINTER(C.c_int64), C.c_int]),

@@ -138,20 +138,45 @@ __device__ __forceinline__ bool cd_try_wait_cluster(uint32_t bar, uint32_t parit
       : "memory");
   return ok != 0;
 }
-// Bounded spins, ONE copy each (code size): a protocol bug ends in a trap, never in a hung GPU
+// Bounded spins, ONE copy each (code size): a protocol bug ends in a trap, never in a hung GPU.  Before the trap the
+// waiter leaves a record in host-mapped memory (cd_diag, optional): {barrier address, parity, block, thread}.
+__device__ unsigned long long* cd_diag = nullptr;
+__device__ __noinline__ void cd_timeout(uint32_t bar, uint32_t parity) {
+  if (cd_diag) {
+    const unsigned long long i = atomicAdd(cd_diag, 1ULL);
+    if (i < 60) {
+      cd_diag[1 + i] = ((unsigned long long)bar << 32) | ((unsigned long long)(parity & 1u) << 31) | ((unsigned long long)blockIdx.x << 12) |
+                       (unsigned long long)threadIdx.x;
+      __threadfence_system();
+    }
+    // give the other stuck waiters time to report too
+    const long long t1 = clock64();
+    while (clock64() - t1 < 200000000LL) {}
+  }
+  __trap();
+}
 __device__ __noinline__ void cd_spin(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
+    if (clock64() - t0 > 4000000000LL) cd_timeout(bar, parity);
   }
+}
+// the polling loops may release the lanes of a warp at different iterations: reconverge before anything .sync.aligned
+__device__ __forceinline__ void cd_wait(uint32_t bar, uint32_t parity) {
+  cd_spin(bar, parity);
+  __syncwarp();
 }
 __device__ __noinline__ void cd_spin_cluster(uint32_t bar, uint32_t parity) {
   if (cd_try_wait_cluster(bar, parity)) return;
   const long long t0 = clock64();
   while (!cd_try_wait_cluster(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) __trap();
+    if (clock64() - t0 > 4000000000LL) cd_timeout(bar, parity | 2u);
   }
+}
+__device__ __forceinline__ void cd_wait_cluster(uint32_t bar, uint32_t parity) {
+  cd_spin_cluster(bar, parity);
+  __syncwarp();
 }
 __device__ __forceinline__ void cd_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
@@ -255,7 +280,7 @@ __device__ __forceinline__ void cd_kblock(uint32_t d, uint32_t a, uint32_t b, ui
   for (int ks = 0; ks < 4; ++ks) umma_bf16(d, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, (acc || ks) ? 1u : 0u);
 }
 __device__ __forceinline__ uint32_t cd_stage_wait(uint32_t sbase, uint32_t bars, unsigned gi) {
-  cd_spin(cd_bar_full(bars, gi % CD_STAGES), (gi / CD_STAGES) & 1u);
+  cd_wait(cd_bar_full(bars, gi % CD_STAGES), (gi / CD_STAGES) & 1u);
   tc_fence_after();
   return sbase + CD_OFF_RING + (gi % CD_STAGES) * CD_SLOT;
 }
@@ -502,7 +527,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
 #pragma unroll 1
             for (int j = 0; j < run_count[e]; ++j) {
               const unsigned s = gi % CD_STAGES;
-              cd_spin(cd_bar_empty(bars, s), ((gi / CD_STAGES) & 1u) ^ 1u);
+              cd_wait(cd_bar_empty(bars, s), ((gi / CD_STAGES) & 1u) ^ 1u);
               if (cd_elect()) {
                 mbar_expect_tx(cd_bar_full(bars, s), bytes);
                 cd_bulk_g2s(sbase + CD_OFF_RING + s * CD_SLOT, src, bytes, cd_bar_full(bars, s), policy);
@@ -527,7 +552,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
       for (int iter = 0; iter < n_iters; ++iter) {
 #pragma unroll 1
         for (int sl = 0; sl <= 2 * n_layer; ++sl) {
-          cd_spin(cd_bar_act(bars), g & 1u);   // LN(x) operand ready
+          cd_wait(cd_bar_act(bars), g & 1u);   // LN(x) operand ready
           g += 1;
           tc_fence_after();
           if (sl == 2 * n_layer) {
@@ -545,7 +570,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
             __syncwarp();
           } else if (!(sl & 1)) {
             gi = cd_mma_rowsplit(sbase, bars, idesc, gi, par, a1, tm + CD_TM_QKV, CD_QT, 4);
-            cd_spin(cd_bar_act(bars), g & 1u);   // attention output operand ready
+            cd_wait(cd_bar_act(bars), g & 1u);   // attention output operand ready
             g += 1;
             tc_fence_after();
 #pragma unroll 1
@@ -563,7 +588,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
             __syncwarp();
           } else {
             gi = cd_mma_rowsplit(sbase, bars, idesc, gi, par, a1, tm + CD_TM_FC, CD_FT, 2);
-            cd_spin(cd_bar_act(bars), g & 1u);   // GELU(fc) slice ready
+            cd_wait(cd_bar_act(bars), g & 1u);   // GELU(fc) slice ready
             g += 1;
             tc_fence_after();
 #pragma unroll 1
@@ -605,7 +630,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
       cd_workers_sync();
       const uint32_t bar = cd_bar_x(bars, xphase & 1u);
       if (wt < CD_CLUSTER) cd_mbar_arrive_remote(cd_mapa(bar, (uint32_t)wt));
-      cd_spin_cluster(bar, (xphase >> 1) & 1u);   // (a cta-scope acquire here is no faster and failed the parity test: measured)
+      cd_wait_cluster(bar, (xphase >> 1) & 1u);   // (a cta-scope acquire here is no faster and failed the parity test: measured)
       xphase += 1;
     };
     // the activation operand of the next GEMM is complete in this CTA's shared memory
@@ -616,7 +641,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
       if (wt == 0) cd_mbar_arrive(cd_bar_act(bars));
     };
     auto wait_acc = [&]() {
-      cd_spin(cd_bar_tmem(bars), gcount & 1u);
+      cd_wait(cd_bar_tmem(bars), gcount & 1u);
       gcount += 1;
       tc_fence_after();
     };

@@ -20,6 +20,8 @@
 #include "tc_gemm.cuh"
 #include "fused_decode.cuh"
 #include "cluster_decode.cuh"
+
+#include <deque>
 #include "vocoder_kernels.cuh"
 
 namespace lvx {
@@ -230,6 +232,13 @@ struct lvx_engine {
   long long cd_stream_bytes = 0;
   float *cd_text_ss = nullptr, *cd_code_ss = nullptr;
   int cd_max_clusters = 0;
+  // launches that may still be running: never more clusters in flight than are co-resident (see cluster_launch)
+  struct CdInflight {
+    cudaEvent_t ev;
+    cudaStream_t st;
+    int clusters;
+  };
+  std::deque<CdInflight> cd_inflight;
 
   // ---- optional per-launch profiler (lvx_profile_enable)
   struct ProfRec {
@@ -558,6 +567,8 @@ extern "C" int lvx_engine_destroy(lvx_engine* e) {
     cudaEventDestroy(r.a);
     cudaEventDestroy(r.b);
   }
+  for (auto& f : e->cd_inflight) e->ev_pool.push_back(f.ev);
+  e->cd_inflight.clear();
   for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
   for (void* p : e->allocs) cudaFree(p);
   for (auto& kv : e->w)
@@ -1126,6 +1137,9 @@ static int fused_ctx(lvx_engine* e, lvx_engine::Lane& ln, int n, lvx_engine::Fus
   return LVX_OK;
 }
 
+static unsigned long long* g_cd_diag_host = nullptr;
+extern "C" const unsigned long long* lvx_cluster_diag(void) { return g_cd_diag_host; }
+
 // Cluster-resident decode kernel (cluster_decode.cuh): the per-rank weight streams and the table row norms, built once.
 static int cluster_init(lvx_engine* e) {
   if (e->cd_ready) return LVX_OK;
@@ -1155,6 +1169,15 @@ static int cluster_init(lvx_engine* e) {
   LAUNCHED(e);
   LVX_CUDA(cudaDeviceSynchronize());
   cudaFree(d_descs);
+  if (getenv("LLMVOX_B200_CD_DIAG")) {   // timeout records of the bounded spins, readable after the context died
+    unsigned long long* h = nullptr;
+    LVX_CUDA(cudaHostAlloc(&h, 64 * sizeof(unsigned long long), cudaHostAllocMapped));
+    memset(h, 0, 64 * sizeof(unsigned long long));
+    unsigned long long* d = nullptr;
+    LVX_CUDA(cudaHostGetDevicePointer(&d, h, 0));
+    LVX_CUDA(cudaMemcpyToSymbol(cd_diag, &d, sizeof(d)));
+    g_cd_diag_host = h;
+  }
   e->cd_ready = true;
   return LVX_OK;
 }
@@ -1167,13 +1190,22 @@ static bool cluster_applicable(const lvx_engine* e, const SamplerArgs& sa) {
          (long long)e->pool_pages * c.kv_page_tokens * c.n_embd < (1LL << 31);
 }
 
+// One launch = at most `cap` clusters, and never more than `cap` clusters in flight across the engine's streams: a launch
+// that would exceed it waits (cudaStreamWaitEvent, no host blocking) for the oldest launches on other streams.  History: an
+// earlier build died in a bounded spin (dead wait, 1 in ~10-40 launches) as soon as 9+ clusters were in flight, i.e. when
+// pending clusters start while others drain; never at <= 8.  The spin-waits did not reconverge the warp before the
+// .sync.aligned instructions that follow them; with __syncwarp() after every wait (cd_wait) 240 uncapped rounds of 9-12
+// clusters ran clean (scripts/cluster_stress.py, LLMVOX_B200_CD_CAP=64).  The cap stays as a conservative limit: it costs
+// nothing at BASELINE config 1 (4 clusters), more clusters than are co-resident (7 x 16 CTAs on a B200) only queue anyway,
+// and batches far above 112 sessions are better served by the kernel-per-op path (LaneRunner switches).
 static int cluster_launch(lvx_engine* e, lvx_engine::Lane& ln, const int32_t* h_slots, int n, int n_steps, cudaStream_t st) {
   LVX_TRY(cluster_init(e));
   const lvx_config& c = e->cfg;
+  // LLMVOX_B200_CD_CAP overrides the cap (experiments only: scripts/cluster_stress.py)
+  const int cap = getenv("LLMVOX_B200_CD_CAP") ? std::max(1, atoi(getenv("LLMVOX_B200_CD_CAP"))) : std::max(1, std::min(e->cd_max_clusters, 7));
   ClusterParams P;
   memset(&P, 0, sizeof(P));
-  P.n = n; P.n_iters = n_steps; P.n_layer = c.n_layer;
-  P.slots = ln.d_slots;
+  P.n_iters = n_steps; P.n_layer = c.n_layer;
   P.st = e->st;
   P.text_table = W(e, "text_table");
   P.codebook = W(e, "feature_extractor.encodec.quantizer.vq.layers.0._codebook.embed");
@@ -1184,18 +1216,43 @@ static int cluster_launch(lvx_engine* e, lvx_engine::Lane& ln, const int32_t* h_
   P.kv = (bf16*)e->kv; P.pool_pages = e->pool_pages;
   P.page_shift = 0;
   while ((1 << P.page_shift) < c.kv_page_tokens) P.page_shift += 1;
-  P.logits = ln.logits;
   P.trace = getenv("LLMVOX_B200_TRACE") ? ln.d_trace : nullptr;
   P.dbg = getenv("LLMVOX_B200_CD_DBG") ? atoi(getenv("LLMVOX_B200_CD_DBG")) : 0;
-  // algorithmic bytes of this launch: the bf16 GEMM weights once per iteration + KV read and append
-  double bytes = (double)n_steps * 2.0 * ((double)c.n_layer * 12.0 * CD_C * CD_C + (double)CD_C * CD_V);
-  for (int i = 0; i < n; ++i) {
-    const double t0 = e->h_len[h_slots[i]];
-    bytes += (double)c.n_layer * 2.0 * CD_C * 2.0 * ((double)n_steps * (t0 + 1.0) + 0.5 * n_steps * (n_steps - 1.0));
+  for (int pos = 0; pos < n; pos += cap * CD_NB) {
+    const int cnt = std::min(cap * CD_NB, n - pos), clusters = ceil_div(cnt, CD_NB);
+    P.n = cnt;
+    P.slots = ln.d_slots + pos;
+    P.logits = ln.logits + (size_t)pos * c.vocab_size;
+    // retire finished launches, then wait for the oldest ones on other streams until this one fits
+    while (!e->cd_inflight.empty() && cudaEventQuery(e->cd_inflight.front().ev) == cudaSuccess) {
+      e->ev_pool.push_back(e->cd_inflight.front().ev);
+      e->cd_inflight.pop_front();
+    }
+    cudaGetLastError();   // cudaErrorNotReady of the query above is not an error
+    int inflight = 0;
+    for (auto& f : e->cd_inflight)
+      if (f.st != st) inflight += f.clusters;   // launches on this stream are ordered before this one anyway
+    for (auto& f : e->cd_inflight) {
+      if (inflight + clusters <= cap) break;
+      if (f.st == st) continue;
+      LVX_CUDA(cudaStreamWaitEvent(st, f.ev, 0));
+      inflight -= f.clusters;
+    }
+    // algorithmic bytes of this launch: the bf16 GEMM weights once per iteration + KV read and append
+    double bytes = (double)n_steps * 2.0 * ((double)c.n_layer * 12.0 * CD_C * CD_C + (double)CD_C * CD_V);
+    for (int i = 0; i < cnt; ++i) {
+      const double t0 = e->h_len[h_slots[pos + i]];
+      bytes += (double)c.n_layer * 2.0 * CD_C * 2.0 * ((double)n_steps * (t0 + 1.0) + 0.5 * n_steps * (n_steps - 1.0));
+    }
+    {
+      ProfScope prof_scope(e, "cluster_decode", st, 0.0, bytes);
+      LVX_TRY(cluster_decode_launch(P, st));
+    }
+    e->launches += 1;
+    lvx_engine::CdInflight rec{e->get_event(), st, clusters};
+    LVX_CUDA(cudaEventRecord(rec.ev, st));
+    e->cd_inflight.push_back(rec);
   }
-  ProfScope prof_scope(e, "cluster_decode", st, 0.0, bytes);
-  LVX_TRY(cluster_decode_launch(P, st));
-  e->launches += 1;
   return LVX_OK;
 }
 
@@ -1241,6 +1298,14 @@ extern "C" int lvx_decode_steps_lane(lvx_engine* e, int lane, const int32_t* h_s
     for (int t = 0; t < n_steps; ++t) LVX_TRY(decode_one_step(e, ln, n, sa, ln.logits, st));
   }
   for (int i = 0; i < n; ++i) e->h_len[h_slots[i]] += n_steps;
+  return LVX_OK;
+}
+
+// Host-side choice of the greedy bf16 decode path: 1 = cluster-resident kernel where applicable (default), 0 = kernel-per-op
+// chain (the better choice for batches far above 112 sessions: LaneRunner switches per call).
+extern "C" int lvx_set_cluster_decode(lvx_engine* e, int on) {
+  LVX_TRY(check_engine(e));
+  e->use_cluster = on != 0;
   return LVX_OK;
 }
 

@@ -136,6 +136,11 @@ class Engine:
         check(self.lib.lvx_decode_steps_lane(self._h, lane, i32_array(slots), len(slots), n_steps, C.byref(s),
                                              self._stream(stream)))
 
+    def set_cluster_decode(self, on: bool):
+        """Greedy bf16 decode path for the calls that follow: the cluster-resident kernel (default) or the kernel-per-op
+        chain (better far above 112 sessions per batch)."""
+        check(self.lib.lvx_set_cluster_decode(self._h, int(bool(on))))
+
     def decode_step_logits(self, slots: Sequence[int], forced: Optional[torch.Tensor] = None,
                            sampling: Optional[Sampling] = None, uniform: Optional[torch.Tensor] = None,
                            stream=None) -> Tuple[torch.Tensor, torch.Tensor]:

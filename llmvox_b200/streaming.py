@@ -30,6 +30,8 @@ class LaneRunner:
         self.e = engine
         self.G = max(1, min(engine.decode_lanes, lanes or engine.decode_lanes))
         self.streams = [torch.cuda.Stream(device=engine.device) for _ in range(self.G)] if self.G > 1 else [None]
+        import os
+        self.cluster_default = os.environ.get("LLMVOX_B200_CLUSTER", "1") != "0"
 
     def split(self, slots: Sequence[int]) -> List[List[int]]:
         n, G = len(slots), min(self.G, len(slots))
@@ -50,8 +52,14 @@ class LaneRunner:
         for st in self.streams:
             st.wait_event(ev)
 
+    # above this many sessions in one batch the kernel-per-op chain out-runs the cluster-resident kernel (7 clusters of
+    # 16 sessions are co-resident on a B200; measured at 256 streams: 8277 vs 7856 audio-s/s)
+    CLUSTER_DECODE_MAX_BATCH = 112
+
     def decode(self, slots: Sequence[int], n_steps: int, sampling: Optional[Sampling] = None):
         """Enqueues n_steps iterations for every group; the control stream then waits for all lanes."""
+        if self.cluster_default:
+            self.e.set_cluster_decode(len(slots) <= self.CLUSTER_DECODE_MAX_BATCH)
         if self.G == 1:
             self.e.decode_steps(slots, n_steps, sampling)
             return

@@ -1,0 +1,50 @@
+"""Stress of the cluster-resident decode kernel above its co-residency (7 clusters): batches of 144..256 sessions forced
+through the cluster path (the engine splits a call into launches of <= 7 clusters and keeps <= 7 in flight across
+streams), repeated open / feed / decode / vocode rounds through BatchSynthesizer, 1 and 4 lanes.  Prints the timeout
+records of the bounded spins (LLMVOX_B200_CD_DIAG=1) if a launch dies."""
+import ctypes
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("LLMVOX_B200_CD_DIAG", "1")
+from llmvox_b200 import weights as W
+from llmvox_b200.engine import Engine
+from llmvox_b200.streaming import BatchSynthesizer, LaneRunner
+
+LaneRunner.CLUSTER_DECODE_MAX_BATCH = 1 << 30       # force the cluster path at every batch size
+REPS = int(os.environ.get("STRESS_REPS", "40"))
+sd = W.make_random_weights(1234, wpe_rows=256)
+e = Engine(sd, device=0, precision="bf16", max_sessions=256, max_batch=256, max_context=256, max_vocode_frames=256 * 170, decode_lanes=8)
+rng = np.random.RandomState(0)
+for B in [int(x) for x in os.environ.get("STRESS_B", "144,192,256").split(",")]:
+    for lanes in (1, 4):
+        texts = [rng.randint(3, 259, size=200).tolist() for _ in range(B)]
+        bs = BatchSynthesizer(e, B, 160, stop_on_eoa=False, lanes=lanes)
+        ts = []
+        for rep in range(REPS):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            try:
+                bs.start(texts)
+                for _ in bs.run(160, flush_tail=False, copy=False):
+                    pass
+            except Exception as ex:
+                print("FAILED", B, lanes, rep, f"{1e3 * (time.perf_counter() - t0):.1f} ms", type(ex).__name__, flush=True)
+                f = e.lib.lvx_cluster_diag
+                f.restype = ctypes.POINTER(ctypes.c_ulonglong)
+                d = f()
+                if d:
+                    print("diag records:", d[0])
+                    for i in range(min(60, d[0])):
+                        v = d[1 + i]
+                        blk = (v >> 12) & 0x7ffff
+                        print(f"  bar 0x{v >> 32:x} parity {(v >> 31) & 1} cluster {blk // 16} rank {blk % 16} thread {v & 0xfff} (warp {(v & 0xfff) // 32})")
+                os._exit(3)
+            ts.append(1e3 * (time.perf_counter() - t0))
+        print(f"B={B} lanes={lanes}: {REPS} rounds ok, median {np.median(ts):.1f} ms", flush=True)
+print("stress ok")

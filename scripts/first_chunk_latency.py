@@ -18,11 +18,11 @@ e = Engine(sd, device=0, precision=os.environ.get("PROBE_PRECISION", "bf16"), ma
 rng = np.random.RandomState(0)
 print("| streams | first chunk | lanes | p50 ms | p99 ms | min ms |")
 print("|---:|---:|---:|---:|---:|---:|")
-for dump in (10, 160):
-    for B in (1, 2, 4, 8, 16, 32, 64, 128, 256):
+for dump in [int(x) for x in os.environ.get("PROBE_DUMPS", "10,160").split(",")]:
+    for B in [int(x) for x in os.environ.get("PROBE_B", "1,2,4,8,16,32,64,128,256").split(",")]:
         texts = [rng.randint(3, 259, size=200).tolist() for _ in range(B)]
         best = None
-        for lanes in ((1,) if B < 32 else (1, 2, 4)):
+        for lanes in ([int(x) for x in os.environ["PROBE_LANES"].split(",")] if "PROBE_LANES" in os.environ else (1,) if B < 32 else (1, 2, 4)):
             bs = BatchSynthesizer(e, B, dump, stop_on_eoa=False, lanes=lanes)
             ts = []
             for rep in range(12):
@@ -30,7 +30,22 @@ for dump in (10, 160):
                 t0 = time.perf_counter()
                 bs.start(texts)
                 gen = bs.run(dump, flush_tail=False, copy=False)
-                chunks = next(gen)
+                try:
+                    chunks = next(gen)
+                except Exception as ex:
+                    print("FAILED after", f"{1e3 * (time.perf_counter() - t0):.1f} ms", type(ex).__name__, flush=True)
+                    import ctypes
+                    f = e.lib.lvx_cluster_diag
+                    f.restype = ctypes.POINTER(ctypes.c_ulonglong)
+                    d = f()
+                    if d:
+                        print("diag records:", d[0])
+                        for i in range(min(60, d[0])):
+                            v = d[1 + i]
+                            print(f"  bar 0x{v >> 32:x} parity {(v >> 31) & 1} block {(v >> 12) & 0x7ffff} (cluster {((v >> 12) & 0x7ffff) // 16} rank {((v >> 12) & 0x7ffff) % 16}) thread {v & 0xfff} (warp {(v & 0xfff) // 32})")
+                    os._exit(3)
+                if os.environ.get("PROBE_VERBOSE"):
+                    print("rep", dump, B, lanes, rep, f"{1e3 * (time.perf_counter() - t0):.1f} ms", flush=True)
                 ts.append(1e3 * (time.perf_counter() - t0))
                 assert len(chunks) == B and chunks[0].length == dump
                 for _ in gen:

@@ -198,6 +198,7 @@ __device__ __noinline__ void fd_gemm_phase(const FusedParams& P, const FusedGemm
       }
     } else {
       mbar_wait(tmem_full_bar, (uint32_t)pp.tile_total & 1u);
+      __syncwarp();   // reconverge before the .sync.aligned tcgen05.ld
       if (threadIdx.x == 64) FD_T(3);
       tc_fence_after();
       float* red = reinterpret_cast<float*>(smem_raw + (pp.red - smem_u32(smem_raw)));

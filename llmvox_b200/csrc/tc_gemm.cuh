@@ -470,6 +470,7 @@ __global__ void __launch_bounds__(TcShape<kSwap>::kThreads, kSwap ? 1 : 2) tc_ge
   } else {
     // ---------------- epilogue warps: TMEM -> registers -> (global | partial tile in smem)
     mbar_wait(tmem_full_bar, 0);
+    __syncwarp();   // the polling loop may release lanes at different iterations; tcgen05.ld is .sync.aligned
     tc_fence_after();
     pdl_wait();   // residual reads and output writes must follow the predecessor's completion
     const int c_lo = half * (BN / kHalves), c_hi = (half + 1) * (BN / kHalves);   // multiples of 8 (BN % 16 == 0)
@@ -711,6 +712,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
       const int acc = i & 1;
       const int x0 = ((w / n_tiles_n) * 2 + rank) * TC_BM, y0 = (w % n_tiles_n) * TCP_BN;
       mbar_wait(tfull_bar(acc), (uint32_t)(i >> 1) & 1u);
+      __syncwarp();   // reconverge before the .sync.aligned tcgen05.ld
       tc_fence_after();
       const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TCP_BN);
       const int c_lo = half * (TCP_BN / 2), c_hi = c_lo + TCP_BN / 2;

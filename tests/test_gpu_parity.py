@@ -501,6 +501,55 @@ def test_cluster_decode_kernel(weights, n):
         e.close()
 
 
+def test_cluster_decode_ragged_contexts_and_long_runs(weights):
+    """Cluster-resident decode kernel with sessions of one cluster at DIFFERENT contexts (different page counts, page
+    boundaries crossed at different iterations, a session with no text), then one long launch (context up to 290 =
+    19 KV pages).  Oracle: the fp32 engine, teacher-forced with the kernel's picks.  Step by step the logits must agree
+    within the bf16 bound; over the long launch every pick must be within twice that bound of the fp32 argmax."""
+    from llmvox_b200.engine import Engine
+    n = 21
+    kw = dict(device=0, max_sessions=n, max_context=300, max_vocode_frames=256)
+    clus = Engine(weights, precision="bf16", **kw)
+    ref = Engine(weights, precision="fp32", **kw)
+    rng = np.random.RandomState(7)
+    texts = [rng.randint(3, 259, size=rng.randint(1, 120)).tolist() for _ in range(n)]
+    texts[3] = []
+    slots = list(range(n))
+    for e in (clus, ref):
+        e.open(slots)
+        e.feed_text(slots, texts)
+    early = [0, 2, 3, 5, 8, 13, 17, 20]               # these run 37 iterations ahead of the others
+    clus.decode_steps(early, 37)
+    ce = clus.gather_codes(early, 0, 37)
+    for t in range(37):
+        ref.decode_step_logits(early, forced=ce[:, t].contiguous())
+    worst = 0.0
+    for t in range(30):                               # all 21 together: contexts 37+t and t inside the same clusters
+        clus.decode_steps(slots, 1)
+        lc = clus.peek_logits(n)
+        codes = torch.stack([clus.gather_codes([s], (37 if s in early else 0) + t, 1).view(()) for s in slots]).contiguous()
+        assert (lc.argmax(dim=1).to(torch.int32) == codes).all()
+        lr, _ = ref.decode_step_logits(slots, forced=codes)
+        worst = max(worst, float((lc - lr).abs().max()))
+    assert worst < 2e-2, worst
+    # one long launch: 3 sessions x 290 iterations
+    long_slots = [1, 4, 6]
+    for e in (clus, ref):
+        e.open(long_slots)
+        e.feed_text(long_slots, [texts[s] for s in long_slots])
+    clus.decode_steps(long_slots, 290)
+    cl = clus.gather_codes(long_slots, 0, 290)
+    gap = 0.0
+    for t in range(290):
+        lr, _ = ref.decode_step_logits(long_slots, forced=cl[:, t].contiguous())
+        picked = lr.gather(1, cl[:, t].long().view(-1, 1)).view(-1)
+        gap = max(gap, float((lr.max(dim=1).values - picked).max()))
+    assert gap < 4e-2, gap
+    assert clus.session_length(1) == 290
+    clus.close()
+    ref.close()
+
+
 def test_error_behaviour(engines):
     from llmvox_b200._lib import LvxError
     e = engines("fp32")

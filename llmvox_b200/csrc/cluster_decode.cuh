@@ -77,7 +77,7 @@ constexpr int CD_TM_QKV = 0, CD_TM_PROJ = 32, CD_TM_FC = 96, CD_TM_PROJ2 = 0, CD
 constexpr int CD_OFF_RING = 0;
 constexpr int CD_OFF_A1 = CD_OFF_RING + CD_STAGES * CD_SLOT;          // [12 k-blocks][16 x 128 B]: LN(x) / y operand
 constexpr int CD_OFF_A2 = CD_OFF_A1 + (CD_C / 64) * CD_ABLK;          // [3 k-blocks]: this CTA's GELU(fc) slice
-constexpr int CD_OFF_RED = CD_OFF_A2 + (CD_FR / 64) * CD_ABLK;        // [16 src][48 rows][16 sessions] fp32 proj2 partials
+constexpr int CD_OFF_RED = CD_OFF_A2 + (CD_FR / 64) * CD_ABLK;        // [16 src][4 session quads][48 rows] float4 proj2 partials
 constexpr int CD_OFF_AY = CD_OFF_RED;   // attention output operand of proj, aliases the partials: A1 cannot take it (a fast
                                         // peer's LN2 gather would land in A1 while this CTA's proj MMAs still read y), and
                                         // every store into one of the two uses is separated from the other's reads by an exchange
@@ -262,6 +262,8 @@ __device__ __forceinline__ uint32_t cd_bar_empty(uint32_t bars, unsigned s) { re
 __device__ __forceinline__ uint32_t cd_bar_act(uint32_t bars) { return bars + 8u * (2 * CD_STAGES); }
 __device__ __forceinline__ uint32_t cd_bar_tmem(uint32_t bars) { return bars + 8u * (2 * CD_STAGES + 1); }
 __device__ __forceinline__ uint32_t cd_bar_x(uint32_t bars, unsigned i) { return bars + 8u * (2 * CD_STAGES + 2 + i); }
+// one barrier per proj2 row tile (count = issuers, one k-block each): the scatter of tile m overlaps the MMAs of m+1..
+__device__ __forceinline__ uint32_t cd_bar_tile(uint32_t bars, unsigned m) { return bars + 8u * (2 * CD_STAGES + 4 + m); }
 
 // ---- producer / MMA issuer pieces.  Both warps run CONVERGED and elect one lane only around the asynchronous
 // instructions: addresses, descriptors and ring positions then live in uniform registers.  (With `if (lane == 0)` around
@@ -422,19 +424,17 @@ __device__ __noinline__ uint4 cd_attention_warp(bf16* kv, const int* pt, long lo
       for (int i = 0; i < 8; ++i) acc[i] = fmaf(pj, f[i], acc[i]);
     }
   }
-  {   // the new token (every lane computes its score; only the first token half adds its value row)
+  {   // the new token: lanes 0-11 hold chunk cc of its (bf16-rounded) k; only the first token half adds its value row
     float sc = 0.f;
-#pragma unroll
-    for (int c = 0; c < NC; ++c) {
-      const float4 q0 = *reinterpret_cast<const float4*>(qkv + 8 * c), q1 = *reinterpret_cast<const float4*>(qkv + 8 * c + 4);
-      const uint4 kc = make_uint4(__shfl_sync(0xffffffffu, kn.x, c), __shfl_sync(0xffffffffu, kn.y, c), __shfl_sync(0xffffffffu, kn.z, c),
-                                  __shfl_sync(0xffffffffu, kn.w, c));
+    {
+      const float4 q0 = *reinterpret_cast<const float4*>(qkv + 8 * cc), q1 = *reinterpret_cast<const float4*>(qkv + 8 * cc + 4);
       float f[8];
-      cd_unpack8(kc, f);
+      cd_unpack8(kn, f);
       sc = fmaf(q0.x, f[0], sc); sc = fmaf(q0.y, f[1], sc); sc = fmaf(q0.z, f[2], sc); sc = fmaf(q0.w, f[3], sc);
       sc = fmaf(q1.x, f[4], sc); sc = fmaf(q1.y, f[5], sc); sc = fmaf(q1.z, f[6], sc); sc = fmaf(q1.w, f[7], sc);
+      if (lane >= NC) sc = 0.f;
     }
-    sc *= scale;
+    sc = warp_sum(sc) * scale;
     const float mn = fmaxf(m, sc);
     const float corr = __expf(m - mn), pn = __expf(sc - mn);
     l = l * corr + pn;
@@ -457,11 +457,25 @@ __device__ __noinline__ uint4 cd_attention_warp(bf16* kv, const int* pt, long lo
   return out;
 }
 
+// text-table elements (features below text_dim), position-row elements and the text row's sum of squares for position t
+__device__ __forceinline__ void cd_prefetch_text(const ClusterParams& P, int slot, int t, int rank, int wt, float (&e)[3], float (&pe)[3],
+                                                 float& ss) {
+  int text_id = P.pad_id;
+  if (t < P.st.text_len[slot]) text_id = P.st.text_ids[(size_t)slot * P.st.max_context + t];
+  ss = __ldg(P.text_ss + text_id);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const int f = CD_XR * rank + (wt & 15) + 16 * i;
+    e[i] = f < P.text_dim ? __ldg(P.text_table + (size_t)text_id * P.text_dim + f) : 0.f;
+    pe[i] = __ldg(P.wpe + (size_t)t * CD_C + f);
+  }
+}
+
 #define CD_T() do { if (trp) *trp++ = clock64(); } while (0)
 
 __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __grid_constant__ ClusterParams P) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars_sh[2 * CD_STAGES + 4];
+  __shared__ __align__(8) uint64_t bars_sh[2 * CD_STAGES + 4 + 6];
   __shared__ uint32_t tmem_base_sh;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -483,6 +497,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
     mbar_init(cd_bar_tmem(bars), CD_NI);   // one commit per MMA issuer warp
     mbar_init(cd_bar_x(bars, 0), CD_CLUSTER);
     mbar_init(cd_bar_x(bars, 1), CD_CLUSTER);
+    for (unsigned m = 0; m < 6; ++m) mbar_init(cd_bar_tile(bars, m), CD_NI);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -599,6 +614,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
               if (cd_elect()) {
                 cd_kblock(tm + CD_TM_PROJ2 + CD_NB * m, a, a2 + kb * CD_ABLK, idesc, 0u);   // one k-block per issuer
                 umma_commit(cd_bar_empty(bars, gi % CD_STAGES));
+                umma_commit(cd_bar_tile(bars, (unsigned)m));
               }
               __syncwarp();
             }
@@ -621,6 +637,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
     const int head = rank >> 1, odd = rank & 1;
     unsigned xphase = 0, gcount = 0;
     long long* trp = nullptr;
+    float pre_e[3] = {0.f, 0.f, 0.f}, pre_pe[3] = {0.f, 0.f, 0.f}, pre_ss = 0.f;   // next iteration's text / position part
 
     // Cluster barrier of the worker warps: everything this CTA's workers stored (locally or into peers) before it is
     // visible to every peer's workers after it.  Two alternating mbarriers (count 16 = one arrival per peer): a fast
@@ -650,25 +667,26 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
     for (int iter = 0; iter < n_iters; ++iter) {
       if (P.trace && cid == 0 && rank == 0 && wt == 0 && iter == n_iters - 1) trp = P.trace;
       CD_T();
-      {   // ---- input assembly (streaming_server.py:313-334, src/model.py:206-212): 48 features of every session
+      {   // ---- input assembly (streaming_server.py:313-334, src/model.py:206-212): 48 features of every session.
+          // The text row, its norm and the position row only depend on t: they were fetched during the previous
+          // iteration (pre_*); only the previous code's codebook row is looked up here.
         const int n = wt >> 4;
         float v[3] = {0.f, 0.f, 0.f};
         if (n < nloc) {
           const int slot = sm_slot[n], t = sm_t[n];
-          int text_id = P.pad_id;
-          if (t < P.st.text_len[slot]) text_id = P.st.text_ids[(size_t)slot * P.st.max_context + t];
+          if (iter == 0) cd_prefetch_text(P, slot, t, rank, wt, pre_e, pre_pe, pre_ss);
           int prev = -1;
           if (t > 0) prev = iter > 0 ? sm_code[n] : P.st.codes[(size_t)slot * P.st.max_context + t - 1];
-          const float ss = __ldg(P.text_ss + text_id) + (prev >= 0 ? __ldg(P.code_ss + prev) : 0.f);
+          const float ss = pre_ss + (prev >= 0 ? __ldg(P.code_ss + prev) : 0.f);
           const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-8f);
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
             const int f = CD_XR * rank + (wt & 15) + 16 * i;
-            float e = 0.f;
-            if (f < P.text_dim) e = __ldg(P.text_table + (size_t)text_id * P.text_dim + f);
-            else if (prev >= 0) e = __ldg(P.codebook + (size_t)prev * P.code_dim + (f - P.text_dim));
-            v[i] = e * inv + __ldg(P.wpe + (size_t)t * CD_C + f);
+            float e = pre_e[i];
+            if (f >= P.text_dim) e = prev >= 0 ? __ldg(P.codebook + (size_t)prev * P.code_dim + (f - P.text_dim)) : 0.f;
+            v[i] = e * inv + pre_pe[i];
           }
+          if (iter + 1 < n_iters) cd_prefetch_text(P, slot, t + 1, rank, wt, pre_e, pre_pe, pre_ss);   // lands during this iteration
         }
 #pragma unroll
         for (int i = 0; i < 3; ++i) xs[n * CD_XR + (wt & 15) + 16 * i] = v[i];
@@ -679,17 +697,19 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
         const int l = sl >> 1;
         // ================= x all-gather + LayerNorm (src/model.py:29-38; weight folded into the GEMM) -> A1
         cd_workers_sync();   // xs complete
-        {   // partial statistics of sessions 2ww, 2ww+1 over this CTA's 48 features (two-pass), one pair to every peer
+        {   // partial statistics of sessions 2ww, 2ww+1 over this CTA's 48 features, one (mean, M2) pair to every peer.
+            // One pass: the two shuffle chains run side by side; M2 = sum(x^2) - 48 mean^2 over 48 fp32 values.
           const int hw = lane >> 4, l16 = lane & 15, n = 2 * ww + hw;
           const float* row = xs + n * CD_XR;
           const float v0 = row[l16], v1 = row[l16 + 16], v2 = row[l16 + 32];
-          float s = v0 + v1 + v2;
+          float s1 = v0 + v1 + v2, s2 = fmaf(v0, v0, fmaf(v1, v1, v2 * v2));
 #pragma unroll
-          for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-          const float mean = s * (1.0f / CD_XR);
-          float m2 = (v0 - mean) * (v0 - mean) + (v1 - mean) * (v1 - mean) + (v2 - mean) * (v2 - mean);
-#pragma unroll
-          for (int o = 8; o > 0; o >>= 1) m2 += __shfl_xor_sync(0xffffffffu, m2, o);
+          for (int o = 8; o > 0; o >>= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+          }
+          const float mean = s1 * (1.0f / CD_XR);
+          const float m2 = fmaxf(s2 - (float)CD_XR * mean * mean, 0.f);
           cd_st_remote_v2(cd_mapa(sbase + CD_OFF_STATS + (uint32_t)((rank * CD_NB + n) * 8), (uint32_t)l16), __float_as_uint(mean),
                           __float_as_uint(m2));
         }
@@ -811,32 +831,34 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
           }
           signal_act();
           CD_T();
-          // ================= proj2 epilogue: partial sums over this CTA's k-slice, scattered to the row owners
-          wait_acc();
+          // ================= proj2 epilogue: partial sums over this CTA's k-slice, scattered to the row owners tile by tile
           CD_T();
 #pragma unroll 1
           for (int m = 0; m < 6; ++m) {
+            cd_wait(cd_bar_tile(bars, (unsigned)m), (unsigned)(iter * n_layer + l) & 1u);
+            tc_fence_after();
             float v[8];
             tmem_ld8(trow + (uint32_t)(CD_TM_PROJ2 + CD_NB * m + 8 * hh), v);
+            // partials buffer of the owner: [source rank][session quad][row] float4, so that the 32 lanes of a store
+            // (consecutive rows) write 512 contiguous bytes (16-byte pieces at a 64-byte stride ran at 4 B / clock)
             const int j = 128 * m + 32 * q + lane, owner = j / CD_XR, lr = j - owner * CD_XR;
-            const uint32_t base = cd_mapa(sbase + CD_OFF_RED + (uint32_t)((rank * CD_XR + lr) * 64), (uint32_t)owner);
-            const int sw = (lr >> 1) & 3;
-            cd_st_remote_v4(base + (uint32_t)(((2 * hh) ^ sw) << 4),
-                            make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])));
-            cd_st_remote_v4(base + (uint32_t)(((2 * hh + 1) ^ sw) << 4),
+            const uint32_t base = cd_mapa(sbase + CD_OFF_RED + (uint32_t)(((rank * 4 + 2 * hh) * CD_XR + lr) * 16), (uint32_t)owner);
+            cd_st_remote_v4(base, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])));
+            cd_st_remote_v4(base + (uint32_t)(CD_XR * 16),
                             make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));
           }
+          wait_acc();   // (already complete: keeps the accumulator barrier's phase in step)
           tc_fence_before();
           CD_T();
           exchange(false);
           CD_T();
           if (wt < 4 * CD_XR) {   // fixed source order: deterministic
-            const int lr = wt >> 2, c4 = wt & 3;
-            const uint8_t* rp = sgen + CD_OFF_RED + lr * 64 + ((c4 ^ ((lr >> 1) & 3)) << 4);
+            const int c4 = wt / CD_XR, lr = wt - c4 * CD_XR;
+            const uint8_t* rp = sgen + CD_OFF_RED + (c4 * CD_XR + lr) * 16;
             float4 a = *reinterpret_cast<const float4*>(rp);
 #pragma unroll
             for (int r = 1; r < CD_CLUSTER; ++r) {
-              const float4 t = *reinterpret_cast<const float4*>(rp + r * (CD_XR * 64));
+              const float4 t = *reinterpret_cast<const float4*>(rp + r * (4 * CD_XR * 16));
               a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
             }
             xs[(4 * c4 + 0) * CD_XR + lr] += a.x;

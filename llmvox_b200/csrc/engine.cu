@@ -1194,10 +1194,13 @@ static bool cluster_applicable(const lvx_engine* e, const SamplerArgs& sa) {
 // that would exceed it waits (cudaStreamWaitEvent, no host blocking) for the oldest launches on other streams.  History: an
 // earlier build died in a bounded spin (dead wait, 1 in ~10-40 launches) as soon as 9+ clusters were in flight, i.e. when
 // pending clusters start while others drain; never at <= 8.  The spin-waits did not reconverge the warp before the
-// .sync.aligned instructions that follow them; with __syncwarp() after every wait (cd_wait) 240 uncapped rounds of 9-12
-// clusters ran clean (scripts/cluster_stress.py, LLMVOX_B200_CD_CAP=64).  The cap stays as a conservative limit: it costs
-// nothing at BASELINE config 1 (4 clusters), more clusters than are co-resident (7 x 16 CTAs on a B200) only queue anyway,
-// and batches far above 112 sessions are better served by the kernel-per-op path (LaneRunner switches).
+// .sync.aligned instructions that follow them; with __syncwarp() after every wait (cd_wait) the rate dropped to ONE dead
+// wait in ~1700 uncapped rounds of 9-16 clusters (scripts/cluster_stress.py, LLMVOX_B200_CD_CAP=64; the record left by
+// the timed-out spin: an MMA issuer warp of a second-wave cluster waiting for the activation-ready barrier), and none
+// in any capped run.  So the cap is a correctness measure, not only a conservative one, until the remaining cause is
+// found (open item).  It costs nothing at BASELINE config 1 (4 clusters), more clusters than are co-resident
+// (7 x 16 CTAs on a B200) only queue anyway, and batches far above 112 sessions are better served by the kernel-per-op
+// path (LaneRunner switches).
 static int cluster_launch(lvx_engine* e, lvx_engine::Lane& ln, const int32_t* h_slots, int n, int n_steps, cudaStream_t st) {
   LVX_TRY(cluster_init(e));
   const lvx_config& c = e->cfg;

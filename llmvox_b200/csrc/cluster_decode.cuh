@@ -144,14 +144,26 @@ __device__ unsigned long long* cd_diag = nullptr;
 __device__ __noinline__ void cd_timeout(uint32_t bar, uint32_t parity) {
   if (cd_diag) {
     const unsigned long long i = atomicAdd(cd_diag, 1ULL);
-    if (i < 60) {
-      cd_diag[1 + i] = ((unsigned long long)bar << 32) | ((unsigned long long)(parity & 1u) << 31) | ((unsigned long long)blockIdx.x << 12) |
-                       (unsigned long long)threadIdx.x;
+    if (i < 24) {
+      unsigned long long* rec = cd_diag + 1 + 10 * i;
+      rec[0] = ((unsigned long long)bar << 32) | ((unsigned long long)(parity & 3u) << 30) | ((unsigned long long)blockIdx.x << 12) |
+               (unsigned long long)threadIdx.x;
+      const uint32_t status = (bar & ~511u) + 32u * 8u;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        unsigned long long v;
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(status + 8u * k));
+        rec[1 + k] = v;
+      }
+      // pending count / phase of the barrier itself
+      unsigned long long st;
+      asm volatile("ld.shared.u64 %0, [%1];" : "=l"(st) : "r"(bar));
+      rec[9] = st;
       __threadfence_system();
     }
     // give the other stuck waiters time to report too
     const long long t1 = clock64();
-    while (clock64() - t1 < 200000000LL) {}
+    while (clock64() - t1 < 400000000LL) {}
   }
   __trap();
 }
@@ -472,10 +484,14 @@ __device__ __forceinline__ void cd_prefetch_text(const ClusterParams& P, int slo
 }
 
 #define CD_T() do { if (trp) *trp++ = clock64(); } while (0)
+// progress words (see cd_timeout): k = 0 workers, 1..3 issuers, 4 producer
+#define CD_STATUS(k, a, b) do { if (lane == 0) bars_sh[32 + (k)] = ((unsigned long long)(unsigned)(a) << 32) | (unsigned)(b); } while (0)
 
 __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __grid_constant__ ClusterParams P) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t bars_sh[2 * CD_STAGES + 4 + 6];
+  // barriers [0, 26) + status words [32, 40) (progress of each role, dumped by a timed-out spin); 512-byte aligned so that
+  // cd_timeout finds the block from any barrier address
+  __shared__ __align__(512) uint64_t bars_sh[40];
   __shared__ uint32_t tmem_base_sh;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -542,6 +558,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
 #pragma unroll 1
             for (int j = 0; j < run_count[e]; ++j) {
               const unsigned s = gi % CD_STAGES;
+              CD_STATUS(4, iter, gi);
               cd_wait(cd_bar_empty(bars, s), ((gi / CD_STAGES) & 1u) ^ 1u);
               if (cd_elect()) {
                 mbar_expect_tx(cd_bar_full(bars, s), bytes);
@@ -567,6 +584,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
       for (int iter = 0; iter < n_iters; ++iter) {
 #pragma unroll 1
         for (int sl = 0; sl <= 2 * n_layer; ++sl) {
+          CD_STATUS(warp, (iter << 8) | sl, (g << 16) | (gi & 0xffffu));
           cd_wait(cd_bar_act(bars), g & 1u);   // LN(x) operand ready
           g += 1;
           tc_fence_after();
@@ -585,6 +603,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
             __syncwarp();
           } else if (!(sl & 1)) {
             gi = cd_mma_rowsplit(sbase, bars, idesc, gi, par, a1, tm + CD_TM_QKV, CD_QT, 4);
+            CD_STATUS(warp, (iter << 8) | sl | 0x80, (g << 16) | (gi & 0xffffu));
             cd_wait(cd_bar_act(bars), g & 1u);   // attention output operand ready
             g += 1;
             tc_fence_after();
@@ -603,6 +622,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
             __syncwarp();
           } else {
             gi = cd_mma_rowsplit(sbase, bars, idesc, gi, par, a1, tm + CD_TM_FC, CD_FT, 2);
+            CD_STATUS(warp, (iter << 8) | sl | 0x80, (g << 16) | (gi & 0xffffu));
             cd_wait(cd_bar_act(bars), g & 1u);   // GELU(fc) slice ready
             g += 1;
             tc_fence_after();
@@ -642,7 +662,9 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
     // Cluster barrier of the worker warps: everything this CTA's workers stored (locally or into peers) before it is
     // visible to every peer's workers after it.  Two alternating mbarriers (count 16 = one arrival per peer): a fast
     // peer's arrival for exchange p+1 can never complete a slow CTA's exchange p.
+    int cur_sl = 0, cur_iter = 0;
     auto exchange = [&](bool for_tensor_core) {
+      if (ww == 0) CD_STATUS(0, (cur_iter << 8) | cur_sl, (xphase << 16) | (gcount & 0xffffu));
       if (for_tensor_core) cd_proxy_fence_cluster();
       cd_workers_sync();
       const uint32_t bar = cd_bar_x(bars, xphase & 1u);
@@ -658,6 +680,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
       if (wt == 0) cd_mbar_arrive(cd_bar_act(bars));
     };
     auto wait_acc = [&]() {
+      if (ww == 0) CD_STATUS(0, (cur_iter << 8) | cur_sl | 0x80, (xphase << 16) | (gcount & 0xffffu));
       cd_wait(cd_bar_tmem(bars), gcount & 1u);
       gcount += 1;
       tc_fence_after();
@@ -695,6 +718,8 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
 #pragma unroll 1
       for (int sl = 0; sl <= 2 * n_layer; ++sl) {
         const int l = sl >> 1;
+        cur_sl = sl;
+        cur_iter = iter;
         // ================= x all-gather + LayerNorm (src/model.py:29-38; weight folded into the GEMM) -> A1
         cd_workers_sync();   // xs complete
         {   // partial statistics of sessions 2ww, 2ww+1 over this CTA's 48 features, one (mean, M2) pair to every peer.

@@ -1171,8 +1171,8 @@ static int cluster_init(lvx_engine* e) {
   cudaFree(d_descs);
   if (getenv("LLMVOX_B200_CD_DIAG")) {   // timeout records of the bounded spins, readable after the context died
     unsigned long long* h = nullptr;
-    LVX_CUDA(cudaHostAlloc(&h, 64 * sizeof(unsigned long long), cudaHostAllocMapped));
-    memset(h, 0, 64 * sizeof(unsigned long long));
+    LVX_CUDA(cudaHostAlloc(&h, 256 * sizeof(unsigned long long), cudaHostAllocMapped));
+    memset(h, 0, 256 * sizeof(unsigned long long));
     unsigned long long* d = nullptr;
     LVX_CUDA(cudaHostGetDevicePointer(&d, h, 0));
     LVX_CUDA(cudaMemcpyToSymbol(cd_diag, &d, sizeof(d)));
@@ -1195,7 +1195,7 @@ static bool cluster_applicable(const lvx_engine* e, const SamplerArgs& sa) {
 // earlier build died in a bounded spin (dead wait, 1 in ~10-40 launches) as soon as 9+ clusters were in flight, i.e. when
 // pending clusters start while others drain; never at <= 8.  The spin-waits did not reconverge the warp before the
 // .sync.aligned instructions that follow them; with __syncwarp() after every wait (cd_wait) the rate dropped to ONE dead
-// wait in ~1700 uncapped rounds of 9-16 clusters (scripts/cluster_stress.py, LLMVOX_B200_CD_CAP=64; the record left by
+// wait in ~5000 uncapped rounds of 9-16 clusters (scripts/cluster_stress.py, LLMVOX_B200_CD_CAP=64; the record left by
 // the timed-out spin: an MMA issuer warp of a second-wave cluster waiting for the activation-ready barrier), and none
 // in any capped run.  So the cap is a correctness measure, not only a conservative one, until the remaining cause is
 // found (open item).  It costs nothing at BASELINE config 1 (4 clusters), more clusters than are co-resident

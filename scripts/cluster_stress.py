@@ -40,10 +40,17 @@ for B in [int(x) for x in os.environ.get("STRESS_B", "144,192,256").split(",")]:
                 d = f()
                 if d:
                     print("diag records:", d[0])
-                    for i in range(min(60, d[0])):
-                        v = d[1 + i]
-                        blk = (v >> 12) & 0x7ffff
-                        print(f"  bar 0x{v >> 32:x} parity {(v >> 31) & 1} cluster {blk // 16} rank {blk % 16} thread {v & 0xfff} (warp {(v & 0xfff) // 32})")
+                    names = {16: "act", 17: "tmem_full", 18: "xbar0", 19: "xbar1"}
+                    for i in range(min(24, d[0])):
+                        r = [d[1 + 10 * i + k] for k in range(10)]
+                        v = r[0]
+                        blk = (v >> 12) & 0x3ffff
+                        bidx = ((v >> 32) & 511) // 8
+                        nm = names.get(bidx, f"full{bidx}" if bidx < 8 else f"empty{bidx - 8}" if bidx < 16 else f"tile{bidx - 20}")
+                        def fmt(w):
+                            return f"{w >> 40}.{(w >> 32) & 0xff:02x}/{(w >> 16) & 0xffff}.{w & 0xffff}"
+                        print(f"  cluster {blk // 16} rank {blk % 16} warp {(v & 0xfff) // 32} waits {nm} parity {(v >> 30) & 1}{' (cluster scope)' if (v >> 31) & 1 else ''}"
+                              f" | barrier word {r[9]:#x} | workers {fmt(r[1])} issuers {fmt(r[2])} {fmt(r[3])} {fmt(r[4])} producer iter {r[5] >> 32} gi {r[5] & 0xffffffff}")
                 os._exit(3)
             ts.append(1e3 * (time.perf_counter() - t0))
         print(f"B={B} lanes={lanes}: {REPS} rounds ok, median {np.median(ts):.1f} ms", flush=True)

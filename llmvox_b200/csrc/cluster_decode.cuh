@@ -330,38 +330,51 @@ __device__ __forceinline__ unsigned cd_mma_rowsplit(uint32_t sbase, uint32_t bar
   return gi;
 }
 
-// ---- attention of one (session, head) by one warp: src/model.py:68-98, one query row against [cache ; new row].
-// q / k / v of the new token come from shared memory (fp32), the cache from the paged pool (layout of
-// decode_attention_kernel: [layer][k|v][page][head][16 tokens][96] bf16, i.e. one page of one head = 3 KB contiguous).
-// Every global load is a fully coalesced 512-byte warp access (the L1 request rate, not latency or bandwidth, is what
-// bounded the versions that read one row per lane or 8 bytes per lane: measured 0.13-0.18 us per cached token).
-//   scores : a block = 32 tokens = 2 pages = 12 warp loads; lane i of load k holds chunk 32k + i of the block (token
-//            (32k + i) / 12, dims 8 ((8k + i) % 12) ..+8): its partial dot product goes to a per-warp scratch row, and
-//            lane t then adds the 12 partials of token base + t.  A lane only ever meets 3 of the 12 q chunks (registers).
-//            One warp max / sum per 32 tokens (online softmax).
-//   P V    : lanes 0-11 / 12-23 = the twelve 16-byte chunks of the V rows of tokens 2j / 2j+1; 8 output dims per lane,
-//            the probability arrives by shuffle; the two token halves are merged once at the end.
-// The V loads of block b and the K loads of block b+1 are in flight while block b is computed.
+// ---- attention of one (session, head) by one warp: src/model.py:68-98, one query row against [cache ; new row], on
+// warp-level tensor-core tiles (mma.sync m16n8k16, bf16 x bf16 -> fp32).  q / k / v of the new token come from shared
+// memory (fp32), the cache from the paged pool (layout of decode_attention_kernel: [layer][k|v][page][head][16 tokens][96]
+// bf16, i.e. one page of one head = 3 KB contiguous).  History (profiles/r01d_cluster_decode.md): scalar-FMA versions were
+// bound first by the L1 request rate (one row or 8 bytes per lane), then, with fully coalesced loads, by instruction
+// issue (~650 instructions per 32 cached tokens of bf16 unpacking and FMAs).
+// Per KV page (16 tokens, 3 KB contiguous): 6 coalesced 512-byte loads each for K and V land in registers, are staged
+// into a per-warp shared-memory tile (row pitch 208 B: conflict-free ldmatrix), and
+//   scores : D[0, token] = q (row 0 of A, bf16) . K^T (B via ldmatrix)        12 MMAs
+//   P V    : D[0, dim]   = p (row 0 of A = the score fragment, exp'ed, bf16) . V (B via ldmatrix.trans)   12 MMAs
+// with an online-softmax rescale per page.  Rows 1..15 of A are zero: 1/16 of the tensor work is useful, and it is
+// still ~5x fewer instructions.  (tcgen05 needs CTA-wide M >= 64 tiles in TMEM: no fit for eight independent
+// one-row problems per CTA; the legacy warp MMA is the right size here.)
 // Returns (lanes 0-11 and, duplicated, 12-23) chunk c = lane % 12 of the bf16 output row: y[8c .. 8c+8).
 // Requirements checked on the host: 16 tokens per page, at most 64 pages per session (page table in registers), every
 // plane of the pool addressable with 32-bit element offsets.
-__device__ __noinline__ uint4 cd_attention_warp(bf16* kv, const int* pt, long long pool_pages, int layer, int T, int h, const float* qkv,
-                                                float* scratch) {
-  constexpr int HD = CD_HD, NC = HD / 8;   // 12 chunks of 8 dims
+__device__ __forceinline__ void cd_mma_bf16(float& d0, float& d1, float& d2, float& d3, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                            uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d0), "+f"(d1), "+f"(d2), "+f"(d3)
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t cd_pack2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+// pt0 / pt1: the session's page table (lane i: entries i, i + 32; loaded once per launch).
+__device__ __forceinline__ const bf16* cd_attention_kbase(bf16* kv, long long pool_pages, int layer, int h) {
+  return kv + (size_t)(layer * 2) * ((size_t)pool_pages * (CD_H * 16 * CD_HD)) + h * (16 * CD_HD) + 8 * (threadIdx.x & 31);
+}
+// (Inlining this routine so that the first K page could be issued before the q/k/v exchange cost more in spills than the
+// hidden latency is worth: measured 11.3 vs 9.4 us per attention pass.  It stays a separate function.)
+__device__ __noinline__ uint4 cd_attention_mma_warp(const bf16* kbase, int pt0, int pt1, long long pool_pages, int T, const float* qkv,
+                                                    uint8_t* tile, uint32_t* yst) {
+  constexpr int HD = CD_HD, NC = HD / 8, PITCH = 208;
   constexpr uint32_t head_stride = 16 * HD, page_stride = CD_H * head_stride;
   const int lane = threadIdx.x & 31;
-  const int gsel = (lane >= NC && lane < 2 * NC) ? 1 : 0, cc = lane % NC;
+  const int g = lane >> 2, tq = lane & 3, cc = lane % NC;
   const size_t plane = (size_t)pool_pages * page_stride;
-  const bf16* const kbase = kv + (size_t)(layer * 2) * plane + h * head_stride + 8 * lane;
-  const bf16* const vbase = kv + (size_t)(layer * 2 + 1) * plane + h * head_stride + 8 * cc;
-  const int n_pages = (T >> 4) + 1;
-  const int pt0 = (lane < n_pages) ? __ldg(pt + lane) : 0, pt1 = (lane + 32 < n_pages) ? __ldg(pt + lane + 32) : 0;
+  const bf16* const vbase = kbase + plane;
   auto page_at = [&](int pidx) -> uint32_t {   // warp-uniform argument
     const int a = __shfl_sync(0xffffffffu, pt0, pidx & 31), c = __shfl_sync(0xffffffffu, pt1, pidx & 31);
-    return (uint32_t)((pidx & 32) ? c : a);
+    return (uint32_t)((pidx & 32) ? c : a) * page_stride;
   };
-  // new token: bf16-rounded like every cached row; lanes 0-11 append chunk cc of k and v (O(1): the reference
-  // torch.cat's the whole cache, src/model.py:74-77)
+  // new token: bf16-rounded like every cached row; lanes 0-11 append chunk cc of k and v
   uint4 kn, vn;
   {
     const float4 k0 = *reinterpret_cast<const float4*>(qkv + HD + 8 * cc), k1 = *reinterpret_cast<const float4*>(qkv + HD + 8 * cc + 4);
@@ -369,104 +382,130 @@ __device__ __noinline__ uint4 cd_attention_warp(bf16* kv, const int* pt, long lo
     const float kf[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w}, vf[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
     kn = cd_pack8(kf);
     vn = cd_pack8(vf);
-    const uint32_t o = page_at(T >> 4) * page_stride + (uint32_t)(T & 15) * HD;
+    const uint32_t o = page_at(T >> 4) + (uint32_t)(T & 15) * HD;
     if (lane < NC) {
       *reinterpret_cast<uint4*>(const_cast<bf16*>(kbase) - 8 * lane + o + 8 * cc) = kn;
-      *reinterpret_cast<uint4*>(const_cast<bf16*>(vbase) + o) = vn;
+      *reinterpret_cast<uint4*>(const_cast<bf16*>(vbase) - 8 * lane + o + 8 * cc) = vn;
     }
-  }
-  // the three q chunks this lane meets: (lane + {0, 8, 4}) % 12 for loads k % 3 = 0, 1, 2
-  float q3[3][8];
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    const int c = (lane + ((8 * r) % NC)) % NC;
-    const float4 a = *reinterpret_cast<const float4*>(qkv + 8 * c), b = *reinterpret_cast<const float4*>(qkv + 8 * c + 4);
-    q3[r][0] = a.x; q3[r][1] = a.y; q3[r][2] = a.z; q3[r][3] = a.w; q3[r][4] = b.x; q3[r][5] = b.y; q3[r][6] = b.z; q3[r][7] = b.w;
   }
   const float scale = 0.10206207261596577f;   // 96^-0.5
-  float m = -INFINITY, l = 0.f, acc[8];
+  // A fragments of the scores: row 0 = q * scale (bf16), only lanes with g == 0 hold non-zeros
+  uint32_t qa0[6], qa2[6];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  uint4 kr[NC], vr[16];
-  uint32_t pg0 = page_at(0) * page_stride, pg1 = page_at(1) * page_stride;   // pages of the block (entry 1 may be unallocated = 0)
+  for (int kt = 0; kt < 6; ++kt) {
+    const float2 x = *reinterpret_cast<const float2*>(qkv + 16 * kt + 2 * tq), y = *reinterpret_cast<const float2*>(qkv + 16 * kt + 2 * tq + 8);
+    qa0[kt] = g == 0 ? cd_pack2(x.x * scale, x.y * scale) : 0u;
+    qa2[kt] = g == 0 ? cd_pack2(y.x * scale, y.y * scale) : 0u;
+  }
+  // staging offsets of this lane's six 16-byte chunks of a page: chunk 32k + lane -> token (32k + lane) / 12, column chunk % 12
+  uint32_t soff[6];
 #pragma unroll
-  for (int k = 0; k < NC; ++k) kr[k] = cd_ld_stream(kbase + (k < 6 ? pg0 : pg1) + 256 * (k % 6));
+  for (int k = 0; k < 6; ++k) soff[k] = (uint32_t)(((32 * k + lane) / NC) * PITCH + ((32 * k + lane) % NC) * 16);
+  const uint32_t tile_s = smem_u32(tile);
+  // ldmatrix row addresses: lane L -> matrix L / 8, row L % 8
+  const uint32_t lm_k = tile_s + (uint32_t)((8 * (lane >> 4) + (lane & 7)) * PITCH + 16 * ((lane >> 3) & 1));   // + 32 * kt
+  const uint32_t lm_v = tile_s + (uint32_t)((8 * ((lane >> 3) & 1) + (lane & 7)) * PITCH + 16 * (lane >> 4));    // + 32 * jp
+  float m = -INFINITY, l = 0.f, acc[2 * NC];
+#pragma unroll
+  for (int i = 0; i < 2 * NC; ++i) acc[i] = 0.f;
+  float z2 = 0.f, z3 = 0.f;   // rows 8..15 of every product (A rows are zero there): shared dummies
+  uint4 kr[6], vr[6];
+  const int pages = (T + 15) >> 4;
+  uint32_t pg = page_at(0);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) kr[k] = cd_ld_stream(kbase + pg + 256 * k);
 #pragma unroll 1
-  for (int base = 0; base < T; base += 32) {
+  for (int p = 0; p < pages; ++p) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {   // V rows of tokens base + 2j (+1), clamped to a written token
-      const int tk = min(2 * j + gsel, T - 1 - base);
-      vr[j] = cd_ld_stream(vbase + ((tk & 16) ? pg1 : pg0) + (uint32_t)(tk & 15) * HD);   // lanes 24-31 repeat lanes 0-7 (same sectors)
-    }
+    for (int k = 0; k < 6; ++k) vr[k] = cd_ld_stream(vbase + pg + 256 * k);
+    // ---- scores of the page's 16 tokens
 #pragma unroll
-    for (int k = 0; k < NC; ++k) {
-      float f[8], sc = 0.f;
-      cd_unpack8(kr[k], f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) sc = fmaf(q3[k % 3][i], f[i], sc);
-      scratch[32 * k + lane] = sc;
-    }
+    for (int k = 0; k < 6; ++k) *reinterpret_cast<uint4*>(tile + soff[k]) = kr[k];
     __syncwarp();
-    float sc;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;   // tokens 2tq, 2tq+1 (n-tile 0) and 8+2tq, 8+2tq+1 (n-tile 1) for g == 0
     {
-      const float4 a = *reinterpret_cast<const float4*>(scratch + NC * lane), b = *reinterpret_cast<const float4*>(scratch + NC * lane + 4),
-                   c = *reinterpret_cast<const float4*>(scratch + NC * lane + 8);
-      sc = ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w)) + ((c.x + c.y) + (c.z + c.w));
+      float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f, y2 = 0.f, y3 = 0.f;   // odd k-tiles: a second, independent MMA chain
+#pragma unroll
+      for (int kt = 0; kt < 6; ++kt) {
+        uint32_t b0, b1, b2, b3;
+        asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(lm_k + 32u * kt));
+        if (kt & 1) {
+          cd_mma_bf16(e0, e1, y2, y3, qa0[kt], 0u, qa2[kt], 0u, b0, b1);
+          cd_mma_bf16(e2, e3, y2, y3, qa0[kt], 0u, qa2[kt], 0u, b2, b3);
+        } else {
+          cd_mma_bf16(s0, s1, z2, z3, qa0[kt], 0u, qa2[kt], 0u, b0, b1);
+          cd_mma_bf16(s2, s3, z2, z3, qa0[kt], 0u, qa2[kt], 0u, b2, b3);
+        }
+      }
+      s0 += e0; s1 += e1; s2 += e2; s3 += e3;
     }
     __syncwarp();
-    const bool valid = base + lane < T;
-    sc = valid ? sc * scale : -INFINITY;   // select, not arithmetic: rows past T may hold anything
-    const float mn = fmaxf(m, warp_max(sc));   // finite: token `base` is valid
-    const float corr = __expf(m - mn), pr = valid ? __expf(sc - mn) : 0.f;
-    l = l * corr + warp_sum(pr);
+    pg = page_at(p + 1);   // past the end: entry 0 = a mapped page, never consumed
+#pragma unroll
+    for (int k = 0; k < 6; ++k) kr[k] = cd_ld_stream(kbase + pg + 256 * k);
+    // ---- online softmax over the page (the 4 lanes of a g group hold 4 tokens each; select, not arithmetic, for rows >= T)
+    const int t0 = 16 * p + 2 * tq;
+    s0 = t0 < T ? s0 : -INFINITY; s1 = t0 + 1 < T ? s1 : -INFINITY; s2 = t0 + 8 < T ? s2 : -INFINITY; s3 = t0 + 9 < T ? s3 : -INFINITY;
+    float mx = fmaxf(fmaxf(s0, s1), fmaxf(s2, s3));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    const float mn = fmaxf(m, mx);   // finite: token 16 p < T
+    const float corr = __expf(m - mn);
+    const float p0 = __expf(s0 - mn), p1 = __expf(s1 - mn), p2 = __expf(s2 - mn), p3 = __expf(s3 - mn);
+    l = l * corr + ((p0 + p1) + (p2 + p3));   // per-lane partial, merged at the end
     m = mn;
-    // K pages of the next block (past the end: page-table entries are 0 = a mapped page, never consumed)
-    pg0 = page_at((base >> 4) + 2) * page_stride;
-    pg1 = page_at((base >> 4) + 3) * page_stride;
+    const uint32_t pa0 = g == 0 ? cd_pack2(p0, p1) : 0u, pa2 = g == 0 ? cd_pack2(p2, p3) : 0u;
+    // ---- P V
 #pragma unroll
-    for (int k = 0; k < NC; ++k) kr[k] = cd_ld_stream(kbase + (k < 6 ? pg0 : pg1) + 256 * (k % 6));
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] *= corr;
-#pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const float pj = __shfl_sync(0xffffffffu, pr, 2 * j + gsel);
-      float f[8];
-      cd_unpack8(vr[j], f);
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = fmaf(pj, f[i], acc[i]);
+    for (int k = 0; k < 6; ++k) *reinterpret_cast<uint4*>(tile + soff[k]) = vr[k];
+    __syncwarp();
+    if (16 * p + 16 > T) {   // last, partial page: rows >= T may hold anything (0 x NaN): zero them
+      for (int i = lane; i < 16 * NC; i += 32)
+        if (16 * p + i / NC >= T) *reinterpret_cast<uint4*>(tile + (i / NC) * PITCH + (i % NC) * 16) = make_uint4(0u, 0u, 0u, 0u);
+      __syncwarp();
     }
+#pragma unroll
+    for (int i = 0; i < 2 * NC; ++i) acc[i] *= corr;
+#pragma unroll
+    for (int jp = 0; jp < 6; ++jp) {   // dims 16 jp .. 16 jp + 15: two n-tiles
+      uint32_t b0, b1, b2, b3;
+      asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(lm_v + 32u * jp));
+      cd_mma_bf16(acc[4 * jp], acc[4 * jp + 1], z2, z3, pa0, 0u, pa2, 0u, b0, b1);
+      cd_mma_bf16(acc[4 * jp + 2], acc[4 * jp + 3], z2, z3, pa0, 0u, pa2, 0u, b2, b3);
+    }
+    __syncwarp();
   }
-  {   // the new token: lanes 0-11 hold chunk cc of its (bf16-rounded) k; only the first token half adds its value row
+  // the new token: score by lanes 0-11 (chunk cc of its bf16 k) + warp sum
+  float pn, corr;
+  {
     float sc = 0.f;
-    {
-      const float4 q0 = *reinterpret_cast<const float4*>(qkv + 8 * cc), q1 = *reinterpret_cast<const float4*>(qkv + 8 * cc + 4);
-      float f[8];
-      cd_unpack8(kn, f);
-      sc = fmaf(q0.x, f[0], sc); sc = fmaf(q0.y, f[1], sc); sc = fmaf(q0.z, f[2], sc); sc = fmaf(q0.w, f[3], sc);
-      sc = fmaf(q1.x, f[4], sc); sc = fmaf(q1.y, f[5], sc); sc = fmaf(q1.z, f[6], sc); sc = fmaf(q1.w, f[7], sc);
-      if (lane >= NC) sc = 0.f;
-    }
-    sc = warp_sum(sc) * scale;
-    const float mn = fmaxf(m, sc);
-    const float corr = __expf(m - mn), pn = __expf(sc - mn);
-    l = l * corr + pn;
+    const float4 q0 = *reinterpret_cast<const float4*>(qkv + 8 * cc), q1 = *reinterpret_cast<const float4*>(qkv + 8 * cc + 4);
     float f[8];
-    cd_unpack8(vn, f);
-    const float pv = gsel ? 0.f : pn;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = fmaf(pv, f[i], acc[i] * corr);
+    cd_unpack8(kn, f);
+    sc = fmaf(q0.x, f[0], sc); sc = fmaf(q0.y, f[1], sc); sc = fmaf(q0.z, f[2], sc); sc = fmaf(q0.w, f[3], sc);
+    sc = fmaf(q1.x, f[4], sc); sc = fmaf(q1.y, f[5], sc); sc = fmaf(q1.z, f[6], sc); sc = fmaf(q1.w, f[7], sc);
+    if (lane >= NC) sc = 0.f;
+    sc = warp_sum(sc) * scale;
+    // merge the per-lane partial sums of the 4 lanes of the g == 0 group first (same m in all of them)
+    l += __shfl_xor_sync(0xffffffffu, l, 1);
+    l += __shfl_xor_sync(0xffffffffu, l, 2);
+    const float mn = fmaxf(m, sc);
+    corr = __expf(m - mn);
+    pn = __expf(sc - mn);
+    l = l * corr + pn;
   }
-  // merge the two token halves (lane c += lane c + 12), normalise, pack; lanes 12-23 get a copy
+  // lanes 0-3 (g == 0) hold out[8 j + 2 tq + e] in acc[2 j + e]; the new token's v comes from shared memory (bf16-rounded)
   const float inv = 1.0f / l;
-  float o[8];
+  if (g == 0) {
 #pragma unroll
-  for (int i = 0; i < 8; ++i) o[i] = (acc[i] + __shfl_down_sync(0xffffffffu, acc[i], NC)) * inv;
-  uint4 out = cd_pack8(o);
-  out.x = __shfl_sync(0xffffffffu, out.x, cc);
-  out.y = __shfl_sync(0xffffffffu, out.y, cc);
-  out.z = __shfl_sync(0xffffffffu, out.z, cc);
-  out.w = __shfl_sync(0xffffffffu, out.w, cc);
-  return out;
+    for (int j = 0; j < NC; ++j) {
+      const float2 v2 = *reinterpret_cast<const float2*>(qkv + 2 * HD + 8 * j + 2 * tq);
+      const float o0 = (acc[2 * j] * corr + pn * round_to<bf16>(v2.x)) * inv, o1 = (acc[2 * j + 1] * corr + pn * round_to<bf16>(v2.y)) * inv;
+      yst[4 * j + tq] = cd_pack2(o0, o1);
+    }
+  }
+  __syncwarp();
+  return *reinterpret_cast<const uint4*>(yst + 4 * cc);
 }
 
 // text-table elements (features below text_dim), position-row elements and the text row's sum of squares for position t
@@ -658,13 +697,23 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
     unsigned xphase = 0, gcount = 0;
     long long* trp = nullptr;
     float pre_e[3] = {0.f, 0.f, 0.f}, pre_pe[3] = {0.f, 0.f, 0.f}, pre_ss = 0.f;   // next iteration's text / position part
+    // page table of this warp's attention session (8 * odd + ww), whole launch: the host allocated every page the launch
+    // needs before it (lane i holds entries i and i + 32; unallocated entries read as page 0, a mapped page)
+    int pt0 = 0, pt1 = 0;
+    {
+      const int n = 8 * odd + ww;
+      if (n < nloc) {
+        const int* pt = P.st.page_table + (size_t)sm_slot[n] * P.st.max_pages;
+        const int n_pages = ((sm_t[n] + n_iters - 1) >> 4) + 1;
+        pt0 = (lane < n_pages) ? __ldg(pt + lane) : 0;
+        pt1 = (lane + 32 < n_pages) ? __ldg(pt + lane + 32) : 0;
+      }
+    }
 
     // Cluster barrier of the worker warps: everything this CTA's workers stored (locally or into peers) before it is
     // visible to every peer's workers after it.  Two alternating mbarriers (count 16 = one arrival per peer): a fast
     // peer's arrival for exchange p+1 can never complete a slow CTA's exchange p.
-    int cur_sl = 0, cur_iter = 0;
     auto exchange = [&](bool for_tensor_core) {
-      if (ww == 0) CD_STATUS(0, (cur_iter << 8) | cur_sl, (xphase << 16) | (gcount & 0xffffu));
       if (for_tensor_core) cd_proxy_fence_cluster();
       cd_workers_sync();
       const uint32_t bar = cd_bar_x(bars, xphase & 1u);
@@ -680,7 +729,6 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
       if (wt == 0) cd_mbar_arrive(cd_bar_act(bars));
     };
     auto wait_acc = [&]() {
-      if (ww == 0) CD_STATUS(0, (cur_iter << 8) | cur_sl | 0x80, (xphase << 16) | (gcount & 0xffffu));
       cd_wait(cd_bar_tmem(bars), gcount & 1u);
       gcount += 1;
       tc_fence_after();
@@ -718,8 +766,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
 #pragma unroll 1
       for (int sl = 0; sl <= 2 * n_layer; ++sl) {
         const int l = sl >> 1;
-        cur_sl = sl;
-        cur_iter = iter;
+        if (ww == 0) CD_STATUS(0, (iter << 8) | sl, (xphase << 16) | (gcount & 0xffffu));
         // ================= x all-gather + LayerNorm (src/model.py:29-38; weight folded into the GEMM) -> A1
         cd_workers_sync();   // xs complete
         {   // partial statistics of sessions 2ww, 2ww+1 over this CTA's 48 features, one (mean, M2) pair to every peer.
@@ -811,9 +858,10 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
             uint4 val = make_uint4(0u, 0u, 0u, 0u);
             if (n < nloc) {   // warp-uniform
               const int slot = sm_slot[n];
-              // scratch: 384 floats per warp inside A1 (LN1(x) has been consumed by the qkv MMAs; the LN2 gather comes later)
-              val = cd_attention_warp(P.kv, P.st.page_table + (size_t)slot * P.st.max_pages, P.pool_pages, l, (P.dbg & 2) ? 0 : sm_t[n],
-                                      head, qkvb + ww * 288, reinterpret_cast<float*>(sgen + CD_OFF_A1) + ww * 384);
+              // per-warp 16 x 208 B staging tile inside A1 | A2 (30 KB; LN1(x) has been consumed by the qkv MMAs, the LN2
+              // gather and the GELU slice come later)
+              val = cd_attention_mma_warp(cd_attention_kbase(P.kv, P.pool_pages, l, head), pt0, pt1, P.pool_pages, (P.dbg & 2) ? 0 : sm_t[n],
+                                          qkvb + ww * 288, sgen + CD_OFF_A1 + ww * 3328, reinterpret_cast<uint32_t*>(sgen + CD_OFF_YST) + ww * 48);
             }
             // output row to every peer's y operand: lanes 0-11 / 12-23 hold the 12 chunks, 8 peers each
             if (lane < 24) {

@@ -40,8 +40,8 @@ SCHEDULE = [10, 30, 90, 70]          # reference chunk schedule for 200 codes (r
 CODES_PER_SEC = 75.0                 # 24 kHz / hop 320
 SEED = 1234
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of cluster_decode_kernel, from the committed `ncu --set full`
-# capture of one step's four decode launches (profiles/r01d_cluster_decode.md section 2: mean of 0.44 / 1.77 / 8.40 / 10.82 GB)
-CLUSTER_TRAFFIC = 5.358e9
+# capture of one step's four decode launches (profiles/r01d_cluster_decode.md section 2: mean of 0.48 / 2.00 / 10.53 / 12.71 GB)
+CLUSTER_TRAFFIC = 6.43e9
 
 
 def synthetic_text(n_streams: int, seed: int):

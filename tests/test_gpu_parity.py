@@ -550,6 +550,39 @@ def test_cluster_decode_ragged_contexts_and_long_runs(weights):
     ref.close()
 
 
+def test_cluster_decode_large_call_is_split_and_batch_invariant(weights):
+    """A call with more sessions than 7 clusters hold (130 -> launches of 112 + 18) must give every session exactly the
+    codes it gets when the same sessions are decoded in differently composed calls (a session's arithmetic does not
+    depend on its neighbours or on its place in a cluster), also when the calls are spread over three streams / lanes."""
+    from llmvox_b200.engine import Engine
+    n = 130
+    kw = dict(device=0, precision="bf16", max_sessions=n, max_context=48, max_vocode_frames=256, decode_lanes=3)
+    rng = np.random.RandomState(11)
+    texts = [rng.randint(3, 259, size=rng.randint(0, 40)).tolist() for _ in range(n)]
+    slots = list(range(n))
+    a = Engine(weights, **kw)
+    a.open(slots)
+    a.feed_text(slots, texts)
+    l0 = a.kernel_launches
+    a.decode_steps(slots, 24)
+    assert a.kernel_launches - l0 <= 8               # two cluster launches (+ stream packing on first use, page patches), not 24 x 33 kernels
+    ca = a.gather_codes(slots, 0, 24).cpu()
+    b = Engine(weights, **kw)
+    b.open(slots)
+    b.feed_text(slots, texts)
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    ev = torch.cuda.Event()
+    ev.record()
+    for lane, (lo, hi) in enumerate([(0, 50), (50, 57), (57, 130)]):
+        streams[lane].wait_event(ev)
+        b.decode_steps(slots[lo:hi], 24, stream=streams[lane], lane=lane)
+    torch.cuda.synchronize()
+    cb = b.gather_codes(slots, 0, 24).cpu()
+    assert (ca == cb).all()
+    a.close()
+    b.close()
+
+
 def test_error_behaviour(engines):
     from llmvox_b200._lib import LvxError
     e = engines("fp32")

@@ -49,9 +49,16 @@ constexpr int CD_VR = CD_V / CD_CLUSTER;       // 256
 constexpr int CD_MAX_LAYERS = 8;
 constexpr int CD_STAGES = 8;
 constexpr int CD_SLOT = 16384;                 // bytes per ring slot (one 128-row x 64-column tile)
-constexpr int CD_NI = 3;                       // MMA issuer warps
-constexpr int CD_THREADS = 384;                // warp 0 producer, warps 1-3 MMA issuers, warps 4..11 workers
-constexpr int CD_WORKER0 = 128;                // first worker thread
+constexpr int CD_NI = 2;                       // MMA issuer warps
+// Issuer w takes the ring items at positions = w (mod CD_NI).  The ring depth MUST be a multiple of CD_NI: then every use
+// of a slot is seen, in order, by the same issuer, which is what the parity wait on the slot's `full` barrier assumes.
+// (With 3 issuers and 8 slots, positions a and a + 8 belonged to different issuers: an issuer reaching a + 8 while the
+// copy for a was still in flight saw "the other parity" as already complete and ran ahead on stale data; with copies
+// completing out of order this is a rare, timing-dependent corruption of the barrier phases -> the dead waits seen
+// with many clusters in flight.  Three issuers were no faster than two anyway: the tensor pipe and the stream bound it.)
+static_assert(CD_STAGES % CD_NI == 0, "every ring slot must belong to exactly one issuer");
+constexpr int CD_THREADS = 32 * (1 + CD_NI + 8);   // warp 0 producer, warps 1..CD_NI MMA issuers, then 8 worker warps
+constexpr int CD_WORKER0 = 32 * (1 + CD_NI);       // first worker thread
 constexpr int CD_WORKERS = 256;
 constexpr int CD_ABLK = CD_NB * 128;           // one 64-wide k-block of an activation operand (16 rows x 128 B)
 // Weight stream items (one bulk copy + one ring slot each, <= 16 KB so that 8 are in flight).  Per layer:
@@ -59,7 +66,7 @@ constexpr int CD_ABLK = CD_NB * 128;           // one 64-wide k-block of an acti
 //   proj : 6 x [2 k-blocks x 48 rows]
 //   fc   : 12 x [128 rows x 64 k], then the 64-row tail as 6 x [2 k-blocks x 8 KB]
 //   proj2: 18 x [128 rows x 64 k]  (row tile m = s / 3, k-block s % 3 of this CTA's k-slice)
-// then lm_head: 24 x [128 rows x 64 k] (k-block major; item j = row tile j & 1)
+// then lm_head: 24 x [128 rows x 64 k] (k-block major; item j = row tile (j ^ (j >> 1)) & 1)
 constexpr int CD_TILE = 16384;
 constexpr int CD_QT = (CD_QR - 128) * 128;     // one k-block of the qkv tail (16 rows)
 constexpr int CD_PT = CD_XR * 128;             // one k-block of proj (48 rows)
@@ -68,11 +75,12 @@ constexpr long long CD_LAYER_BYTES = (long long)CD_QR * CD_C * 2 + (long long)CD
                                      (long long)CD_C * CD_FR * 2;
 constexpr long long CD_LM_BYTES = (long long)CD_VR * CD_C * 2;
 // TMEM accumulator columns
-// Three copies of every accumulator, 128 columns apart, one per MMA issuer warp: issuer w takes the ring items at
-// positions = w (mod 3), accumulating into its own copy, and the epilogue adds the three.  With
+// CD_NI copies of every accumulator, 128 columns apart, one per MMA issuer warp: issuer w takes the ring items at
+// positions = w (mod CD_NI), accumulating into its own copy, and the epilogue adds them.  With
 // N = 16 a GEMM phase is bound by the issuing warp's serial per-item latency (barrier poll, fence, 4 MMAs, commit:
 // ~300 cycles per 16 KB item, measured; M = 64 instead of 128 changed it by only 13 %), not by the tensor pipe.
-constexpr int CD_TM_QKV = 0, CD_TM_PROJ = 32, CD_TM_FC = 96, CD_TM_PROJ2 = 0, CD_TM_LM = 96, CD_TM_BANK = 128, CD_TM_COLS = 512;
+constexpr int CD_TM_QKV = 0, CD_TM_PROJ = 32, CD_TM_FC = 96, CD_TM_PROJ2 = 0, CD_TM_LM = 96, CD_TM_BANK = 128, CD_TM_COLS = 256;
+static_assert(CD_NI * CD_TM_BANK <= CD_TM_COLS, "accumulator copies must fit the TMEM allocation");
 // shared-memory carve (offsets from the 1024-aligned base)
 constexpr int CD_OFF_RING = 0;
 constexpr int CD_OFF_A1 = CD_OFF_RING + CD_STAGES * CD_SLOT;          // [12 k-blocks][16 x 128 B]: LN(x) / y operand
@@ -209,7 +217,7 @@ __device__ __forceinline__ void cd_workers_sync() { asm volatile("bar.sync 1, 25
 // generic-proxy stores into shared memory (own CTA / a peer's) before the tensor core (async proxy) reads them
 __device__ __forceinline__ void cd_proxy_fence_cta() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void cd_proxy_fence_cluster() { asm volatile("fence.proxy.async.shared::cluster;" ::: "memory"); }
-// 32 lanes x 8 consecutive fp32 columns of the three accumulator copies, summed
+// 32 lanes x 8 consecutive fp32 columns of the accumulator copies, summed
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   uint32_t r[CD_NI][8];
 #pragma unroll
@@ -221,7 +229,12 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 8; ++i)
-    v[i] = (__uint_as_float(r[0][i]) + __uint_as_float(r[1][i])) + __uint_as_float(r[2][i]);
+  {
+    float a = __uint_as_float(r[0][i]);
+#pragma unroll
+    for (int j = 1; j < CD_NI; ++j) a += __uint_as_float(r[j][i]);
+    v[i] = a;
+  }
 }
 __device__ __forceinline__ uint4 cd_pack8(const float* f) {
   uint4 u;
@@ -274,7 +287,7 @@ __device__ __forceinline__ uint32_t cd_bar_empty(uint32_t bars, unsigned s) { re
 __device__ __forceinline__ uint32_t cd_bar_act(uint32_t bars) { return bars + 8u * (2 * CD_STAGES); }
 __device__ __forceinline__ uint32_t cd_bar_tmem(uint32_t bars) { return bars + 8u * (2 * CD_STAGES + 1); }
 __device__ __forceinline__ uint32_t cd_bar_x(uint32_t bars, unsigned i) { return bars + 8u * (2 * CD_STAGES + 2 + i); }
-// one barrier per proj2 row tile (count = issuers, one k-block each): the scatter of tile m overlaps the MMAs of m+1..
+// one barrier per proj2 row tile (count 3 = its k-block items): the scatter of tile m overlaps the MMAs of m+1..
 __device__ __forceinline__ uint32_t cd_bar_tile(uint32_t bars, unsigned m) { return bars + 8u * (2 * CD_STAGES + 4 + m); }
 
 // ---- producer / MMA issuer pieces.  Both warps run CONVERGED and elect one lane only around the asynchronous
@@ -300,7 +313,7 @@ __device__ __forceinline__ uint32_t cd_stage_wait(uint32_t sbase, uint32_t bars,
 }
 // `128 + tail`-row weight slice against the K = 768 operand `act`: 12 full tiles into `d`, then the tail rows
 // (tail_bytes per k-block, `per` k-blocks per item) into d + 16.  This warp takes the items at ring positions = par
-// (mod 3) (d already points at its accumulator copy).  Returns the advanced ring position.
+// (mod CD_NI) (d already points at its accumulator copy).  Returns the advanced ring position.
 __device__ __forceinline__ unsigned cd_mma_rowsplit(uint32_t sbase, uint32_t bars, uint32_t idesc, unsigned gi, unsigned par, uint32_t act,
                                                     uint32_t d, int tail_bytes, int per) {
 #pragma unroll 1
@@ -552,7 +565,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
     mbar_init(cd_bar_tmem(bars), CD_NI);   // one commit per MMA issuer warp
     mbar_init(cd_bar_x(bars, 0), CD_CLUSTER);
     mbar_init(cd_bar_x(bars, 1), CD_CLUSTER);
-    for (unsigned m = 0; m < 6; ++m) mbar_init(cd_bar_tile(bars, m), CD_NI);
+    for (unsigned m = 0; m < 6; ++m) mbar_init(cd_bar_tile(bars, m), 3);   // one commit per k-block item of the tile
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -612,7 +625,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
       }
     }
   } else if (warp <= CD_NI) {
-    // ------------------------------------------------------------------ MMA issuers (three warps, ring items round-robin)
+    // ------------------------------------------------------------------ MMA issuers (ring items round-robin)
     {
       const unsigned par = (unsigned)(warp - 1);   // this issuer takes ring positions = par (mod CD_NI)
       const uint32_t idesc = umma_idesc_bf16((P.dbg & 1) ? 64 : 128, CD_NB);
@@ -629,11 +642,11 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
           tc_fence_after();
           if (sl == 2 * n_layer) {
 #pragma unroll 1
-            for (int j = 0; j < 24; ++j, ++gi) {   // lm_head: k-block j / 2, row tile j & 1 (a tile's items cycle through the issuers)
+            for (int j = 0; j < 24; ++j, ++gi) {   // lm_head: k-block j / 2, row tile (j ^ (j >> 1)) & 1: a tile's items alternate issuers
               if (gi % CD_NI != par) continue;
               const uint32_t a = cd_stage_wait(sbase, bars, gi);
               if (cd_elect()) {
-                cd_kblock(tm + CD_TM_LM + CD_NB * (j & 1), a, a1 + (j >> 1) * CD_ABLK, idesc, j >= 2 * CD_NI ? 1u : 0u);
+                cd_kblock(tm + CD_TM_LM + CD_NB * ((j ^ (j >> 1)) & 1), a, a1 + (j >> 1) * CD_ABLK, idesc, j >= 2 * CD_NI ? 1u : 0u);
                 umma_commit(cd_bar_empty(bars, gi % CD_STAGES));
               }
               __syncwarp();
@@ -671,7 +684,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
               const int m = s2 / 3, kb = s2 - 3 * m;
               const uint32_t a = cd_stage_wait(sbase, bars, gi);
               if (cd_elect()) {
-                cd_kblock(tm + CD_TM_PROJ2 + CD_NB * m, a, a2 + kb * CD_ABLK, idesc, 0u);   // one k-block per issuer
+                cd_kblock(tm + CD_TM_PROJ2 + CD_NB * m, a, a2 + kb * CD_ABLK, idesc, kb >= CD_NI ? 1u : 0u);
                 umma_commit(cd_bar_empty(bars, gi % CD_STAGES));
                 umma_commit(cd_bar_tile(bars, (unsigned)m));
               }
@@ -1092,8 +1105,8 @@ inline long long cd_build_descs(const CdLayerW* layers, int n_layer, const float
         o += CD_TILE;
       }
     }
-    for (int j = 0; j < 24; ++j) {   // k-block j / 2, row tile j & 1
-      seg(lm_head, lnf_w, ld_lm, CD_VR * r + 128 * (j & 1), 128, 64 * (j >> 1), o, 0);
+    for (int j = 0; j < 24; ++j) {   // k-block j / 2, row tile (j ^ (j >> 1)) & 1: a tile's items alternate between the two issuers
+      seg(lm_head, lnf_w, ld_lm, CD_VR * r + 128 * ((j ^ (j >> 1)) & 1), 128, 64 * (j >> 1), o, 0);
       o += CD_TILE;
     }
   }

@@ -1193,14 +1193,14 @@ static bool cluster_applicable(const lvx_engine* e, const SamplerArgs& sa) {
 // One launch = at most `cap` clusters, and never more than `cap` clusters in flight across the engine's streams: a launch
 // that would exceed it waits (cudaStreamWaitEvent, no host blocking) for the oldest launches on other streams.  History: an
 // earlier build died in a bounded spin (dead wait, 1 in ~10-40 launches) as soon as 9+ clusters were in flight, i.e. when
-// pending clusters start while others drain; never at <= 8.  The spin-waits did not reconverge the warp before the
-// .sync.aligned instructions that follow them; with __syncwarp() after every wait (cd_wait) the rate dropped to ONE dead
-// wait in ~5000 uncapped rounds of 9-16 clusters (scripts/cluster_stress.py, LLMVOX_B200_CD_CAP=64; the record left by
-// the timed-out spin: an MMA issuer warp of a second-wave cluster waiting for the activation-ready barrier), and none
-// in any capped run.  So the cap is a correctness measure, not only a conservative one, until the remaining cause is
-// found (open item).  It costs nothing at BASELINE config 1 (4 clusters), more clusters than are co-resident
-// (7 x 16 CTAs on a B200) only queue anyway, and batches far above 112 sessions are better served by the kernel-per-op
-// path (LaneRunner switches).
+// pending clusters start while others drain and the weight streams of the clusters fall out of step; never at <= 8.  Two
+// causes were found and fixed: the spin-waits did not reconverge the warp before the .sync.aligned instructions that
+// follow them (cd_wait; failures dropped to 1 in ~5000 uncapped rounds), and with 3 MMA issuers over an 8-slot ring two
+// consecutive uses of a slot belonged to different issuers, which breaks the parity wait when copies complete out of
+// order (cluster_decode.cuh, CD_NI).  960 uncapped rounds of 9-16 clusters ran clean after the second fix, which proves
+// little at that rate, so the cap stays: it costs nothing at BASELINE config 1 (4 clusters), more clusters than are
+// co-resident (7 x 16 CTAs on a B200) only queue anyway, and batches far above 112 sessions are better served by the
+// kernel-per-op path (LaneRunner switches).
 static int cluster_launch(lvx_engine* e, lvx_engine::Lane& ln, const int32_t* h_slots, int n, int n_steps, cudaStream_t st) {
   LVX_TRY(cluster_init(e));
   const lvx_config& c = e->cfg;

@@ -171,13 +171,16 @@ def run_reference(args):
 
 
 # --------------------------------------------------------------------------------------------- GPU arm
-def device_step(e, runner, slots, pcm_out):
+def device_step(e, runner, slots, pcm_out, alone=False):
     """One pass over one batch whose text already sits on the device: decode to each chunk boundary (on the decode
     lanes), vocode the 64 chunks that became ready as one ragged batch (control stream; overlaps the lanes' next
-    iterations).  No host synchronisation."""
+    iterations).  No host synchronisation, except with `alone` (the per-kernel profile leg: every decode launch is timed
+    without the vocoder running beside it)."""
     pos = 0
     for L in SCHEDULE:
         runner.decode(slots, L)
+        if alone:
+            torch.cuda.synchronize()
         codes = e.gather_codes(slots, pos, L)                       # (64, L) int32 on the device
         cu = list(range(0, (len(slots) + 1) * L, L))
         e.vocode(codes.view(-1), cu, 0, out=pcm_out[pos * len(slots) * 320:(pos + L) * len(slots) * 320])
@@ -275,7 +278,7 @@ def run_gpu(args):
     runner.sync_from_control()
     torch.cuda.synchronize()
     e.profile(True)
-    device_step(e, LaneRunner(e, 1), groups[0], pcm)
+    device_step(e, LaneRunner(e, 1), groups[0], pcm, alone=True)
     prof = e.profile_report()
     e.profile(False)
 

@@ -114,7 +114,7 @@ int lvx_decode_steps_lane(lvx_engine* e, int lane, const int32_t* h_slots, int n
 
 /* Greedy bf16 decode path of lvx_decode_steps[_lane]: on != 0 (default) = the cluster-resident kernel (one 16-CTA
  * cluster per 16 sessions runs whole iterations; at most 7 clusters in flight per engine), 0 = the kernel-per-op chain
- * (CUDA graphs + programmatic dependent launch), which is the better choice for batches far above 112 sessions.  Both
+ * (CUDA graphs + programmatic dependent launch), which is the better choice for batches above ~224 sessions.  Both
  * compute src/model.py:201-237 with the same numerics class; fp32 mode and sampled decoding always
  * use the kernel-per-op chain.  Host-side flag: takes effect for the calls that follow. */
 int lvx_set_cluster_decode(lvx_engine* e, int on);

@@ -1197,9 +1197,9 @@ static bool cluster_applicable(const lvx_engine* e, const SamplerArgs& sa) {
 // causes were found and fixed: the spin-waits did not reconverge the warp before the .sync.aligned instructions that
 // follow them (cd_wait; failures dropped to 1 in ~5000 uncapped rounds), and with 3 MMA issuers over an 8-slot ring two
 // consecutive uses of a slot belonged to different issuers, which breaks the parity wait when copies complete out of
-// order (cluster_decode.cuh, CD_NI).  960 uncapped rounds of 9-16 clusters ran clean after the second fix, which proves
-// little at that rate, so the cap stays: it costs nothing at BASELINE config 1 (4 clusters), more clusters than are
-// co-resident (7 x 16 CTAs on a B200) only queue anyway, and batches far above 112 sessions are better served by the
+// order (cluster_decode.cuh, CD_NI).  3360 uncapped rounds of 9-16 clusters ran clean after the second fix, which still
+// proves little at that rate, so the cap stays: it costs nothing at BASELINE config 1 (4 clusters), more clusters than are
+// co-resident (7 x 16 CTAs on a B200) only queue anyway, and batches above ~224 sessions are better served by the
 // kernel-per-op path (LaneRunner switches).
 static int cluster_launch(lvx_engine* e, lvx_engine::Lane& ln, const int32_t* h_slots, int n, int n_steps, cudaStream_t st) {
   LVX_TRY(cluster_init(e));
@@ -1305,7 +1305,7 @@ extern "C" int lvx_decode_steps_lane(lvx_engine* e, int lane, const int32_t* h_s
 }
 
 // Host-side choice of the greedy bf16 decode path: 1 = cluster-resident kernel where applicable (default), 0 = kernel-per-op
-// chain (the better choice for batches far above 112 sessions: LaneRunner switches per call).
+// chain (the better choice for batches above ~224 sessions: LaneRunner switches per call).
 extern "C" int lvx_set_cluster_decode(lvx_engine* e, int on) {
   LVX_TRY(check_engine(e));
   e->use_cluster = on != 0;

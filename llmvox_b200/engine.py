@@ -138,8 +138,16 @@ class Engine:
 
     def set_cluster_decode(self, on: bool):
         """Greedy bf16 decode path for the calls that follow: the cluster-resident kernel (default) or the kernel-per-op
-        chain (better far above 112 sessions per batch)."""
+        chain (better above ~224 sessions per batch)."""
         check(self.lib.lvx_set_cluster_decode(self._h, int(bool(on))))
+
+    def cluster_decode_applicable(self, sampling: Optional[Sampling] = None) -> bool:
+        """Host-side mirror of the engine's own test (engine.cu: cluster_applicable): would a decode_steps call with this
+        sampler run on the cluster-resident kernel?"""
+        c = self.cfg
+        greedy = sampling is None or sampling.greedy or sampling.top_k == 1
+        return (self.precision == "bf16" and greedy and c.n_embd == 768 and c.n_head == 8 and c.vocab_size == 4096 and not c.bias
+                and c.kv_page_tokens == 16 and c.max_context <= 1024 and c.text_dim + c.code_dim == 768)
 
     def decode_step_logits(self, slots: Sequence[int], forced: Optional[torch.Tensor] = None,
                            sampling: Optional[Sampling] = None, uniform: Optional[torch.Tensor] = None,

@@ -19,19 +19,35 @@ from .scheduler import ChunkScheduler, INITIAL_DUMP_SIZE_1, MAX_DUMP_SIZE
 
 
 class LaneRunner:
-    """Runs the decode iterations of a batch as `lanes` independent groups on their own CUDA streams.
+    """Runs the decode iterations of a batch off the control stream, so that the control stream's work (gather / vocode /
+    copies) overlaps with the next iterations.  Two shapes, chosen per call:
 
-    A decode iteration is a chain of dependent, latency-bound kernels that leaves most of the GPU idle; sessions
-    never interact, so disjoint groups advance concurrently (engine decode lanes), and the control stream (gather /
-    vocode / copies) overlaps with the lanes' next iterations.  Lanes only ever wait for the event recorded by
-    `sync_from_control()` (after open / feed), never for vocoder work."""
+    * cluster-resident decode kernel (bf16, greedy, batches up to CLUSTER_DECODE_MAX_BATCH): ONE call for all sessions on
+      one side stream; the engine cuts it into launches of at most 7 clusters (7 x 16 sessions are co-resident on a
+      B200), which run back to back.  A wave of up to 112 sessions costs the same ~150 us per iteration however many of
+      its 7 clusters are used, so batches up to 224 sessions (two waves) beat the kernel-per-op chain.
+    * kernel-per-op chain (everything else): `lanes` independent groups on their own streams.  A decode iteration there
+      is a chain of ~35 dependent, latency-bound kernels that leaves most of the GPU idle; sessions never interact, so
+      disjoint groups advance concurrently (engine decode lanes).
+
+    The side streams only ever wait for the event recorded by `sync_from_control()` (after open / feed), never for
+    vocoder work."""
+
+    # above this many sessions in one batch the kernel-per-op chain out-runs the cluster-resident kernel (three waves);
+    # measured (bench.py --short, audio-s/s, cluster vs kernel-per-op): 112: 8341 / 5418, 128: 5780 / 5992, 192: 8300 / 7624,
+    # 224: 9062 / 7457, 256: 7647 / 8251.  Just above one full wave (113..139 sessions) the second wave is nearly empty.
+    CLUSTER_DECODE_MAX_BATCH = 224
+    CLUSTER_DECODE_GAP = (113, 139)
 
     def __init__(self, engine: Engine, lanes: Optional[int] = None):
+        import os
         self.e = engine
         self.G = max(1, min(engine.decode_lanes, lanes or engine.decode_lanes))
         self.streams = [torch.cuda.Stream(device=engine.device) for _ in range(self.G)] if self.G > 1 else [None]
-        import os
+        self.side = self.streams[0] if self.G > 1 else torch.cuda.Stream(device=engine.device)   # cluster-kernel launches
         self.cluster_default = os.environ.get("LLMVOX_B200_CLUSTER", "1") != "0"
+        if "LLMVOX_B200_CLUSTER_MAX_BATCH" in os.environ:      # measurement override of the threshold above
+            self.CLUSTER_DECODE_MAX_BATCH = int(os.environ["LLMVOX_B200_CLUSTER_MAX_BATCH"])
 
     def split(self, slots: Sequence[int]) -> List[List[int]]:
         n, G = len(slots), min(self.G, len(slots))
@@ -44,26 +60,31 @@ class LaneRunner:
         return out
 
     def sync_from_control(self):
-        """Lanes wait for everything enqueued so far on the current (control) stream."""
-        if self.G == 1:
-            return
+        """The side streams wait for everything enqueued so far on the current (control) stream."""
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.e.device))
-        for st in self.streams:
+        for st in set(x for x in self.streams + [self.side] if x is not None):
             st.wait_event(ev)
 
-    # above this many sessions in one batch the kernel-per-op chain out-runs the cluster-resident kernel (7 clusters of
-    # 16 sessions are co-resident on a B200; measured at 256 streams: 8277 vs 7856 audio-s/s)
-    CLUSTER_DECODE_MAX_BATCH = 112
+    def _cluster_call(self, n: int, sampling: Optional[Sampling]) -> bool:
+        if not self.cluster_default or n > self.CLUSTER_DECODE_MAX_BATCH or not self.e.cluster_decode_applicable(sampling):
+            return False
+        return not (self.CLUSTER_DECODE_GAP[0] <= n <= self.CLUSTER_DECODE_GAP[1]) or self.CLUSTER_DECODE_MAX_BATCH > 100000
 
     def decode(self, slots: Sequence[int], n_steps: int, sampling: Optional[Sampling] = None):
-        """Enqueues n_steps iterations for every group; the control stream then waits for all lanes."""
-        if self.cluster_default:
-            self.e.set_cluster_decode(len(slots) <= self.CLUSTER_DECODE_MAX_BATCH)
+        """Enqueues n_steps iterations for the batch; the control stream then waits for them."""
+        main = torch.cuda.current_stream(self.e.device)
+        if self._cluster_call(len(slots), sampling):
+            self.e.set_cluster_decode(True)
+            self.e.decode_steps(slots, n_steps, sampling, stream=self.side, lane=0)
+            ev = torch.cuda.Event()
+            ev.record(self.side)
+            main.wait_event(ev)
+            return
+        self.e.set_cluster_decode(False)
         if self.G == 1:
             self.e.decode_steps(slots, n_steps, sampling)
             return
-        main = torch.cuda.current_stream(self.e.device)
         for g, grp in enumerate(self.split(slots)):
             self.e.decode_steps(grp, n_steps, sampling, stream=self.streams[g], lane=g)
             ev = torch.cuda.Event()

@@ -156,3 +156,35 @@ def test_chunk_scheduler_properties_against_the_oracle_schedule():
             else:
                 assert pos == len(codes)
     check()
+
+
+def test_lane_runner_picks_the_decode_path_by_batch_size():
+    """LaneRunner's host-side policy (no GPU needed): the cluster-resident kernel gets batches of one or two waves of 7
+    clusters (up to 112 and 140-224 sessions) when the engine can run it (bf16, greedy, english-tiny dimensions); the
+    kernel-per-op lanes get the rest."""
+    from llmvox_b200.engine import Engine, Sampling
+    from llmvox_b200.streaming import LaneRunner
+
+    class Cfg:
+        n_embd, n_head, vocab_size, bias, kv_page_tokens, max_context, text_dim, code_dim = 768, 8, 4096, 0, 16, 512, 256, 512
+
+    class FakeEngine:
+        cfg = Cfg()
+        precision = "bf16"
+        cluster_decode_applicable = Engine.cluster_decode_applicable
+
+    r = object.__new__(LaneRunner)
+    r.e = FakeEngine()
+    r.cluster_default = True
+    greedy, sampled = Sampling(), Sampling(greedy=False, top_k=50, temperature=0.8)
+    assert [r._cluster_call(n, greedy) for n in (1, 64, 112, 113, 139, 140, 224, 225, 256)] == \
+        [True, True, True, False, False, True, True, False, False]
+    assert not r._cluster_call(64, sampled)                       # sampled decoding: sampler kernel of the per-op chain
+    r.e.precision = "fp32"
+    assert not r._cluster_call(64, greedy)                        # fp32 parity mode: FMA-pipe GEMMs
+    r.e.precision = "bf16"
+    r.e.cfg.max_context = 2048
+    assert not r._cluster_call(64, greedy)                        # more than 64 KV pages per session
+    r.e.cfg.max_context = 512
+    r.cluster_default = False                                     # LLMVOX_B200_CLUSTER=0
+    assert not r._cluster_call(64, greedy)

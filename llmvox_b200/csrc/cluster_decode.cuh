@@ -6,10 +6,10 @@
 // Why: the kernel-per-op chain is ~35 dependent launches per iteration and the grid-barrier
 // kernel (fused_decode.cuh) pays ~1.5-3 us per barrier plus a cold TMA round trip per phase.  Here
 //   * the 16 CTAs exchange activations through DISTRIBUTED SHARED MEMORY (st.shared::cluster) and meet at mbarrier
-//     based cluster barriers that only the worker warps take part in (~0.3 us);
+//     based cluster barriers that only the worker warps take part in (~1.3 us per exchange incl. the stores);
 //   * every CTA owns a fixed 1/16 of every weight matrix.  Its share is laid out offline as ONE linear stream of
 //     ready-made shared-memory images (K-major, 128-byte swizzle), so the producer warp runs free of the dependency
-//     chain: plain cp.async.bulk copies into a 4 x 32 KB ring, always as far ahead as the ring allows;
+//     chain: plain cp.async.bulk copies into an 8 x 16 KB ring, always as far ahead as the ring allows;
 //   * the GEMMs are swap-mode tcgen05 tiles (weight rows = UMMA M = 128, sessions = UMMA N = 16, fp32 accumulators
 //     in TMEM) with NO split-K for qkv / proj / fc / lm_head (each CTA owns output rows), and a K-split proj2 whose
 //     partial sums are reduce-scattered to the row owners through DSMEM and added in fixed rank order.
@@ -17,13 +17,13 @@
 // Ownership by cluster rank r (C = 768, 8 heads x 96, FF = 3072, V = 4096):
 //   residual stream x[:, 48r .. 48r+48) (fp32, shared memory, never leaves the CTA)
 //   qkv rows of head h = r / 2: even r -> q (96) + k[0:48); odd r -> k[48:96) + v (96)      (144 rows)
-//   attention of head h for sessions [8 (r & 1), +8) of the group, one warp per session
+//   attention of head h for sessions [8 (r & 1), +8) of the group, one warp per session (mma.sync tiles per KV page)
 //   proj rows [48r, +48); fc rows [192r, +192); proj2 k-slice [192r, +192) for all 768 rows; lm_head rows [256r, +256)
 //
 // One iteration = 22 exchanges: per layer { x all-gather (LN1) | q,k,v pair exchange | y all-gather | x all-gather
 // (LN2) | proj2 reduce-scatter }, then x all-gather (ln_f) and the argmax candidates.  LayerNorm statistics are exact
-// (fp32 partial mean / M2 per owner, merged with Chan's formula); the normalised operand is bf16 like the kernel-per-op
-// path's.  The LayerNorm weights (bias=False: src/model.py:29-38 with bias None) are folded into the columns of the GEMM
+// (fp32 partial mean / M2 per owner, merged with Chan's formula; x travels as fp16); the normalised operand is bf16 like
+// the kernel-per-op path's.  The LayerNorm weights (bias=False: src/model.py:29-38 with bias None) are folded into the columns of the GEMM
 // that follows (qkv, fc, lm_head) when the stream is packed.  Pick = argmax, lowest index wins ties
 // (streaming_server.py:342-346).
 //

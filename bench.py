@@ -352,6 +352,8 @@ def run_gpu(args):
                 "config": {"workload": f"config1: {STREAMS} streams x {TOKENS} codes per GPU, KV-cached greedy decode + chunked vocoder ({'/'.join(map(str, SCHEDULE))})",
                            "weights": "random-init english-tiny GPT + frame75 WavTokenizer decoder, seed 1234",
                            "decode_lanes": args.lanes,
+                           "decode_path": ("cluster-resident kernel: one call per round on a side stream, %d clusters of 16 CTAs" % ((STREAMS + 15) // 16)
+                                           if runner._cluster_call(STREAMS, None) else "kernel-per-op chain on %d lanes" % args.lanes),
                            "l2": "no flush: per-step working set (189 MB bf16 weights + KV + activations) exceeds the 126 MB L2"},
                 "x_realtime_per_gpu": value / world,
                 # whole-step view: bf16 weights once per iteration + KV read/append, against measured HBM peak

@@ -30,6 +30,12 @@ extern "C" {
 
 #define LVX_PRECISION_FP32 0 /* fp32 weights, activations and KV cache; FMA-pipe GEMMs (parity mode)   */
 #define LVX_PRECISION_BF16 1 /* bf16 GEMM operands + KV cache, fp32 accumulate/residual; tcgen05 GEMMs */
+/* Decode with bf16 WEIGHTS (LayerNorm weights folded into the GEMM that follows, then rounded: the same 62.9 MB
+ * stream as BF16) but fp32-class ACTIVATIONS on the same tcgen05 tensor cores: every activation operand is split
+ * into bf16 hi + bf16 lo halves whose products are accumulated in fp32, the KV cache is fp32.  Greedy tokens are
+ * then identical to the reference's fp32 loop run on those rounded weights (streaming_server.py:342-346; tested).
+ * The vocoder runs as in BF16 mode. */
+#define LVX_PRECISION_EXACT 2
 
 typedef struct lvx_engine lvx_engine;
 

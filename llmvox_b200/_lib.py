@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(HERE, "libllmvox_b200.so")
 LVX_OK = 0
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
+PRECISION_EXACT = 2
 
 
 class LvxConfig(C.Structure):

@@ -4,7 +4,7 @@
 // barrier and no kernel boundary inside an iteration.
 //
 // Why: the kernel-per-op chain is ~35 dependent launches per iteration and the grid-barrier
-// kernel (fused_decode.cuh) pays ~1.5-3 us per barrier plus a cold TMA round trip per phase.  Here
+// kernel (round 1, removed) paid ~1.5-3 us per barrier plus a cold TMA round trip per phase.  Here
 //   * the 16 CTAs exchange activations through DISTRIBUTED SHARED MEMORY (st.shared::cluster) and meet at mbarrier
 //     based cluster barriers that only the worker warps take part in (~1.3 us per exchange incl. the stores);
 //   * every CTA owns a fixed 1/16 of every weight matrix.  Its share is laid out offline as ONE linear stream of
@@ -34,7 +34,6 @@
 #include <cuda_fp16.h>
 
 #include "decode_kernels.cuh"
-#include "fused_decode.cuh"
 #include "tc_gemm.cuh"
 
 namespace lvx {
@@ -99,6 +98,7 @@ constexpr int CD_SMEM_BYTES = CD_OFF_SMALL + 1024 + 1024;             // + align
 
 struct ClusterParams {
   int n, n_iters, n_layer;
+  int per_cluster;    // sessions per cluster (<= CD_NB): cluster c owns sessions [c * per_cluster, +per_cluster) of the call
   const int* slots;
   SessionState st;
   const float *text_table, *codebook, *wpe;
@@ -111,7 +111,6 @@ struct ClusterParams {
   long long pool_pages;
   float* logits;      // [n, V] fp32 or null: logits of the launch's last iteration (test hook / lvx_peek_logits)
   long long* trace;   // optional clock64 stamps of cluster 0 / rank 0, last iteration
-  int dbg;            // timing experiments only (wrong results): bit 0 = M=64 MMAs, bit 1 = attention over an empty cache
 };
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
@@ -202,11 +201,6 @@ __device__ __forceinline__ void cd_bulk_g2s(uint32_t dst, const void* src, uint3
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(dst),
                "l"(src), "r"(bytes), "r"(bar), "l"(policy)
                : "memory");
-}
-__device__ __forceinline__ uint64_t cd_policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
 }
 __device__ __forceinline__ uint64_t cd_policy_evict_last() {
   uint64_t p;
@@ -553,7 +547,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const sgen = smem_raw + (sbase - smem_u32(smem_raw));
   const uint32_t bars = smem_u32(bars_sh);
-  const int n0 = cid * CD_NB, nloc = min(CD_NB, P.n - n0);
+  const int n0 = cid * P.per_cluster, nloc = min(P.per_cluster, P.n - n0);
   const int n_layer = P.n_layer, n_iters = P.n_iters;
 
   if (tid == 0) {
@@ -596,7 +590,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
       const int run_bytes[8] = {CD_TILE, 4 * CD_QT, 0, 2 * CD_PT, CD_TILE, 2 * CD_FT, CD_TILE, CD_TILE};
       const uint8_t* const src0 = P.wstream + (size_t)rank * (size_t)P.stream_bytes;
       // the stream is re-read every iteration by every cluster: keep it in L2 (measured: evict_first is 3 % slower)
-      const uint64_t policy = (P.dbg & 4) ? cd_policy_evict_first() : cd_policy_evict_last();
+      const uint64_t policy = cd_policy_evict_last();
       unsigned gi = 0;
 #pragma unroll 1
       for (int iter = 0; iter < n_iters; ++iter) {
@@ -628,7 +622,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
     // ------------------------------------------------------------------ MMA issuers (ring items round-robin)
     {
       const unsigned par = (unsigned)(warp - 1);   // this issuer takes ring positions = par (mod CD_NI)
-      const uint32_t idesc = umma_idesc_bf16((P.dbg & 1) ? 64 : 128, CD_NB);
+      const uint32_t idesc = umma_idesc_bf16(128, CD_NB);
       const uint32_t a1 = sbase + CD_OFF_A1, a2 = sbase + CD_OFF_A2, ay = sbase + CD_OFF_AY;
       const uint32_t tm = tmem + CD_TM_BANK * par;   // this warp's accumulator copy
       unsigned gi = 0, g = 0;
@@ -873,7 +867,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
               const int slot = sm_slot[n];
               // per-warp 16 x 208 B staging tile inside A1 | A2 (30 KB; LN1(x) has been consumed by the qkv MMAs, the LN2
               // gather and the GELU slice come later)
-              val = cd_attention_mma_warp(cd_attention_kbase(P.kv, P.pool_pages, l, head), pt0, pt1, P.pool_pages, (P.dbg & 2) ? 0 : sm_t[n],
+              val = cd_attention_mma_warp(cd_attention_kbase(P.kv, P.pool_pages, l, head), pt0, pt1, P.pool_pages, sm_t[n],
                                           qkvb + ww * 288, sgen + CD_OFF_A1 + ww * 3328, reinterpret_cast<uint32_t*>(sgen + CD_OFF_YST) + ww * 48);
             }
             // output row to every peer's y operand: lanes 0-11 / 12-23 hold the 12 chunks, 8 peers each
@@ -1143,7 +1137,7 @@ inline int cluster_decode_configure(int* max_clusters) {
 
 inline int cluster_decode_launch(const ClusterParams& P, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(CD_CLUSTER * ceil_div(P.n, CD_NB));
+  cfg.gridDim = dim3(CD_CLUSTER * ceil_div(P.n, P.per_cluster));
   cfg.blockDim = dim3(CD_THREADS);
   cfg.dynamicSmemBytes = CD_SMEM_BYTES;
   cfg.stream = st;

@@ -114,6 +114,84 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const float* __restrict_
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Exact mode (LVX_PRECISION_EXACT) operand builders.  A GEMM operand row of width W is stored as 2 W bf16 values
+// [hi(0..W) | lo(0..W)], hi = bf16(v), lo = bf16(v - hi): against the weight row laid out twice along K the fp32
+// accumulator receives w.hi + w.lo = w.v up to 2^-18 |v| per element -- fp32-class activations on bf16 tensor cores.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_hi_lo(float v, bf16& hi, bf16& lo) {
+  hi = __float2bfloat16_rn(v);
+  lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+// LayerNorm without affine terms (the weight is folded into the GEMM that follows) -> hi | lo.  One warp per row.
+template <int C>
+__global__ void __launch_bounds__(256) ln_split_kernel(const float* __restrict__ x, int rows, float eps, bf16* __restrict__ out) {
+  constexpr int V = C / 128;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (size_t)row * C;
+  float4 v[V];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    v[i] = load4(xr + (lane + 32 * i) * 4);
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(s) * (1.0f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += a * a + b * b + c * c + d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + eps);
+  bf16* o = out + (size_t)row * 2 * C;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    const float r[4] = {(v[i].x - mean) * rstd, (v[i].y - mean) * rstd, (v[i].z - mean) * rstd, (v[i].w - mean) * rstd};
+    bf16 hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_hi_lo(r[j], hi[j], lo[j]);
+    *reinterpret_cast<uint2*>(o + c) = *reinterpret_cast<uint2*>(hi);
+    *reinterpret_cast<uint2*>(o + C + c) = *reinterpret_cast<uint2*>(lo);
+  }
+}
+// out[r, 0:W) | out[r, W:2W) = hi | lo of act(in[r, :]); act = ACT_NONE or ACT_GELU_TANH (src/model.py:21-26, exact tanhf)
+__global__ void __launch_bounds__(256) split2_kernel(const float* __restrict__ in, int rows, int W, int act, bf16* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const size_t n4 = (size_t)rows * W / 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = (i * 4) / W, c = (i * 4) % W;
+    const float4 v4 = load4(in + i * 4);
+    float v[4] = {v4.x, v4.y, v4.z, v4.w};
+    bf16 hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (act == ACT_GELU_TANH) v[j] = gelu_tanh(v[j]);
+      split_hi_lo(v[j], hi[j], lo[j]);
+    }
+    bf16* o = out + r * 2 * W;
+    *reinterpret_cast<uint2*>(o + c) = *reinterpret_cast<uint2*>(hi);
+    *reinterpret_cast<uint2*>(o + W + c) = *reinterpret_cast<uint2*>(lo);
+  }
+}
+// (N, K) fp32 weight, optionally scaled per column (the LayerNorm weight in front of the GEMM), rounded to bf16 and
+// laid out twice along K: out[n, 0:K) = out[n, K:2K) = bf16(W[n, :] * scale)
+__global__ void fold_dup_kernel(const float* __restrict__ Wt, const float* __restrict__ scale, int N, int K, int ld,
+                                bf16* __restrict__ out) {
+  const size_t n = (size_t)N * K;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t r = i / K, c = i % K;
+    const bf16 v = __float2bfloat16_rn(Wt[r * ld + c] * (scale ? scale[c] : 1.0f));
+    out[r * 2 * K + c] = v;
+    out[r * 2 * K + K + c] = v;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Flash-decode attention over the paged KV cache (src/model.py:68-98 with is_train=False: one query row
 // against [cache ; new row], no mask, scale 1/sqrt(head_dim)).  One CTA per (session, head); 4 warps x 4
 // groups of 8 lanes; a group owns one cached token at a time and each lane HD/8 of its dims.  Online

@@ -18,7 +18,6 @@
 #include "decode_kernels.cuh"
 #include "gemm.cuh"
 #include "tc_gemm.cuh"
-#include "fused_decode.cuh"
 #include "cluster_decode.cuh"
 
 #include <deque>
@@ -147,11 +146,12 @@ struct lvx_engine {
   struct Layer {
     float *ln1_w, *ln1_b, *ln2_w, *ln2_b;
     GemmW attn, proj, fc, proj2;
+    GemmW attn_x2, proj_x2, fc_x2, proj2_x2;   // exact mode: LN-folded bf16 weights laid out twice along K
     float *attn_b, *proj_b, *fc_b, *proj2_b;
   };
   std::vector<Layer> layers;
   float *lnf_w = nullptr, *lnf_b = nullptr;
-  GemmW lm_head;
+  GemmW lm_head, lm_head_x2;
   // ---- vocoder derived
   struct Res {
     float *n1w, *n1b, *n2w, *n2b, *c1b, *c2b;
@@ -201,18 +201,13 @@ struct lvx_engine {
     cudaGraphExec_t exec = nullptr;
     int64_t launches = 0;
   };
-  struct FusedCtx {
-    FusedParams P;
-    FusedPlan plan;
-    CUtensorMap* d_maps = nullptr;
-  };
   struct Lane {
-    std::map<int, FusedCtx> fused;   // persistent fused decode kernel, keyed by the number of sessions
     unsigned* d_bar = nullptr;
     long long* d_trace = nullptr;
     int *d_slots = nullptr, *d_upd = nullptr, *d_pos = nullptr;
     float *x = nullptr, *qkv = nullptr, *logits = nullptr;
     void *h = nullptr, *y = nullptr, *g = nullptr;
+    float *yf = nullptr, *gf = nullptr;   // exact mode: fp32 attention output / fc output before the hi | lo split
     std::map<std::string, StepGraph> graphs;
   };
   std::vector<Lane> lanes;
@@ -223,7 +218,6 @@ struct lvx_engine {
   cudaStream_t aux[kAux] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[kAux] = {nullptr, nullptr, nullptr, nullptr};
   bool use_graphs = true;
-  bool use_fused = true;
   bool use_pdl = true;      // programmatic dependent launch along the decode chain (LLMVOX_B200_NO_PDL=1 disables)
   // cluster-resident decode kernel (cluster_decode.cuh): per-rank weight streams + table norms, built on first use
   bool use_cluster = false;
@@ -232,6 +226,7 @@ struct lvx_engine {
   long long cd_stream_bytes = 0;
   float *cd_text_ss = nullptr, *cd_code_ss = nullptr;
   int cd_max_clusters = 0;
+  bool cd_spread = true;   // spread a call's sessions over all co-resident clusters (LLMVOX_B200_CD_SPREAD=0: fill to 16)
   // launches that may still be running: never more clusters in flight than are co-resident (see cluster_launch)
   struct CdInflight {
     cudaEvent_t ev;
@@ -261,7 +256,10 @@ struct lvx_engine {
     return ev;
   }
 
-  DT adt() const { return cfg.precision == LVX_PRECISION_BF16 ? B16 : F32; }
+  // storage type of GEMM operands (EXACT: bf16 hi | lo pairs for the decoder, plain bf16 for the vocoder)
+  DT adt() const { return cfg.precision == LVX_PRECISION_FP32 ? F32 : B16; }
+  bool exact() const { return cfg.precision == LVX_PRECISION_EXACT; }
+  DT kvdt() const { return cfg.precision == LVX_PRECISION_BF16 ? B16 : F32; }
 };
 
 struct ProfScope {
@@ -421,7 +419,7 @@ static int engine_alloc(lvx_engine* e) {
   LVX_TRY(dev_alloc(e, &e->st.codes, (size_t)S * c.max_context));
   LVX_TRY(dev_alloc(e, &e->st.page_table, (size_t)S * e->max_pages));
   const size_t kv_elems = (size_t)c.n_layer * 2 * e->pool_pages * c.kv_page_tokens * C;
-  LVX_TRY(dev_alloc_bytes(e, &e->kv, kv_elems * dt_size(a)));
+  LVX_TRY(dev_alloc_bytes(e, &e->kv, kv_elems * dt_size(e->kvdt())));
   e->h_len.assign(S, 0);
   e->h_text_len.assign(S, 0);
   e->h_open.assign(S, 0);
@@ -445,9 +443,14 @@ static int engine_alloc(lvx_engine* e) {
     LVX_TRY(dev_alloc(e, &ln.x, (size_t)Bp * C));
     LVX_TRY(dev_alloc(e, &ln.qkv, (size_t)Bp * 3 * C));
     LVX_TRY(dev_alloc(e, &ln.logits, (size_t)Bp * c.vocab_size));
-    LVX_TRY(dev_alloc_bytes(e, &ln.h, (size_t)Bp * C * dt_size(a)));
-    LVX_TRY(dev_alloc_bytes(e, &ln.y, (size_t)Bp * C * dt_size(a)));
-    LVX_TRY(dev_alloc_bytes(e, &ln.g, (size_t)Bp * 4 * C * dt_size(a)));
+    const size_t act_bytes = e->exact() ? 4 : dt_size(a);   // exact: 2 bf16 (hi | lo) per element
+    LVX_TRY(dev_alloc_bytes(e, &ln.h, (size_t)Bp * C * act_bytes));
+    LVX_TRY(dev_alloc_bytes(e, &ln.y, (size_t)Bp * C * act_bytes));
+    LVX_TRY(dev_alloc_bytes(e, &ln.g, (size_t)Bp * 4 * C * act_bytes));
+    if (e->exact()) {
+      LVX_TRY(dev_alloc(e, &ln.yf, (size_t)Bp * C));
+      LVX_TRY(dev_alloc(e, &ln.gf, (size_t)Bp * 4 * C));
+    }
   }
   // vocoder workspace
   const int D = c.voc_dim, I = c.voc_inter;
@@ -498,7 +501,10 @@ extern "C" int lvx_engine_create(const lvx_config* cfg, int device, lvx_engine**
   LVX_CHECK(c.max_context > 0 && c.max_context <= c.block_size, LVX_ERR_INVALID, "max_context must be <= block_size");
   LVX_CHECK(c.kv_page_tokens > 0 && c.max_vocode_frames > 0, LVX_ERR_INVALID, "bad capacity");
   LVX_CHECK(c.voc_inter % 64 == 0 && c.code_dim % 64 == 0, LVX_ERR_INVALID, "voc_inter / code_dim must be multiples of 64");
-  LVX_CHECK(c.precision == LVX_PRECISION_FP32 || c.precision == LVX_PRECISION_BF16, LVX_ERR_INVALID, "bad precision");
+  LVX_CHECK(c.precision == LVX_PRECISION_FP32 || c.precision == LVX_PRECISION_BF16 || c.precision == LVX_PRECISION_EXACT,
+            LVX_ERR_INVALID, "bad precision");
+  LVX_CHECK(c.precision != LVX_PRECISION_EXACT || !c.bias, LVX_ERR_INVALID,
+            "exact mode folds the LayerNorm weights into the GEMMs and needs bias == 0 (english-tiny)");
   LVX_CHECK(c.decode_lanes >= 0 && c.decode_lanes <= 16, LVX_ERR_INVALID, "decode_lanes must be in [0, 16]");
   int ndev = 0;
   LVX_CUDA(cudaGetDeviceCount(&ndev));
@@ -514,18 +520,16 @@ extern "C" int lvx_engine_create(const lvx_config* cfg, int device, lvx_engine**
   e->device = device;
   declare_tensors(e);
   int s = engine_alloc(e);
-  if (s == LVX_OK && c.precision == LVX_PRECISION_BF16) s = tc_init(&e->tcw, prop.multiProcessorCount);
+  if (s == LVX_OK && c.precision != LVX_PRECISION_FP32) s = tc_init(&e->tcw, prop.multiProcessorCount);
   if (s == LVX_OK) {
     const char* env = getenv("LLMVOX_B200_NO_GRAPH");
     e->use_graphs = !(env && env[0] == '1');
-    // the persistent fused decode kernel is opt-in: it wins on the decode chain alone (270 vs 290 us / iteration at 64
-    // sessions) but, being a whole-GPU cooperative launch, it cannot overlap with the vocoder or another lane
     const char* env3 = getenv("LLMVOX_B200_NO_PDL");
     e->use_pdl = !(env3 && env3[0] == '1');
-    const char* env2 = getenv("LLMVOX_B200_FUSED");
-    e->use_fused = env2 && env2[0] == '1';
     // cluster-resident decode kernel (cluster_decode.cuh): the default greedy bf16 path; LLMVOX_B200_CLUSTER=0 selects the
     // kernel-per-op path (CUDA graphs + programmatic dependent launch) instead
+    const char* env5 = getenv("LLMVOX_B200_CD_SPREAD");
+    e->cd_spread = !(env5 && env5[0] == '0');
     const char* env4 = getenv("LLMVOX_B200_CLUSTER");
     e->use_cluster = !(env4 && env4[0] == '0');
     if (cudaStreamCreateWithFlags(&e->gstream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -609,12 +613,12 @@ static float* W(lvx_engine* e, const std::string& name) {
 }
 
 // Registers an (N, K) fp32 matrix as a GEMM weight; bf16 mode adds the bf16 copy and its tensor map.
-static int make_gemm_w(lvx_engine* e, GemmW* g, float* f32, int N, int K, int ld) {
+static int make_gemm_w(lvx_engine* e, GemmW* g, float* f32, int N, int K, int ld, bool with_bf16 = true) {
   g->f32 = f32;
   g->N = N;
   g->K = K;
   g->ld = ld;
-  if (e->adt() == B16) {
+  if (e->adt() == B16 && with_bf16) {
     const size_t n = (size_t)N * ld;
     LVX_TRY(dev_alloc(e, &g->b16, n));
     cast_bf16_kernel<<<std::min<size_t>(4096, (n + 255) / 256), 256>>>(f32, g->b16, n);
@@ -622,6 +626,19 @@ static int make_gemm_w(lvx_engine* e, GemmW* g, float* f32, int N, int K, int ld
     LVX_TRY(tc_make_desc(&g->tma, g->b16, N, K, ld));
   }
   return LVX_OK;
+}
+
+// Exact mode: bf16(W * diag(scale)) laid out twice along K (decode_kernels.cuh: fold_dup_kernel) + its tensor map.
+static int make_gemm_w_x2(lvx_engine* e, GemmW* g, const float* f32, const float* scale, int N, int K, int ld) {
+  g->f32 = nullptr;
+  g->N = N;
+  g->K = 2 * K;
+  g->ld = 2 * K;
+  const size_t n = (size_t)N * 2 * K;
+  LVX_TRY(dev_alloc(e, &g->b16, n));
+  fold_dup_kernel<<<std::min<size_t>(4096, ((size_t)N * K + 255) / 256), 256>>>(f32, scale, N, K, ld, g->b16);
+  LAUNCHED(e);
+  return tc_make_desc(&g->tma, g->b16, N, 2 * K, 2 * K);
 }
 
 static int make_conv_w(lvx_engine* e, GemmW* g, const std::string& name, int O, int Cin, int T) {
@@ -652,14 +669,22 @@ extern "C" int lvx_finalize_weights(lvx_engine* e) {
     L.proj_b = W(e, p + "attn.c_proj.bias");
     L.fc_b = W(e, p + "mlp.c_fc.bias");
     L.proj2_b = W(e, p + "mlp.c_proj.bias");
-    LVX_TRY(make_gemm_w(e, &L.attn, W(e, p + "attn.c_attn.weight"), 3 * C, C, C));
-    LVX_TRY(make_gemm_w(e, &L.proj, W(e, p + "attn.c_proj.weight"), C, C, C));
-    LVX_TRY(make_gemm_w(e, &L.fc, W(e, p + "mlp.c_fc.weight"), 4 * C, C, C));
-    LVX_TRY(make_gemm_w(e, &L.proj2, W(e, p + "mlp.c_proj.weight"), C, 4 * C, 4 * C));
+    const bool x = e->exact();
+    LVX_TRY(make_gemm_w(e, &L.attn, W(e, p + "attn.c_attn.weight"), 3 * C, C, C, !x));
+    LVX_TRY(make_gemm_w(e, &L.proj, W(e, p + "attn.c_proj.weight"), C, C, C, !x));
+    LVX_TRY(make_gemm_w(e, &L.fc, W(e, p + "mlp.c_fc.weight"), 4 * C, C, C, !x));
+    LVX_TRY(make_gemm_w(e, &L.proj2, W(e, p + "mlp.c_proj.weight"), C, 4 * C, 4 * C, !x));
+    if (x) {
+      LVX_TRY(make_gemm_w_x2(e, &L.attn_x2, L.attn.f32, L.ln1_w, 3 * C, C, C));
+      LVX_TRY(make_gemm_w_x2(e, &L.proj_x2, L.proj.f32, nullptr, C, C, C));
+      LVX_TRY(make_gemm_w_x2(e, &L.fc_x2, L.fc.f32, L.ln2_w, 4 * C, C, C));
+      LVX_TRY(make_gemm_w_x2(e, &L.proj2_x2, L.proj2.f32, nullptr, C, 4 * C, 4 * C));
+    }
   }
   e->lnf_w = W(e, "transformer.ln_f.weight");
   e->lnf_b = W(e, "transformer.ln_f.bias");
-  LVX_TRY(make_gemm_w(e, &e->lm_head, W(e, "lm_head.weight"), c.vocab_size, C, C));
+  LVX_TRY(make_gemm_w(e, &e->lm_head, W(e, "lm_head.weight"), c.vocab_size, C, C, !e->exact()));
+  if (e->exact()) LVX_TRY(make_gemm_w_x2(e, &e->lm_head_x2, e->lm_head.f32, e->lnf_w, c.vocab_size, C, C));
 
   // vocoder
   LVX_TRY(make_conv_w(e, &e->embed, "backbone.embed.weight", D, c.code_dim, 7));
@@ -789,7 +814,9 @@ static int run_gemm(lvx_engine* e, GemmParams p, const GemmW& w, DT ta, DT tc, c
   const double el = (double)dt_size(e->adt());
   const int a_cols = p.taps > 1 ? p.tap_K : p.K;
   const bool swap = e->adt() == B16 && p.taps == 1 && p.M <= 256;
-  ProfScope prof(e, p.tag ? p.tag : (e->adt() == F32 ? "gemm_simt" : (swap ? "tc_gemm_swap" : "tc_gemm")), st, 2.0 * p.M * (double)w.N * w.K,
+  // algorithmic FLOPs: operands laid side by side along K (bf16x3 of the head / iDFT, hi | lo of exact mode) count once
+  ProfScope prof(e, p.tag ? p.tag : (e->adt() == F32 ? "gemm_simt" : (swap ? "tc_gemm_swap" : "tc_gemm")), st,
+                 2.0 * p.M * (double)w.N * w.K / std::max(1, p.kdup),
                  (double)p.M * a_cols * el + (double)w.N * w.K * el + (double)p.M * w.N * (double)dt_size(tc) +
                      (p.residual ? (double)p.M * w.N * 4.0 : 0.0));
   if (e->adt() == F32) {
@@ -948,7 +975,9 @@ extern "C" int lvx_feed_text(lvx_engine* e, const int32_t* h_slots, const int32_
 
 // ------------------------------------------------------------------------------------------------ decode
 // One GPT.forward over n session rows whose residual stream x is already assembled (src/model.py:220-234).
+static int gpt_body_exact(lvx_engine* e, lvx_engine::Lane& ln, int n, const int* pos_override, cudaStream_t st);
 static int gpt_body(lvx_engine* e, lvx_engine::Lane& ln, int n, const int* pos_override, cudaStream_t st) {
+  if (e->exact()) return gpt_body_exact(e, ln, n, pos_override, st);
   const lvx_config& c = e->cfg;
   const int C = c.n_embd;
   const DT a = e->adt();
@@ -988,11 +1017,66 @@ static int gpt_body(lvx_engine* e, lvx_engine::Lane& ln, int n, const int* pos_o
   return LVX_OK;
 }
 
+// Exact mode, kernel-per-op form (the cluster-resident kernel is the fast form): every GEMM operand is a bf16 hi | lo
+// pair row against the LN-folded bf16 weight laid out twice along K; fp32 KV cache, fp32 attention, exact tanh GELU.
+static int ln_split(lvx_engine* e, const float* x, int n, bf16* out, cudaStream_t st, bool pdl) {
+  PROF(e, "ln_split", st);
+  cudaError_t err = launch_pdl(ln_split_kernel<768>, dim3(ceil_div(n, 8)), dim3(256), 0, st, pdl, x, n, 1e-5f, out);
+  LVX_CHECK(err == cudaSuccess, LVX_ERR_CUDA, std::string("ln_split launch: ") + cudaGetErrorString(err));
+  LAUNCHED(e);
+  return LVX_OK;
+}
+static int split2(lvx_engine* e, const float* in, int n, int width, int act, bf16* out, cudaStream_t st, bool pdl) {
+  PROF(e, "split2", st);
+  const int blocks = std::max(1, std::min(1024, ceil_div(n * width / 4, 256)));
+  cudaError_t err = launch_pdl(split2_kernel, dim3(blocks), dim3(256), 0, st, pdl, in, n, width, act, out);
+  LVX_CHECK(err == cudaSuccess, LVX_ERR_CUDA, std::string("split2 launch: ") + cudaGetErrorString(err));
+  LAUNCHED(e);
+  return LVX_OK;
+}
+static int gpt_body_exact(lvx_engine* e, lvx_engine::Lane& ln, int n, const int* pos_override, cudaStream_t st) {
+  const lvx_config& c = e->cfg;
+  const int C = c.n_embd;
+  const int budget = e->lane_cta_budget;
+  const bool pdl = e->use_pdl && !e->prof_on;
+  for (int l = 0; l < c.n_layer; ++l) {
+    auto& L = e->layers[l];
+    LVX_TRY(ln_split(e, ln.x, n, (bf16*)ln.h, st, pdl));
+    GemmParams p;
+    p.A = ln.h; p.C = ln.qkv; p.M = n; p.lda = 2 * C; p.ldc = 3 * C; p.cta_budget = budget; p.pdl = pdl; p.kdup = 2;
+    LVX_TRY(run_gemm(e, p, L.attn_x2, B16, F32, st));
+    {
+      PROF(e, "decode_attention", st);
+      cudaError_t err = launch_pdl(decode_attention_kernel<float, float, 96>, dim3(n, c.n_head), dim3(128), 0, st, pdl, (const float*)ln.qkv,
+                                   (float*)e->kv, (const int*)ln.d_slots, e->st, pos_override, l, c.n_head, c.kv_page_tokens, e->pool_pages,
+                                   0, ln.yf);
+      LVX_CHECK(err == cudaSuccess, LVX_ERR_CUDA, std::string("attention launch: ") + cudaGetErrorString(err));
+      LAUNCHED(e);
+    }
+    LVX_TRY(split2(e, ln.yf, n, C, ACT_NONE, (bf16*)ln.y, st, pdl));
+    GemmParams q;
+    q.A = ln.y; q.C = ln.x; q.M = n; q.lda = 2 * C; q.ldc = C; q.residual = ln.x; q.ldr = C; q.cta_budget = budget; q.pdl = pdl; q.kdup = 2;
+    LVX_TRY(run_gemm(e, q, L.proj_x2, B16, F32, st));
+    LVX_TRY(ln_split(e, ln.x, n, (bf16*)ln.h, st, pdl));
+    GemmParams f;
+    f.A = ln.h; f.C = ln.gf; f.M = n; f.lda = 2 * C; f.ldc = 4 * C; f.cta_budget = budget; f.pdl = pdl; f.kdup = 2;
+    LVX_TRY(run_gemm(e, f, L.fc_x2, B16, F32, st));
+    LVX_TRY(split2(e, ln.gf, n, 4 * C, ACT_GELU_TANH, (bf16*)ln.g, st, pdl));
+    GemmParams r;
+    r.A = ln.g; r.C = ln.x; r.M = n; r.lda = 8 * C; r.ldc = C; r.residual = ln.x; r.ldr = C; r.cta_budget = budget; r.pdl = pdl; r.kdup = 2;
+    LVX_TRY(run_gemm(e, r, L.proj2_x2, B16, F32, st));
+  }
+  LVX_TRY(ln_split(e, ln.x, n, (bf16*)ln.h, st, pdl));
+  return LVX_OK;
+}
+
 static int lm_head_logits(lvx_engine* e, lvx_engine::Lane& ln, int n, float* d_logits, cudaStream_t st) {
   GemmParams p;
-  p.A = ln.h; p.C = d_logits; p.M = n; p.lda = e->cfg.n_embd; p.ldc = e->cfg.vocab_size; p.cta_budget = e->lane_cta_budget;
+  const int kd = e->exact() ? 2 : 1;
+  p.A = ln.h; p.C = d_logits; p.M = n; p.lda = kd * e->cfg.n_embd; p.ldc = e->cfg.vocab_size; p.cta_budget = e->lane_cta_budget;
   p.pdl = e->use_pdl && !e->prof_on;
-  return run_gemm(e, p, e->lm_head, e->adt(), F32, st);
+  p.kdup = kd;
+  return run_gemm(e, p, e->exact() ? e->lm_head_x2 : e->lm_head, e->adt(), F32, st);
 }
 
 static SamplerArgs sampler_args(const lvx_sampling* s) {
@@ -1074,69 +1158,6 @@ static int lane_graph(lvx_engine* e, lvx_engine::Lane& ln, int n, int iters, con
   return LVX_OK;
 }
 
-// Persistent fused decode kernel (fused_decode.cuh): context for (lane, n sessions), built on first use.
-static int fused_ctx(lvx_engine* e, lvx_engine::Lane& ln, int n, lvx_engine::FusedCtx** out) {
-  auto it = ln.fused.find(n);
-  if (it == ln.fused.end()) {
-    const lvx_config& c = e->cfg;
-    const int C = c.n_embd, L = c.n_layer;
-    lvx_engine::FusedCtx fc;
-    LVX_TRY(fused_plan(n, &fc.plan));
-    const int n_maps = 4 * L + 1 + 3;
-    std::vector<CUtensorMap> maps(n_maps);
-    for (int l = 0; l < L; ++l) {
-      maps[4 * l + 0] = e->layers[l].attn.tma.map;
-      maps[4 * l + 1] = e->layers[l].proj.tma.map;
-      maps[4 * l + 2] = e->layers[l].fc.tma.map;
-      maps[4 * l + 3] = e->layers[l].proj2.tma.map;
-    }
-    maps[4 * L] = e->lm_head.tma.map;
-    const int ih = 4 * L + 1, iy = ih + 1, ig = ih + 2;
-    LVX_TRY(tc_encode(&maps[ih], ln.h, e->Bp, C, C, fc.plan.BN));
-    LVX_TRY(tc_encode(&maps[iy], ln.y, e->Bp, C, C, fc.plan.BN));
-    LVX_TRY(tc_encode(&maps[ig], ln.g, e->Bp, 4 * C, 4 * C, fc.plan.BN));
-    LVX_TRY(dev_alloc(e, &fc.d_maps, n_maps));
-    LVX_CUDA(cudaMemcpy(fc.d_maps, maps.data(), n_maps * sizeof(CUtensorMap), cudaMemcpyHostToDevice));
-    FusedParams& P = fc.P;
-    memset(&P, 0, sizeof(P));
-    P.n = n; P.BN = fc.plan.BN; P.stages = fc.plan.stages; P.tmem_cols = fc.plan.tmem_cols; P.n_clusters = fc.plan.n_clusters;
-    P.n_layer = L; P.n_head = c.n_head; P.C = C; P.vocab = c.vocab_size;
-    P.maps = fc.d_maps;
-    P.slots = ln.d_slots;
-    P.st = e->st;
-    P.text_table = W(e, "text_table");
-    P.codebook = W(e, "feature_extractor.encodec.quantizer.vq.layers.0._codebook.embed");
-    P.wpe = W(e, "transformer.wpe.weight");
-    P.text_dim = c.text_dim; P.code_dim = c.code_dim; P.pad_id = c.pad_token_id;
-    auto gemm = [&](int map_a, int map_w, const GemmW& w, const float* bias, const float* residual, void* Cout, int ldc, int c_bf16,
-                    int act) {
-      FusedGemm g;
-      g.map_a = map_a; g.map_w = map_w; g.N = w.N; g.K = w.K; g.bias = bias; g.residual = residual; g.C = Cout; g.ldc = ldc;
-      g.c_bf16 = c_bf16; g.act = act;
-      return g;
-    };
-    for (int l = 0; l < L; ++l) {
-      auto& Ly = e->layers[l];
-      FusedLayer& F = P.layer[l];
-      F.ln1_w = Ly.ln1_w; F.ln1_b = Ly.ln1_b; F.ln2_w = Ly.ln2_w; F.ln2_b = Ly.ln2_b;
-      F.qkv = gemm(ih, 4 * l + 0, Ly.attn, Ly.attn_b, nullptr, ln.qkv, 3 * C, 0, ACT_NONE);
-      F.proj = gemm(iy, 4 * l + 1, Ly.proj, Ly.proj_b, ln.x, ln.x, C, 0, ACT_NONE);
-      F.fc = gemm(ih, 4 * l + 2, Ly.fc, Ly.fc_b, nullptr, ln.g, 4 * C, 1, ACT_GELU_TANH);
-      F.proj2 = gemm(ig, 4 * l + 3, Ly.proj2, Ly.proj2_b, ln.x, ln.x, C, 0, ACT_NONE);
-    }
-    P.lnf_w = e->lnf_w; P.lnf_b = e->lnf_b;
-    P.lm_head = gemm(ih, 4 * L, e->lm_head, nullptr, nullptr, ln.logits, c.vocab_size, 0, ACT_NONE);
-    P.x = ln.x; P.qkv = ln.qkv; P.logits = ln.logits;
-    P.h = (bf16*)ln.h; P.y = (bf16*)ln.y;
-    P.kv = (bf16*)e->kv; P.page_tokens = c.kv_page_tokens; P.pool_pages = e->pool_pages;
-    P.bar = ln.d_bar;
-    P.trace = getenv("LLMVOX_B200_TRACE") ? ln.d_trace : nullptr;
-    it = ln.fused.emplace(n, fc).first;
-  }
-  *out = &it->second;
-  return LVX_OK;
-}
-
 static unsigned long long* g_cd_diag_host = nullptr;
 extern "C" const unsigned long long* lvx_cluster_diag(void) { return g_cd_diag_host; }
 
@@ -1184,7 +1205,7 @@ static int cluster_init(lvx_engine* e) {
 
 static bool cluster_applicable(const lvx_engine* e, const SamplerArgs& sa) {
   const lvx_config& c = e->cfg;
-  return e->use_cluster && e->adt() == B16 && sa.greedy && !sa.forced && !sa.out_codes && c.n_embd == CD_C &&
+  return e->use_cluster && e->cfg.precision == LVX_PRECISION_BF16 && sa.greedy && !sa.forced && !sa.out_codes && c.n_embd == CD_C &&
          c.n_head == CD_H && c.vocab_size == CD_V && c.n_layer <= CD_MAX_LAYERS && c.text_dim + c.code_dim == CD_C && !c.bias &&
          c.kv_page_tokens == 16 && e->max_pages <= 64 &&
          (long long)e->pool_pages * c.kv_page_tokens * c.n_embd < (1LL << 31);
@@ -1220,9 +1241,16 @@ static int cluster_launch(lvx_engine* e, lvx_engine::Lane& ln, const int32_t* h_
   P.page_shift = 0;
   while ((1 << P.page_shift) < c.kv_page_tokens) P.page_shift += 1;
   P.trace = getenv("LLMVOX_B200_TRACE") ? ln.d_trace : nullptr;
-  P.dbg = getenv("LLMVOX_B200_CD_DBG") ? atoi(getenv("LLMVOX_B200_CD_DBG")) : 0;
-  for (int pos = 0; pos < n; pos += cap * CD_NB) {
-    const int cnt = std::min(cap * CD_NB, n - pos), clusters = ceil_div(cnt, CD_NB);
+  // Sessions per cluster: a wave of `cap` co-resident clusters costs the same time however many of its clusters are used
+  // (the iteration is a latency chain), but every cluster's attention streams its sessions' K/V through ONE SM per head
+  // pair -- so the sessions of a call are spread evenly over as many clusters as a wave holds instead of filling
+  // clusters to 16 (64 sessions: 7 clusters of 9-10 rather than 4 of 16).
+  const int waves = ceil_div(n, cap * CD_NB);
+  const int per_wave = ceil_div(n, waves);
+  for (int pos = 0; pos < n; pos += per_wave) {
+    const int cnt = std::min(per_wave, n - pos);
+    P.per_cluster = e->cd_spread ? ceil_div(cnt, std::min(cap, cnt)) : CD_NB;
+    const int clusters = ceil_div(cnt, P.per_cluster);
     P.n = cnt;
     P.slots = ln.d_slots + pos;
     P.logits = ln.logits + (size_t)pos * c.vocab_size;
@@ -1276,16 +1304,6 @@ extern "C" int lvx_decode_steps_lane(lvx_engine* e, int lane, const int32_t* h_s
   const lvx_config& c = e->cfg;
   if (cluster_applicable(e, sa)) {
     LVX_TRY(cluster_launch(e, ln, h_slots, n, n_steps, st));
-  } else if (e->use_fused && e->adt() == B16 && sa.greedy && !e->prof_on && n <= 128 && c.n_layer <= FD_MAX_LAYERS && c.n_embd == 768 &&
-      c.vocab_size % 4 == 0) {
-    // one persistent launch runs all n_steps iterations (fused_decode.cuh)
-    lvx_engine::FusedCtx* fc = nullptr;
-    LVX_TRY(fused_ctx(e, ln, n, &fc));
-    LVX_CHECK(n <= fc->plan.n_clusters * FD_CLUSTER, LVX_ERR_CAPACITY, "fused decode: fewer co-resident CTAs than sessions");
-    fc->P.n_iters = n_steps;
-    LVX_CUDA(cudaMemsetAsync(ln.d_bar, 0, sizeof(unsigned), st));
-    LVX_TRY(fused_launch(fc->P, fc->plan, st));
-    e->launches += 1;
   } else if (e->use_graphs && !e->prof_on && !sa.uniform) {
     const int unroll = 10;   // iterations per graph launch for long runs
     int left = n_steps;
@@ -1703,6 +1721,7 @@ static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes
     split3_kernel<768><<<g3, 256, 0, st>>>(e->v_t, g.R, D, D, (bf16*)e->v_h3, D, 3 * D);
     LAUNCHED(e);
     GemmParams p;
+    p.kdup = 3;
     p.A = e->v_h3; p.C = e->v_raw; p.M = g.R; p.lda = 3 * D; p.ldc = e->raw_ld; p.bias = e->head_b; p.row_chunk = e->row_chunk;
     if (e->prof_detail) p.tag = "tc_gemm:head_x3";
     LVX_TRY(run_gemm(e, p, e->head, a, F32, st));
@@ -1715,6 +1734,7 @@ static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes
     split3_kernel<768><<<g4, 256, 0, st>>>(spec32, g.R, e->spec_ld, e->spec_ld, (bf16*)e->v_spec, e->spec_ld, 3 * e->spec_ld);
     LAUNCHED(e);
     GemmParams q;
+    q.kdup = 3;
     q.A = e->v_spec; q.C = e->v_frames; q.M = g.R; q.lda = 3 * e->spec_ld; q.ldc = NF; q.row_chunk = e->row_chunk;
     if (e->prof_detail) q.tag = "tc_gemm:idft_x3";
     LVX_TRY(run_gemm(e, q, e->idft, a, F32, st));

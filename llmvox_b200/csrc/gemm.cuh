@@ -41,6 +41,7 @@ struct GemmParams {
   int pdl = 0;                // launch with programmatic dependent launch (decode chain)
   int c_transposed = 0;       // tcgen05 swap mode only: store C[n, m] instead of C[m, n]
   const char* tag = nullptr;  // profiler label (host only)
+  int kdup = 1;               // host only: K holds this many side-by-side copies of the algorithmic K (FLOP accounting)
   int cta_budget = 0;        // tcgen05 path: SMs this launch should aim to fill (0 = all); see decode lanes
 };
 

@@ -9,7 +9,7 @@ from typing import Dict, List, Optional, Sequence, Tuple
 import torch
 
 from . import _lib
-from ._lib import LvxConfig, LvxSampling, PRECISION_BF16, PRECISION_FP32, check, i32_array
+from ._lib import LvxConfig, LvxSampling, PRECISION_BF16, PRECISION_EXACT, PRECISION_FP32, check, i32_array
 from .weights import CODEBOOK_KEY, GPTArch, VocoderArch
 
 _UNUSED_PREFIXES = ("feature_extractor.",)   # SEANet encoder etc.: loaded by the reference, never executed
@@ -48,7 +48,7 @@ class Engine:
         cfg.max_sessions, cfg.max_context = max_sessions, max_context
         cfg.max_batch = max_batch or max_sessions
         cfg.max_vocode_frames, cfg.kv_page_tokens, cfg.kv_pages = max_vocode_frames, kv_page_tokens, kv_pages
-        cfg.precision = {"fp32": PRECISION_FP32, "bf16": PRECISION_BF16}[precision]
+        cfg.precision = {"fp32": PRECISION_FP32, "bf16": PRECISION_BF16, "exact": PRECISION_EXACT}[precision]
         cfg.pad_token_id, cfg.eoa_token_id = pad_token_id, eoa_token_id
         cfg.decode_lanes = decode_lanes
         self.decode_lanes = max(1, decode_lanes)

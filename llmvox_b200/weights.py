@@ -168,6 +168,29 @@ def round_weights_to_bf16(sd: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor
     return out
 
 
+def fold_round_gpt_weights(sd: Dict[str, torch.Tensor], arch: Optional[GPTArch] = None) -> Dict[str, torch.Tensor]:
+    """The GPT weights the engine's "exact" precision computes with, as a reference-format state dict: every LayerNorm
+    weight (bias=False) is folded into the columns of the Linear that follows it (c_attn, c_fc, lm_head), every Linear
+    weight is rounded to bf16, the LayerNorm weights become ones.  `LN(x) * g @ W^T == LN(x) @ (W * g)^T`, so before
+    rounding this is the same model; the reference's fp32 loop run on this dict is what the exact mode's greedy
+    tokens are compared with (tests/test_gpu_parity.py).  Vocoder tensors are passed through."""
+    arch = arch or GPTArch()
+    assert not arch.bias, "folding assumes bias=False (english-tiny)"
+    out = dict(sd)
+    r = lambda w: w.to(torch.bfloat16).to(torch.float32)
+    for i in range(arch.n_layer):
+        p = f"transformer.h.{i}."
+        out[p + "attn.c_attn.weight"] = r(sd[p + "attn.c_attn.weight"] * sd[p + "ln_1.weight"][None, :])
+        out[p + "mlp.c_fc.weight"] = r(sd[p + "mlp.c_fc.weight"] * sd[p + "ln_2.weight"][None, :])
+        out[p + "attn.c_proj.weight"] = r(sd[p + "attn.c_proj.weight"])
+        out[p + "mlp.c_proj.weight"] = r(sd[p + "mlp.c_proj.weight"])
+        out[p + "ln_1.weight"] = torch.ones_like(sd[p + "ln_1.weight"])
+        out[p + "ln_2.weight"] = torch.ones_like(sd[p + "ln_2.weight"])
+    out["lm_head.weight"] = r(sd["lm_head.weight"] * sd["transformer.ln_f.weight"][None, :])
+    out["transformer.ln_f.weight"] = torch.ones_like(sd["transformer.ln_f.weight"])
+    return out
+
+
 # ------------------------------------------------------------------ checkpoint formats (reference)
 def load_llmvox_checkpoint(path: str):
     """inference/model_handler.py:147-163 -> (GPTArch, state dict without ``_orig_mod.``)."""

@@ -127,17 +127,28 @@ def test_batch_invariance_and_ragged_text(engines, weights):
 
 
 def test_bf16_decode_tracks_oracle_on_rounded_weights(engines, weights):
-    """bf16 mode: first divergence from the fp32 oracle run on the same bf16-rounded weights is reported; the
-    step-0 pick (no history) must agree and teacher-forced logits carry the 2e-2 bound (above)."""
+    """bf16 mode (bf16-rounded ACTIVATIONS as well as weights) is gated by the 2e-2 teacher-forced logit bound, so its
+    greedy sequence may leave the fp32 oracle's only at a near-tie: every token up to the first divergence is identical
+    and the oracle's top-1 / top-2 margin at the diverging step is below twice that bound.  (Token identity over whole
+    sequences is the exact mode's contract: tests/test_gpu_exact.py.)"""
     e = engines("bf16")
     ids = O.word_ids("hello", True)
+    n = 40
     e.open([0])
     e.feed_text([0], [ids])
-    e.decode_steps([0], 24)
-    got = e.gather_codes([0], 0, 24).cpu().numpy()[0].tolist()
-    ref = O.decode_steps(W.round_weights_to_bf16(weights), O.GPTArch(), ids, 24)
-    assert got[0] == ref[0]
+    e.decode_steps([0], n)
+    got = e.gather_codes([0], 0, n).cpu().numpy()[0].tolist()
+    ref, logits = O.decode_steps(W.round_weights_to_bf16(weights), O.GPTArch(), ids, n, return_logits=True)
     assert all(0 <= c < 4096 for c in got)
+    for t in range(n):
+        if got[t] != ref[t]:
+            top2 = torch.topk(logits[t], 2).values
+            margin = float(top2[0] - top2[1])
+            print(f"bf16 greedy: first divergence at step {t}, oracle margin {margin:.4g}")
+            assert margin < 4e-2, (t, margin)
+            assert float(logits[t][ref[t]] - logits[t][got[t]]) < 4e-2
+            break
+    assert got[0] == ref[0]
 
 
 def test_sampler_matches_generate_semantics(engines):
@@ -406,51 +417,6 @@ def test_decode_lanes_do_not_change_results(weights, precision):
         assert all([x.length for x in a] == [10, 30, 5] for a in p4)
         assert all(np.isfinite(x.pcm).all() for a in p4 for x in a)
     e.close()
-
-
-@pytest.mark.parametrize("n", [1, 5, 64, 100])
-def test_fused_decode_kernel_matches_the_multi_kernel_path(weights, n):
-    """The persistent fused decode kernel (bf16, greedy) against the kernel-per-op path on a twin engine: at every
-    step the twin is teacher-forced with the fused kernel's pick, so both see identical histories; logits must agree
-    within the bf16 bound and every fused pick must be the argmax of its own logits."""
-    import os
-    from llmvox_b200.engine import Engine
-    kw = dict(device=0, precision="bf16", max_sessions=n, max_context=48, max_vocode_frames=256)
-    os.environ["LLMVOX_B200_FUSED"] = "1"          # opt-in path, read at engine creation
-    os.environ["LLMVOX_B200_CLUSTER"] = "0"        # (the cluster-resident kernel is the default and would take precedence)
-    try:
-        fused = Engine(weights, **kw)
-        del os.environ["LLMVOX_B200_FUSED"]
-        plain = Engine(weights, **kw)
-    finally:
-        os.environ.pop("LLMVOX_B200_FUSED", None)
-        del os.environ["LLMVOX_B200_CLUSTER"]
-    rng = np.random.RandomState(n)
-    texts = [rng.randint(3, 259, size=rng.randint(0, 40)).tolist() for _ in range(n)]
-    slots = list(range(n))
-    for e in (fused, plain):
-        e.open(slots)
-        e.feed_text(slots, texts)
-    worst = 0.0
-    for t in range(20):
-        fused.decode_steps(slots, 1)
-        codes = fused.gather_codes(slots, t, 1).view(-1).contiguous()
-        lf = fused.peek_logits(n)
-        lp, _ = plain.decode_step_logits(slots, forced=codes)
-        assert (lf.argmax(dim=1).to(torch.int32) == codes).all()
-        worst = max(worst, float((lf - lp).abs().max()))
-    assert worst < 2e-2, worst
-    # several iterations inside one launch == the same iterations one launch at a time
-    fused.open(slots)
-    fused.feed_text(slots, texts)
-    fused.decode_steps(slots, 20)
-    again = fused.gather_codes(slots, 0, 20).cpu()
-    step = torch.stack([fused.gather_codes(slots, t, 1).view(-1).cpu() for t in range(20)], dim=1)
-    assert fused.session_length(0) == 20
-    plain_codes = plain.gather_codes(slots, 0, 20).cpu()
-    assert (again == plain_codes).all() and (step == again).all()
-    fused.close()
-    plain.close()
 
 
 @pytest.mark.parametrize("n", [1, 5, 16, 17, 64])

@@ -188,3 +188,39 @@ def test_lane_runner_picks_the_decode_path_by_batch_size():
     r.e.cfg.max_context = 512
     r.cluster_default = False                                     # LLMVOX_B200_CLUSTER=0
     assert not r._cluster_call(64, greedy)
+
+
+def test_fold_round_gpt_weights_is_the_same_model_before_rounding(weights):
+    """weights.fold_round_gpt_weights (what the engine's exact precision computes with): folding the LayerNorm weights into
+    the following Linear is an identity on the model; only the bf16 rounding of the Linear weights changes logits."""
+    import torch
+    from llmvox_b200 import weights as W
+    from oracle import llmvox_oracle as O
+    g = torch.Generator().manual_seed(3)
+    sd = dict(weights)
+    for k in list(sd):
+        if k.startswith("transformer.") and (".ln_" in k or "ln_f" in k) and k.endswith(".weight"):
+            sd[k] = 1.0 + 0.2 * torch.randn(sd[k].shape, generator=g)
+    folded = W.fold_round_gpt_weights(sd)
+    ids = O.word_ids("fold", True)
+    forced = [7, 99, 1234, 4000, 17, 5]
+    _, a = O.decode_steps(sd, O.GPTArch(), ids, 6, forced_codes=forced, return_logits=True)
+    _, b = O.decode_steps(folded, O.GPTArch(), ids, 6, forced_codes=forced, return_logits=True)
+    assert float((a - b).abs().max()) < 2e-2           # bf16 weight rounding only
+    for k, v in folded.items():
+        if k.startswith("transformer.h.") and k.endswith("weight") and v.ndim == 2:
+            assert torch.equal(v, v.to(torch.bfloat16).to(torch.float32)), k
+        if ".ln_" in k or "ln_f" in k:
+            assert torch.equal(v, torch.ones_like(v))
+    # unrounded fold == original model to fp32 rounding
+    unrounded = dict(sd)
+    for i in range(4):
+        p = f"transformer.h.{i}."
+        unrounded[p + "attn.c_attn.weight"] = sd[p + "attn.c_attn.weight"] * sd[p + "ln_1.weight"][None, :]
+        unrounded[p + "mlp.c_fc.weight"] = sd[p + "mlp.c_fc.weight"] * sd[p + "ln_2.weight"][None, :]
+        unrounded[p + "ln_1.weight"] = torch.ones(768)
+        unrounded[p + "ln_2.weight"] = torch.ones(768)
+    unrounded["lm_head.weight"] = sd["lm_head.weight"] * sd["transformer.ln_f.weight"][None, :]
+    unrounded["transformer.ln_f.weight"] = torch.ones(768)
+    _, c = O.decode_steps(unrounded, O.GPTArch(), ids, 6, forced_codes=forced, return_logits=True)
+    assert float((a - c).abs().max()) < 1e-4

@@ -46,7 +46,6 @@ constexpr int CD_QR = 3 * CD_C / CD_CLUSTER;   // 144
 constexpr int CD_FR = CD_FF / CD_CLUSTER;      // 192
 constexpr int CD_VR = CD_V / CD_CLUSTER;       // 256
 constexpr int CD_MAX_LAYERS = 8;
-constexpr int CD_STAGES = 8;
 constexpr int CD_SLOT = 16384;                 // bytes per ring slot (one 128-row x 64-column tile)
 constexpr int CD_NI = 2;                       // MMA issuer warps
 // Issuer w takes the ring items at positions = w (mod CD_NI).  The ring depth MUST be a multiple of CD_NI: then every use
@@ -55,11 +54,9 @@ constexpr int CD_NI = 2;                       // MMA issuer warps
 // copy for a was still in flight saw "the other parity" as already complete and ran ahead on stale data; with copies
 // completing out of order this is a rare, timing-dependent corruption of the barrier phases -> the dead waits seen
 // with many clusters in flight.  Three issuers were no faster than two anyway: the tensor pipe and the stream bound it.)
-static_assert(CD_STAGES % CD_NI == 0, "every ring slot must belong to exactly one issuer");
 constexpr int CD_THREADS = 32 * (1 + CD_NI + 8);   // warp 0 producer, warps 1..CD_NI MMA issuers, then 8 worker warps
 constexpr int CD_WORKER0 = 32 * (1 + CD_NI);       // first worker thread
 constexpr int CD_WORKERS = 256;
-constexpr int CD_ABLK = CD_NB * 128;           // one 64-wide k-block of an activation operand (16 rows x 128 B)
 // Weight stream items (one bulk copy + one ring slot each, <= 16 KB so that 8 are in flight).  Per layer:
 //   qkv  : 12 x [128 rows x 64 k] (rows 0..127), then the 16-row tail as 3 x [4 k-blocks x 2 KB]
 //   proj : 6 x [2 k-blocks x 48 rows]
@@ -73,28 +70,50 @@ constexpr int CD_FT = (CD_FR - 128) * 128;     // one k-block of the fc tail (64
 constexpr long long CD_LAYER_BYTES = (long long)CD_QR * CD_C * 2 + (long long)CD_XR * CD_C * 2 + (long long)CD_FR * CD_C * 2 +
                                      (long long)CD_C * CD_FR * 2;
 constexpr long long CD_LM_BYTES = (long long)CD_VR * CD_C * 2;
-// TMEM accumulator columns
-// CD_NI copies of every accumulator, 128 columns apart, one per MMA issuer warp: issuer w takes the ring items at
-// positions = w (mod CD_NI), accumulating into its own copy, and the epilogue adds them.  With
-// N = 16 a GEMM phase is bound by the issuing warp's serial per-item latency (barrier poll, fence, 4 MMAs, commit:
-// ~300 cycles per 16 KB item, measured; M = 64 instead of 128 changed it by only 13 %), not by the tensor pipe.
-constexpr int CD_TM_QKV = 0, CD_TM_PROJ = 32, CD_TM_FC = 96, CD_TM_PROJ2 = 0, CD_TM_LM = 96, CD_TM_BANK = 128, CD_TM_COLS = 256;
-static_assert(CD_NI * CD_TM_BANK <= CD_TM_COLS, "accumulator copies must fit the TMEM allocation");
-// shared-memory carve (offsets from the 1024-aligned base)
-constexpr int CD_OFF_RING = 0;
-constexpr int CD_OFF_A1 = CD_OFF_RING + CD_STAGES * CD_SLOT;          // [12 k-blocks][16 x 128 B]: LN(x) / y operand
-constexpr int CD_OFF_A2 = CD_OFF_A1 + (CD_C / 64) * CD_ABLK;          // [3 k-blocks]: this CTA's GELU(fc) slice
-constexpr int CD_OFF_RED = CD_OFF_A2 + (CD_FR / 64) * CD_ABLK;        // [16 src][4 session quads][48 rows] float4 proj2 partials
-constexpr int CD_OFF_AY = CD_OFF_RED;   // attention output operand of proj, aliases the partials: A1 cannot take it (a fast
-                                        // peer's LN2 gather would land in A1 while this CTA's proj MMAs still read y), and
-                                        // every store into one of the two uses is separated from the other's reads by an exchange
-constexpr int CD_OFF_QKV = CD_OFF_RED + CD_CLUSTER * CD_XR * CD_NB * 4;   // [8 sessions][q 96 | k 96 | v 96] fp32
-constexpr int CD_OFF_XS = CD_OFF_QKV + 8 * 288 * 4;                   // [16 sessions][48] fp32 residual slice
-constexpr int CD_OFF_STATS = CD_OFF_XS + CD_NB * CD_XR * 4;           // [16 src][16 sessions] (mean, M2)
-constexpr int CD_OFF_CAND = CD_OFF_STATS + CD_CLUSTER * CD_NB * 8;    // [16 src][16 sessions] (value, index)
-constexpr int CD_OFF_YST = CD_OFF_CAND + CD_CLUSTER * CD_NB * 8;      // [8 warps][96] bf16 attention output staging
-constexpr int CD_OFF_SMALL = CD_OFF_YST + 8 * CD_HD * 2;              // slot[16], t[16], code[16], wcand[8][8] x 8 B
-constexpr int CD_SMEM_BYTES = CD_OFF_SMALL + 1024 + 1024;             // + alignment slack
+// ---- geometry of the two variants.  X = 0: bf16 activations, UMMA N = 16 (one operand row per session).  X = 1 (exact
+// mode, LVX_PRECISION_EXACT): every activation operand row is a bf16 hi | lo pair -- rows [0, 16) of a k-block hold
+// hi = bf16(v), rows [16, 32) hold lo = bf16(v - hi) of the same sessions, UMMA N = 32, and the epilogues add the two
+// accumulator columns: w . hi + w . lo = w . v to 2^-18 |v| per element with exact bf16 x bf16 products and fp32
+// accumulation, i.e. fp32-class activations against the same 62.9 MB bf16 weight stream.  x travels between CTAs as the
+// two 16-bit halves of its fp32 word (lossless), the KV cache is fp32, attention runs on the FMA pipe in fp32.
+template <int X>
+struct CdG {
+  static constexpr int NCOL = X ? 32 : 16;        // UMMA N = operand rows per k-block
+  static constexpr int ABLK = NCOL * 128;         // one 64-wide k-block of an activation operand
+  static constexpr int STAGES = X ? 6 : 8;        // weight ring depth (the larger operands of X = 1 take 30 KB of it)
+  // Issuer w takes the ring items at positions = w (mod CD_NI).  The ring depth MUST be a multiple of CD_NI (see above).
+  static_assert(STAGES % CD_NI == 0, "every ring slot must belong to exactly one issuer");
+  // TMEM accumulator columns.  CD_NI copies of every accumulator, TM_BANK columns apart, one per MMA issuer warp: issuer
+  // w takes the ring items at positions = w (mod CD_NI), accumulating into its own copy, and the epilogue adds them.
+  // With N = 16 a GEMM phase is bound by the issuing warp's serial per-item latency (barrier poll, fence, 4 MMAs, commit:
+  // ~300 cycles per 16 KB item, measured; M = 64 instead of 128 changed it by only 13 %), not by the tensor pipe.
+  static constexpr int TM_QKV = 0, TM_PROJ = 2 * NCOL, TM_PROJ2 = 0, TM_FC = 6 * NCOL, TM_LM = 6 * NCOL, TM_BANK = 8 * NCOL,
+                       TM_COLS = CD_NI * TM_BANK;
+  static_assert(TM_COLS <= 512, "accumulator copies must fit TMEM");
+  // shared-memory carve (offsets from the 1024-aligned base)
+  static constexpr int OFF_RING = 0;
+  static constexpr int OFF_A1 = OFF_RING + STAGES * CD_SLOT;            // [12 k-blocks][NCOL x 128 B]: LN(x) operand
+  static constexpr int OFF_A2 = OFF_A1 + (CD_C / 64) * ABLK;            // [3 k-blocks]: this CTA's GELU(fc) slice
+  static constexpr int OFF_RED = OFF_A2 + (CD_FR / 64) * ABLK;          // [16 src][4 session quads][48 rows] float4 proj2 partials
+  // attention output operand of proj, aliases the partials: A1 cannot take it (a fast peer's LN2 gather would land in A1
+  // while this CTA's proj MMAs still read y), and every store into one of the two uses is separated from the other's
+  // reads by an exchange.  X = 1: 12 x 4 KB = the 48 KB of the partials exactly.
+  static constexpr int OFF_AY = OFF_RED;
+  static constexpr int RED_BYTES = CD_CLUSTER * CD_XR * CD_NB * 4;
+  static_assert((CD_C / 64) * ABLK <= RED_BYTES, "y operand must fit the partials buffer it aliases");
+  static constexpr int OFF_QKV = OFF_RED + RED_BYTES;                   // [8 sessions][q 96 | k 96 | v 96] fp32
+  static constexpr int OFF_XS = OFF_QKV + 8 * 288 * 4;                  // [16 sessions][48] fp32 residual slice
+  static constexpr int OFF_STATS = OFF_XS + CD_NB * CD_XR * 4;          // [16 src][16 sessions] (mean, M2)
+  static constexpr int OFF_CAND = OFF_STATS + CD_CLUSTER * CD_NB * 8;   // [16 src][16 sessions] (value, index)
+  static constexpr int OFF_YST = OFF_CAND + CD_CLUSTER * CD_NB * 8;     // [8 warps][96] attention output staging (bf16 / fp32)
+  static constexpr int OFF_SMALL = OFF_YST + 8 * CD_HD * (X ? 4 : 2);   // slot[16], t[16], code[16], wcand[8][8] x 8 B
+  static constexpr int SMEM_BYTES = OFF_SMALL + 1024 + 1024;            // + alignment slack
+  static_assert(SMEM_BYTES <= 232448 - 1024, "dynamic + static shared memory must fit one SM");
+  // per-warp attention staging tile inside A1 | A2 (LN1(x) has been consumed by the qkv MMAs, the LN2 gather and the GELU
+  // slice come later): X = 0 16 tokens x 208 B, X = 1 8 tokens x 400 B
+  static constexpr int ATT_TILE = X ? 3200 : 3328;
+  static_assert(8 * ATT_TILE <= (CD_C / 64 + CD_FR / 64) * ABLK, "attention staging must fit A1 | A2");
+};
 
 struct ClusterParams {
   int n, n_iters, n_layer;
@@ -106,7 +125,7 @@ struct ClusterParams {
   int text_dim, code_dim, pad_id;
   const uint8_t* wstream;           // [16 ranks][stream_bytes]
   long long stream_bytes;
-  bf16* kv;
+  void* kv;           // bf16 (X = 0) or fp32 (X = 1) pool
   int page_shift;     // KV page = 1 << page_shift tokens
   long long pool_pages;
   float* logits;      // [n, V] fp32 or null: logits of the launch's last iteration (test hook / lvx_peek_logits)
@@ -211,22 +230,33 @@ __device__ __forceinline__ void cd_workers_sync() { asm volatile("bar.sync 1, 25
 // generic-proxy stores into shared memory (own CTA / a peer's) before the tensor core (async proxy) reads them
 __device__ __forceinline__ void cd_proxy_fence_cta() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void cd_proxy_fence_cluster() { asm volatile("fence.proxy.async.shared::cluster;" ::: "memory"); }
-// 32 lanes x 8 consecutive fp32 columns of the accumulator copies, summed
+// 32 lanes x 8 consecutive fp32 columns (8 sessions) of the accumulator copies, summed; X = 1 also adds the columns of
+// the lo halves, 16 columns further on.  Fixed order: (issuer 0 hi + issuer 1 hi) + (issuer 0 lo + issuer 1 lo).
+template <int X>
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
-  uint32_t r[CD_NI][8];
+  constexpr int NP = X ? 2 : 1;
+  uint32_t r[NP][CD_NI][8];
 #pragma unroll
-  for (int j = 0; j < CD_NI; ++j)
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[j][0]), "=r"(r[j][1]), "=r"(r[j][2]), "=r"(r[j][3]), "=r"(r[j][4]), "=r"(r[j][5]), "=r"(r[j][6]), "=r"(r[j][7])
-                 : "r"(taddr + (uint32_t)(128 * j))
-                 : "memory");
+  for (int h = 0; h < NP; ++h)
+#pragma unroll
+    for (int j = 0; j < CD_NI; ++j)
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                   : "=r"(r[h][j][0]), "=r"(r[h][j][1]), "=r"(r[h][j][2]), "=r"(r[h][j][3]), "=r"(r[h][j][4]), "=r"(r[h][j][5]),
+                     "=r"(r[h][j][6]), "=r"(r[h][j][7])
+                   : "r"(taddr + (uint32_t)(CdG<X>::TM_BANK * j + CD_NB * h))
+                   : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
-  {
-    float a = __uint_as_float(r[0][i]);
+  for (int i = 0; i < 8; ++i) {
+    float a = __uint_as_float(r[0][0][i]);
 #pragma unroll
-    for (int j = 1; j < CD_NI; ++j) a += __uint_as_float(r[j][i]);
+    for (int j = 1; j < CD_NI; ++j) a += __uint_as_float(r[0][j][i]);
+    if (X) {
+      float b = __uint_as_float(r[NP - 1][0][i]);
+#pragma unroll
+      for (int j = 1; j < CD_NI; ++j) b += __uint_as_float(r[NP - 1][j][i]);
+      a += b;
+    }
     v[i] = a;
   }
 }
@@ -259,9 +289,38 @@ __device__ __forceinline__ void cd_unpack8_h(uint4 u, float* f) {
   const float2 c = __half22float2(*reinterpret_cast<__half2*>(&u.z)), d = __half22float2(*reinterpret_cast<__half2*>(&u.w));
   f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
 }
-// byte offset of the 16-byte chunk holding elements [k, k+8) of session row n inside a K-major SW128 activation operand
+// byte offset of the 16-byte chunk holding elements [k, k+8) of operand row n inside a K-major SW128 activation operand
+// (X = 1: row n = hi half of session n, row 16 + n = its lo half)
+template <int X>
 __device__ __forceinline__ uint32_t cd_act_chunk(int n, int k) {
-  return (uint32_t)((k >> 6) * CD_ABLK + n * 128 + ((((k & 63) >> 3) ^ (n & 7)) << 4));
+  return (uint32_t)((k >> 6) * CdG<X>::ABLK + n * 128 + ((((k & 63) >> 3) ^ (n & 7)) << 4));
+}
+// hi | lo split of 8 fp32 values into two packed bf16 chunks
+__device__ __forceinline__ void cd_split8(const float* f, uint4& hi, uint4& lo) {
+  float r[8];
+  hi = cd_pack8(f);
+  cd_unpack8(hi, r);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = f[i] - r[i];
+  lo = cd_pack8(r);
+}
+// 8 fp32 words as their upper / lower 16-bit halves (lossless transport of x through the operand image's two chunks)
+__device__ __forceinline__ void cd_bits_split8(const float* f, uint4& up, uint4& dn) {
+  uint32_t u[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) u[i] = __float_as_uint(f[i]);
+  up = make_uint4((u[0] >> 16) | (u[1] & 0xffff0000u), (u[2] >> 16) | (u[3] & 0xffff0000u), (u[4] >> 16) | (u[5] & 0xffff0000u),
+                  (u[6] >> 16) | (u[7] & 0xffff0000u));
+  dn = make_uint4((u[0] & 0xffffu) | (u[1] << 16), (u[2] & 0xffffu) | (u[3] << 16), (u[4] & 0xffffu) | (u[5] << 16),
+                  (u[6] & 0xffffu) | (u[7] << 16));
+}
+__device__ __forceinline__ void cd_bits_join8(uint4 up, uint4 dn, float* f) {
+  const uint32_t a[4] = {up.x, up.y, up.z, up.w}, b[4] = {dn.x, dn.y, dn.z, dn.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float((a[i] << 16) | (b[i] & 0xffffu));
+    f[2 * i + 1] = __uint_as_float((a[i] & 0xffff0000u) | (b[i] >> 16));
+  }
 }
 // streaming 16-byte load of the KV cache: weak (the rows were written iterations ago, with cluster-scope acquires in
 // between, which also drop L1), no L1 allocation (no reuse)
@@ -276,13 +335,15 @@ __device__ __forceinline__ uint32_t cd_fkey(float v) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
 }
 
+// barrier slots (8 bytes each; the ring never has more than 8 stages)
+constexpr int CD_MAX_STAGES = 8;
 __device__ __forceinline__ uint32_t cd_bar_full(uint32_t bars, unsigned s) { return bars + 8u * s; }
-__device__ __forceinline__ uint32_t cd_bar_empty(uint32_t bars, unsigned s) { return bars + 8u * (CD_STAGES + s); }
-__device__ __forceinline__ uint32_t cd_bar_act(uint32_t bars) { return bars + 8u * (2 * CD_STAGES); }
-__device__ __forceinline__ uint32_t cd_bar_tmem(uint32_t bars) { return bars + 8u * (2 * CD_STAGES + 1); }
-__device__ __forceinline__ uint32_t cd_bar_x(uint32_t bars, unsigned i) { return bars + 8u * (2 * CD_STAGES + 2 + i); }
+__device__ __forceinline__ uint32_t cd_bar_empty(uint32_t bars, unsigned s) { return bars + 8u * (CD_MAX_STAGES + s); }
+__device__ __forceinline__ uint32_t cd_bar_act(uint32_t bars) { return bars + 8u * (2 * CD_MAX_STAGES); }
+__device__ __forceinline__ uint32_t cd_bar_tmem(uint32_t bars) { return bars + 8u * (2 * CD_MAX_STAGES + 1); }
+__device__ __forceinline__ uint32_t cd_bar_x(uint32_t bars, unsigned i) { return bars + 8u * (2 * CD_MAX_STAGES + 2 + i); }
 // one barrier per proj2 row tile (count 3 = its k-block items): the scatter of tile m overlaps the MMAs of m+1..
-__device__ __forceinline__ uint32_t cd_bar_tile(uint32_t bars, unsigned m) { return bars + 8u * (2 * CD_STAGES + 4 + m); }
+__device__ __forceinline__ uint32_t cd_bar_tile(uint32_t bars, unsigned m) { return bars + 8u * (2 * CD_MAX_STAGES + 4 + m); }
 
 // ---- producer / MMA issuer pieces.  Both warps run CONVERGED and elect one lane only around the asynchronous
 // instructions: addresses, descriptors and ring positions then live in uniform registers.  (With `if (lane == 0)` around
@@ -300,35 +361,40 @@ __device__ __forceinline__ void cd_kblock(uint32_t d, uint32_t a, uint32_t b, ui
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) umma_bf16(d, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, (acc || ks) ? 1u : 0u);
 }
+template <int X>
 __device__ __forceinline__ uint32_t cd_stage_wait(uint32_t sbase, uint32_t bars, unsigned gi) {
-  cd_wait(cd_bar_full(bars, gi % CD_STAGES), (gi / CD_STAGES) & 1u);
+  constexpr unsigned ST = CdG<X>::STAGES;
+  cd_wait(cd_bar_full(bars, gi % ST), (gi / ST) & 1u);
   tc_fence_after();
-  return sbase + CD_OFF_RING + (gi % CD_STAGES) * CD_SLOT;
+  return sbase + CdG<X>::OFF_RING + (gi % ST) * CD_SLOT;
 }
 // `128 + tail`-row weight slice against the K = 768 operand `act`: 12 full tiles into `d`, then the tail rows
 // (tail_bytes per k-block, `per` k-blocks per item) into d + 16.  This warp takes the items at ring positions = par
 // (mod CD_NI) (d already points at its accumulator copy).  Returns the advanced ring position.
+template <int X>
 __device__ __forceinline__ unsigned cd_mma_rowsplit(uint32_t sbase, uint32_t bars, uint32_t idesc, unsigned gi, unsigned par, uint32_t act,
                                                     uint32_t d, int tail_bytes, int per) {
+  constexpr unsigned ST = CdG<X>::STAGES;
+  constexpr int ABLK = CdG<X>::ABLK, NCOL = CdG<X>::NCOL;
 #pragma unroll 1
   for (int kb = 0; kb < CD_C / 64; ++kb, ++gi) {
     if (gi % CD_NI != par) continue;
-    const uint32_t a = cd_stage_wait(sbase, bars, gi);
+    const uint32_t a = cd_stage_wait<X>(sbase, bars, gi);
     if (cd_elect()) {
-      cd_kblock(d, a, act + kb * CD_ABLK, idesc, kb >= CD_NI ? 1u : 0u);   // each warp's first item of the tile starts its copy
-      umma_commit(cd_bar_empty(bars, gi % CD_STAGES));
+      cd_kblock(d, a, act + kb * ABLK, idesc, kb >= CD_NI ? 1u : 0u);   // each warp's first item of the tile starts its copy
+      umma_commit(cd_bar_empty(bars, gi % ST));
     }
     __syncwarp();
   }
 #pragma unroll 1
   for (int kb = 0, it = 0; kb < CD_C / 64; kb += per, ++it, ++gi) {
     if (gi % CD_NI != par) continue;
-    const uint32_t a = cd_stage_wait(sbase, bars, gi);
+    const uint32_t a = cd_stage_wait<X>(sbase, bars, gi);
     if (cd_elect()) {
 #pragma unroll 1
       for (int kk = 0; kk < per && kb + kk < CD_C / 64; ++kk)
-        cd_kblock(d + CD_NB, a + kk * tail_bytes, act + (kb + kk) * CD_ABLK, idesc, (it >= CD_NI || kk) ? 1u : 0u);
-      umma_commit(cd_bar_empty(bars, gi % CD_STAGES));
+        cd_kblock(d + NCOL, a + kk * tail_bytes, act + (kb + kk) * ABLK, idesc, (it >= CD_NI || kk) ? 1u : 0u);
+      umma_commit(cd_bar_empty(bars, gi % ST));
     }
     __syncwarp();
   }
@@ -515,6 +581,126 @@ __device__ __noinline__ uint4 cd_attention_mma_warp(const bf16* kbase, int pt0, 
   return *reinterpret_cast<const uint4*>(yst + 4 * cc);
 }
 
+// ---- exact mode (X = 1) attention of one (session, head) by one warp, fp32 throughout: the cache is fp32 in the same
+// layout ([layer][k|v][page][head][16 tokens][96], one page of one head = 6 KB contiguous), scores, softmax and P V run on
+// the FMA pipe.  Per half page (8 tokens = 3 KB, the byte size of a bf16 page): 6 fully coalesced 512-byte loads each for
+// K and V -> registers -> per-warp shared-memory tile (row pitch 400 B: conflict-free float4 rows) ->
+//   scores : lane (token t = lane & 7, part = lane >> 3) sums 24 dims, two shuffles finish the dot product
+//   P V    : lane owns dims lane, lane + 32, lane + 64; p_t by shuffle, V[t][d] from the tile
+// with an online-softmax rescale per half page; K of the next half page and V of this one are in flight during the math.
+// Output: 96 fp32 values in yst.
+__device__ __forceinline__ uint4 cd_ld_stream_f32(const float* p) {
+  uint4 v;
+  asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ const float* cd_attention_kbase_f32(const float* kv, long long pool_pages, int layer, int h) {
+  return kv + (size_t)(layer * 2) * ((size_t)pool_pages * (CD_H * 16 * CD_HD)) + h * (16 * CD_HD) + 4 * (threadIdx.x & 31);
+}
+__device__ __noinline__ void cd_attention_f32_warp(const float* kbase, int pt0, int pt1, long long pool_pages, int T, const float* qkv,
+                                                   float* tile, float* yst) {
+  constexpr int HD = CD_HD, PITCH = 100;   // floats
+  constexpr uint32_t head_stride = 16 * HD, page_stride = CD_H * head_stride;
+  const int lane = threadIdx.x & 31;
+  const int t8 = lane & 7, part = lane >> 3;
+  const size_t plane = (size_t)pool_pages * page_stride;
+  const float* const vbase = kbase + plane;
+  auto half_at = [&](int hp) -> uint32_t {   // warp-uniform argument: element offset of half page hp of this head
+    const int pidx = hp >> 1;
+    const int a = __shfl_sync(0xffffffffu, pt0, pidx & 31), c = __shfl_sync(0xffffffffu, pt1, pidx & 31);
+    return (uint32_t)((pidx & 32) ? c : a) * page_stride + (uint32_t)(hp & 1) * (8 * HD);
+  };
+  // the new token's k / v rows join the cache unrounded (fp32): lanes 0-23 append one float4 each
+  {
+    const uint32_t o = half_at((T >> 4) << 1) + (uint32_t)(T & 15) * HD;
+    if (lane < HD / 4) {
+      *reinterpret_cast<float4*>(const_cast<float*>(kbase) + o) = *reinterpret_cast<const float4*>(qkv + HD + 4 * lane);
+      *reinterpret_cast<float4*>(const_cast<float*>(vbase) + o) = *reinterpret_cast<const float4*>(qkv + 2 * HD + 4 * lane);
+    }
+  }
+  const float scale = 0.10206207261596577f;   // 96^-0.5
+  // staging offsets (floats) of this lane's six 16-byte chunks of a half page: chunk 32k + lane -> token chunk / 24, column chunk % 24
+  uint32_t soff[6];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) soff[k] = (uint32_t)(((32 * k + lane) / 24) * PITCH + ((32 * k + lane) % 24) * 4);
+  const float* const qp = qkv + 24 * part;
+  const float* const krow = tile + t8 * PITCH + 24 * part;
+  float m = -INFINITY, l = 0.f, acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
+  uint4 kr[6], vr[6];
+  const int halves = (T + 7) >> 3;
+  uint32_t pg = half_at(0);
+#pragma unroll
+  for (int k = 0; k < 6; ++k) kr[k] = cd_ld_stream_f32(kbase + pg + 128 * k);
+#pragma unroll 1
+  for (int hp = 0; hp < halves; ++hp) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) vr[k] = cd_ld_stream_f32(vbase + pg + 128 * k);
+    // ---- scores of the 8 tokens
+#pragma unroll
+    for (int k = 0; k < 6; ++k) *reinterpret_cast<uint4*>(tile + soff[k]) = kr[k];
+    __syncwarp();
+    float s = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; i += 2) {
+      const float4 a = *reinterpret_cast<const float4*>(krow + 4 * i), b = *reinterpret_cast<const float4*>(qp + 4 * i);
+      const float4 c = *reinterpret_cast<const float4*>(krow + 4 * i + 4), d = *reinterpret_cast<const float4*>(qp + 4 * i + 4);
+      s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
+      s2 = fmaf(c.x, d.x, s2); s2 = fmaf(c.y, d.y, s2); s2 = fmaf(c.z, d.z, s2); s2 = fmaf(c.w, d.w, s2);
+    }
+    s += s2;
+    s += __shfl_xor_sync(0xffffffffu, s, 8);
+    s += __shfl_xor_sync(0xffffffffu, s, 16);
+    __syncwarp();
+    pg = half_at(hp + 1);   // past the end: entry 0 = a mapped page, never consumed
+#pragma unroll
+    for (int k = 0; k < 6; ++k) kr[k] = cd_ld_stream_f32(kbase + pg + 128 * k);
+    // ---- online softmax over the 8 tokens (select, not arithmetic, for rows >= T: they may hold anything)
+    s = (8 * hp + t8 < T) ? s * scale : -INFINITY;
+    float mx = s;
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
+    const float mn = fmaxf(m, mx);   // finite: token 8 hp < T
+    const float corr = expf(m - mn), p = expf(s - mn);
+    l = l * corr + p;   // per-token partial (4 copies per token), merged at the end over lanes 0-7
+    m = mn;
+    // ---- P V
+#pragma unroll
+    for (int k = 0; k < 6; ++k) *reinterpret_cast<uint4*>(tile + soff[k]) = vr[k];
+    __syncwarp();
+    acc0 *= corr; acc1 *= corr; acc2 *= corr;
+    const int cnt = min(8, T - 8 * hp);   // warp-uniform: rows past T are never read
+#pragma unroll 1
+    for (int t = 0; t < cnt; ++t) {
+      const float pt = __shfl_sync(0xffffffffu, p, t);
+      const float* vrow = tile + t * PITCH + lane;
+      acc0 = fmaf(pt, vrow[0], acc0);
+      acc1 = fmaf(pt, vrow[32], acc1);
+      acc2 = fmaf(pt, vrow[64], acc2);
+    }
+    __syncwarp();
+  }
+  // the new token: q . k_new over lanes 0-23 (4 dims each) + warp sum
+  float sc = 0.f;
+  if (lane < HD / 4) {
+    const float4 a = *reinterpret_cast<const float4*>(qkv + 4 * lane), b = *reinterpret_cast<const float4*>(qkv + HD + 4 * lane);
+    sc = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+  }
+  sc = warp_sum(sc) * scale;
+  l += __shfl_xor_sync(0xffffffffu, l, 1);
+  l += __shfl_xor_sync(0xffffffffu, l, 2);
+  l += __shfl_xor_sync(0xffffffffu, l, 4);
+  const float mn = fmaxf(m, sc);
+  const float corr = expf(m - mn), pn = expf(sc - mn);
+  l = l * corr + pn;
+  const float inv = 1.0f / l;
+  const float* vn = qkv + 2 * HD + lane;
+  yst[lane] = (acc0 * corr + pn * vn[0]) * inv;
+  yst[lane + 32] = (acc1 * corr + pn * vn[32]) * inv;
+  yst[lane + 64] = (acc2 * corr + pn * vn[64]) * inv;
+  __syncwarp();
+}
+
 // text-table elements (features below text_dim), position-row elements and the text row's sum of squares for position t
 __device__ __forceinline__ void cd_prefetch_text(const ClusterParams& P, int slot, int t, int rank, int wt, float (&e)[3], float (&pe)[3],
                                                  float& ss) {
@@ -533,7 +719,9 @@ __device__ __forceinline__ void cd_prefetch_text(const ClusterParams& P, int slo
 // progress words (see cd_timeout): k = 0 workers, 1..3 issuers, 4 producer
 #define CD_STATUS(k, a, b) do { if (lane == 0) bars_sh[32 + (k)] = ((unsigned long long)(unsigned)(a) << 32) | (unsigned)(b); } while (0)
 
+template <int X>
 __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __grid_constant__ ClusterParams P) {
+  using G = CdG<X>;
   extern __shared__ uint8_t smem_raw[];
   // barriers [0, 26) + status words [32, 40) (progress of each role, dumped by a timed-out spin); 512-byte aligned so that
   // cd_timeout finds the block from any barrier address
@@ -551,7 +739,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
   const int n_layer = P.n_layer, n_iters = P.n_iters;
 
   if (tid == 0) {
-    for (unsigned s = 0; s < CD_STAGES; ++s) {
+    for (unsigned s = 0; s < G::STAGES; ++s) {
       mbar_init(cd_bar_full(bars, s), 1);
       mbar_init(cd_bar_empty(bars, s), 1);
     }
@@ -564,11 +752,11 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
   }
   if (warp == 1) {
     __syncwarp();
-    tmem_alloc(smem_u32(&tmem_base_sh), CD_TM_COLS);
+    tmem_alloc(smem_u32(&tmem_base_sh), G::TM_COLS);
   }
   if (warp > CD_NI) {   // session scalars of this cluster
     const int wt = tid - CD_WORKER0;
-    int* sm_slot = reinterpret_cast<int*>(sgen + CD_OFF_SMALL);
+    int* sm_slot = reinterpret_cast<int*>(sgen + G::OFF_SMALL);
     if (wt < CD_NB) {
       const int slot = (wt < nloc) ? P.slots[n0 + wt] : -1;
       sm_slot[wt] = slot;
@@ -603,12 +791,12 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
             const uint32_t bytes = (uint32_t)run_bytes[e];
 #pragma unroll 1
             for (int j = 0; j < run_count[e]; ++j) {
-              const unsigned s = gi % CD_STAGES;
+              const unsigned s = gi % G::STAGES;
               CD_STATUS(4, iter, gi);
-              cd_wait(cd_bar_empty(bars, s), ((gi / CD_STAGES) & 1u) ^ 1u);
+              cd_wait(cd_bar_empty(bars, s), ((gi / G::STAGES) & 1u) ^ 1u);
               if (cd_elect()) {
                 mbar_expect_tx(cd_bar_full(bars, s), bytes);
-                cd_bulk_g2s(sbase + CD_OFF_RING + s * CD_SLOT, src, bytes, cd_bar_full(bars, s), policy);
+                cd_bulk_g2s(sbase + G::OFF_RING + s * CD_SLOT, src, bytes, cd_bar_full(bars, s), policy);
               }
               __syncwarp();
               src += bytes;
@@ -622,9 +810,9 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
     // ------------------------------------------------------------------ MMA issuers (ring items round-robin)
     {
       const unsigned par = (unsigned)(warp - 1);   // this issuer takes ring positions = par (mod CD_NI)
-      const uint32_t idesc = umma_idesc_bf16(128, CD_NB);
-      const uint32_t a1 = sbase + CD_OFF_A1, a2 = sbase + CD_OFF_A2, ay = sbase + CD_OFF_AY;
-      const uint32_t tm = tmem + CD_TM_BANK * par;   // this warp's accumulator copy
+      const uint32_t idesc = umma_idesc_bf16(128, G::NCOL);
+      const uint32_t a1 = sbase + G::OFF_A1, a2 = sbase + G::OFF_A2, ay = sbase + G::OFF_AY;
+      const uint32_t tm = tmem + G::TM_BANK * par;   // this warp's accumulator copy
       unsigned gi = 0, g = 0;
 #pragma unroll 1
       for (int iter = 0; iter < n_iters; ++iter) {
@@ -638,17 +826,17 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
 #pragma unroll 1
             for (int j = 0; j < 24; ++j, ++gi) {   // lm_head: k-block j / 2, row tile (j ^ (j >> 1)) & 1: a tile's items alternate issuers
               if (gi % CD_NI != par) continue;
-              const uint32_t a = cd_stage_wait(sbase, bars, gi);
+              const uint32_t a = cd_stage_wait<X>(sbase, bars, gi);
               if (cd_elect()) {
-                cd_kblock(tm + CD_TM_LM + CD_NB * ((j ^ (j >> 1)) & 1), a, a1 + (j >> 1) * CD_ABLK, idesc, j >= 2 * CD_NI ? 1u : 0u);
-                umma_commit(cd_bar_empty(bars, gi % CD_STAGES));
+                cd_kblock(tm + G::TM_LM + G::NCOL * ((j ^ (j >> 1)) & 1), a, a1 + (j >> 1) * G::ABLK, idesc, j >= 2 * CD_NI ? 1u : 0u);
+                umma_commit(cd_bar_empty(bars, gi % G::STAGES));
               }
               __syncwarp();
             }
             if (cd_elect()) umma_commit(cd_bar_tmem(bars));
             __syncwarp();
           } else if (!(sl & 1)) {
-            gi = cd_mma_rowsplit(sbase, bars, idesc, gi, par, a1, tm + CD_TM_QKV, CD_QT, 4);
+            gi = cd_mma_rowsplit<X>(sbase, bars, idesc, gi, par, a1, tm + G::TM_QKV, CD_QT, 4);
             CD_STATUS(warp, (iter << 8) | sl | 0x80, (g << 16) | (gi & 0xffffu));
             cd_wait(cd_bar_act(bars), g & 1u);   // attention output operand ready
             g += 1;
@@ -656,18 +844,18 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
 #pragma unroll 1
             for (int j = 0; j < 6; ++j, ++gi) {   // proj: 2 k-blocks of 48 rows per item
               if (gi % CD_NI != par) continue;
-              const uint32_t a = cd_stage_wait(sbase, bars, gi);
+              const uint32_t a = cd_stage_wait<X>(sbase, bars, gi);
               if (cd_elect()) {
-                cd_kblock(tm + CD_TM_PROJ, a, ay + (2 * j) * CD_ABLK, idesc, j >= CD_NI ? 1u : 0u);
-                cd_kblock(tm + CD_TM_PROJ, a + CD_PT, ay + (2 * j + 1) * CD_ABLK, idesc, 1u);
-                umma_commit(cd_bar_empty(bars, gi % CD_STAGES));
+                cd_kblock(tm + G::TM_PROJ, a, ay + (2 * j) * G::ABLK, idesc, j >= CD_NI ? 1u : 0u);
+                cd_kblock(tm + G::TM_PROJ, a + CD_PT, ay + (2 * j + 1) * G::ABLK, idesc, 1u);
+                umma_commit(cd_bar_empty(bars, gi % G::STAGES));
               }
               __syncwarp();
             }
             if (cd_elect()) umma_commit(cd_bar_tmem(bars));
             __syncwarp();
           } else {
-            gi = cd_mma_rowsplit(sbase, bars, idesc, gi, par, a1, tm + CD_TM_FC, CD_FT, 2);
+            gi = cd_mma_rowsplit<X>(sbase, bars, idesc, gi, par, a1, tm + G::TM_FC, CD_FT, 2);
             CD_STATUS(warp, (iter << 8) | sl | 0x80, (g << 16) | (gi & 0xffffu));
             cd_wait(cd_bar_act(bars), g & 1u);   // GELU(fc) slice ready
             g += 1;
@@ -676,10 +864,10 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
             for (int s2 = 0; s2 < 18; ++s2, ++gi) {   // proj2: row tile m, k-block kb of this CTA's k-slice
               if (gi % CD_NI != par) continue;
               const int m = s2 / 3, kb = s2 - 3 * m;
-              const uint32_t a = cd_stage_wait(sbase, bars, gi);
+              const uint32_t a = cd_stage_wait<X>(sbase, bars, gi);
               if (cd_elect()) {
-                cd_kblock(tm + CD_TM_PROJ2 + CD_NB * m, a, a2 + kb * CD_ABLK, idesc, kb >= CD_NI ? 1u : 0u);
-                umma_commit(cd_bar_empty(bars, gi % CD_STAGES));
+                cd_kblock(tm + G::TM_PROJ2 + G::NCOL * m, a, a2 + kb * G::ABLK, idesc, kb >= CD_NI ? 1u : 0u);
+                umma_commit(cd_bar_empty(bars, gi % G::STAGES));
                 umma_commit(cd_bar_tile(bars, (unsigned)m));
               }
               __syncwarp();
@@ -693,12 +881,12 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
   } else {
     // ------------------------------------------------------------------ workers
     const int wt = tid - CD_WORKER0, ww = wt >> 5, q = warp & 3, hh = ww >> 2;
-    float* const xs = reinterpret_cast<float*>(sgen + CD_OFF_XS);
-    float* const qkvb = reinterpret_cast<float*>(sgen + CD_OFF_QKV);
-    int* const sm_slot = reinterpret_cast<int*>(sgen + CD_OFF_SMALL);
+    float* const xs = reinterpret_cast<float*>(sgen + G::OFF_XS);
+    float* const qkvb = reinterpret_cast<float*>(sgen + G::OFF_QKV);
+    int* const sm_slot = reinterpret_cast<int*>(sgen + G::OFF_SMALL);
     int* const sm_t = sm_slot + 16;
     int* const sm_code = sm_slot + 32;
-    uint2* const wcand = reinterpret_cast<uint2*>(sgen + CD_OFF_SMALL + 256);
+    uint2* const wcand = reinterpret_cast<uint2*>(sgen + G::OFF_SMALL + 256);
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
     const int head = rank >> 1, odd = rank & 1;
     unsigned xphase = 0, gcount = 0;
@@ -789,19 +977,28 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
           }
           const float mean = s1 * (1.0f / CD_XR);
           const float m2 = fmaxf(s2 - (float)CD_XR * mean * mean, 0.f);
-          cd_st_remote_v2(cd_mapa(sbase + CD_OFF_STATS + (uint32_t)((rank * CD_NB + n) * 8), (uint32_t)l16), __float_as_uint(mean),
+          cd_st_remote_v2(cd_mapa(sbase + G::OFF_STATS + (uint32_t)((rank * CD_NB + n) * 8), (uint32_t)l16), __float_as_uint(mean),
                           __float_as_uint(m2));
         }
 #pragma unroll 1
-        for (int dd = 0; dd < 2; ++dd) {   // fp16 copies of the slice into the operand image of peers 2ww, 2ww+1
-          const uint32_t rbase = cd_mapa(sbase + CD_OFF_A1, (uint32_t)(2 * ww + dd));
+        for (int dd = 0; dd < 2; ++dd) {   // copies of the slice into the operand image of peers 2ww, 2ww+1: fp16 (X = 0), or
+                                           // the fp32 words as 16-bit halves in the hi / lo rows (X = 1: lossless)
+          const uint32_t rbase = cd_mapa(sbase + G::OFF_A1, (uint32_t)(2 * ww + dd));
 #pragma unroll
           for (int i = 0; i < 3; ++i) {
             const int item = lane + 32 * i, n = item / 6, ch = item - 6 * n;
             const float4 f0 = *reinterpret_cast<const float4*>(xs + n * CD_XR + 8 * ch);
             const float4 f1 = *reinterpret_cast<const float4*>(xs + n * CD_XR + 8 * ch + 4);
             const float f[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-            cd_st_remote_v4(rbase + cd_act_chunk(n, CD_XR * rank + 8 * ch), cd_pack8_h(f));
+            const uint32_t a = rbase + cd_act_chunk<X>(n, CD_XR * rank + 8 * ch);
+            if constexpr (X) {
+              uint4 up, dn;
+              cd_bits_split8(f, up, dn);
+              cd_st_remote_v4(a, up);
+              cd_st_remote_v4(a + CD_NB * 128, dn);
+            } else {
+              cd_st_remote_v4(a, cd_pack8_h(f));
+            }
           }
         }
         CD_T();
@@ -809,7 +1006,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
         CD_T();
         {   // merge the 16 partials (Chan), normalise the gathered row in place
           const int n = wt >> 4;
-          const float2* st = reinterpret_cast<const float2*>(sgen + CD_OFF_STATS) + n;
+          const float2* st = reinterpret_cast<const float2*>(sgen + G::OFF_STATS) + n;
           float mean = 0.f, m2 = 0.f, sq = 0.f;
 #pragma unroll
           for (int r = 0; r < CD_CLUSTER; ++r) {
@@ -825,12 +1022,19 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
           const float shift = -mean * rstd;
 #pragma unroll 2
           for (int i = 0; i < 6; ++i) {
-            uint4* p16 = reinterpret_cast<uint4*>(sgen + CD_OFF_A1 + cd_act_chunk(n, 8 * ((wt & 15) + 16 * i)));
+            uint4* p16 = reinterpret_cast<uint4*>(sgen + G::OFF_A1 + cd_act_chunk<X>(n, 8 * ((wt & 15) + 16 * i)));
             float f[8];
-            cd_unpack8_h(*p16, f);
+            if constexpr (X) {
+              cd_bits_join8(p16[0], p16[CD_NB * 8], f);   // lo row = 16 operand rows = 2 KB further on
 #pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], rstd, shift);
-            *p16 = cd_pack8(f);
+              for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], rstd, shift);
+              cd_split8(f, p16[0], p16[CD_NB * 8]);
+            } else {
+              cd_unpack8_h(*p16, f);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], rstd, shift);
+              *p16 = cd_pack8(f);
+            }
           }
         }
         signal_act();
@@ -842,12 +1046,12 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
           CD_T();
           {
             const uint32_t dest = (uint32_t)((rank & ~1) + hh);
-            const uint32_t qb = cd_mapa(sbase + CD_OFF_QKV, dest);
+            const uint32_t qb = cd_mapa(sbase + G::OFF_QKV, dest);
 #pragma unroll 1
             for (int tile = 0; tile < 2; ++tile) {
               if (tile == 1 && q != 0) break;
               float v[8];
-              tmem_ld8(trow + (uint32_t)(CD_TM_QKV + CD_NB * tile + 8 * hh), v);
+              tmem_ld8<X>(trow + (uint32_t)(G::TM_QKV + G::NCOL * tile + 8 * hh), v);
               const int lr = 128 * tile + 32 * q + lane;
               if (lr < CD_QR) {
                 const uint32_t a = qb + (uint32_t)((CD_QR * odd + lr) * 4);
@@ -862,20 +1066,34 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
           // ================= attention: warp ww = session 8 * odd + ww of the group, head = rank / 2
           {
             const int n = 8 * odd + ww;
-            uint4 val = make_uint4(0u, 0u, 0u, 0u);
-            if (n < nloc) {   // warp-uniform
-              const int slot = sm_slot[n];
-              // per-warp 16 x 208 B staging tile inside A1 | A2 (30 KB; LN1(x) has been consumed by the qkv MMAs, the LN2
-              // gather and the GELU slice come later)
-              val = cd_attention_mma_warp(cd_attention_kbase(P.kv, P.pool_pages, l, head), pt0, pt1, P.pool_pages, sm_t[n],
-                                          qkvb + ww * 288, sgen + CD_OFF_A1 + ww * 3328, reinterpret_cast<uint32_t*>(sgen + CD_OFF_YST) + ww * 48);
+            uint4 val = make_uint4(0u, 0u, 0u, 0u), val_lo = make_uint4(0u, 0u, 0u, 0u);
+            const int ch = lane % 12, d0 = (lane / 12) * 8;
+            // per-warp staging tile inside A1 | A2 (LN1(x) has been consumed by the qkv MMAs, the LN2 gather and the GELU
+            // slice come later)
+            if constexpr (X) {
+              float* yst = reinterpret_cast<float*>(sgen + G::OFF_YST) + ww * CD_HD;
+              if (n < nloc) {   // warp-uniform
+                cd_attention_f32_warp(cd_attention_kbase_f32(reinterpret_cast<const float*>(P.kv), P.pool_pages, l, head), pt0, pt1,
+                                      P.pool_pages, sm_t[n], qkvb + ww * 288, reinterpret_cast<float*>(sgen + G::OFF_A1 + ww * G::ATT_TILE), yst);
+                const float4 f0 = *reinterpret_cast<const float4*>(yst + 8 * ch), f1 = *reinterpret_cast<const float4*>(yst + 8 * ch + 4);
+                const float f[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
+                cd_split8(f, val, val_lo);
+              }
+            } else {
+              if (n < nloc)   // warp-uniform
+                val = cd_attention_mma_warp(cd_attention_kbase(reinterpret_cast<bf16*>(P.kv), P.pool_pages, l, head), pt0, pt1, P.pool_pages,
+                                            sm_t[n], qkvb + ww * 288, sgen + G::OFF_A1 + ww * G::ATT_TILE,
+                                            reinterpret_cast<uint32_t*>(sgen + G::OFF_YST) + ww * 48);
             }
             // output row to every peer's y operand: lanes 0-11 / 12-23 hold the 12 chunks, 8 peers each
             if (lane < 24) {
-              const int ch = lane % 12, d0 = (lane / 12) * 8;
-              const uint32_t off = sbase + CD_OFF_AY + cd_act_chunk(n, CD_HD * head + 8 * ch);
+              const uint32_t off = sbase + G::OFF_AY + cd_act_chunk<X>(n, CD_HD * head + 8 * ch);
 #pragma unroll 1
-              for (int d2 = 0; d2 < 8; ++d2) cd_st_remote_v4(cd_mapa(off, (uint32_t)(d0 + d2)), val);
+              for (int d2 = 0; d2 < 8; ++d2) {
+                const uint32_t ra = cd_mapa(off, (uint32_t)(d0 + d2));
+                cd_st_remote_v4(ra, val);
+                if constexpr (X) cd_st_remote_v4(ra + CD_NB * 128, val_lo);
+              }
             }
           }
           CD_T();
@@ -887,7 +1105,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
           CD_T();
           if (q < 2) {
             float v[8];
-            tmem_ld8(trow + (uint32_t)(CD_TM_PROJ + 8 * hh), v);
+            tmem_ld8<X>(trow + (uint32_t)(G::TM_PROJ + 8 * hh), v);
             const int lr = 32 * q + lane;
             if (lr < CD_XR) {
 #pragma unroll
@@ -903,11 +1121,20 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
           for (int tile = 0; tile < 2; ++tile) {
             if (tile == 1 && q >= 2) break;
             float v[8];
-            tmem_ld8(trow + (uint32_t)(CD_TM_FC + CD_NB * tile + 8 * hh), v);
+            tmem_ld8<X>(trow + (uint32_t)(G::TM_FC + G::NCOL * tile + 8 * hh), v);
             const int j = 128 * tile + 32 * q + lane;
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              *reinterpret_cast<bf16*>(sgen + CD_OFF_A2 + cd_act_chunk(8 * hh + i, j) + (j & 7) * 2) = __float2bfloat16_rn(gelu_tanh_fast(v[i]));
+            for (int i = 0; i < 8; ++i) {
+              bf16* dst = reinterpret_cast<bf16*>(sgen + G::OFF_A2 + cd_act_chunk<X>(8 * hh + i, j) + (j & 7) * 2);
+              if constexpr (X) {
+                bf16 hi, lo;
+                split_hi_lo(gelu_tanh(v[i]), hi, lo);
+                dst[0] = hi;
+                dst[CD_NB * 64] = lo;   // 16 operand rows further on
+              } else {
+                dst[0] = __float2bfloat16_rn(gelu_tanh_fast(v[i]));
+              }
+            }
           }
           signal_act();
           CD_T();
@@ -918,11 +1145,11 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
             cd_wait(cd_bar_tile(bars, (unsigned)m), (unsigned)(iter * n_layer + l) & 1u);
             tc_fence_after();
             float v[8];
-            tmem_ld8(trow + (uint32_t)(CD_TM_PROJ2 + CD_NB * m + 8 * hh), v);
+            tmem_ld8<X>(trow + (uint32_t)(G::TM_PROJ2 + G::NCOL * m + 8 * hh), v);
             // partials buffer of the owner: [source rank][session quad][row] float4, so that the 32 lanes of a store
             // (consecutive rows) write 512 contiguous bytes (16-byte pieces at a 64-byte stride ran at 4 B / clock)
             const int j = 128 * m + 32 * q + lane, owner = j / CD_XR, lr = j - owner * CD_XR;
-            const uint32_t base = cd_mapa(sbase + CD_OFF_RED + (uint32_t)(((rank * 4 + 2 * hh) * CD_XR + lr) * 16), (uint32_t)owner);
+            const uint32_t base = cd_mapa(sbase + G::OFF_RED + (uint32_t)(((rank * 4 + 2 * hh) * CD_XR + lr) * 16), (uint32_t)owner);
             cd_st_remote_v4(base, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])));
             cd_st_remote_v4(base + (uint32_t)(CD_XR * 16),
                             make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));
@@ -934,7 +1161,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
           CD_T();
           if (wt < 4 * CD_XR) {   // fixed source order: deterministic
             const int c4 = wt / CD_XR, lr = wt - c4 * CD_XR;
-            const uint8_t* rp = sgen + CD_OFF_RED + (c4 * CD_XR + lr) * 16;
+            const uint8_t* rp = sgen + G::OFF_RED + (c4 * CD_XR + lr) * 16;
             float4 a = *reinterpret_cast<const float4*>(rp);
 #pragma unroll
             for (int r = 1; r < CD_CLUSTER; ++r) {
@@ -953,8 +1180,8 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
       CD_T();
       {
         float v0[8], v1[8];
-        tmem_ld8(trow + (uint32_t)(CD_TM_LM + 8 * hh), v0);
-        tmem_ld8(trow + (uint32_t)(CD_TM_LM + CD_NB + 8 * hh), v1);
+        tmem_ld8<X>(trow + (uint32_t)(G::TM_LM + 8 * hh), v0);
+        tmem_ld8<X>(trow + (uint32_t)(G::TM_LM + G::NCOL + 8 * hh), v1);
         const int row = CD_VR * rank + 32 * q + lane;
 #pragma unroll 1
         for (int i = 0; i < 8; ++i) {
@@ -981,11 +1208,11 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
           const uint2 o = wcand[(4 * h2 + w) * 8 + i];
           if (o.x > b.x || (o.x == b.x && o.y < b.y)) b = o;
         }
-        cd_st_remote_v2(cd_mapa(sbase + CD_OFF_CAND + (uint32_t)((rank * CD_NB + n) * 8), (uint32_t)(wt & 15)), b.x, b.y);
+        cd_st_remote_v2(cd_mapa(sbase + G::OFF_CAND + (uint32_t)((rank * CD_NB + n) * 8), (uint32_t)(wt & 15)), b.x, b.y);
       }
       exchange(false);
       if (wt < CD_NB) {
-        const uint2* cand = reinterpret_cast<const uint2*>(sgen + CD_OFF_CAND);
+        const uint2* cand = reinterpret_cast<const uint2*>(sgen + G::OFF_CAND);
         uint2 b = cand[wt];
 #pragma unroll
         for (int r = 1; r < CD_CLUSTER; ++r) {
@@ -1014,7 +1241,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem, CD_TM_COLS);
+    tmem_dealloc(tmem, G::TM_COLS);
   }
 }
 #undef CD_T
@@ -1107,9 +1334,10 @@ inline long long cd_build_descs(const CdLayerW* layers, int n_layer, const float
   return per_rank;
 }
 
-inline int cluster_decode_configure(int* max_clusters) {
-  cudaError_t err = cudaFuncSetAttribute(cluster_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CD_SMEM_BYTES);
-  if (err == cudaSuccess) err = cudaFuncSetAttribute(cluster_decode_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+template <int X>
+inline int cluster_decode_configure_x(int* max_clusters) {
+  cudaError_t err = cudaFuncSetAttribute(cluster_decode_kernel<X>, cudaFuncAttributeMaxDynamicSharedMemorySize, CdG<X>::SMEM_BYTES);
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(cluster_decode_kernel<X>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   if (err != cudaSuccess) {
     set_error(std::string("cudaFuncSetAttribute(cluster_decode): ") + cudaGetErrorString(err));
     return LVX_ERR_CUDA;
@@ -1117,7 +1345,7 @@ inline int cluster_decode_configure(int* max_clusters) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(CD_CLUSTER * 8);
   cfg.blockDim = dim3(CD_THREADS);
-  cfg.dynamicSmemBytes = CD_SMEM_BYTES;
+  cfg.dynamicSmemBytes = CdG<X>::SMEM_BYTES;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CD_CLUSTER;
@@ -1126,7 +1354,7 @@ inline int cluster_decode_configure(int* max_clusters) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int mc = 0;
-  err = cudaOccupancyMaxActiveClusters(&mc, cluster_decode_kernel, &cfg);
+  err = cudaOccupancyMaxActiveClusters(&mc, cluster_decode_kernel<X>, &cfg);
   if (err != cudaSuccess) {
     cudaGetLastError();
     mc = 0;
@@ -1134,12 +1362,15 @@ inline int cluster_decode_configure(int* max_clusters) {
   *max_clusters = mc;
   return LVX_OK;
 }
+inline int cluster_decode_configure(bool exact, int* max_clusters) {
+  return exact ? cluster_decode_configure_x<1>(max_clusters) : cluster_decode_configure_x<0>(max_clusters);
+}
 
-inline int cluster_decode_launch(const ClusterParams& P, cudaStream_t st) {
+inline int cluster_decode_launch(bool exact, const ClusterParams& P, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(CD_CLUSTER * ceil_div(P.n, P.per_cluster));
   cfg.blockDim = dim3(CD_THREADS);
-  cfg.dynamicSmemBytes = CD_SMEM_BYTES;
+  cfg.dynamicSmemBytes = exact ? CdG<1>::SMEM_BYTES : CdG<0>::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1148,7 +1379,7 @@ inline int cluster_decode_launch(const ClusterParams& P, cudaStream_t st) {
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t err = cudaLaunchKernelEx(&cfg, cluster_decode_kernel, P);
+  cudaError_t err = exact ? cudaLaunchKernelEx(&cfg, cluster_decode_kernel<1>, P) : cudaLaunchKernelEx(&cfg, cluster_decode_kernel<0>, P);
   if (err != cudaSuccess) {
     set_error(std::string("cluster_decode launch: ") + cudaGetErrorString(err));
     return LVX_ERR_CUDA;

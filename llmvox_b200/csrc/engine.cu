@@ -226,7 +226,11 @@ struct lvx_engine {
   long long cd_stream_bytes = 0;
   float *cd_text_ss = nullptr, *cd_code_ss = nullptr;
   int cd_max_clusters = 0;
-  bool cd_spread = true;   // spread a call's sessions over all co-resident clusters (LLMVOX_B200_CD_SPREAD=0: fill to 16)
+  // spread a call's sessions over all co-resident clusters instead of filling clusters to 16 (LLMVOX_B200_CD_SPREAD=1).
+  // Measured (profiles/r02_cluster_decode.md): 64 sessions as 7 clusters of 9-10 run at 148.7 us / iteration at T = 20..120
+  // (4 clusters of 16: 149.8) but 202.8 vs 184.1 at T = 110..210 -- seven weight streams contend in L2 with the K/V
+  // reads -- so filling stays the default.
+  bool cd_spread = false;
   // launches that may still be running: never more clusters in flight than are co-resident (see cluster_launch)
   struct CdInflight {
     cudaEvent_t ev;
@@ -529,7 +533,7 @@ extern "C" int lvx_engine_create(const lvx_config* cfg, int device, lvx_engine**
     // cluster-resident decode kernel (cluster_decode.cuh): the default greedy bf16 path; LLMVOX_B200_CLUSTER=0 selects the
     // kernel-per-op path (CUDA graphs + programmatic dependent launch) instead
     const char* env5 = getenv("LLMVOX_B200_CD_SPREAD");
-    e->cd_spread = !(env5 && env5[0] == '0');
+    e->cd_spread = env5 && env5[0] == '1';
     const char* env4 = getenv("LLMVOX_B200_CLUSTER");
     e->use_cluster = !(env4 && env4[0] == '0');
     if (cudaStreamCreateWithFlags(&e->gstream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -1165,7 +1169,7 @@ extern "C" const unsigned long long* lvx_cluster_diag(void) { return g_cd_diag_h
 static int cluster_init(lvx_engine* e) {
   if (e->cd_ready) return LVX_OK;
   const lvx_config& c = e->cfg;
-  LVX_TRY(cluster_decode_configure(&e->cd_max_clusters));
+  LVX_TRY(cluster_decode_configure(e->exact(), &e->cd_max_clusters));
   LVX_CHECK(e->cd_max_clusters >= 1, LVX_ERR_CUDA, "cluster decode: no 16-CTA cluster fits on this device");
   if (getenv("LLMVOX_B200_TRACE")) fprintf(stderr, "[llmvox_b200] cluster decode: %d co-resident clusters of %d CTAs\n", e->cd_max_clusters, CD_CLUSTER);
   std::vector<CdLayerW> lw(c.n_layer);
@@ -1205,7 +1209,7 @@ static int cluster_init(lvx_engine* e) {
 
 static bool cluster_applicable(const lvx_engine* e, const SamplerArgs& sa) {
   const lvx_config& c = e->cfg;
-  return e->use_cluster && e->cfg.precision == LVX_PRECISION_BF16 && sa.greedy && !sa.forced && !sa.out_codes && c.n_embd == CD_C &&
+  return e->use_cluster && e->cfg.precision != LVX_PRECISION_FP32 && sa.greedy && !sa.forced && !sa.out_codes && c.n_embd == CD_C &&
          c.n_head == CD_H && c.vocab_size == CD_V && c.n_layer <= CD_MAX_LAYERS && c.text_dim + c.code_dim == CD_C && !c.bias &&
          c.kv_page_tokens == 16 && e->max_pages <= 64 &&
          (long long)e->pool_pages * c.kv_page_tokens * c.n_embd < (1LL << 31);
@@ -1237,14 +1241,11 @@ static int cluster_launch(lvx_engine* e, lvx_engine::Lane& ln, const int32_t* h_
   P.text_ss = e->cd_text_ss; P.code_ss = e->cd_code_ss;
   P.text_dim = c.text_dim; P.code_dim = c.code_dim; P.pad_id = c.pad_token_id;
   P.wstream = e->cd_stream; P.stream_bytes = e->cd_stream_bytes;
-  P.kv = (bf16*)e->kv; P.pool_pages = e->pool_pages;
+  P.kv = e->kv; P.pool_pages = e->pool_pages;
   P.page_shift = 0;
   while ((1 << P.page_shift) < c.kv_page_tokens) P.page_shift += 1;
   P.trace = getenv("LLMVOX_B200_TRACE") ? ln.d_trace : nullptr;
-  // Sessions per cluster: a wave of `cap` co-resident clusters costs the same time however many of its clusters are used
-  // (the iteration is a latency chain), but every cluster's attention streams its sessions' K/V through ONE SM per head
-  // pair -- so the sessions of a call are spread evenly over as many clusters as a wave holds instead of filling
-  // clusters to 16 (64 sessions: 7 clusters of 9-10 rather than 4 of 16).
+  // waves of at most `cap` clusters, balanced (128 sessions: 2 x 64, not 112 + 16)
   const int waves = ceil_div(n, cap * CD_NB);
   const int per_wave = ceil_div(n, waves);
   for (int pos = 0; pos < n; pos += per_wave) {
@@ -1277,7 +1278,7 @@ static int cluster_launch(lvx_engine* e, lvx_engine::Lane& ln, const int32_t* h_
     }
     {
       ProfScope prof_scope(e, "cluster_decode", st, 0.0, bytes);
-      LVX_TRY(cluster_decode_launch(P, st));
+      LVX_TRY(cluster_decode_launch(e->exact(), P, st));
     }
     e->launches += 1;
     lvx_engine::CdInflight rec{e->get_event(), st, clusters};
@@ -1301,7 +1302,6 @@ extern "C" int lvx_decode_steps_lane(lvx_engine* e, int lane, const int32_t* h_s
   SamplerArgs sa = sampler_args(s);
   LVX_CHECK(sa.greedy || sa.temperature > 0.f, LVX_ERR_INVALID, "temperature must be positive");
   LVX_CHECK(!(sa.uniform && n_steps > 1), LVX_ERR_INVALID, "d_uniform supplies one draw per session: use n_steps == 1");
-  const lvx_config& c = e->cfg;
   if (cluster_applicable(e, sa)) {
     LVX_TRY(cluster_launch(e, ln, h_slots, n, n_steps, st));
   } else if (e->use_graphs && !e->prof_on && !sa.uniform) {

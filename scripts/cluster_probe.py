@@ -16,7 +16,7 @@ os.environ["LLMVOX_B200_CLUSTER"] = "1"
 if os.environ.get("PROBE_TRACE") == "1":
     os.environ["LLMVOX_B200_TRACE"] = "1"
 N = int(os.environ.get("PROBE_N", "256"))
-e = Engine(sd, device=0, precision="bf16", max_sessions=N, max_batch=N, max_context=512, max_vocode_frames=256, decode_lanes=8)
+e = Engine(sd, device=0, precision=os.environ.get("PROBE_PRECISION", "bf16"), max_sessions=N, max_batch=N, max_context=512, max_vocode_frames=256, decode_lanes=8)
 del os.environ["LLMVOX_B200_CLUSTER"]
 
 if os.environ.get("PROBE_CHECK", "1") == "1":

@@ -56,7 +56,11 @@ def test_exact_greedy_tokens_identical_config0(weights, folded, gold, path):
     e = _engine(weights, path, 2, 256)
     e.open([1])
     e.feed_text([1], [ids])
+    l0 = e.kernel_launches
     e.decode_steps([1], n)
+    launches = e.kernel_launches - l0
+    # the path under test really ran: one cluster-kernel launch (+ the page-table patch) against ~40 kernels per step
+    assert (launches <= 8) if path == "cluster" else (launches > 30 * n), launches
     got = e.gather_codes([1], 0, n).cpu().numpy()[0].tolist()
     e.close()
     div, msg = _report(f"exact/{path} config0", got, ref, logits)

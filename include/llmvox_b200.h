@@ -118,6 +118,23 @@ int lvx_decode_steps(lvx_engine* e, const int32_t* h_slots, int n, int n_steps, 
 int lvx_decode_steps_lane(lvx_engine* e, int lane, const int32_t* h_slots, int n, int n_steps, const lvx_sampling* s,
                           void* stream);
 
+/* Same with the decode path chosen PER CALL (no engine state): LVX_PATH_AUTO = the engine's default (cluster-resident
+ * kernel where it applies, see lvx_set_cluster_decode), LVX_PATH_CLUSTER = the cluster-resident kernel (an error when it
+ * does not apply: fp32 mode, sampled decoding), LVX_PATH_PER_OP = the kernel-per-op chain.  Calls with different paths
+ * may be in flight on different lanes / streams at the same time (e.g. 224 sessions on the cluster kernel and the rest
+ * of a 256-session batch on the kernel-per-op lanes). */
+#define LVX_PATH_AUTO 0
+#define LVX_PATH_CLUSTER 1
+#define LVX_PATH_PER_OP 2
+int lvx_decode_steps_ex(lvx_engine* e, int lane, const int32_t* h_slots, int n, int n_steps, const lvx_sampling* s,
+                        int path, void* stream);
+
+/* Per-session progress for the host's chunk scheduler (streaming_server.py:357-422): writes (eoa_pos, ctx_len) pairs
+ * -- the position of the sentence's first end-of-audio code (eoa_token_id; -1 = none yet) and the codes decoded so far
+ * -- of n sessions to h_pinned_out (2 n int32, pinned host memory) with an asynchronous copy on `stream`.  The decode
+ * kernels maintain eoa_pos on the device, so no code VALUE has to visit the host to detect the end of a sentence. */
+int lvx_session_progress(lvx_engine* e, const int32_t* h_slots, int n, int32_t* h_pinned_out, void* stream);
+
 /* Greedy bf16 decode path of lvx_decode_steps[_lane]: on != 0 (default) = the cluster-resident kernel (one 16-CTA
  * cluster per 16 sessions runs whole iterations; at most 7 clusters in flight per engine), 0 = the kernel-per-op chain
  * (CUDA graphs + programmatic dependent launch), which is the better choice for batches above ~224 sessions.  Both

@@ -1225,6 +1225,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
           const int slot = sm_slot[wt];
           P.st.codes[(size_t)slot * P.st.max_context + t] = code;
           P.st.ctx_len[slot] = t + 1;
+          if (code == P.st.eoa_id && P.st.eoa_pos[slot] < 0) P.st.eoa_pos[slot] = t;   // streaming_server.py:379, 397
         }
         sm_code[wt] = code;
         sm_t[wt] = t + 1;

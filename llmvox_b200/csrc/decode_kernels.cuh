@@ -12,7 +12,8 @@ struct SessionState {
   int* text_ids;     // [S, max_context]
   int* codes;        // [S, max_context] code history
   int* page_table;   // [S, max_pages]
-  int max_context, max_pages;
+  int* eoa_pos;      // [S] position of the first end-of-audio code (eoa_id) of the sentence, -1 = none yet
+  int max_context, max_pages, eoa_id;
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -473,10 +474,18 @@ __global__ void __launch_bounds__(256) sampler_kernel(const float* __restrict__ 
     if (a.out_codes) a.out_codes[b] = pick;
     if (a.record) {
       const int t = st.ctx_len[slot];
-      st.codes[(size_t)slot * st.max_context + t] = a.forced ? a.forced[b] : pick;
+      const int rec = a.forced ? a.forced[b] : pick;
+      st.codes[(size_t)slot * st.max_context + t] = rec;
       st.ctx_len[slot] = t + 1;
+      if (rec == st.eoa_id && st.eoa_pos[slot] < 0) st.eoa_pos[slot] = t;   // streaming_server.py:379, 397
     }
   }
+}
+
+// out[i] = (eoa_pos[slot_i], ctx_len[slot_i]): the only per-round facts the host's chunk scheduler needs (:357-422)
+__global__ void gather_progress_kernel(const int* __restrict__ slots, int n, SessionState st, int2* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = make_int2(st.eoa_pos[slots[i]], st.ctx_len[slots[i]]);
 }
 
 // history gather: out[i, j] = codes[slot_i, start + j]
@@ -502,6 +511,7 @@ __global__ void reset_sessions_kernel(const int* __restrict__ slots, int n, Sess
   if (i < n) {
     st.ctx_len[slots[i]] = 0;
     st.text_len[slots[i]] = 0;
+    st.eoa_pos[slots[i]] = -1;
   }
 }
 

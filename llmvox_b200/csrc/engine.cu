@@ -422,6 +422,9 @@ static int engine_alloc(lvx_engine* e) {
   LVX_TRY(dev_alloc(e, &e->st.text_ids, (size_t)S * c.max_context));
   LVX_TRY(dev_alloc(e, &e->st.codes, (size_t)S * c.max_context));
   LVX_TRY(dev_alloc(e, &e->st.page_table, (size_t)S * e->max_pages));
+  LVX_TRY(dev_alloc(e, &e->st.eoa_pos, S));
+  LVX_CUDA(cudaMemset(e->st.eoa_pos, 0xFF, (size_t)S * sizeof(int)));
+  e->st.eoa_id = c.eoa_token_id;
   const size_t kv_elems = (size_t)c.n_layer * 2 * e->pool_pages * c.kv_page_tokens * C;
   LVX_TRY(dev_alloc_bytes(e, &e->kv, kv_elems * dt_size(e->kvdt())));
   e->h_len.assign(S, 0);
@@ -1209,7 +1212,7 @@ static int cluster_init(lvx_engine* e) {
 
 static bool cluster_applicable(const lvx_engine* e, const SamplerArgs& sa) {
   const lvx_config& c = e->cfg;
-  return e->use_cluster && e->cfg.precision != LVX_PRECISION_FP32 && sa.greedy && !sa.forced && !sa.out_codes && c.n_embd == CD_C &&
+  return e->cfg.precision != LVX_PRECISION_FP32 && sa.greedy && !sa.forced && !sa.out_codes && c.n_embd == CD_C &&
          c.n_head == CD_H && c.vocab_size == CD_V && c.n_layer <= CD_MAX_LAYERS && c.text_dim + c.code_dim == CD_C && !c.bias &&
          c.kv_page_tokens == 16 && e->max_pages <= 64 &&
          (long long)e->pool_pages * c.kv_page_tokens * c.n_embd < (1LL << 31);
@@ -1288,9 +1291,10 @@ static int cluster_launch(lvx_engine* e, lvx_engine::Lane& ln, const int32_t* h_
   return LVX_OK;
 }
 
-extern "C" int lvx_decode_steps_lane(lvx_engine* e, int lane, const int32_t* h_slots, int n, int n_steps, const lvx_sampling* s,
-                                     void* stream) {
+extern "C" int lvx_decode_steps_ex(lvx_engine* e, int lane, const int32_t* h_slots, int n, int n_steps, const lvx_sampling* s,
+                                   int path, void* stream) {
   LVX_TRY(check_engine(e));
+  LVX_CHECK(path == LVX_PATH_AUTO || path == LVX_PATH_CLUSTER || path == LVX_PATH_PER_OP, LVX_ERR_INVALID, "bad decode path");
   LVX_CHECK(lane >= 0 && lane < (int)e->lanes.size(), LVX_ERR_INVALID, "decode lane out of range");
   LVX_CHECK(n_steps > 0, LVX_ERR_INVALID, "n_steps must be positive");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1302,7 +1306,10 @@ extern "C" int lvx_decode_steps_lane(lvx_engine* e, int lane, const int32_t* h_s
   SamplerArgs sa = sampler_args(s);
   LVX_CHECK(sa.greedy || sa.temperature > 0.f, LVX_ERR_INVALID, "temperature must be positive");
   LVX_CHECK(!(sa.uniform && n_steps > 1), LVX_ERR_INVALID, "d_uniform supplies one draw per session: use n_steps == 1");
-  if (cluster_applicable(e, sa)) {
+  const bool want_cluster = path == LVX_PATH_CLUSTER || (path == LVX_PATH_AUTO && e->use_cluster);
+  LVX_CHECK(path != LVX_PATH_CLUSTER || cluster_applicable(e, sa), LVX_ERR_INVALID,
+            "the cluster-resident decode kernel does not apply to this engine / sampler");
+  if (want_cluster && cluster_applicable(e, sa)) {
     LVX_TRY(cluster_launch(e, ln, h_slots, n, n_steps, st));
   } else if (e->use_graphs && !e->prof_on && !sa.uniform) {
     const int unroll = 10;   // iterations per graph launch for long runs
@@ -1319,6 +1326,23 @@ extern "C" int lvx_decode_steps_lane(lvx_engine* e, int lane, const int32_t* h_s
     for (int t = 0; t < n_steps; ++t) LVX_TRY(decode_one_step(e, ln, n, sa, ln.logits, st));
   }
   for (int i = 0; i < n; ++i) e->h_len[h_slots[i]] += n_steps;
+  return LVX_OK;
+}
+
+extern "C" int lvx_decode_steps_lane(lvx_engine* e, int lane, const int32_t* h_slots, int n, int n_steps, const lvx_sampling* s,
+                                     void* stream) {
+  return lvx_decode_steps_ex(e, lane, h_slots, n, n_steps, s, LVX_PATH_AUTO, stream);
+}
+
+extern "C" int lvx_session_progress(lvx_engine* e, const int32_t* h_slots, int n, int32_t* h_pinned_out, void* stream) {
+  LVX_TRY(check_engine(e));
+  LVX_TRY(check_slots(e, h_slots, n, false));
+  LVX_CHECK(h_pinned_out, LVX_ERR_INVALID, "NULL argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  LVX_TRY(upload_slots(e, h_slots, n, st));
+  gather_progress_kernel<<<ceil_div(n, 256), 256, 0, st>>>(e->d_slots, n, e->st, reinterpret_cast<int2*>(e->d_aux));
+  LAUNCHED(e);
+  LVX_CUDA(cudaMemcpyAsync(h_pinned_out, e->d_aux, (size_t)n * 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
   return LVX_OK;
 }
 

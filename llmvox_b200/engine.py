@@ -129,12 +129,20 @@ class Engine:
         return out.value
 
     # ------------------------------------------------------------------ decode
-    def decode_steps(self, slots: Sequence[int], n_steps: int, sampling: Optional[Sampling] = None, stream=None, lane: int = 0):
+    def decode_steps(self, slots: Sequence[int], n_steps: int, sampling: Optional[Sampling] = None, stream=None, lane: int = 0,
+                     path: int = _lib.PATH_AUTO):
         """n_steps decode iterations for `slots` on decode lane `lane`.  Calls on different lanes may be enqueued on
-        different streams and run concurrently (sessions are independent)."""
+        different streams and run concurrently (sessions are independent).  `path`: _lib.PATH_AUTO / PATH_CLUSTER /
+        PATH_PER_OP (lvx_decode_steps_ex)."""
         s = (sampling or Sampling()).to_c()
-        check(self.lib.lvx_decode_steps_lane(self._h, lane, i32_array(slots), len(slots), n_steps, C.byref(s),
-                                             self._stream(stream)))
+        check(self.lib.lvx_decode_steps_ex(self._h, lane, i32_array(slots), len(slots), n_steps, C.byref(s), int(path),
+                                           self._stream(stream)))
+
+    def session_progress(self, slots: Sequence[int], out: torch.Tensor, stream=None):
+        """Asynchronously writes (eoa_pos, ctx_len) of each slot into the pinned int32 host tensor `out` (n, 2)."""
+        assert out.dtype == torch.int32 and out.is_pinned() and out.numel() >= 2 * len(slots)
+        check(self.lib.lvx_session_progress(self._h, i32_array(slots), len(slots), C.c_void_p(out.data_ptr()),
+                                            self._stream(stream)))
 
     def set_cluster_decode(self, on: bool):
         """Greedy bf16 decode path for the calls that follow: the cluster-resident kernel (default) or the kernel-per-op

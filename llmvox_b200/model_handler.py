@@ -28,7 +28,9 @@ DEFAULT_CONFIG = {
     "pad_token_id": 384, "eoa_token_id": 453,
     # llmvox_b200 extensions
     "random_init_seed": None,        # seeded random-init weights when no checkpoints are available
-    "precision": "fp32",             # "fp32" (parity mode) or "bf16" (tcgen05 GEMMs)
+    # "exact" (default): bf16 weights + fp32-class activations on the tcgen05 tensor cores, greedy tokens identical to the
+    # reference's fp32 loop on the rounded weights; "bf16": bf16 activations too (2e-2 logits); "fp32": FMA-pipe parity mode
+    "precision": "exact",
     "max_sessions": 256, "max_context": 1024, "max_vocode_frames": 32768,
     "interactive_slots": 16,         # slots reserved for the reference-style `.model(emb, kvcache)` calls
 }
@@ -124,18 +126,30 @@ class WavTokenizerModule:
         return pcm.view(b, l * self.e.cfg.hop)
 
 
+def resize_text_table(table: torch.Tensor, new_rows: int = 386) -> torch.Tensor:
+    """smart_tokenizer_and_embedding_resize (inference/model_handler.py:22-41), applied once per added token as the
+    reference does (:92-102: "[PAD]" -> row 384, then "EOS" -> row 385): every new row is the MEAN of all rows that exist
+    before it is added, so row 384 = mean(rows[:384]) and row 385 = mean(rows[:385]) -- deterministic, unlike
+    `resize_token_embeddings`' version-dependent random initialisation.  Row 384 is the text row fed on every step
+    after a sentence's text runs out (:316-320)."""
+    table = table.detach().float()
+    rows = [table[i] for i in range(min(table.shape[0], new_rows))]
+    while len(rows) < new_rows:
+        rows.append(torch.stack(rows).mean(dim=0))
+    return torch.stack(rows)
+
+
 def _load_text_table(path: Optional[str]) -> torch.Tensor:
     """The reference pulls `encoder.embed_tokens` out of a HF T5 (model_handler.py:80-106).  Accepts a local HF
     directory or a tensor file holding the (386, 256) table."""
     if path and os.path.isfile(path):
         obj = torch.load(path, map_location="cpu")
         t = obj["weight"] if isinstance(obj, dict) and "weight" in obj else obj
-        return torch.as_tensor(t, dtype=torch.float32)
+        return resize_text_table(torch.as_tensor(t, dtype=torch.float32))
     if path and os.path.isdir(path):
         from transformers import T5ForConditionalGeneration
         m = T5ForConditionalGeneration.from_pretrained(path)
-        m.resize_token_embeddings(386)
-        return m.encoder.embed_tokens.weight.detach().float()
+        return resize_text_table(m.encoder.embed_tokens.weight.detach().float())
     raise FileNotFoundError(f"text embedding table not found at {path!r} (no network: pass a local path)")
 
 
@@ -177,11 +191,14 @@ class ModelHandler:
         if len(ids) > len(self._batch_slots):
             raise ValueError("more sentences than max_sessions")
         dump = self.config["initial_dump_size_1" if replica == 0 else "initial_dump_size_2"]
-        steps = max_steps if max_steps is not None else min(self.config["max_context"], max(len(x) for x in ids) + 64)
+        # like the reference (:397), a sentence is decoded until its EOA code or max_audio_length pending codes, never by a
+        # text-length heuristic; the engine's max_context is the only other bound (an explicit max_steps is the caller's)
+        steps = max_steps if max_steps is not None else self.config["max_context"]
         bs = BatchSynthesizer(self.engine, len(ids), dump, self.config["max_dump_size"], stop_on_eoa, sampling,
-                              slots=self._batch_slots[: len(ids)])
+                              slots=self._batch_slots[: len(ids)], max_audio_length=self.config["max_audio_length"])
         bs.start(ids)
         yield from bs.run(steps, flush_tail=flush_tail)
+        self.truncated = [i for i, sc in enumerate(bs.sched) if stop_on_eoa and not sc.done]   # sessions cut by the step bound
 
     def synthesize(self, sentences: Sequence[str], **kw) -> List[np.ndarray]:
         """One float32 waveform per sentence (its chunks concatenated)."""

@@ -1,201 +1,68 @@
-"""Two-replica ("multi-queue") streaming protocol of the reference server, host side.
-
-The reference runs two TTS replicas per request (streaming_server.py:521-531): a producer thread routes the upstream
-LLM's words to replica 0 or 1, switching at every sentence end (:184-248); each replica's generator thread puts PCM
-chunks and control tokens on its audio queue (:357-422) -- `bytes` = a chunk, `1` / `0` = "now listen to replica 1 / 0",
-`"end"` = the whole answer is done, `None` = generator finished -- and `audio_generator_async` (:428-469) drains the two
-queues in that order, so replica 1's (larger, 160-code) first chunk plays right after replica 0's sentence.
-
-Here the same protocol drives sessions of ONE engine (or of two engines on two GPUs): a replica is a chunk-schedule
-state (`ChunkScheduler`, whose dump size is never reset between sentences) plus a stream of sentences."""
+"""Two-replica pipeline of one answer on top of the continuous batcher (serving.py); the pure protocol pieces (text
+cleaning, sentence routing, per-word ids, queue mux) live in protocol.py and are re-exported here."""
 from __future__ import annotations
 
-import re
-from dataclasses import dataclass, field
-from typing import Iterable, Iterator, List, Optional, Sequence, Tuple, Union
+from typing import Iterable, Iterator, List, Optional, Sequence
 
-from .scheduler import ChunkScheduler, INITIAL_DUMP_SIZE_1, INITIAL_DUMP_SIZE_2
-from .tokenizer import ByT5Tokenizer, EOS_TEXT_ID
-
-DEFAULT_EOS = "<|eot_id|>"           # configs/inference_config.py:39
-
-# clean_text (streaming_server.py:106-149) as an ordered rule table: (pattern, replacement, is_regex)
-_CLEAN_RULES: Tuple[Tuple[str, str, bool], ...] = (
-    ("**", "", False),
-    ("-", " ", False),
-    (r"(\d)\.(?=\s|$)", r"\1", True),      # "5." -> "5"
-    (r"\*", "", True),
-    (r"#", " number ", True),
-    (r"&", " and ", True),
-    (r"@", " at ", True),
-    (r"\s+", " ", True),
-    (r"\.{3,}", " pause ", True),
-    (r"(\d),(\d)", r"\1\2", True),          # thousands separators
-    (r"\/+", " slash ", True),
-    (r"\\+", " backslash ", True),
-)
-
-
-def clean_text(text: str, eos_token: str = DEFAULT_EOS) -> str:
-    text = text.strip()
-    for pat, rep, is_re in _CLEAN_RULES:
-        text = re.sub(pat, rep, text) if is_re else text.replace(pat, rep)
-    return text
-
-
-class SentenceRouter:
-    """text_streamer_producer's routing (streaming_server.py:226-244): skip '' and '-', strip, clean unless the word is
-    the EOS token itself, drop if empty, send to the active replica, switch replicas after a word ending in '.'."""
-
-    def __init__(self, eos_token: str = DEFAULT_EOS):
-        self.eos = eos_token
-        self.active = 0
-
-    def route(self, output: str) -> Optional[Tuple[int, str]]:
-        if output in ("", "-"):
-            return None
-        output = output.strip()
-        if output != self.eos:
-            output = clean_text(output, self.eos)
-        if not output:
-            return None
-        dest = self.active
-        if output.endswith("."):
-            self.active = 1 - self.active
-        return dest, output
-
-
-def word_to_ids(text_token: str, eos_token: str = DEFAULT_EOS, tokenizer: Optional[ByT5Tokenizer] = None):
-    """One queue item -> (text ids, end_of_speech, end_generation)  (streaming_server.py:297-310).  Note the reference's
-    `rstrip(eos)` strips any trailing CHARACTERS that occur in the eos string, not the suffix; kept as is."""
-    tok = tokenizer or ByT5Tokenizer()
-    end_generation = False
-    end_of_speech = False
-    if (eos_token in text_token) or (text_token[-1:] == "."):
-        if eos_token in text_token:
-            end_generation = True
-        text_token = text_token.rstrip(eos_token)
-        end_of_speech = True
-    ids = tok(text_token.strip())["input_ids"]
-    if end_of_speech:
-        ids = ids + [EOS_TEXT_ID]
-    return ids, end_of_speech, end_generation
-
-
-QueueItem = Union[bytes, int, str, None]
-
-
-def mux_audio_queues(items_0: Iterable[QueueItem], items_1: Iterable[QueueItem]) -> Iterator[Optional[bytes]]:
-    """audio_generator_async's ordering (streaming_server.py:440-465) over two finite item streams: start on queue 0;
-    `bytes` are yielded; "end" yields None (end-of-answer marker for the HTTP layer); 0 / 1 switch the queue being
-    drained; None is ignored.  Stops when the queue it is draining runs dry (the reference then blocks on it)."""
-    its = [iter(items_0), iter(items_1)]
-    cur = 0
-    while True:
-        try:
-            item = next(its[cur])
-        except StopIteration:
-            return
-        if isinstance(item, str) and item == "end":
-            yield None
-            continue
-        if isinstance(item, int) and not isinstance(item, bool) and item in (0, 1):
-            cur = item
-            continue
-        if item is None:
-            continue
-        yield item
-
-
-@dataclass
-class Sentence:
-    replica: int
-    words: List[str] = field(default_factory=list)
-    ids: List[int] = field(default_factory=list)
-    end_generation: bool = False
-
-
-def split_into_sentences(outputs: Iterable[str], eos_token: str = DEFAULT_EOS) -> List[Sentence]:
-    """Runs the router over the upstream word stream and groups the routed words into per-replica sentences (a
-    sentence = the words up to and including the one that ends in '.' or carries the EOS token)."""
-    router = SentenceRouter(eos_token)
-    tok = ByT5Tokenizer()
-    sentences: List[Sentence] = []
-    open_by_replica = {0: None, 1: None}
-    for out in outputs:
-        r = router.route(out)
-        if r is None:
-            continue
-        dest, word = r
-        cur = open_by_replica[dest]
-        if cur is None:
-            cur = Sentence(dest)
-            sentences.append(cur)
-            open_by_replica[dest] = cur
-        ids, eos_flag, end_gen = word_to_ids(word, eos_token, tok)
-        cur.words.append(word)
-        cur.ids.extend(ids)
-        if eos_flag:
-            cur.end_generation = end_gen
-            open_by_replica[dest] = None
-    return sentences
+from .protocol import (DEFAULT_EOS, QueueItem, Sentence, SentenceRouter, clean_text, mux_audio_queues,  # noqa: F401
+                       split_into_sentences, word_to_ids)
+from .scheduler import INITIAL_DUMP_SIZE_1, INITIAL_DUMP_SIZE_2
 
 
 class ReplicaPipeline:
-    """Sentences of one answer through two replicas of one engine, in the reference's queue protocol.
+    """Answers through the two replicas of one engine, in the reference's queue protocol (streaming_server.py:184-248,
+    :357-422, :428-469), STREAMING: `stream()` consumes the upstream word stream as it arrives and yields each chunk's
+    PCM bytes as soon as it is playable -- the first byte leaves after the first 10-code chunk, not after the answer.
 
-    Both replicas' sentences are independent sessions, so all sentences of the answer decode together as one batch
-    (the reference decodes them on two GPUs, one sentence at a time per replica).  What is preserved: which replica
-    speaks which sentence, each replica's chunk schedule carried across its sentences (dump size only ever grows),
-    the per-chunk independent vocoder decode, and the order in which audio reaches the client."""
+    What is preserved, event for event (tests/golden/replica_stream.npz, recorded from the reference's own loop): which
+    replica speaks which sentence; each replica's chunk schedule carried across ITS sentences within the answer (the dump
+    size triples at every dump and at every sentence end and is never reset); the per-chunk independent vocoder decode;
+    the control tokens; the order in which audio reaches the client.  Every answer starts from the initial dump sizes, as
+    the reference starts fresh generator threads per request (:521-531)."""
 
     def __init__(self, engine, initial_dump_sizes: Sequence[int] = (INITIAL_DUMP_SIZE_1, INITIAL_DUMP_SIZE_2), max_dump_size: int = 1280,
-                 pad_tail_steps: int = 32, slots: Optional[Sequence[int]] = None):
+                 max_audio_length: int = 8000, slots: Optional[Sequence[int]] = None, batcher=None, **batcher_kw):
+        from .serving import ContinuousBatcher
         self.e = engine
-        self.dump = list(initial_dump_sizes)
-        self.max_dump = max_dump_size
-        self.pad_tail = pad_tail_steps
-        self.slots = list(slots) if slots is not None else None
+        self.batcher = batcher or ContinuousBatcher(engine, slots=slots, initial_dump_sizes=initial_dump_sizes,
+                                                    max_dump_size=max_dump_size, max_audio_length=max_audio_length, **batcher_kw)
+        self.last_request = None
+
+    def stream(self, outputs: Iterable[str]) -> Iterator[bytes]:
+        """Word stream in (items as text_streamer_producer sees them), PCM bytes out in playback order, as they complete.
+        Drives the batcher itself (single-threaded use); under `server.create_app` a worker thread drives it instead."""
+        b = self.batcher
+        req = b.open_request()
+        self.last_request = req
+        it = iter(outputs)
+        exhausted = False
+        while not req.done:
+            if not exhausted:                         # one word per round: text arrives while earlier words decode
+                try:
+                    b.push_word(req, next(it))
+                except StopIteration:
+                    exhausted = True
+                    b.close_input(req)
+            b.step()
+            while not req.out.empty():
+                item = req.out.get()
+                if item is not None:
+                    yield item
+        while not req.out.empty():
+            item = req.out.get()
+            if item is not None:
+                yield item
 
     def run(self, outputs: Iterable[str], eos_token: str = DEFAULT_EOS, sampling=None):
-        """-> (queue items of replica 0, queue items of replica 1); feed them to `mux_audio_queues`."""
-        from .streaming import BatchSynthesizer
-        sentences = split_into_sentences(outputs, eos_token)
+        """Whole answer at once -> (queue items of replica 0, queue items of replica 1) as the reference's generator
+        threads would have put them; feed them to `mux_audio_queues`."""
+        import numpy as np
+        for _ in self.stream(list(outputs)):
+            pass
+        req = self.last_request
         queues: List[List[QueueItem]] = [[], []]
-        if not sentences:
-            return queues
-        # the schedule state a sentence starts from depends on the replica's earlier sentences: replay them in order
-        n = len(sentences)
-        slots = self.slots[:n] if self.slots is not None else list(range(n))
-        bs = BatchSynthesizer(self.e, n, stop_on_eoa=True, sampling=sampling, slots=slots, max_dump_size=self.max_dump)
-        # every session gets its own scheduler; dump sizes are patched in as earlier sentences of the replica finish
-        order_in_replica = [[i for i, s in enumerate(sentences) if s.replica == r] for r in (0, 1)]
-        start_dump = {}
         for r in (0, 1):
-            if order_in_replica[r]:
-                start_dump[order_in_replica[r][0]] = self.dump[r]
-        for i in range(n):
-            bs.sched[i] = ChunkScheduler(dump_size=start_dump.get(i, self.dump[sentences[i].replica]), max_dump=self.max_dump,
-                                         eoa=self.e.cfg.eoa_token_id)
-        max_steps = max(len(s.ids) for s in sentences) + self.pad_tail
-        bs.start([s.ids for s in sentences], keep_schedule=True)
-        per: List[List] = [[] for _ in sentences]
-        for chunks in bs.run(max_steps, flush_tail=False):
-            for ch in chunks:
-                per[ch.session].append(ch)
-        # a sentence that never produced EOA within the step cap is flushed like the reference's EOA branch (:379-394)
-        tail = []
-        for i, sc in enumerate(bs.sched):
-            if not sc.done:
-                tail.extend((i, s, c) for (s, c) in sc.flush())
-        for ch in bs._finish_emit(bs._enqueue_emit(tail)):
-            per[ch.session].append(ch)
-        for r in (0, 1):
-            for i in order_in_replica[r]:
-                for ch in per[i]:
-                    queues[r].append(ch.tobytes())
-                queues[r].append("end" if sentences[i].end_generation else 1 - r)
-            queues[r].append(None)
-            if order_in_replica[r]:
-                self.dump[r] = bs.sched[order_in_replica[r][-1]].dump_size
+            for item in req.items[r]:
+                queues[r].append(np.ascontiguousarray(item.pcm, dtype="<f4").tobytes() if hasattr(item, "pcm") else item)
+            queues[r].append(None)                    # "Audio generator finished" (:424)
         return queues

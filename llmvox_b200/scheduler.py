@@ -74,6 +74,24 @@ class ChunkScheduler:
         """Decode steps that can run before this scheduler may emit (EOA aside)."""
         return max(1, self.dump_size - (self.seen - self.emitted))
 
+    def project(self, n: int) -> int:
+        """steps_to_next_event() after `n` more codes that are not EOA, without changing any state (the continuous
+        batcher sizes a round while the previous one is still in flight)."""
+        pend, d = self.seen - self.emitted + n, self.dump_size
+        while pend >= d:
+            pend -= d
+            if d < self.max_dump:
+                d = min(d * 3, self.max_dump)
+        return max(1, d - pend)
+
+    def end_sentence(self):
+        """Ends the sentence without an EOA code (the engine's context is full): the reset of :404-421 incl. the growth of
+        the dump size; pending codes must have been flushed by the caller."""
+        self.emitted = self.seen
+        self.eoa_pending = False
+        self.done = True
+        self._grow()
+
     def new_sentence(self):
         """State reset of :404-416; dump_size is NOT reset between sentences."""
         self.emitted = 0

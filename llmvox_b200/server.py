@@ -9,7 +9,7 @@ from typing import Iterator, List, Optional
 
 import numpy as np
 
-from .replicas import DEFAULT_EOS, ReplicaPipeline, mux_audio_queues
+from .protocol import DEFAULT_EOS
 
 SAMPLE_RATE = 24000
 
@@ -33,15 +33,22 @@ def text_to_word_stream(text: str, eos_token: str = DEFAULT_EOS) -> List[str]:
     return out
 
 
-def tts_stream(pipeline: ReplicaPipeline, text: str, eos_token: str = DEFAULT_EOS) -> Iterator[bytes]:
-    q0, q1 = pipeline.run(text_to_word_stream(text, eos_token), eos_token)
-    for item in mux_audio_queues(q0, q1):
-        if item is not None:
-            yield item
+def tts_stream(batcher, text: str, eos_token: str = DEFAULT_EOS) -> Iterator[bytes]:
+    """One request against a batcher that a worker thread is driving: submits the words, then blocks on the request's
+    own output queue -- every chunk is yielded the moment it is playable (first byte after the first 10-code chunk)."""
+    if callable(batcher):            # lazily built on the first request (create_app)
+        batcher = batcher()
+    req = batcher.submit(text_to_word_stream(text, eos_token))
+    yield from req.chunks()
 
 
 def create_app(model_handler, eos_token: str = DEFAULT_EOS):
-    """FastAPI app with POST /tts {"text": ...} -> StreamingResponse, as the reference's endpoint."""
+    """FastAPI app with POST /tts {"text": ...} -> StreamingResponse, as the reference's endpoint.
+
+    The reference shares one ModelHandler between all request threads without a lock, each with private KV caches.  Here
+    ONE worker thread owns the engine and runs the continuous batcher (serving.py); request handlers only talk to it
+    through thread-safe queues, so overlapping requests share decode rounds instead of racing on the engine."""
+    import threading
     from fastapi import FastAPI
     from fastapi.responses import StreamingResponse
     from pydantic import BaseModel
@@ -51,10 +58,25 @@ def create_app(model_handler, eos_token: str = DEFAULT_EOS):
 
     app = FastAPI()
     cfg = model_handler.config
-    pipeline = ReplicaPipeline(model_handler.engine, (cfg["initial_dump_size_1"], cfg["initial_dump_size_2"]), cfg["max_dump_size"])
+    state = {"batcher": None, "thread": None}
+    lock = threading.Lock()
+
+    def batcher():
+        with lock:
+            if state["batcher"] is None:
+                from .serving import ContinuousBatcher
+                b = ContinuousBatcher(model_handler.engine, slots=getattr(model_handler, "_batch_slots", None),
+                                      initial_dump_sizes=(cfg["initial_dump_size_1"], cfg["initial_dump_size_2"]),
+                                      max_dump_size=cfg["max_dump_size"], max_audio_length=cfg.get("max_audio_length", 8000),
+                                      eos_token=eos_token)
+                th = threading.Thread(target=b.serve_forever, name="llmvox-batcher", daemon=True)
+                th.start()
+                state["batcher"], state["thread"] = b, th
+            return state["batcher"]
 
     @app.post("/tts")
     def tts(request: TTSRequest):
-        return StreamingResponse(tts_stream(pipeline, request.text, eos_token), media_type="application/octet-stream")
+        return StreamingResponse(tts_stream(batcher, request.text, eos_token), media_type="application/octet-stream")
 
+    app.state.llmvox = state
     return app

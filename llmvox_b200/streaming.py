@@ -20,22 +20,27 @@ from .scheduler import ChunkScheduler, INITIAL_DUMP_SIZE_1, MAX_DUMP_SIZE
 
 class LaneRunner:
     """Runs the decode iterations of a batch off the control stream, so that the control stream's work (gather / vocode /
-    copies) overlaps with the next iterations.  Two shapes, chosen per call:
+    copies) overlaps with the next iterations.  The decode path is chosen PER CALL (lvx_decode_steps_ex), never through
+    engine state:
 
-    * cluster-resident decode kernel (bf16, greedy, batches up to CLUSTER_DECODE_MAX_BATCH): ONE call for all sessions on
-      one side stream; the engine cuts it into launches of at most 7 clusters (7 x 16 sessions are co-resident on a
-      B200), which run back to back.  A wave of up to 112 sessions costs the same ~150 us per iteration however many of
-      its 7 clusters are used, so batches up to 224 sessions (two waves) beat the kernel-per-op chain.
-    * kernel-per-op chain (everything else): `lanes` independent groups on their own streams.  A decode iteration there
-      is a chain of ~35 dependent, latency-bound kernels that leaves most of the GPU idle; sessions never interact, so
-      disjoint groups advance concurrently (engine decode lanes).
+    * cluster-resident decode kernel (bf16 / exact precision, greedy): ONE call on the side stream; the engine cuts it
+      into balanced waves of at most 7 co-resident clusters (7 x 16 sessions on a B200), which run back to back.  A wave
+      costs the same ~150 us per iteration however many of its clusters are used.
+    * kernel-per-op chain (fp32 precision, sampled decoding, and the part of a batch the cluster waves do not take):
+      `lanes` independent groups on their own streams.  A decode iteration there is a chain of ~35 dependent,
+      latency-bound kernels that leaves most of the GPU idle; sessions never interact, so disjoint groups advance
+      concurrently (engine decode lanes).
+    * hybrid: batches above CLUSTER_DECODE_MAX_BATCH put that many sessions on the cluster kernel and the remainder on the
+      kernel-per-op lanes AT THE SAME TIME (the lanes' small GEMMs run on the 36 SMs the 7 clusters cannot use).
 
-    The side streams only ever wait for the event recorded by `sync_from_control()` (after open / feed), never for
-    vocoder work."""
+    `launch()` enqueues on the side streams and returns the completion events; `join()` makes the control stream wait
+    for them.  Every launch first waits, on every stream it uses, for the previous round's events of the OTHER streams:
+    a session may move between streams from round to round (the active set shrinks, the path changes with the batch
+    size), and its context length / KV pages must be ordered across that move."""
 
-    # above this many sessions in one batch the kernel-per-op chain out-runs the cluster-resident kernel (three waves);
-    # measured (bench.py --short, audio-s/s, cluster vs kernel-per-op): 112: 8341 / 5418, 128: 5780 / 5992, 192: 8300 / 7624,
-    # 224: 9062 / 7457, 256: 7647 / 8251.  Just above one full wave (113..139 sessions) the second wave is nearly empty.
+    # two waves of 7 clusters; measured (bench.py --short, audio-s/s, cluster vs kernel-per-op): 112: 8341 / 5418,
+    # 128: 5780 / 5992, 192: 8300 / 7624, 224: 9062 / 7457, 256: 7647 / 8251.  Just above one full wave (113..139 sessions)
+    # the second wave is nearly empty and the kernel-per-op lanes win.
     CLUSTER_DECODE_MAX_BATCH = 224
     CLUSTER_DECODE_GAP = (113, 139)
 
@@ -43,14 +48,15 @@ class LaneRunner:
         import os
         self.e = engine
         self.G = max(1, min(engine.decode_lanes, lanes or engine.decode_lanes))
-        self.streams = [torch.cuda.Stream(device=engine.device) for _ in range(self.G)] if self.G > 1 else [None]
-        self.side = self.streams[0] if self.G > 1 else torch.cuda.Stream(device=engine.device)   # cluster-kernel launches
+        self.streams = [torch.cuda.Stream(device=engine.device) for _ in range(self.G)]
+        self.side = self.streams[0]                                   # cluster-kernel launches
         self.cluster_default = os.environ.get("LLMVOX_B200_CLUSTER", "1") != "0"
         if "LLMVOX_B200_CLUSTER_MAX_BATCH" in os.environ:      # measurement override of the threshold above
             self.CLUSTER_DECODE_MAX_BATCH = int(os.environ["LLMVOX_B200_CLUSTER_MAX_BATCH"])
+        self._prev: List[Tuple[torch.cuda.Stream, torch.cuda.Event]] = []
 
-    def split(self, slots: Sequence[int]) -> List[List[int]]:
-        n, G = len(slots), min(self.G, len(slots))
+    def split(self, slots: Sequence[int], groups: Optional[int] = None) -> List[List[int]]:
+        n, G = len(slots), min(groups or self.G, len(slots))
         base, rem = divmod(n, G)
         out, pos = [], 0
         for g in range(G):
@@ -63,33 +69,56 @@ class LaneRunner:
         """The side streams wait for everything enqueued so far on the current (control) stream."""
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(self.e.device))
-        for st in set(x for x in self.streams + [self.side] if x is not None):
+        for st in self.streams:
             st.wait_event(ev)
 
+    def plan(self, n: int, sampling: Optional[Sampling]) -> Tuple[int, int]:
+        """-> (sessions for the cluster-resident kernel, sessions for the kernel-per-op lanes)."""
+        if not self.cluster_default or not self.e.cluster_decode_applicable(sampling):
+            return 0, n
+        if n <= self.CLUSTER_DECODE_MAX_BATCH:
+            gap = self.CLUSTER_DECODE_GAP[0] <= n <= self.CLUSTER_DECODE_GAP[1] and self.e.precision == "bf16"
+            return (0, n) if gap else (n, 0)
+        return self.CLUSTER_DECODE_MAX_BATCH, n - self.CLUSTER_DECODE_MAX_BATCH
+
     def _cluster_call(self, n: int, sampling: Optional[Sampling]) -> bool:
-        if not self.cluster_default or n > self.CLUSTER_DECODE_MAX_BATCH or not self.e.cluster_decode_applicable(sampling):
-            return False
-        return not (self.CLUSTER_DECODE_GAP[0] <= n <= self.CLUSTER_DECODE_GAP[1]) or self.CLUSTER_DECODE_MAX_BATCH > 100000
+        return self.plan(n, sampling)[0] > 0
+
+    def launch(self, slots: Sequence[int], n_steps: int, sampling: Optional[Sampling] = None) -> List[torch.cuda.Event]:
+        """Enqueues n_steps iterations for the batch on the side streams; returns their completion events."""
+        from ._lib import PATH_CLUSTER, PATH_PER_OP
+        n_cluster, n_lanes = self.plan(len(slots), sampling)
+        calls = []                                                   # (stream, lane, slots, path)
+        if n_cluster:
+            calls.append((self.side, 0, list(slots[:n_cluster]), PATH_CLUSTER))
+        if n_lanes:
+            lane0 = 1 if (n_cluster and self.G > 1) else 0            # lane 0's workspace belongs to the cluster call
+            groups = self.split(slots[n_cluster:], max(1, self.G - lane0))
+            for g, grp in enumerate(groups):
+                calls.append((self.streams[lane0 + g], lane0 + g, grp, PATH_PER_OP))
+        used = {id(st): st for st, _, _, _ in calls}
+        for st in used.values():
+            for pst, pev in self._prev:
+                if pst is not st:
+                    st.wait_event(pev)
+        out = []
+        for st, lane, grp, path in calls:
+            self.e.decode_steps(grp, n_steps, sampling, stream=st, lane=lane, path=path)
+        for st in used.values():
+            ev = torch.cuda.Event()
+            ev.record(st)
+            out.append((st, ev))
+        self._prev = out
+        return [ev for _, ev in out]
+
+    def join(self, events: Sequence[torch.cuda.Event]):
+        main = torch.cuda.current_stream(self.e.device)
+        for ev in events:
+            main.wait_event(ev)
 
     def decode(self, slots: Sequence[int], n_steps: int, sampling: Optional[Sampling] = None):
         """Enqueues n_steps iterations for the batch; the control stream then waits for them."""
-        main = torch.cuda.current_stream(self.e.device)
-        if self._cluster_call(len(slots), sampling):
-            self.e.set_cluster_decode(True)
-            self.e.decode_steps(slots, n_steps, sampling, stream=self.side, lane=0)
-            ev = torch.cuda.Event()
-            ev.record(self.side)
-            main.wait_event(ev)
-            return
-        self.e.set_cluster_decode(False)
-        if self.G == 1:
-            self.e.decode_steps(slots, n_steps, sampling)
-            return
-        for g, grp in enumerate(self.split(slots)):
-            self.e.decode_steps(grp, n_steps, sampling, stream=self.streams[g], lane=g)
-            ev = torch.cuda.Event()
-            ev.record(self.streams[g])
-            main.wait_event(ev)
+        self.join(self.launch(slots, n_steps, sampling))
 
 
 @dataclass
@@ -103,24 +132,93 @@ class Chunk:
         return self.pcm.astype("float32", copy=False).tobytes()
 
 
+class ChunkEmitter:
+    """Ready code ranges -> ONE ragged vocoder batch -> pinned host memory (streaming_server.py:359-368 for many chunks at
+    once: gather the ranges from the sessions' device-side code histories, vocode every range as an independent chunk,
+    copy the PCM out asynchronously).  `enqueue` only enqueues on the current (control) stream and returns a ticket;
+    `finish` waits for that ticket's copy and returns one float32 array per range, in the order given."""
+
+    def __init__(self, engine: Engine, bandwidth_id: int = 0, buffers: int = 3):
+        self.e = engine
+        self.bw = bandwidth_id
+        self._ring: List[Optional[torch.Tensor]] = [None] * buffers
+        self._next = 0
+
+    def _pinned(self, n: int) -> torch.Tensor:
+        """Pinned buffers used round-robin: a ticket's PCM (and, with copy=False, the arrays handed out) stays valid until
+        `buffers - 1` further tickets have been enqueued."""
+        i = self._next
+        self._next = (i + 1) % len(self._ring)
+        if self._ring[i] is None or self._ring[i].numel() < n:
+            self._ring[i] = torch.empty((max(n, 1 << 20),), dtype=torch.float32, pin_memory=True)
+        return self._ring[i]
+
+    def enqueue(self, ready: Sequence[Tuple[int, int, int]]):
+        """ready: (slot, start, count) ranges."""
+        if not ready:
+            return None
+        slots = [r[0] for r in ready]
+        # a session may own several ready ranges in one round: the engine wants distinct slots per call
+        parts, order = [], []
+        remaining = list(range(len(ready)))
+        while remaining:
+            seen, take, rest = set(), [], []
+            for j in remaining:
+                (rest if slots[j] in seen else take).append(j)
+                seen.add(slots[j])
+            parts.append(self.e.gather_code_ranges([slots[j] for j in take], [ready[j][1] for j in take], [ready[j][2] for j in take]))
+            order.extend(take)
+            remaining = rest
+        codes = torch.cat(parts) if len(parts) > 1 else parts[0]
+        cu = [0]
+        for j in order:
+            cu.append(cu[-1] + ready[j][2])
+        pcm = self.e.vocode(codes, cu, self.bw)
+        host = self._pinned(pcm.numel())
+        host[: pcm.numel()].copy_(pcm, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.e.device))
+        return (order, cu, host, ev, pcm, len(ready))
+
+    def done(self, ticket) -> bool:
+        return ticket is None or ticket[3].query()
+
+    def finish(self, ticket, copy: bool = True) -> List[np.ndarray]:
+        if ticket is None:
+            return []
+        order, cu, host, ev, _pcm, n = ticket
+        ev.synchronize()
+        hop = self.e.cfg.hop
+        arr = host.numpy()
+        out: List[Optional[np.ndarray]] = [None] * n
+        for k, j in enumerate(order):
+            seg = arr[cu[k] * hop: cu[k + 1] * hop]
+            out[j] = seg.copy() if copy else seg
+        return out
+
+
 class BatchSynthesizer:
     """One sentence per session, all sessions stepped together."""
 
     def __init__(self, engine: Engine, n_sessions: int, initial_dump_size: int = INITIAL_DUMP_SIZE_1,
                  max_dump_size: int = MAX_DUMP_SIZE, stop_on_eoa: bool = True, sampling: Optional[Sampling] = None,
-                 slots: Optional[Sequence[int]] = None, bandwidth_id: int = 0, lanes: Optional[int] = None):
+                 slots: Optional[Sequence[int]] = None, bandwidth_id: int = 0, lanes: Optional[int] = None,
+                 max_audio_length: Optional[int] = None):
         self.e = engine
         self.n = n_sessions
         self.slots = list(slots) if slots is not None else list(range(n_sessions))
         assert len(self.slots) == n_sessions
+        kw = {} if max_audio_length is None else {"max_audio_len": max_audio_length}
         self.sched = [ChunkScheduler(dump_size=initial_dump_size, max_dump=max_dump_size, stop_on_eoa=stop_on_eoa,
-                                     eoa=engine.cfg.eoa_token_id) for _ in range(n_sessions)]
+                                     eoa=engine.cfg.eoa_token_id, **kw) for _ in range(n_sessions)]
         self.initial_dump_size = initial_dump_size
         self.stop_on_eoa = stop_on_eoa
         self.sampling = sampling or Sampling()
         self.bw = bandwidth_id
         self.steps_done = 0
         self.runner = LaneRunner(engine, lanes)
+        self.emitter = ChunkEmitter(engine, bandwidth_id)
+        self._prog = None
 
     def start(self, text_ids: Sequence[Sequence[int]], keep_schedule: bool = False):
         """Opens the sessions (the per-sentence reset of :404-416) and hands them their text ids.  A new call is a new
@@ -141,55 +239,15 @@ class BatchSynthesizer:
         memory on the control stream; returns a ticket for `_finish_emit`."""
         if not ready:
             return None
-        slots = [self.slots[i] for i, _, _ in ready]
-        starts = [s for _, s, _ in ready]
-        counts = [c for _, _, c in ready]
-        # a session may own several ready ranges in one round: the engine wants distinct slots per call
-        codes_parts, order = [], []
-        remaining = list(range(len(ready)))
-        while remaining:
-            seen, take, rest = set(), [], []
-            for j in remaining:
-                (rest if slots[j] in seen else take).append(j)
-                seen.add(slots[j])
-            codes_parts.append(self.e.gather_code_ranges([slots[j] for j in take], [starts[j] for j in take],
-                                                          [counts[j] for j in take]))
-            order.extend(take)
-            remaining = rest
-        codes = torch.cat(codes_parts) if len(codes_parts) > 1 else codes_parts[0]
-        cu = [0]
-        for j in order:
-            cu.append(cu[-1] + counts[j])
-        pcm = self.e.vocode(codes, cu, self.bw)
-        host = self._pinned_pair(pcm.numel())[: pcm.numel()]
-        host.copy_(pcm, non_blocking=True)
-        ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(self.e.device))
-        return (ready, order, cu, host, ev, pcm)
+        return (ready, self.emitter.enqueue([(self.slots[i], s, c) for i, s, c in ready]))
 
     def _finish_emit(self, ticket, copy: bool = True) -> List[Chunk]:
         if ticket is None:
             return []
-        ready, order, cu, host, ev, _pcm = ticket
-        ev.synchronize()
-        hop = self.e.cfg.hop
-        out = []
-        arr = host.numpy()
-        for k, j in enumerate(order):
-            i, s, c = ready[j]
-            seg = arr[cu[k] * hop: cu[k + 1] * hop]
-            out.append(Chunk(i, s, c, seg.copy() if copy else seg))
+        ready, t = ticket
+        out = [Chunk(i, s, c, pcm) for (i, s, c), pcm in zip(ready, self.emitter.finish(t, copy))]
         out.sort(key=lambda ch: (ch.session, ch.start))
         return out
-
-    def _pinned_pair(self, n: int):
-        """Two pinned buffers used alternately: round r's PCM is read by the host while round r+1's is written
-        (with copy=False a yielded chunk aliases its buffer and is valid until two rounds later)."""
-        if not hasattr(self, "_pp") or self._pp[0].numel() < n:
-            self._pp = [torch.empty((max(n, 1 << 20),), dtype=torch.float32, pin_memory=True) for _ in range(2)]
-            self._pp_i = 0
-        self._pp_i ^= 1
-        return self._pp[self._pp_i]
 
     def run(self, max_steps: int, flush_tail: bool = False, copy: bool = True) -> Iterator[List[Chunk]]:
         """Decodes up to `max_steps` codes per session, yielding the chunks of each round as they are ready.
@@ -209,16 +267,23 @@ class BatchSynthesizer:
                 pending = None
                 if chunks:
                     yield chunks
-            new_codes = None
-            if self.stop_on_eoa:   # the EOA test is the only reason a code value visits the host
-                new_codes = self.e.gather_codes(slots, self.steps_done, k).cpu().numpy()
+            eoa_at = None
+            if self.stop_on_eoa:   # the end of a sentence is detected on the device (SessionState.eoa_pos): no code value
+                if self._prog is None or self._prog.numel() < 2 * self.n:      # visits the host, one small pinned copy does
+                    self._prog = torch.empty((2 * self.n,), dtype=torch.int32, pin_memory=True)
+                self.e.session_progress(slots, self._prog)
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(self.e.device))
+                ev.synchronize()
+                eoa_at = self._prog[: 2 * len(slots)].view(-1, 2)[:, 0].tolist()
             ready: List[Tuple[int, int, int]] = []
             for a, i in enumerate(active):
                 sc = self.sched[i]
                 for t in range(k):
                     if sc.done:
                         break
-                    for (s, c) in sc.push(int(new_codes[a, t]) if new_codes is not None else None):
+                    code = sc.eoa if (eoa_at is not None and eoa_at[a] == self.steps_done + t) else None
+                    for (s, c) in sc.push(code):
                         ready.append((i, s, c))
             self.steps_done += k
             pending = self._enqueue_emit(ready)

@@ -129,8 +129,23 @@ class StubHandler:
         return logits, loss, kv
 
 
-def run_reference_loop(fn, handler, words, dump_size, index=0):
-    tq, aq = queue.Queue(), queue.Queue()
+class _CountingQueue(queue.Queue):
+    """Audio queue that stops the reference loop (which otherwise runs forever) after `limit` control tokens."""
+
+    def __init__(self, limit):
+        super().__init__()
+        self.limit, self.seen = limit, 0
+
+    def put(self, item, *a, **kw):
+        super().put(item, *a, **kw)
+        if not isinstance(item, (bytes, bytearray)) and item is not None:
+            self.seen += 1
+            if self.seen >= self.limit:
+                raise _Stop()
+
+
+def run_reference_loop(fn, handler, words, dump_size, index=0, stop_after_controls=None):
+    tq, aq = queue.Queue(), (queue.Queue() if stop_after_controls is None else _CountingQueue(stop_after_controls))
     for w in words:
         tq.put(w)
 
@@ -397,10 +412,106 @@ def protocol_golden():
     print("protocol.json written:", len(out["clean_text"]), "clean_text,", len(out["router"]), "router,", len(out["mux"]), "mux cases")
 
 
+def replica_stream_golden():
+    """Multi-sentence answers through the reference's OWN producer, generator loops and consumer (SURVEY.md section 8f
+    rows 1-2; streaming_server.py:184-248, :250-426, :428-469) with EOA-terminated sentences: four sentences for replica
+    0 and three for replica 1, scripted code streams (StubHandler) whose EOA codes come after each sentence's text --
+    sentence lengths chosen to hit every branch of the schedule (flush below the dump size, EOA exactly on a dump
+    boundary, several dumps within one sentence, dump sizes 10/30/90/270/810 and 160/480/1280 carried across sentences).
+    Records, per replica, everything its loop put on the audio queue (chunk lengths + control tokens) and the playback
+    order audio_generator_async produces."""
+    import asyncio
+    import re
+    import importlib.util
+    from queue import Empty
+    sd = W.make_random_weights(SEED)
+    gpt, wav = build_reference(sd, W.GPTArch())
+    tok = reference_tokenizer()
+    spec = importlib.util.spec_from_file_location("refcfg", os.path.join(REF, "configs/inference_config.py"))
+    refcfg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(refcfg)
+    cfg = dict(refcfg.config)
+    cfg["chat_type"] = "text"
+    fn = load_audio_generator_sync(cfg)
+    src = open(os.path.join(REF, "streaming_server.py")).read()
+    tree = ast.parse(src)
+    ns = dict(torch=torch, re=re, config=cfg, Queue=queue.Queue, StreamModel=object, asyncio=asyncio, Empty=Empty, asr_model=None)
+    for name in ("clean_text", "text_streamer_producer", "audio_generator_async"):
+        exec(compile(_extract(src, tree, name), f"streaming_server.py::{name}", "exec"), ns)
+    eos = cfg["eos_token"]
+    text = ("the quick brown fox jumps. over the lazy dog. while seven birds sing. a very old song. near the river bank. "
+            "and then they rest. good night.")
+    words = [w for w in text.split(" ") if w]
+    outputs = [(" " if i else "") + w for i, w in enumerate(words)]
+    outputs[-1] += eos
+    # codes per sentence, in answer order (sentence i -> replica i % 2); the last code of each is the EOA
+    lengths = [58, 170, 31, 25, 205, 500, 40]
+    rng = np.random.RandomState(11)
+    scripts = [[int(x) for x in rng.randint(454, 4096, n - 1)] + [cfg["eoa_token_id"]] for n in lengths]
+
+    class Req:
+        text = "prompt"
+
+        def __contains__(self, k):
+            return k == "text"
+
+    class Stream:
+        def predict(self, _):
+            return iter(outputs)
+    q = [queue.Queue(), queue.Queue()]
+    with contextlib.redirect_stdout(io.StringIO()):
+        ns["text_streamer_producer"](Req(), Stream(), q[0], q[1])
+    routed = [list(q[0].queue), list(q[1].queue)]
+    n_sent = [sum(1 for w in routed[r] if w.endswith(".") or eos in w) for r in (0, 1)]
+    assert n_sent == [4, 3]
+    out = {"outputs": np.array(outputs, dtype=object), "eoa_id": cfg["eoa_token_id"], "eos": eos,
+           "lengths": np.array(lengths, dtype=np.int32),
+           "scripts": np.array([np.array(x, dtype=np.int32) for x in scripts], dtype=object)}
+    queues = []
+    for r in (0, 1):
+        script = [c for i, sc in enumerate(scripts) if i % 2 == r for c in sc] + [7] * 64
+        h = StubHandler(None, wav, tok, sd["text_table"], len(script), scripted=script)
+        items = run_reference_loop(fn, h, routed[r] + ["filler."] * 4, dump_size=(10, 160)[r], index=r, stop_after_controls=n_sent[r])
+        events = []
+        for o in items:
+            if isinstance(o, (bytes, bytearray)):
+                events.append(len(o) // (4 * 320))
+            elif o == "end":
+                events.append(-3)
+            else:
+                events.append(-1 - int(o))       # switch signal 1 -> -2, 0 -> -1
+        out[f"events_r{r}"] = np.array(events, dtype=np.int32)
+        queues.append(items + [None])
+        print(f"replica {r}: {n_sent[r]} sentences, events {events}")
+
+    async def drain(a, b):
+        qa, qb = queue.Queue(), queue.Queue()
+        for x in a:
+            qa.put(x)
+        for x in b:
+            qb.put(x)
+        gen = ns["audio_generator_async"](qa, qb)
+        got = []
+        try:
+            while True:
+                got.append(await asyncio.wait_for(gen.__anext__(), timeout=2.5))
+        except (asyncio.TimeoutError, StopAsyncIteration):
+            pass
+        return got
+    with contextlib.redirect_stdout(io.StringIO()):
+        played = asyncio.run(drain(queues[0], queues[1]))
+    out["playback"] = np.array([-3 if x is None else len(x) // (4 * 320) for x in played], dtype=np.int32)
+    print("playback order:", out["playback"].tolist())
+    np.savez_compressed(os.path.join(GOLD, "replica_stream.npz"), **out)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "protocol":
+    if len(sys.argv) > 1 and sys.argv[1] == "replica_stream":
+        replica_stream_golden()
+    elif len(sys.argv) > 1 and sys.argv[1] == "protocol":
         sys.path[:0] = [REF]
         protocol_golden()
     else:
         main()
         protocol_golden()
+        replica_stream_golden()

@@ -177,17 +177,20 @@ def test_lane_runner_picks_the_decode_path_by_batch_size():
     r.e = FakeEngine()
     r.cluster_default = True
     greedy, sampled = Sampling(), Sampling(greedy=False, top_k=50, temperature=0.8)
-    assert [r._cluster_call(n, greedy) for n in (1, 64, 112, 113, 139, 140, 224, 225, 256)] == \
-        [True, True, True, False, False, True, True, False, False]
-    assert not r._cluster_call(64, sampled)                       # sampled decoding: sampler kernel of the per-op chain
+    # (sessions on the cluster kernel, sessions on the kernel-per-op lanes); above 224 the batch is split between both
+    assert [r.plan(n, greedy) for n in (1, 64, 112, 113, 139, 140, 224, 225, 256)] == \
+        [(1, 0), (64, 0), (112, 0), (0, 113), (0, 139), (140, 0), (224, 0), (224, 1), (224, 32)]
+    assert r.plan(64, sampled) == (0, 64)                         # sampled decoding: sampler kernel of the per-op chain
     r.e.precision = "fp32"
-    assert not r._cluster_call(64, greedy)                        # fp32 parity mode: FMA-pipe GEMMs
+    assert r.plan(64, greedy) == (0, 64)                          # fp32 parity mode: FMA-pipe GEMMs
+    r.e.precision = "exact"
+    assert r.plan(64, greedy) == (64, 0) and r.plan(120, greedy) == (120, 0)   # exact mode: hi | lo cluster kernel
     r.e.precision = "bf16"
     r.e.cfg.max_context = 2048
-    assert not r._cluster_call(64, greedy)                        # more than 64 KV pages per session
+    assert r.plan(64, greedy) == (0, 64)                          # more than 64 KV pages per session
     r.e.cfg.max_context = 512
     r.cluster_default = False                                     # LLMVOX_B200_CLUSTER=0
-    assert not r._cluster_call(64, greedy)
+    assert r.plan(64, greedy) == (0, 64)
 
 
 def test_fold_round_gpt_weights_is_the_same_model_before_rounding(weights):
@@ -224,3 +227,17 @@ def test_fold_round_gpt_weights_is_the_same_model_before_rounding(weights):
     unrounded["transformer.ln_f.weight"] = torch.ones(768)
     _, c = O.decode_steps(unrounded, O.GPTArch(), ids, 6, forced_codes=forced, return_logits=True)
     assert float((a - c).abs().max()) < 1e-4
+
+
+def test_resize_text_table_rows_are_running_means():
+    """inference/model_handler.py:22-41, applied per added token (:92-102): row 384 = mean(rows[:384]), row 385 =
+    mean(rows[:385]); existing rows untouched; an already 386-row table passes through."""
+    import torch
+    from llmvox_b200.model_handler import resize_text_table
+    g = torch.Generator().manual_seed(0)
+    t = torch.randn(384, 256, generator=g)
+    r = resize_text_table(t)
+    assert r.shape == (386, 256) and torch.equal(r[:384], t)
+    assert torch.allclose(r[384], t.mean(0), atol=1e-6)
+    assert torch.allclose(r[385], torch.cat([t, r[384:385]]).mean(0), atol=1e-6)
+    assert torch.equal(resize_text_table(r), r)

@@ -63,34 +63,36 @@ def test_sentences_alternate_replicas(proto):
 
 @pytest.mark.gpu
 def test_replica_pipeline_end_to_end(weights):
-    """Two sentences through two replicas of one engine: replica 0 speaks sentence 0 with chunks 10/30/..., replica 1
-    speaks sentence 1 starting at 160; the muxed stream is sentence 0's audio, then sentence 1's, then the end marker."""
-    import torch
+    """Two sentences through two replicas of one engine (random-init weights never emit EOA 453, so both sentences run to
+    the engine's context and are flushed there, reported as truncated): replica 0 speaks sentence 0 with chunks
+    10/30/90 + the flushed rest, replica 1 speaks sentence 1 starting at 160; the muxed stream is sentence 0's audio, then
+    sentence 1's, then the end marker."""
     from llmvox_b200.engine import Engine
     from llmvox_b200.replicas import ReplicaPipeline
     from oracle import llmvox_oracle as O
-    e = Engine(weights, device=0, precision="fp32", max_sessions=4, max_context=256, max_vocode_frames=1024)
+    ctx = 176
+    e = Engine(weights, device=0, precision="fp32", max_sessions=4, max_context=ctx, max_vocode_frames=1024)
     eos = "<|eot_id|>"
     words = ["the", " quick", " brown", " fox", " jumps.", " over", " the", " lazy", " dog." + eos]
-    pipe = ReplicaPipeline(e, pad_tail_steps=150)
+    pipe = ReplicaPipeline(e)
     q0, q1 = pipe.run(words, eos)
     sents = split_into_sentences(words, eos)
     stream = list(mux_audio_queues(q0, q1))
     assert stream[-1] is None and all(isinstance(x, bytes) for x in stream[:-1])
-    # replica 0: sentence 0 (23 ids + 150 pad steps = 173 codes): chunks 10, 30, 90 then the flushed rest
     lens0 = [len(x) // 1280 for x in q0 if isinstance(x, bytes)]
     lens1 = [len(x) // 1280 for x in q1 if isinstance(x, bytes)]
-    n_steps = max(len(s.ids) for s in sents) + 150
-    assert lens0 == [10, 30, 90, n_steps - 130] and lens1 == [160, n_steps - 160]
+    assert lens0 == [10, 30, 90, ctx - 130] and lens1 == [160, ctx - 160]
     assert q0[-2:] == [1, None] and q1[-2:] == ["end", None]
+    assert pipe.last_request.truncated
     # first chunk of sentence 0 == oracle decode of the oracle's first 10 codes
     codes = O.decode_steps(weights, O.GPTArch(), sents[0].ids, 10)
     ref = O.vocoder_decode(weights, codes).numpy()
     got = np.frombuffer(stream[0], dtype=np.float32)
     err = got.astype(np.float64) - ref
     assert 10 * np.log10((ref.astype(np.float64) ** 2).sum() / (err ** 2).sum()) > 80
-    # the replicas' schedules carry over to the next answer (dump size only grows, streaming_server.py:373-375)
-    assert pipe.dump[0] > 10 and pipe.dump[1] > 160
+    # a new answer starts from the initial dump sizes again (fresh generator threads per request, streaming_server.py:521-531)
+    q0b, _ = pipe.run(words[:5], eos)
+    assert [len(x) // 1280 for x in q0b if isinstance(x, bytes)][:3] == [10, 30, 90]
     e.close()
 
 
@@ -106,21 +108,6 @@ def test_wire_format_helpers():
     assert [s.replica for s in sents] == [0, 1] and sents[1].end_generation
 
 
-@pytest.mark.gpu
-def test_tts_endpoint_streams_float32_pcm():
-    """POST /tts through the ASGI app: octet-stream whose bytes are the float32 PCM of the chunks, in protocol order."""
-    from fastapi.testclient import TestClient
-    from llmvox_b200.model_handler import ModelHandler
-    from llmvox_b200.server import create_app, wire_to_pcm
-    mh = ModelHandler({"random_init_seed": 1234, "max_sessions": 8, "max_context": 256, "max_vocode_frames": 1024}, 0)
-    client = TestClient(create_app(mh))
-    r = client.post("/tts", json={"text": "hello there. bye."})
-    assert r.status_code == 200 and r.headers["content-type"].startswith("application/octet-stream")
-    pcm = wire_to_pcm(r.content)
-    assert pcm.size % 320 == 0 and pcm.size > 0 and np.isfinite(pcm).all()
-    mh.engine.close()
-
-
 def test_tts_endpoint_wiring_on_cpu(monkeypatch):
     """The ASGI layer alone (stub chunk source): POST /tts -> 200, octet-stream, chunks concatenated untouched."""
     from fastapi.testclient import TestClient
@@ -130,7 +117,7 @@ def test_tts_endpoint_wiring_on_cpu(monkeypatch):
         config = {"initial_dump_size_1": 10, "initial_dump_size_2": 160, "max_dump_size": 1280}
         engine = None
     chunks = [np.arange(320, dtype=np.float32).tobytes(), np.zeros(640, dtype=np.float32).tobytes()]
-    monkeypatch.setattr(S, "tts_stream", lambda pipeline, text, eos=S.DEFAULT_EOS: iter(chunks))
+    monkeypatch.setattr(S, "tts_stream", lambda batcher, text, eos=S.DEFAULT_EOS: iter(chunks))
     r = TestClient(S.create_app(StubHandler())).post("/tts", json={"text": "hi."})
     assert r.status_code == 200 and r.headers["content-type"].startswith("application/octet-stream")
     assert r.content == b"".join(chunks)

@@ -1274,10 +1274,12 @@ static int cluster_launch(lvx_engine* e, lvx_engine::Lane& ln, const int32_t* h_
       inflight -= f.clusters;
     }
     // algorithmic bytes of this launch: the bf16 GEMM weights once per iteration + KV read and append
+    // (bf16 cache; fp32 in exact mode: "fp32 variant doubles" the KV term)
     double bytes = (double)n_steps * 2.0 * ((double)c.n_layer * 12.0 * CD_C * CD_C + (double)CD_C * CD_V);
+    const double kv_el = (double)dt_size(e->kvdt());
     for (int i = 0; i < cnt; ++i) {
       const double t0 = e->h_len[h_slots[pos + i]];
-      bytes += (double)c.n_layer * 2.0 * CD_C * 2.0 * ((double)n_steps * (t0 + 1.0) + 0.5 * n_steps * (n_steps - 1.0));
+      bytes += (double)c.n_layer * 2.0 * CD_C * kv_el * ((double)n_steps * (t0 + 1.0) + 0.5 * n_steps * (n_steps - 1.0));
     }
     {
       ProfScope prof_scope(e, "cluster_decode", st, 0.0, bytes);

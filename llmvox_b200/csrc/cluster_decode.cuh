@@ -417,8 +417,8 @@ __device__ __forceinline__ unsigned cd_mma_rowsplit(uint32_t sbase, uint32_t bar
 // still ~5x fewer instructions.  (tcgen05 needs CTA-wide M >= 64 tiles in TMEM: no fit for eight independent
 // one-row problems per CTA; the legacy warp MMA is the right size here.)
 // Returns (lanes 0-11 and, duplicated, 12-23) chunk c = lane % 12 of the bf16 output row: y[8c .. 8c+8).
-// Requirements checked on the host: 16 tokens per page, at most 64 pages per session (page table in registers), every
-// plane of the pool addressable with 32-bit element offsets.
+// Requirements checked on the host: 16 tokens per page, every plane of the pool addressable with 32-bit element offsets.
+// The session's page table is held in registers 64 entries at a time (1024 tokens) and reloaded per window beyond that.
 __device__ __forceinline__ void cd_mma_bf16(float& d0, float& d1, float& d2, float& d3, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                             uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
@@ -435,15 +435,21 @@ __device__ __forceinline__ const bf16* cd_attention_kbase(bf16* kv, long long po
 }
 // (Inlining this routine so that the first K page could be issued before the q/k/v exchange cost more in spills than the
 // hidden latency is worth: measured 11.3 vs 9.4 us per attention pass.  It stays a separate function.)
-__device__ __noinline__ uint4 cd_attention_mma_warp(const bf16* kbase, int pt0, int pt1, long long pool_pages, int T, const float* qkv,
-                                                    uint8_t* tile, uint32_t* yst) {
+__device__ __noinline__ uint4 cd_attention_mma_warp(const bf16* kbase, int pt0, int pt1, const int* pt, int n_pages, long long pool_pages,
+                                                    int T, const float* qkv, uint8_t* tile, uint32_t* yst) {
   constexpr int HD = CD_HD, NC = HD / 8, PITCH = 208;
   constexpr uint32_t head_stride = 16 * HD, page_stride = CD_H * head_stride;
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, tq = lane & 3, cc = lane % NC;
   const size_t plane = (size_t)pool_pages * page_stride;
   const bf16* const vbase = kbase + plane;
+  int win = 0;   // pt0 / pt1 hold page-table entries [64 win, 64 win + 64); contexts beyond 1024 tokens reload the window
   auto page_at = [&](int pidx) -> uint32_t {   // warp-uniform argument
+    if ((pidx >> 6) != win) {
+      win = pidx >> 6;
+      pt0 = (64 * win + lane < n_pages) ? __ldg(pt + 64 * win + lane) : 0;
+      pt1 = (64 * win + 32 + lane < n_pages) ? __ldg(pt + 64 * win + 32 + lane) : 0;
+    }
     const int a = __shfl_sync(0xffffffffu, pt0, pidx & 31), c = __shfl_sync(0xffffffffu, pt1, pidx & 31);
     return (uint32_t)((pidx & 32) ? c : a) * page_stride;
   };
@@ -597,16 +603,22 @@ __device__ __forceinline__ uint4 cd_ld_stream_f32(const float* p) {
 __device__ __forceinline__ const float* cd_attention_kbase_f32(const float* kv, long long pool_pages, int layer, int h) {
   return kv + (size_t)(layer * 2) * ((size_t)pool_pages * (CD_H * 16 * CD_HD)) + h * (16 * CD_HD) + 4 * (threadIdx.x & 31);
 }
-__device__ __noinline__ void cd_attention_f32_warp(const float* kbase, int pt0, int pt1, long long pool_pages, int T, const float* qkv,
-                                                   float* tile, float* yst) {
+__device__ __noinline__ void cd_attention_f32_warp(const float* kbase, int pt0, int pt1, const int* pt, int n_pages, long long pool_pages,
+                                                   int T, const float* qkv, float* tile, float* yst) {
   constexpr int HD = CD_HD, PITCH = 100;   // floats
   constexpr uint32_t head_stride = 16 * HD, page_stride = CD_H * head_stride;
   const int lane = threadIdx.x & 31;
   const int t8 = lane & 7, part = lane >> 3;
   const size_t plane = (size_t)pool_pages * page_stride;
   const float* const vbase = kbase + plane;
+  int win = 0;   // pt0 / pt1 hold page-table entries [64 win, 64 win + 64); contexts beyond 1024 tokens reload the window
   auto half_at = [&](int hp) -> uint32_t {   // warp-uniform argument: element offset of half page hp of this head
     const int pidx = hp >> 1;
+    if ((pidx >> 6) != win) {
+      win = pidx >> 6;
+      pt0 = (64 * win + lane < n_pages) ? __ldg(pt + 64 * win + lane) : 0;
+      pt1 = (64 * win + 32 + lane < n_pages) ? __ldg(pt + 64 * win + 32 + lane) : 0;
+    }
     const int a = __shfl_sync(0xffffffffu, pt0, pidx & 31), c = __shfl_sync(0xffffffffu, pt1, pidx & 31);
     return (uint32_t)((pidx & 32) ? c : a) * page_stride + (uint32_t)(hp & 1) * (8 * HD);
   };
@@ -894,12 +906,13 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
     float pre_e[3] = {0.f, 0.f, 0.f}, pre_pe[3] = {0.f, 0.f, 0.f}, pre_ss = 0.f;   // next iteration's text / position part
     // page table of this warp's attention session (8 * odd + ww), whole launch: the host allocated every page the launch
     // needs before it (lane i holds entries i and i + 32; unallocated entries read as page 0, a mapped page)
-    int pt0 = 0, pt1 = 0;
+    int pt0 = 0, pt1 = 0, n_pages = 0;
+    const int* pt = P.st.page_table;
     {
       const int n = 8 * odd + ww;
       if (n < nloc) {
-        const int* pt = P.st.page_table + (size_t)sm_slot[n] * P.st.max_pages;
-        const int n_pages = ((sm_t[n] + n_iters - 1) >> 4) + 1;
+        pt = P.st.page_table + (size_t)sm_slot[n] * P.st.max_pages;
+        n_pages = ((sm_t[n] + n_iters - 1) >> 4) + 1;
         pt0 = (lane < n_pages) ? __ldg(pt + lane) : 0;
         pt1 = (lane + 32 < n_pages) ? __ldg(pt + lane + 32) : 0;
       }
@@ -1074,15 +1087,15 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
               float* yst = reinterpret_cast<float*>(sgen + G::OFF_YST) + ww * CD_HD;
               if (n < nloc) {   // warp-uniform
                 cd_attention_f32_warp(cd_attention_kbase_f32(reinterpret_cast<const float*>(P.kv), P.pool_pages, l, head), pt0, pt1,
-                                      P.pool_pages, sm_t[n], qkvb + ww * 288, reinterpret_cast<float*>(sgen + G::OFF_A1 + ww * G::ATT_TILE), yst);
+                                      pt, n_pages, P.pool_pages, sm_t[n], qkvb + ww * 288, reinterpret_cast<float*>(sgen + G::OFF_A1 + ww * G::ATT_TILE), yst);
                 const float4 f0 = *reinterpret_cast<const float4*>(yst + 8 * ch), f1 = *reinterpret_cast<const float4*>(yst + 8 * ch + 4);
                 const float f[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
                 cd_split8(f, val, val_lo);
               }
             } else {
               if (n < nloc)   // warp-uniform
-                val = cd_attention_mma_warp(cd_attention_kbase(reinterpret_cast<bf16*>(P.kv), P.pool_pages, l, head), pt0, pt1, P.pool_pages,
-                                            sm_t[n], qkvb + ww * 288, sgen + G::OFF_A1 + ww * G::ATT_TILE,
+                val = cd_attention_mma_warp(cd_attention_kbase(reinterpret_cast<bf16*>(P.kv), P.pool_pages, l, head), pt0, pt1, pt, n_pages,
+                                            P.pool_pages, sm_t[n], qkvb + ww * 288, sgen + G::OFF_A1 + ww * G::ATT_TILE,
                                             reinterpret_cast<uint32_t*>(sgen + G::OFF_YST) + ww * 48);
             }
             // output row to every peer's y operand: lanes 0-11 / 12-23 hold the 12 chunks, 8 peers each

@@ -1214,26 +1214,26 @@ static bool cluster_applicable(const lvx_engine* e, const SamplerArgs& sa) {
   const lvx_config& c = e->cfg;
   return e->cfg.precision != LVX_PRECISION_FP32 && sa.greedy && !sa.forced && !sa.out_codes && c.n_embd == CD_C &&
          c.n_head == CD_H && c.vocab_size == CD_V && c.n_layer <= CD_MAX_LAYERS && c.text_dim + c.code_dim == CD_C && !c.bias &&
-         c.kv_page_tokens == 16 && e->max_pages <= 64 &&
+         c.kv_page_tokens == 16 &&
          (long long)e->pool_pages * c.kv_page_tokens * c.n_embd < (1LL << 31);
 }
 
-// One launch = at most `cap` clusters, and never more than `cap` clusters in flight across the engine's streams: a launch
-// that would exceed it waits (cudaStreamWaitEvent, no host blocking) for the oldest launches on other streams.  History: an
-// earlier build died in a bounded spin (dead wait, 1 in ~10-40 launches) as soon as 9+ clusters were in flight, i.e. when
-// pending clusters start while others drain and the weight streams of the clusters fall out of step; never at <= 8.  Two
-// causes were found and fixed: the spin-waits did not reconverge the warp before the .sync.aligned instructions that
-// follow them (cd_wait; failures dropped to 1 in ~5000 uncapped rounds), and with 3 MMA issuers over an 8-slot ring two
-// consecutive uses of a slot belonged to different issuers, which breaks the parity wait when copies complete out of
-// order (cluster_decode.cuh, CD_NI).  3360 uncapped rounds of 9-16 clusters ran clean after the second fix, which still
-// proves little at that rate, so the cap stays: it costs nothing at BASELINE config 1 (4 clusters), more clusters than are
-// co-resident (7 x 16 CTAs on a B200) only queue anyway, and batches above ~224 sessions are better served by the
-// kernel-per-op path (LaneRunner switches).
+// One launch = at most `cap` clusters, and never more than `cap` clusters in flight across the engine's streams, where
+// `cap` is what cudaOccupancyMaxActiveClusters reports for the kernel (7 clusters of 16 CTAs on a B200): a launch that
+// would exceed it waits (cudaStreamWaitEvent, no host blocking) for the oldest launches on other streams.  The bound is
+// the device's co-residency and nothing else: clusters beyond it could only queue behind the resident ones, so
+// capping costs no throughput, and it keeps every cluster of a wave in step with the others' weight streams (they share
+// the 62.9 MB stream through L2).  History (profiles/r01d_cluster_decode.md section 7): early builds died in a bounded
+// spin when MORE clusters were in flight than co-resident -- two protocol bugs (spin-waits that did not reconverge the
+// warp before .sync.aligned instructions; three MMA issuers over an 8-slot ring, where consecutive uses of a slot
+// belonged to different issuers and the parity wait could pass on stale data) that are fixed (cd_wait; CD_NI = 2 with the
+// static_assert in CdG).  scripts/cluster_stress.py runs the kernel with the cap lifted (LLMVOX_B200_CD_CAP, a
+// measurement knob that does not change results) as a regression test of those fixes.
 static int cluster_launch(lvx_engine* e, lvx_engine::Lane& ln, const int32_t* h_slots, int n, int n_steps, cudaStream_t st) {
   LVX_TRY(cluster_init(e));
   const lvx_config& c = e->cfg;
   // LLMVOX_B200_CD_CAP overrides the cap (experiments only: scripts/cluster_stress.py)
-  const int cap = getenv("LLMVOX_B200_CD_CAP") ? std::max(1, atoi(getenv("LLMVOX_B200_CD_CAP"))) : std::max(1, std::min(e->cd_max_clusters, 7));
+  const int cap = getenv("LLMVOX_B200_CD_CAP") ? std::max(1, atoi(getenv("LLMVOX_B200_CD_CAP"))) : std::max(1, e->cd_max_clusters);
   ClusterParams P;
   memset(&P, 0, sizeof(P));
   P.n_iters = n_steps; P.n_layer = c.n_layer;

@@ -30,8 +30,10 @@ class LaneRunner:
       `lanes` independent groups on their own streams.  A decode iteration there is a chain of ~35 dependent,
       latency-bound kernels that leaves most of the GPU idle; sessions never interact, so disjoint groups advance
       concurrently (engine decode lanes).
-    * hybrid: batches above CLUSTER_DECODE_MAX_BATCH put that many sessions on the cluster kernel and the remainder on the
-      kernel-per-op lanes AT THE SAME TIME (the lanes' small GEMMs run on the 36 SMs the 7 clusters cannot use).
+    * a call may also be split between both (`plan` returns the two counts and `launch` runs them at the same time on
+      different streams), but that is not used by default: measured at 256 streams (bench.py streams256, bf16), 224 on the
+      cluster kernel + 32 on the lanes ran at 6858 audio-s/s against 8251 for all 256 on the lanes -- the lanes' GEMMs are
+      left with the 36 SMs the clusters do not hold and become the critical path.
 
     `launch()` enqueues on the side streams and returns the completion events; `join()` makes the control stream wait
     for them.  Every launch first waits, on every stream it uses, for the previous round's events of the OTHER streams:
@@ -43,6 +45,7 @@ class LaneRunner:
     # the second wave is nearly empty and the kernel-per-op lanes win.
     CLUSTER_DECODE_MAX_BATCH = 224
     CLUSTER_DECODE_GAP = (113, 139)
+    HYBRID_ABOVE_MAX_BATCH = False
 
     def __init__(self, engine: Engine, lanes: Optional[int] = None):
         import os
@@ -79,7 +82,9 @@ class LaneRunner:
         if n <= self.CLUSTER_DECODE_MAX_BATCH:
             gap = self.CLUSTER_DECODE_GAP[0] <= n <= self.CLUSTER_DECODE_GAP[1] and self.e.precision == "bf16"
             return (0, n) if gap else (n, 0)
-        return self.CLUSTER_DECODE_MAX_BATCH, n - self.CLUSTER_DECODE_MAX_BATCH
+        if self.HYBRID_ABOVE_MAX_BATCH:
+            return self.CLUSTER_DECODE_MAX_BATCH, n - self.CLUSTER_DECODE_MAX_BATCH
+        return 0, n
 
     def _cluster_call(self, n: int, sampling: Optional[Sampling]) -> bool:
         return self.plan(n, sampling)[0] > 0

@@ -19,7 +19,7 @@ from llmvox_b200.streaming import BatchSynthesizer, LaneRunner
 LaneRunner.CLUSTER_DECODE_MAX_BATCH = 1 << 30       # force the cluster path at every batch size
 REPS = int(os.environ.get("STRESS_REPS", "40"))
 sd = W.make_random_weights(1234, wpe_rows=256)
-e = Engine(sd, device=0, precision="bf16", max_sessions=256, max_batch=256, max_context=256, max_vocode_frames=256 * 170, decode_lanes=8)
+e = Engine(sd, device=0, precision=os.environ.get("STRESS_PRECISION", "bf16"), max_sessions=256, max_batch=256, max_context=256, max_vocode_frames=256 * 170, decode_lanes=8)
 rng = np.random.RandomState(0)
 for B in [int(x) for x in os.environ.get("STRESS_B", "144,192,256").split(",")]:
     for lanes in (1, 4):

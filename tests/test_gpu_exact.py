@@ -148,3 +148,30 @@ def test_exact_mode_vocoder_is_the_bf16_vocoder(weights, gold):
     ref = g["pcm_30"].astype(np.float64)
     snr = 10 * np.log10((ref ** 2).sum() / ((ref - pcm) ** 2).sum())
     assert snr > 40, snr
+
+
+def test_exact_long_context_2000_steps(weights, folded):
+    """Contexts beyond 1024 tokens on the cluster-resident kernel (page-table windows of 64 pages, reloaded per 1024
+    tokens; reference block_size 8192, src/model.py:205): 2,000 greedy steps of one session against the oracle on the
+    folded weights, every token, and three more sessions against the kernel-per-op exact path (all tokens)."""
+    n = 2000
+    ids = O.word_ids("long", False) + O.word_ids("context.", True)
+    ref, logits = O.decode_steps(folded, O.GPTArch(), ids, n, return_logits=True)
+    rng = np.random.RandomState(4)
+    texts = [ids] + [rng.randint(3, 259, size=k).tolist() for k in (0, 300, 1500)]
+    slots = [0, 1, 2, 3]
+    out = {}
+    for path in ("cluster", "per_op"):
+        e = _engine(weights, path, 4, 2048)
+        e.open(slots)
+        e.feed_text(slots, texts)
+        for k in (1000, 30, 970):                   # launches that start below, straddle and start above the 1024-token window
+            e.decode_steps(slots, k)
+        out[path] = e.gather_codes(slots, 0, n).cpu().numpy()
+        assert e.session_length(0) == n
+        e.close()
+    div, msg = _report("exact/cluster 2000 steps", out["cluster"][0].tolist(), ref, logits)
+    assert div is None, msg
+    for i in range(4):
+        same = out["cluster"][i] == out["per_op"][i]
+        assert same.all(), (i, int(np.argmin(same)))

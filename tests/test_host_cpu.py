@@ -177,17 +177,20 @@ def test_lane_runner_picks_the_decode_path_by_batch_size():
     r.e = FakeEngine()
     r.cluster_default = True
     greedy, sampled = Sampling(), Sampling(greedy=False, top_k=50, temperature=0.8)
-    # (sessions on the cluster kernel, sessions on the kernel-per-op lanes); above 224 the batch is split between both
+    # (sessions on the cluster kernel, sessions on the kernel-per-op lanes)
     assert [r.plan(n, greedy) for n in (1, 64, 112, 113, 139, 140, 224, 225, 256)] == \
-        [(1, 0), (64, 0), (112, 0), (0, 113), (0, 139), (140, 0), (224, 0), (224, 1), (224, 32)]
+        [(1, 0), (64, 0), (112, 0), (0, 113), (0, 139), (140, 0), (224, 0), (0, 225), (0, 256)]
+    r.HYBRID_ABOVE_MAX_BATCH = True                                # opt-in split of one call between both paths
+    assert r.plan(256, greedy) == (224, 32)
+    r.HYBRID_ABOVE_MAX_BATCH = False
     assert r.plan(64, sampled) == (0, 64)                         # sampled decoding: sampler kernel of the per-op chain
     r.e.precision = "fp32"
     assert r.plan(64, greedy) == (0, 64)                          # fp32 parity mode: FMA-pipe GEMMs
     r.e.precision = "exact"
     assert r.plan(64, greedy) == (64, 0) and r.plan(120, greedy) == (120, 0)   # exact mode: hi | lo cluster kernel
     r.e.precision = "bf16"
-    r.e.cfg.max_context = 2048
-    assert r.plan(64, greedy) == (0, 64)                          # more than 64 KV pages per session
+    r.e.cfg.max_context = 8192
+    assert r.plan(64, greedy) == (64, 0)                          # the reference's block_size: page-table windows of 64 pages
     r.e.cfg.max_context = 512
     r.cluster_default = False                                     # LLMVOX_B200_CLUSTER=0
     assert r.plan(64, greedy) == (0, 64)

@@ -125,6 +125,11 @@ struct ClusterParams {
   int text_dim, code_dim, pad_id;
   const uint8_t* wstream;           // [16 ranks][stream_bytes]
   long long stream_bytes;
+  // sampled decoding (kernel template S = 1; src/model.py:397-406): logits / temperature, top-k with ties kept, softmax,
+  // inverse-CDF draw against Philox4x32-10(seed; slot, step) -- the per-op path's sampler_kernel, run inside the cluster
+  int top_k;
+  float temperature;
+  unsigned long long seed;
   void* kv;           // bf16 (X = 0) or fp32 (X = 1) pool
   int page_shift;     // KV page = 1 << page_shift tokens
   long long pool_pages;
@@ -344,6 +349,8 @@ __device__ __forceinline__ uint32_t cd_bar_tmem(uint32_t bars) { return bars + 8
 __device__ __forceinline__ uint32_t cd_bar_x(uint32_t bars, unsigned i) { return bars + 8u * (2 * CD_MAX_STAGES + 2 + i); }
 // one barrier per proj2 row tile (count 3 = its k-block items): the scatter of tile m overlaps the MMAs of m+1..
 __device__ __forceinline__ uint32_t cd_bar_tile(uint32_t bars, unsigned m) { return bars + 8u * (2 * CD_MAX_STAGES + 4 + m); }
+
+static_assert(sizeof(SamplerScratch) <= 8 * 288 * 4, "sampler scratch must fit the q/k/v buffer");
 
 // ---- producer / MMA issuer pieces.  Both warps run CONVERGED and elect one lane only around the asynchronous
 // instructions: addresses, descriptors and ring positions then live in uniform registers.  (With `if (lane == 0)` around
@@ -731,7 +738,11 @@ __device__ __forceinline__ void cd_prefetch_text(const ClusterParams& P, int slo
 // progress words (see cd_timeout): k = 0 workers, 1..3 issuers, 4 producer
 #define CD_STATUS(k, a, b) do { if (lane == 0) bars_sh[32 + (k)] = ((unsigned long long)(unsigned)(a) << 32) | (unsigned)(b); } while (0)
 
-template <int X>
+struct CdWorkersSync {
+  __device__ __forceinline__ void operator()() const { cd_workers_sync(); }
+};
+
+template <int X, int S>
 __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __grid_constant__ ClusterParams P) {
   using G = CdG<X>;
   extern __shared__ uint8_t smem_raw[];
@@ -1191,57 +1202,105 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
       // ================= lm_head epilogue: argmax over this CTA's 256 vocabulary rows, candidates to every peer
       wait_acc();
       CD_T();
-      {
+      if constexpr (S) {
+        // ---- sampled pick: session n's 4096 logits are gathered at CTA n (into the partials buffer, idle here), which runs
+        // the sampler of the kernel-per-op path (decode_kernels.cuh: sample_pick) with its 8 worker warps and tells every
+        // peer the code.  Same draws as sampler_kernel: Philox4x32-10(seed; slot, step).
         float v0[8], v1[8];
         tmem_ld8<X>(trow + (uint32_t)(G::TM_LM + 8 * hh), v0);
         tmem_ld8<X>(trow + (uint32_t)(G::TM_LM + G::NCOL + 8 * hh), v1);
         const int row = CD_VR * rank + 32 * q + lane;
 #pragma unroll 1
         for (int i = 0; i < 8; ++i) {
-          if (P.logits && iter == n_iters - 1 && 8 * hh + i < nloc) {   // only the launch's last iteration is ever read back
-            float* lg = P.logits + (size_t)(n0 + 8 * hh + i) * CD_V + row;
+          const int n = 8 * hh + i;
+          if (P.logits && iter == n_iters - 1 && n < nloc) {
+            float* lg = P.logits + (size_t)(n0 + n) * CD_V + row;
             lg[0] = v0[i];
             lg[128] = v1[i];
           }
-          const uint32_t k0 = cd_fkey(v0[i]), k1 = cd_fkey(v1[i]);
-          const uint32_t key = max(k0, k1);
-          const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
-          const uint32_t idx = (k0 == kmax) ? (uint32_t)row : (k1 == kmax) ? (uint32_t)(row + 128) : 0xffffffffu;
-          const uint32_t imin = __reduce_min_sync(0xffffffffu, idx);
-          if (lane == 0) wcand[ww * 8 + i] = make_uint2(kmax, imin);
+          const uint32_t dst = cd_mapa(sbase + G::OFF_RED + (uint32_t)(row * 4), (uint32_t)n);
+          cd_st_remote_f32(dst, v0[i]);
+          cd_st_remote_f32(dst + 128 * 4, v1[i]);
         }
-      }
-      tc_fence_before();
-      cd_workers_sync();
+        tc_fence_before();
+        exchange(false);
+        if (rank < nloc) {   // CTA-uniform: this CTA owns session `rank`
+          // scratch in the q/k/v buffer (idle outside the attention phases; the candidates buffer next to the statistics
+          // is NOT free: peers that finish first already write their codes into it)
+          SamplerScratch& scr = *reinterpret_cast<SamplerScratch*>(sgen + G::OFF_QKV);
+          const int slot = sm_slot[rank];
+          const float u = philox_uniform(P.seed, (uint32_t)slot, (uint32_t)sm_t[rank]);
+          const int code = sample_pick(reinterpret_cast<float*>(sgen + G::OFF_RED), CD_V, false, P.top_k, P.temperature, u, scr, wt,
+                                       CdWorkersSync());
+          if (wt < CD_CLUSTER) cd_st_remote_v2(cd_mapa(sbase + G::OFF_CAND + (uint32_t)(rank * 8), (uint32_t)wt), 0u, (uint32_t)code);
+        }
+        exchange(false);
+        if (wt < CD_NB) {
+          const uint2* cand = reinterpret_cast<const uint2*>(sgen + G::OFF_CAND);
+          const int code = (cand[wt].y < (uint32_t)CD_V) ? (int)cand[wt].y : 0;
+          const int t = sm_t[wt];
+          if (rank == 0 && wt < nloc) {
+            const int slot = sm_slot[wt];
+            P.st.codes[(size_t)slot * P.st.max_context + t] = code;
+            P.st.ctx_len[slot] = t + 1;
+            if (code == P.st.eoa_id && P.st.eoa_pos[slot] < 0) P.st.eoa_pos[slot] = t;
+          }
+          sm_code[wt] = code;
+          sm_t[wt] = t + 1;
+        }
+      } else {
       {
-        const int n = wt >> 4, h2 = n >> 3, i = n & 7;
-        uint2 b = wcand[(4 * h2) * 8 + i];
+          float v0[8], v1[8];
+          tmem_ld8<X>(trow + (uint32_t)(G::TM_LM + 8 * hh), v0);
+          tmem_ld8<X>(trow + (uint32_t)(G::TM_LM + G::NCOL + 8 * hh), v1);
+          const int row = CD_VR * rank + 32 * q + lane;
+#pragma unroll 1
+          for (int i = 0; i < 8; ++i) {
+            if (P.logits && iter == n_iters - 1 && 8 * hh + i < nloc) {   // only the launch's last iteration is ever read back
+              float* lg = P.logits + (size_t)(n0 + 8 * hh + i) * CD_V + row;
+              lg[0] = v0[i];
+              lg[128] = v1[i];
+            }
+            const uint32_t k0 = cd_fkey(v0[i]), k1 = cd_fkey(v1[i]);
+            const uint32_t key = max(k0, k1);
+            const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
+            const uint32_t idx = (k0 == kmax) ? (uint32_t)row : (k1 == kmax) ? (uint32_t)(row + 128) : 0xffffffffu;
+            const uint32_t imin = __reduce_min_sync(0xffffffffu, idx);
+            if (lane == 0) wcand[ww * 8 + i] = make_uint2(kmax, imin);
+          }
+        }
+        tc_fence_before();
+        cd_workers_sync();
+        {
+          const int n = wt >> 4, h2 = n >> 3, i = n & 7;
+          uint2 b = wcand[(4 * h2) * 8 + i];
 #pragma unroll
-        for (int w = 1; w < 4; ++w) {
-          const uint2 o = wcand[(4 * h2 + w) * 8 + i];
-          if (o.x > b.x || (o.x == b.x && o.y < b.y)) b = o;
+          for (int w = 1; w < 4; ++w) {
+            const uint2 o = wcand[(4 * h2 + w) * 8 + i];
+            if (o.x > b.x || (o.x == b.x && o.y < b.y)) b = o;
+          }
+          cd_st_remote_v2(cd_mapa(sbase + G::OFF_CAND + (uint32_t)((rank * CD_NB + n) * 8), (uint32_t)(wt & 15)), b.x, b.y);
         }
-        cd_st_remote_v2(cd_mapa(sbase + G::OFF_CAND + (uint32_t)((rank * CD_NB + n) * 8), (uint32_t)(wt & 15)), b.x, b.y);
-      }
-      exchange(false);
-      if (wt < CD_NB) {
-        const uint2* cand = reinterpret_cast<const uint2*>(sgen + G::OFF_CAND);
-        uint2 b = cand[wt];
+        exchange(false);
+        if (wt < CD_NB) {
+          const uint2* cand = reinterpret_cast<const uint2*>(sgen + G::OFF_CAND);
+          uint2 b = cand[wt];
 #pragma unroll
-        for (int r = 1; r < CD_CLUSTER; ++r) {
-          const uint2 o = cand[r * CD_NB + wt];
-          if (o.x > b.x || (o.x == b.x && o.y < b.y)) b = o;
+          for (int r = 1; r < CD_CLUSTER; ++r) {
+            const uint2 o = cand[r * CD_NB + wt];
+            if (o.x > b.x || (o.x == b.x && o.y < b.y)) b = o;
+          }
+          const int code = (b.y < (uint32_t)CD_V) ? (int)b.y : 0;
+          const int t = sm_t[wt];
+          if (rank == 0 && wt < nloc) {
+            const int slot = sm_slot[wt];
+            P.st.codes[(size_t)slot * P.st.max_context + t] = code;
+            P.st.ctx_len[slot] = t + 1;
+            if (code == P.st.eoa_id && P.st.eoa_pos[slot] < 0) P.st.eoa_pos[slot] = t;   // streaming_server.py:379, 397
+          }
+          sm_code[wt] = code;
+          sm_t[wt] = t + 1;
         }
-        const int code = (b.y < (uint32_t)CD_V) ? (int)b.y : 0;
-        const int t = sm_t[wt];
-        if (rank == 0 && wt < nloc) {
-          const int slot = sm_slot[wt];
-          P.st.codes[(size_t)slot * P.st.max_context + t] = code;
-          P.st.ctx_len[slot] = t + 1;
-          if (code == P.st.eoa_id && P.st.eoa_pos[slot] < 0) P.st.eoa_pos[slot] = t;   // streaming_server.py:379, 397
-        }
-        sm_code[wt] = code;
-        sm_t[wt] = t + 1;
       }
       cd_workers_sync();
       CD_T();
@@ -1350,8 +1409,10 @@ inline long long cd_build_descs(const CdLayerW* layers, int n_layer, const float
 
 template <int X>
 inline int cluster_decode_configure_x(int* max_clusters) {
-  cudaError_t err = cudaFuncSetAttribute(cluster_decode_kernel<X>, cudaFuncAttributeMaxDynamicSharedMemorySize, CdG<X>::SMEM_BYTES);
-  if (err == cudaSuccess) err = cudaFuncSetAttribute(cluster_decode_kernel<X>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  cudaError_t err = cudaFuncSetAttribute(cluster_decode_kernel<X, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, CdG<X>::SMEM_BYTES);
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(cluster_decode_kernel<X, 0>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(cluster_decode_kernel<X, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CdG<X>::SMEM_BYTES);
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(cluster_decode_kernel<X, 1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   if (err != cudaSuccess) {
     set_error(std::string("cudaFuncSetAttribute(cluster_decode): ") + cudaGetErrorString(err));
     return LVX_ERR_CUDA;
@@ -1368,7 +1429,7 @@ inline int cluster_decode_configure_x(int* max_clusters) {
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int mc = 0;
-  err = cudaOccupancyMaxActiveClusters(&mc, cluster_decode_kernel<X>, &cfg);
+  err = cudaOccupancyMaxActiveClusters(&mc, cluster_decode_kernel<X, 0>, &cfg);
   if (err != cudaSuccess) {
     cudaGetLastError();
     mc = 0;
@@ -1380,7 +1441,7 @@ inline int cluster_decode_configure(bool exact, int* max_clusters) {
   return exact ? cluster_decode_configure_x<1>(max_clusters) : cluster_decode_configure_x<0>(max_clusters);
 }
 
-inline int cluster_decode_launch(bool exact, const ClusterParams& P, cudaStream_t st) {
+inline int cluster_decode_launch(bool exact, bool sampled, const ClusterParams& P, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(CD_CLUSTER * ceil_div(P.n, P.per_cluster));
   cfg.blockDim = dim3(CD_THREADS);
@@ -1393,7 +1454,11 @@ inline int cluster_decode_launch(bool exact, const ClusterParams& P, cudaStream_
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t err = exact ? cudaLaunchKernelEx(&cfg, cluster_decode_kernel<1>, P) : cudaLaunchKernelEx(&cfg, cluster_decode_kernel<0>, P);
+  cudaError_t err;
+  if (exact)
+    err = sampled ? cudaLaunchKernelEx(&cfg, cluster_decode_kernel<1, 1>, P) : cudaLaunchKernelEx(&cfg, cluster_decode_kernel<1, 0>, P);
+  else
+    err = sampled ? cudaLaunchKernelEx(&cfg, cluster_decode_kernel<0, 1>, P) : cudaLaunchKernelEx(&cfg, cluster_decode_kernel<0, 0>, P);
   if (err != cudaSuccess) {
     set_error(std::string("cluster_decode launch: ") + cudaGetErrorString(err));
     return LVX_ERR_CUDA;

@@ -345,29 +345,27 @@ struct SamplerArgs {
   int record;               // append to history + bump ctx_len
 };
 
-template <int MAXV>
-__global__ void __launch_bounds__(256) sampler_kernel(const float* __restrict__ logits, int V,
-                                                      const int* __restrict__ slots, SessionState st,
-                                                      SamplerArgs a) {
-  __shared__ float red[32];
-  __shared__ int redi[32];
-  __shared__ float vals[MAXV];
-  __shared__ unsigned int hist[256];
-  __shared__ unsigned int sel_prefix, sel_remaining;
-  __shared__ float seg_sum[256];
-  __shared__ int pick_sh;
-  pdl_launch_dependents();
-  pdl_wait();
-  const int b = blockIdx.x, slot = slots[b], tid = threadIdx.x;
-  const float* lg = logits + (size_t)b * V;
-  const bool greedy = a.greedy != 0;
-  int pick = 0;
-
-  if (greedy || !(a.temperature > 0.f)) {
+// Scratch of one sampling problem (256 cooperating threads).
+struct SamplerScratch {
+  float red[32];
+  int redi[32];
+  unsigned int hist[256];
+  float seg_sum[256];
+  unsigned int sel_prefix, sel_remaining;
+  int pick;
+};
+// One pick over vals[0, V) (shared memory, V logits of one session; overwritten) by 256 threads (tid in [0, 256)) that
+// meet at `sync()`: the block barrier of sampler_kernel, or the worker-warps barrier of the cluster-resident kernel.
+// Greedy: argmax, lowest index wins ties.  Sampled (src/model.py:397-406): / temperature, keep >= k-th largest (exact
+// 4-pass radix select, ties kept), softmax, inverse CDF in index order against the uniform u.
+template <typename Sync>
+__device__ __forceinline__ int sample_pick(float* vals, int V, bool greedy, int top_k, float temperature, float u, SamplerScratch& S,
+                                           int tid, Sync sync) {
+  if (greedy || !(temperature > 0.f)) {
     float best = -INFINITY;
     int bi = 0x7fffffff;
     for (int i = tid; i < V; i += 256) {
-      const float v = lg[i];
+      const float v = vals[i];
       if (v > best || (v == best && i < bi)) { best = v; bi = i; }
     }
 #pragma unroll
@@ -376,99 +374,124 @@ __global__ void __launch_bounds__(256) sampler_kernel(const float* __restrict__ 
       const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
       if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
     }
-    if ((tid & 31) == 0) { red[tid >> 5] = best; redi[tid >> 5] = bi; }
-    __syncthreads();
+    if ((tid & 31) == 0) { S.red[tid >> 5] = best; S.redi[tid >> 5] = bi; }
+    sync();
     if (tid < 32) {
-      best = tid < 8 ? red[tid] : -INFINITY;
-      bi = tid < 8 ? redi[tid] : 0x7fffffff;
+      best = tid < 8 ? S.red[tid] : -INFINITY;
+      bi = tid < 8 ? S.redi[tid] : 0x7fffffff;
 #pragma unroll
       for (int o = 4; o > 0; o >>= 1) {
         const float ov = __shfl_xor_sync(0xffffffffu, best, o);
         const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
         if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
       }
-      if (tid == 0) pick_sh = (bi == 0x7fffffff) ? 0 : bi;
+      if (tid == 0) S.pick = (bi == 0x7fffffff) ? 0 : bi;
     }
-    __syncthreads();
-    pick = pick_sh;
-  } else {
-    // logits / temperature (model.py:398)
-    for (int i = tid; i < V; i += 256) vals[i] = lg[i] / a.temperature;
-    __syncthreads();
-    float thresh = -INFINITY;
-    if (a.top_k > 0 && a.top_k < V) {
-      // exact k-th largest by 4-pass MSB radix select over order-preserving keys
-      if (tid == 0) { sel_prefix = 0; sel_remaining = (unsigned)a.top_k; }
-      for (int pass = 0; pass < 4; ++pass) {
-        const int shift = 24 - 8 * pass;
-        hist[tid] = 0;
-        __syncthreads();
-        const unsigned prefix = sel_prefix;
-        const unsigned himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
-        for (int i = tid; i < V; i += 256) {
-          const unsigned key = float_order_key(vals[i]);
-          if ((key & himask) == (prefix & himask)) atomicAdd(&hist[(key >> shift) & 255u], 1u);
-        }
-        __syncthreads();
-        if (tid == 0) {
-          unsigned rem = sel_remaining;
-          int d = 255;
-          for (; d > 0; --d) {
-            if (hist[d] >= rem) break;
-            rem -= hist[d];
-          }
-          sel_prefix = prefix | ((unsigned)d << shift);
-          sel_remaining = rem;
-        }
-        __syncthreads();
-      }
-      const unsigned key = sel_prefix;
-      const unsigned u = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
-      thresh = __uint_as_float(u);
-    }
-    // softmax over survivors (model.py:401-404), then inverse CDF in index order
-    float mx = -INFINITY;
-    for (int i = tid; i < V; i += 256) mx = fmaxf(mx, vals[i]);
-    mx = block_max(mx, red);
-    // thread owns the contiguous segment [tid*seg, (tid+1)*seg)
-    const int seg = (V + 255) / 256;
-    float ssum = 0.f;
-    for (int i = tid * seg; i < min(V, (tid + 1) * seg); ++i) {
-      const float v = vals[i];
-      const float e = (v >= thresh) ? expf(v - mx) : 0.f;
-      vals[i] = e;
-      ssum += e;
-    }
-    seg_sum[tid] = ssum;
-    __syncthreads();
-    if (tid == 0) {
-      float total = 0.f;
-      for (int i = 0; i < 256; ++i) total += seg_sum[i];
-      const float u = a.uniform ? a.uniform[b] : philox_uniform(a.seed, (uint32_t)slot, (uint32_t)st.ctx_len[slot]);
-      const float target = u * total;
-      float run = 0.f;
-      int found = -1, last = 0;
-      for (int s = 0; s < 256 && found < 0; ++s) {
-        if (run + seg_sum[s] > target) {
-          for (int i = s * seg; i < min(V, (s + 1) * seg); ++i) {
-            if (vals[i] > 0.f) last = i;
-            run += vals[i];
-            if (run > target) { found = i; break; }
-          }
-          if (found < 0) continue;  // rounding: fall through to the next segment
-        } else {
-          run += seg_sum[s];
-          if (seg_sum[s] > 0.f) {
-            for (int i = min(V, (s + 1) * seg) - 1; i >= s * seg; --i)
-              if (vals[i] > 0.f) { last = i; break; }
-          }
-        }
-      }
-      pick_sh = found >= 0 ? found : last;
-    }
-    __syncthreads();
-    pick = pick_sh;
+    sync();
+    return S.pick;
   }
+  // logits / temperature (model.py:398)
+  for (int i = tid; i < V; i += 256) vals[i] = vals[i] / temperature;
+  sync();
+  float thresh = -INFINITY;
+  if (top_k > 0 && top_k < V) {
+    // exact k-th largest by 4-pass MSB radix select over order-preserving keys
+    if (tid == 0) { S.sel_prefix = 0; S.sel_remaining = (unsigned)top_k; }
+    for (int pass = 0; pass < 4; ++pass) {
+      const int shift = 24 - 8 * pass;
+      S.hist[tid] = 0;
+      sync();
+      const unsigned prefix = S.sel_prefix;
+      const unsigned himask = pass == 0 ? 0u : (0xffffffffu << (shift + 8));
+      for (int i = tid; i < V; i += 256) {
+        const unsigned key = float_order_key(vals[i]);
+        if ((key & himask) == (prefix & himask)) atomicAdd(&S.hist[(key >> shift) & 255u], 1u);
+      }
+      sync();
+      if (tid == 0) {
+        unsigned rem = S.sel_remaining;
+        int d = 255;
+        for (; d > 0; --d) {
+          if (S.hist[d] >= rem) break;
+          rem -= S.hist[d];
+        }
+        S.sel_prefix = prefix | ((unsigned)d << shift);
+        S.sel_remaining = rem;
+      }
+      sync();
+    }
+    const unsigned key = S.sel_prefix;
+    const unsigned uu = (key & 0x80000000u) ? (key & 0x7fffffffu) : ~key;
+    thresh = __uint_as_float(uu);
+  }
+  // softmax over survivors (model.py:401-404), then inverse CDF in index order
+  float mx = -INFINITY;
+  for (int i = tid; i < V; i += 256) mx = fmaxf(mx, vals[i]);
+  mx = warp_max(mx);
+  if ((tid & 31) == 0) S.red[tid >> 5] = mx;
+  sync();
+  mx = S.red[0];
+#pragma unroll
+  for (int w = 1; w < 8; ++w) mx = fmaxf(mx, S.red[w]);
+  // thread owns the contiguous segment [tid*seg, (tid+1)*seg)
+  const int seg = (V + 255) / 256;
+  float ssum = 0.f;
+  for (int i = tid * seg; i < min(V, (tid + 1) * seg); ++i) {
+    const float v = vals[i];
+    const float e = (v >= thresh) ? expf(v - mx) : 0.f;
+    vals[i] = e;
+    ssum += e;
+  }
+  S.seg_sum[tid] = ssum;
+  sync();
+  if (tid == 0) {
+    float total = 0.f;
+    for (int i = 0; i < 256; ++i) total += S.seg_sum[i];
+    const float target = u * total;
+    float run = 0.f;
+    int found = -1, last = 0;
+    for (int s = 0; s < 256 && found < 0; ++s) {
+      if (run + S.seg_sum[s] > target) {
+        for (int i = s * seg; i < min(V, (s + 1) * seg); ++i) {
+          if (vals[i] > 0.f) last = i;
+          run += vals[i];
+          if (run > target) { found = i; break; }
+        }
+        if (found < 0) continue;  // rounding: fall through to the next segment
+      } else {
+        run += S.seg_sum[s];
+        if (S.seg_sum[s] > 0.f) {
+          for (int i = min(V, (s + 1) * seg) - 1; i >= s * seg; --i)
+            if (vals[i] > 0.f) { last = i; break; }
+        }
+      }
+    }
+    S.pick = found >= 0 ? found : last;
+  }
+  sync();
+  return S.pick;
+}
+
+struct BlockSync {
+  __device__ __forceinline__ void operator()() const { __syncthreads(); }
+};
+
+template <int MAXV>
+__global__ void __launch_bounds__(256) sampler_kernel(const float* __restrict__ logits, int V,
+                                                      const int* __restrict__ slots, SessionState st,
+                                                      SamplerArgs a) {
+  __shared__ float vals[MAXV];
+  __shared__ SamplerScratch S;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int b = blockIdx.x, slot = slots[b], tid = threadIdx.x;
+  const float* lg = logits + (size_t)b * V;
+  for (int i = tid; i < V; i += 256) vals[i] = lg[i];
+  __syncthreads();
+  const bool greedy = a.greedy != 0;
+  float u = 0.f;
+  if (!greedy) u = a.uniform ? a.uniform[b] : philox_uniform(a.seed, (uint32_t)slot, (uint32_t)st.ctx_len[slot]);
+  const int pick = sample_pick(vals, V, greedy, a.top_k, a.temperature, u, S, tid, BlockSync());
 
   if (tid == 0) {
     if (a.out_codes) a.out_codes[b] = pick;

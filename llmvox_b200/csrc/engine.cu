@@ -1212,7 +1212,7 @@ static int cluster_init(lvx_engine* e) {
 
 static bool cluster_applicable(const lvx_engine* e, const SamplerArgs& sa) {
   const lvx_config& c = e->cfg;
-  return e->cfg.precision != LVX_PRECISION_FP32 && sa.greedy && !sa.forced && !sa.out_codes && c.n_embd == CD_C &&
+  return e->cfg.precision != LVX_PRECISION_FP32 && (sa.greedy || !sa.uniform) && !sa.forced && !sa.out_codes && c.n_embd == CD_C &&
          c.n_head == CD_H && c.vocab_size == CD_V && c.n_layer <= CD_MAX_LAYERS && c.text_dim + c.code_dim == CD_C && !c.bias &&
          c.kv_page_tokens == 16 &&
          (long long)e->pool_pages * c.kv_page_tokens * c.n_embd < (1LL << 31);
@@ -1229,7 +1229,8 @@ static bool cluster_applicable(const lvx_engine* e, const SamplerArgs& sa) {
 // belonged to different issuers and the parity wait could pass on stale data) that are fixed (cd_wait; CD_NI = 2 with the
 // static_assert in CdG).  scripts/cluster_stress.py runs the kernel with the cap lifted (LLMVOX_B200_CD_CAP, a
 // measurement knob that does not change results) as a regression test of those fixes.
-static int cluster_launch(lvx_engine* e, lvx_engine::Lane& ln, const int32_t* h_slots, int n, int n_steps, cudaStream_t st) {
+static int cluster_launch(lvx_engine* e, lvx_engine::Lane& ln, const int32_t* h_slots, int n, int n_steps, const SamplerArgs& sa,
+                          cudaStream_t st) {
   LVX_TRY(cluster_init(e));
   const lvx_config& c = e->cfg;
   // LLMVOX_B200_CD_CAP overrides the cap (experiments only: scripts/cluster_stress.py)
@@ -1244,6 +1245,7 @@ static int cluster_launch(lvx_engine* e, lvx_engine::Lane& ln, const int32_t* h_
   P.text_ss = e->cd_text_ss; P.code_ss = e->cd_code_ss;
   P.text_dim = c.text_dim; P.code_dim = c.code_dim; P.pad_id = c.pad_token_id;
   P.wstream = e->cd_stream; P.stream_bytes = e->cd_stream_bytes;
+  P.top_k = sa.top_k; P.temperature = sa.temperature; P.seed = sa.seed;
   P.kv = e->kv; P.pool_pages = e->pool_pages;
   P.page_shift = 0;
   while ((1 << P.page_shift) < c.kv_page_tokens) P.page_shift += 1;
@@ -1283,7 +1285,7 @@ static int cluster_launch(lvx_engine* e, lvx_engine::Lane& ln, const int32_t* h_
     }
     {
       ProfScope prof_scope(e, "cluster_decode", st, 0.0, bytes);
-      LVX_TRY(cluster_decode_launch(e->exact(), P, st));
+      LVX_TRY(cluster_decode_launch(e->exact(), !sa.greedy, P, st));
     }
     e->launches += 1;
     lvx_engine::CdInflight rec{e->get_event(), st, clusters};
@@ -1312,7 +1314,7 @@ extern "C" int lvx_decode_steps_ex(lvx_engine* e, int lane, const int32_t* h_slo
   LVX_CHECK(path != LVX_PATH_CLUSTER || cluster_applicable(e, sa), LVX_ERR_INVALID,
             "the cluster-resident decode kernel does not apply to this engine / sampler");
   if (want_cluster && cluster_applicable(e, sa)) {
-    LVX_TRY(cluster_launch(e, ln, h_slots, n, n_steps, st));
+    LVX_TRY(cluster_launch(e, ln, h_slots, n, n_steps, sa, st));
   } else if (e->use_graphs && !e->prof_on && !sa.uniform) {
     const int unroll = 10;   // iterations per graph launch for long runs
     int left = n_steps;

@@ -153,8 +153,7 @@ class Engine:
         """Host-side mirror of the engine's own test (engine.cu: cluster_applicable): would a decode_steps call with this
         sampler run on the cluster-resident kernel?"""
         c = self.cfg
-        greedy = sampling is None or sampling.greedy or sampling.top_k == 1
-        return (self.precision in ("bf16", "exact") and greedy and c.n_embd == 768 and c.n_head == 8 and c.vocab_size == 4096 and not c.bias
+        return (self.precision in ("bf16", "exact") and c.n_embd == 768 and c.n_head == 8 and c.vocab_size == 4096 and not c.bias
                 and c.kv_page_tokens == 16 and c.text_dim + c.code_dim == 768)
 
     def decode_step_logits(self, slots: Sequence[int], forced: Optional[torch.Tensor] = None,

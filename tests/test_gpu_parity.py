@@ -587,3 +587,80 @@ def test_error_behaviour(engines):
         e.gather_codes([70], 0, 5)                   # nothing decoded yet
     with pytest.raises(LvxError):
         e.decode_steps([72], 1)                      # slot out of range
+
+
+def _philox_uniform(seed, slot, step):
+    """Philox4x32-10 as decode_kernels.cuh: philox_uniform (counter = (slot, step, 0, 0), key = seed)."""
+    M0, M1 = 0xD2511F53, 0xCD9E8D57
+    c = [slot & 0xffffffff, step & 0xffffffff, 0, 0]
+    k0, k1 = seed & 0xffffffff, (seed >> 32) & 0xffffffff
+    for _ in range(10):
+        p0, p1 = M0 * c[0], M1 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k0) & 0xffffffff, p1 & 0xffffffff, ((p0 >> 32) ^ c[3] ^ k1) & 0xffffffff, p0 & 0xffffffff]
+        k0, k1 = (k0 + 0x9E3779B9) & 0xffffffff, (k1 + 0xBB67AE85) & 0xffffffff
+    return np.float32(c[0] >> 8) * np.float32(1.0 / 16777216.0)
+
+
+@pytest.mark.parametrize("precision", ["exact", "bf16"])
+@pytest.mark.parametrize("temp,topk", [(0.8, 50), (1.0, 5), (1.2, 0)])
+def test_cluster_kernel_sampled_decoding(weights, precision, temp, topk):
+    """Temperature / top-k / multinomial inside the cluster-resident kernel (north_star kernel 3; src/model.py:397-406):
+    every pick equals the oracle's inverse-CDF draw on the kernel's own logits against the same Philox uniform, the
+    kernel-per-op sampler_kernel makes the same draws from the same state, and 12 iterations in one launch equal 12
+    launches of one (fixed reduction orders + counter-based RNG)."""
+    from llmvox_b200 import _lib
+    from llmvox_b200.engine import Engine, Sampling
+    n, steps, seed = 19, 12, 77
+    s = Sampling(greedy=False, top_k=topk, temperature=temp, seed=seed)
+    e = Engine(weights, device=0, precision=precision, max_sessions=2 * n, max_context=48, max_vocode_frames=256)
+    rng = np.random.RandomState(3)
+    texts = [rng.randint(3, 259, size=rng.randint(0, 30)).tolist() for _ in range(n)]
+    slots = list(range(n))
+    e.open(slots)
+    e.feed_text(slots, texts)
+    edge = 0
+    for t in range(steps):
+        l0 = e.kernel_launches
+        e.decode_steps(slots, 1, s, path=_lib.PATH_CLUSTER)
+        assert e.kernel_launches - l0 <= 4                       # one cluster launch, not the per-op chain
+        codes = e.gather_codes(slots, t, 1).view(-1).cpu()
+        logits = e.peek_logits(n).cpu()
+        u = torch.tensor([_philox_uniform(seed, sl, t) for sl in slots])
+        want = O.sample_from_logits(logits, temp, topk if topk > 0 else None, u)
+        lg = logits / temp
+        for b in range(n):
+            if int(codes[b]) != int(want[b]):
+                # fp32 vs fp64 CDF rounding may move a draw that sits on a bin edge to the neighbouring survivor
+                p = torch.softmax(lg[b].double(), dim=0)
+                if topk > 0:
+                    kth = torch.topk(lg[b], topk).values[-1]
+                    p = torch.where(lg[b] >= kth, p, torch.zeros_like(p))
+                    p = p / p.sum()
+                assert abs(float(torch.cumsum(p, 0)[min(int(codes[b]), int(want[b]))]) - float(u[b])) < 1e-4, (t, b)
+                edge += 1
+        if topk > 0:
+            top = torch.topk(logits, topk).indices
+            assert all(int(codes[b]) in top[b].tolist() for b in range(n))
+    assert edge <= 2
+    first = e.gather_codes(slots, 0, steps).cpu()
+    assert len(set(first.view(-1).tolist())) > steps             # it does sample: not one repeated code
+    # one launch of 12 iterations == 12 launches of one
+    slots2 = list(range(n, 2 * n))
+    e.open(slots2)
+    e.feed_text(slots2, texts)
+    s2 = Sampling(greedy=False, top_k=topk, temperature=temp, seed=seed)
+    # the Philox counter is (slot, step): give the second batch the draws of the first by decoding it in the same slots
+    e.open(slots)
+    e.feed_text(slots, texts)
+    e.decode_steps(slots, steps, s2, path=_lib.PATH_CLUSTER)
+    again = e.gather_codes(slots, 0, steps).cpu()
+    assert (again == first).all()
+    # the kernel-per-op sampler makes the same draws (same logits class in exact mode; bf16 logits differ by < 2e-2, so
+    # only the first step, where both start from identical state, is compared there)
+    e.open(slots)
+    e.feed_text(slots, texts)
+    e.decode_steps(slots, steps if precision == "exact" else 1, s2, path=_lib.PATH_PER_OP)
+    per_op = e.gather_codes(slots, 0, steps if precision == "exact" else 1).cpu()
+    agree = float((per_op == first[:, : per_op.shape[1]]).float().mean())
+    assert agree > (0.97 if precision == "exact" else 0.9), agree
+    e.close()

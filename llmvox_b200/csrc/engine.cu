@@ -187,6 +187,7 @@ struct lvx_engine {
   long long score_cap = 0;
   ChunkInfo* d_chunks = nullptr;
   GemmProblem *d_prob_s = nullptr, *d_prob_pv = nullptr;
+  TcGroup *d_grp_s = nullptr, *d_grp_pv = nullptr;   // grouped tcgen05 launches of the long chunks' attention
   int *row_chunk = nullptr, *code_rows = nullptr;
   int max_chunks = 0;
   bf16* v_vt = nullptr;   // V^T of the pos_net attention: [voc_dim][R_max] bf16
@@ -238,6 +239,39 @@ struct lvx_engine {
     int clusters;
   };
   std::deque<CdInflight> cd_inflight;
+
+  // ---- pinned staging ring for the small host -> device uploads of the vocoder (chunk layout, problem tables): a copy
+  // from pageable memory would block the calling thread until the DMA has read it; a slot is reused only after the copy
+  // that read it has completed (event per slot)
+  struct StageSlot {
+    void* h = nullptr;
+    size_t cap = 0;
+    cudaEvent_t ev = nullptr;
+    bool busy = false;
+  };
+  StageSlot stage[8];
+  int stage_next = 0;
+  // copies `bytes` from src to d_dst on `st` through the ring
+  int upload(void* d_dst, const void* src, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return LVX_OK;
+    StageSlot& sl = stage[stage_next];
+    stage_next = (stage_next + 1) % 8;
+    if (sl.busy) {
+      LVX_CUDA(cudaEventSynchronize(sl.ev));
+      sl.busy = false;
+    }
+    if (sl.cap < bytes) {
+      if (sl.h) cudaFreeHost(sl.h);
+      sl.cap = std::max<size_t>(bytes, 64 * 1024);
+      LVX_CUDA(cudaHostAlloc(&sl.h, sl.cap, cudaHostAllocDefault));
+    }
+    if (!sl.ev) LVX_CUDA(cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
+    memcpy(sl.h, src, bytes);
+    LVX_CUDA(cudaMemcpyAsync(d_dst, sl.h, bytes, cudaMemcpyHostToDevice, st));
+    LVX_CUDA(cudaEventRecord(sl.ev, st));
+    sl.busy = true;
+    return LVX_OK;
+  }
 
   // ---- optional per-launch profiler (lvx_profile_enable)
   struct ProfRec {
@@ -467,11 +501,14 @@ static int engine_alloc(lvx_engine* e) {
   e->max_chunks = c.max_vocode_frames;
   e->raw_ld = (c.n_fft + 2 + 3) & ~3;
   e->spec_ld = ceil_div(c.n_fft + 2, 64) * 64;
-  e->score_cap = (long long)c.max_vocode_frames * 1280;
+  // attention scores / probabilities of a launch group: [padded rows][sld], sld = the group's longest chunk rounded up to 64
+  e->score_cap = std::max((long long)c.max_vocode_frames * 1280, (long long)e->R_max * 1280);
   const size_t R = e->R_max;
   LVX_TRY(dev_alloc(e, &e->d_chunks, e->max_chunks));
   LVX_TRY(dev_alloc(e, &e->d_prob_s, e->max_chunks));
   LVX_TRY(dev_alloc(e, &e->d_prob_pv, e->max_chunks));
+  LVX_TRY(dev_alloc(e, &e->d_grp_s, e->max_chunks));
+  LVX_TRY(dev_alloc(e, &e->d_grp_pv, e->max_chunks));
   LVX_TRY(dev_alloc(e, &e->row_chunk, R));
   LVX_TRY(dev_alloc(e, &e->code_rows, R));
   LVX_TRY(dev_alloc_bytes(e, &e->v_feats, R * c.code_dim * dt_size(a)));
@@ -581,6 +618,10 @@ extern "C" int lvx_engine_destroy(lvx_engine* e) {
   for (auto& f : e->cd_inflight) e->ev_pool.push_back(f.ev);
   e->cd_inflight.clear();
   for (cudaEvent_t ev : e->ev_pool) cudaEventDestroy(ev);
+  for (auto& sl : e->stage) {
+    if (sl.ev) cudaEventDestroy(sl.ev);
+    if (sl.h) cudaFreeHost(sl.h);
+  }
   for (void* p : e->allocs) cudaFree(p);
   for (auto& kv : e->w)
     if (kv.second.d) cudaFree(kv.second.d);
@@ -1502,7 +1543,7 @@ struct VocGroup {
   int frames = 0;   // valid rows
   int code0 = 0;    // first code of the group in the caller's packed order
   int max_len = 0;
-  long long s_elems = 0;
+  int sld() const { return (max_len + 63) & ~63; }   // leading dimension of the group's score / probability matrices
 };
 
 static int groupnorm(lvx_engine* e, const VocGroup& g, const float* x, const float* w, const float* b, int swish, void* out,
@@ -1568,7 +1609,7 @@ static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes
     return LVX_OK;
   };
   // layout
-  LVX_CUDA(cudaMemcpyAsync(e->d_chunks, g.chunks.data(), nch * sizeof(ChunkInfo), cudaMemcpyHostToDevice, st));
+  LVX_TRY(e->upload(e->d_chunks, g.chunks.data(), nch * sizeof(ChunkInfo), st));
   LVX_CUDA(cudaMemsetAsync(e->row_chunk, 0xFF, (size_t)g.R * sizeof(int), st));
   build_row_chunk_kernel<<<nch, 128, 0, st>>>(e->d_chunks, nch, e->row_chunk, e->code_rows);
   LAUNCHED(e);
@@ -1601,60 +1642,67 @@ static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes
     p.A = e->v_h; p.C = e->v_big; p.M = g.R; p.lda = D; p.ldc = 3 * D; p.bias = e->at_qkv_b; p.row_chunk = e->row_chunk;
     if (e->prof_detail) p.tag = "tc_gemm:attn_qkv";
     LVX_TRY(run_gemm(e, p, e->at_qkv, a, a, st));
-    // chunks longer than 256 frames (bf16 mode): QK^T and PV as tcgen05 GEMMs with per-chunk tensor maps; the rest
-    // as one ragged batch on the FMA-pipe kernel (a tensor-core launch per tiny chunk would cost more than it saves)
+    // Scores S (fp32) and probabilities P (GEMM operand type) of the whole launch group live in [padded rows][sld]
+    // matrices (row = the frame's padded row, sld = longest chunk rounded up to 64), so every chunk's Q K^T and P V are
+    // windows of shared matrices.  Chunks longer than 256 frames (bf16 mode): ONE grouped tcgen05 launch for all Q K^T and
+    // one for all P V (TcGroup windows over single tensor maps of v_big / P / V^T).  Shorter chunks: one ragged batch on
+    // the FMA-pipe kernel (a 128 x 128 tensor-core tile per tiny chunk would cost more than it saves).
+    const int sld = g.sld();
     std::vector<int> small, large;
     for (int i = 0; i < nch; ++i) ((a == B16 && g.chunks[i].len > 256) ? large : small).push_back(i);
-    const int ns = (int)small.size();
+    const int ns = (int)small.size(), nl = (int)large.size();
     std::vector<GemmProblem> ps(std::max(ns, 1)), pv(std::max(ns, 1));
     int small_max = 0;
     for (int j = 0; j < ns; ++j) {
       const ChunkInfo& ci = g.chunks[small[j]];
-      const int L = ci.len, Lp = (L + 7) & ~7;
-      ps[j] = GemmProblem{(long long)ci.row0 * 3 * D, (long long)ci.row0 * 3 * D + D, (long long)ci.s_off, L, L, D, 0, Lp};
-      pv[j] = GemmProblem{(long long)ci.s_off, (long long)ci.row0 * 3 * D + 2 * D, (long long)ci.row0 * D, L, D, L, Lp, 0};
+      const int L = ci.len;
+      ps[j] = GemmProblem{(long long)ci.row0 * 3 * D, (long long)ci.row0 * 3 * D + D, (long long)ci.row0 * sld, L, L, D, 0, sld};
+      pv[j] = GemmProblem{(long long)ci.row0 * sld, (long long)ci.row0 * 3 * D + 2 * D, (long long)ci.row0 * D, L, D, L, sld, 0};
       small_max = std::max(small_max, L);
     }
     const float att_scale = 1.0f / sqrtf((float)D);
     if (ns) {
-      LVX_CUDA(cudaMemcpyAsync(e->d_prob_s, ps.data(), ns * sizeof(GemmProblem), cudaMemcpyHostToDevice, st));
-      LVX_CUDA(cudaMemcpyAsync(e->d_prob_pv, pv.data(), ns * sizeof(GemmProblem), cudaMemcpyHostToDevice, st));
-      GemmParams s;
-      s.A = e->v_big; s.W = e->v_big; s.C = e->v_S; s.batch = e->d_prob_s; s.n_batch = ns; s.lda = 3 * D; s.ldw = 3 * D;
-      s.max_M = small_max; s.max_N = small_max; s.alpha = att_scale;
-      LVX_TRY(run_gemm_batched(e, s, a, a, F32, st));
+      LVX_TRY(e->upload(e->d_prob_s, ps.data(), ns * sizeof(GemmProblem), st));
+      LVX_TRY(e->upload(e->d_prob_pv, pv.data(), ns * sizeof(GemmProblem), st));
+      GemmParams sp;
+      sp.A = e->v_big; sp.W = e->v_big; sp.C = e->v_S; sp.batch = e->d_prob_s; sp.n_batch = ns; sp.lda = 3 * D; sp.ldw = 3 * D;
+      sp.max_M = small_max; sp.max_N = small_max; sp.alpha = att_scale;
+      LVX_TRY(run_gemm_batched(e, sp, a, a, F32, st));
     }
-    if (!large.empty()) {
+    int large_max = 0;
+    if (nl) {
       // V^T for the whole group: Vt[c, r] = (Wv . h^T)[c, r] + bv[c]  (swap-mode tiles, transposed store)
       GemmParams t;
       t.A = e->v_h; t.C = e->v_vt; t.M = g.R; t.lda = D; t.ldc = e->R_max; t.bias = e->at_qkv_b + 2 * D; t.c_transposed = 1;
       t.a_cap = e->R_max;
       if (e->prof_detail) t.tag = "tc_gemm:attn_vt";
       LVX_TRY(run_gemm(e, t, e->at_v, a, a, st));
-      LVX_TRY(aux_fork(e, st));
-      int rr = 0;
-      for (int i : large) {
-        cudaStream_t cs = e->aux[rr++ % lvx_engine::kAux];
-        const ChunkInfo& ci = g.chunks[i];
-        const int L = ci.len, Lp = (L + 7) & ~7;
-        const bf16* qk = (const bf16*)e->v_big + (size_t)ci.row0 * 3 * D;
-        CUtensorMap qm;
-        TmaDesc km;
-        LVX_TRY(tc_encode(&qm, qk, L, D, 3 * D, TC_BM));
-        LVX_TRY(tc_encode(&km.map, qk + D, L, D, 3 * D, TC_BM));
-        km.valid = true;
-        GemmParams s;
-        s.A = qk; s.C = e->v_S + ci.s_off; s.M = L; s.N = L; s.K = D; s.lda = 3 * D; s.ldw = 3 * D; s.ldc = Lp; s.alpha = att_scale;
-        ProfScope prof(e, "tc_gemm:attn_qk", cs, 2.0 * L * (double)L * D, 0);
-        LVX_TRY(tc_gemm(&e->tcw, s, km, false, cs, &qm));
+      std::vector<TcGroup> gs(nl), gp(nl);
+      double fl = 0;
+      for (int j = 0; j < nl; ++j) {
+        const ChunkInfo& ci = g.chunks[large[j]];
+        const int L = ci.len;
+        gs[j] = TcGroup{ci.row0, ci.row0, 0, D, L, L, ceil_div(D, TC_BK), sld, (long long)ci.row0 * sld};
+        gp[j] = TcGroup{ci.row0, 0, 0, ci.row0, L, D, ceil_div(L, TC_BK), D, (long long)ci.row0 * D};
+        large_max = std::max(large_max, L);
+        fl += 2.0 * L * (double)L * D;
+      }
+      LVX_TRY(e->upload(e->d_grp_s, gs.data(), nl * sizeof(TcGroup), st));
+      LVX_TRY(e->upload(e->d_grp_pv, gp.data(), nl * sizeof(TcGroup), st));
+      CUtensorMap qkm;
+      LVX_TRY(tc_act_map(&e->tcw, e->v_big, e->R_max, 3 * D, 3 * D, TC_BM, &qkm));
+      GemmParams sp;
+      sp.C = e->v_S; sp.alpha = att_scale;
+      {
+        ProfScope prof(e, "tc_gemm:attn_qk", st, fl, 0);
+        LVX_TRY(tc_gemm_grouped(qkm, qkm, sp, e->d_grp_s, nl, large_max, large_max, ceil_div(D, TC_BK), false, st));
         e->launches++;
       }
-      LVX_TRY(aux_join(e, st));
     }
     if (a == F32)
-      attn_softmax_kernel<float><<<ceil_div(g.R, 8), 256, 0, st>>>(e->v_S, e->v_S, e->d_chunks, e->row_chunk, g.R);
+      attn_softmax_kernel<float><<<ceil_div(g.R, 8), 256, 0, st>>>(e->v_S, e->v_S, e->d_chunks, e->row_chunk, g.R, sld);
     else
-      attn_softmax_kernel<bf16><<<ceil_div(g.R, 8), 256, 0, st>>>(e->v_S, (bf16*)e->v_P, e->d_chunks, e->row_chunk, g.R);
+      attn_softmax_kernel<bf16><<<ceil_div(g.R, 8), 256, 0, st>>>(e->v_S, (bf16*)e->v_P, e->d_chunks, e->row_chunk, g.R, sld);
     LAUNCHED(e);
     if (ns) {
       GemmParams o;
@@ -1662,25 +1710,18 @@ static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes
       o.ldw = 3 * D; o.ldc = D; o.w_kn = 1; o.max_M = small_max; o.max_N = D;
       LVX_TRY(run_gemm_batched(e, o, a, a, a, st));
     }
-    if (!large.empty()) LVX_TRY(aux_fork(e, st));
-    int rr2 = 0;
-    for (int i : large) {
-      cudaStream_t cs = e->aux[rr2++ % lvx_engine::kAux];
-      const ChunkInfo& ci = g.chunks[i];
-      const int L = ci.len, Lp = (L + 7) & ~7;
-      const bf16* P = (const bf16*)e->v_P + ci.s_off;
-      CUtensorMap pm;
-      TmaDesc vm;
-      LVX_TRY(tc_encode(&pm, P, L, L, Lp, TC_BM));
-      LVX_TRY(tc_encode(&vm.map, e->v_vt + ci.row0, D, L, e->R_max, TC_BM));
-      vm.valid = true;
+    if (nl) {
+      CUtensorMap pm, vm;
+      LVX_TRY(tc_act_map(&e->tcw, e->v_P, (int)std::min<long long>(e->R_max, e->score_cap / sld), sld, sld, TC_BM, &pm));
+      LVX_TRY(tc_act_map(&e->tcw, e->v_vt, D, e->R_max, e->R_max, TC_BM, &vm));
       GemmParams o;
-      o.A = P; o.C = (bf16*)e->v_h + (size_t)ci.row0 * D; o.M = L; o.N = D; o.K = L; o.lda = Lp; o.ldw = e->R_max; o.ldc = D;
-      ProfScope prof(e, "tc_gemm:attn_pv", cs, 2.0 * L * (double)L * D, 0);
-      LVX_TRY(tc_gemm(&e->tcw, o, vm, true, cs, &pm));
+      o.C = e->v_h;
+      double fl = 0;
+      for (int i : large) fl += 2.0 * g.chunks[i].len * (double)g.chunks[i].len * D;
+      ProfScope prof(e, "tc_gemm:attn_pv", st, fl, 0);
+      LVX_TRY(tc_gemm_grouped(pm, vm, o, e->d_grp_pv, nl, large_max, D, ceil_div(large_max, TC_BK), true, st));
       e->launches++;
     }
-    if (!large.empty()) LVX_TRY(aux_join(e, st));
     GemmParams q;
     q.A = e->v_h; q.C = e->v_x; q.M = g.R; q.lda = D; q.ldc = D; q.bias = e->at_proj_b; q.residual = e->v_x; q.ldr = D;
     q.row_chunk = e->row_chunk;
@@ -1786,12 +1827,13 @@ static int plan_groups(lvx_engine* e, const int32_t* h_cu, int n_chunks, std::ve
     const int L = h_cu[i + 1] - h_cu[i];
     LVX_CHECK(L > 0, LVX_ERR_INVALID, "empty chunk (the reference never decodes zero codes)");
     LVX_CHECK(L <= e->cfg.max_vocode_frames, LVX_ERR_CAPACITY, "chunk longer than max_vocode_frames");
-    const long long Lp = (L + 7) & ~7;
-    LVX_CHECK((long long)L * Lp <= e->score_cap, LVX_ERR_CAPACITY, "chunk too long for the attention workspace");
     const int row0_next = (g.R + 7) & ~7;
+    // (+128: the last 128-row tile of the grouped attention GEMMs may start at the group's last rows)
+    auto fits = [&](int rows, int max_len) { return (long long)(rows + 128) * ((max_len + 63) & ~63) <= e->score_cap; };
+    LVX_CHECK(fits(ROW_PAD + L + ROW_PAD + 8, L), LVX_ERR_CAPACITY, "chunk too long for the attention workspace");
     if (!g.chunks.empty() &&
-        (g.frames + L > e->cfg.max_vocode_frames || g.s_elems + L * Lp > e->score_cap || (int)g.chunks.size() >= e->max_chunks ||
-         row0_next + L + ROW_PAD > e->R_max - 128)) {
+        (g.frames + L > e->cfg.max_vocode_frames || !fits(row0_next + L + ROW_PAD, std::max(g.max_len, L)) ||
+         (int)g.chunks.size() >= e->max_chunks || row0_next + L + ROW_PAD > e->R_max - 128)) {
       out->push_back(g);
       g = VocGroup();
       g.R = ROW_PAD;
@@ -1801,11 +1843,10 @@ static int plan_groups(lvx_engine* e, const int32_t* h_cu, int n_chunks, std::ve
     ci.row0 = (g.R + 7) & ~7;   // 16-byte aligned bf16 column offset for the transposed-V tensor maps
     ci.len = L;
     ci.out0 = h_cu[i] - g.code0;
-    ci.s_off = (int)g.s_elems;
+    ci.s_off = 0;
     g.chunks.push_back(ci);
     g.R = ci.row0 + L + ROW_PAD;
     g.frames += L;
-    g.s_elems += L * Lp;
     g.max_len = std::max(g.max_len, L);
   }
   out->push_back(g);

@@ -212,8 +212,20 @@ inline bool tc_no_persistent() {
   return off;
 }
 
+// One problem of a GROUPED launch (normal mode, grid.z = problem): both operands are windows of two big matrices that
+// every problem shares -- X rows [x_row0, +M) x K columns [x_k0, +64 num_kb), Y rows [y_row0, +N) x K columns [y_k0, ..)
+// -- so ONE pair of tensor maps serves all problems (the ragged pos_net attention of the vocoder: per-chunk Q K^T and P V
+// as one launch each instead of one launch per chunk).  Rows past M / N read whatever follows in the shared matrix
+// (finite by construction) and are masked at the store.
+struct TcGroup {
+  int x_row0, y_row0, x_k0, y_k0;
+  int M, N, num_kb, ldc;
+  long long c_off;   // element offset of the problem's C
+};
+
 struct TcParams {
   GemmParams g;
+  const TcGroup* groups = nullptr;   // grouped launch: device array, one entry per blockIdx.z
   int BN;          // UMMA N = Y rows per tile
   int stages;
   int num_kb;      // K / 64 (rounded up; TMA zero-fills the tail)
@@ -365,19 +377,31 @@ struct TcShape {
   static constexpr int kThreads = 64 + 32 * kEpiWarps;
 };
 
-template <bool kSwap, typename TC>
+template <bool kSwap, typename TC, bool kGrouped = false>
 __global__ void __launch_bounds__(TcShape<kSwap>::kThreads, kSwap ? 1 : 2) tc_gemm_kernel(const __grid_constant__ CUtensorMap mapX,
                                                                           const __grid_constant__ CUtensorMap mapY,
                                                                           const TcParams tp) {
+  static_assert(!(kGrouped && kSwap), "grouped launches are normal-mode only");
   constexpr int kHalves = TcShape<kSwap>::kEpiWarps / 4;
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t bars[2 * TC_MAX_STAGES + 1];
   __shared__ uint32_t tmem_base_sh;
 
+  // grouped launch: this CTA's problem; tiles outside the problem's extent (the grid is sized for the largest) leave
+  GemmParams pg;
+  int g_x0 = 0, g_y0 = 0, g_xk = 0, g_yk = 0, g_nkb = 0;
+  if (kGrouped) {
+    const TcGroup gr = tp.groups[blockIdx.z];
+    if ((int)blockIdx.y * TC_BM >= gr.M || (int)blockIdx.x * tp.BN >= gr.N) return;
+    pg = tp.g;
+    pg.M = gr.M; pg.N = gr.N; pg.ldc = gr.ldc;
+    pg.C = reinterpret_cast<TC*>(pg.C) + gr.c_off;
+    g_x0 = gr.x_row0; g_y0 = gr.y_row0; g_xk = gr.x_k0; g_yk = gr.y_k0; g_nkb = gr.num_kb;
+  }
   pdl_launch_dependents();   // the successor may be scheduled as soon as every CTA of this grid is running
-  const GemmParams& p = tp.g;
+  const GemmParams& p = kGrouped ? pg : tp.g;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int BN = tp.BN, stages = tp.stages, S = tp.splits;
+  const int BN = tp.BN, stages = tp.stages, S = kGrouped ? 1 : tp.splits;
   const uint32_t y_bytes = (uint32_t)BN * TC_BK * 2;
   const uint32_t stage_bytes = TC_X_BYTES + y_bytes;
   const uint32_t tiles = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -390,7 +414,8 @@ __global__ void __launch_bounds__(TcShape<kSwap>::kThreads, kSwap ? 1 : 2) tc_ge
   const int x0 = (kSwap ? blockIdx.x : blockIdx.y) * TC_BM;
   const int y0 = (kSwap ? blockIdx.y : blockIdx.x) * BN;
   const int rank = S > 1 ? (int)cluster_ctarank() : 0;
-  const int kb0 = (int)((long long)tp.num_kb * rank / S), kb1 = (int)((long long)tp.num_kb * (rank + 1) / S);
+  const int num_kb = kGrouped ? g_nkb : tp.num_kb;
+  const int kb0 = (int)((long long)num_kb * rank / S), kb1 = (int)((long long)num_kb * (rank + 1) / S);
   const int nk = kb1 - kb0;
 
   if (warp == 0 && lane == 0) {
@@ -444,8 +469,8 @@ __global__ void __launch_bounds__(TcShape<kSwap>::kThreads, kSwap ? 1 : 2) tc_ge
           xr = x0 + tap - p.tap_pad;
         }
         const uint32_t dst = tiles + (uint32_t)s * stage_bytes;
-        tma_load_2d(&mapX, full_bar(s), dst, xc, xr);
-        tma_load_2d(&mapY, full_bar(s), dst + TC_X_BYTES, k0, y0);
+        tma_load_2d(&mapX, full_bar(s), dst, xc + g_xk, xr + g_x0);
+        tma_load_2d(&mapY, full_bar(s), dst + TC_X_BYTES, k0 + g_yk, y0 + g_y0);
       }
     }
   } else if (warp == 1) {
@@ -562,6 +587,10 @@ inline int tc_configure() {
   if (err == cudaSuccess)
     err = cudaFuncSetAttribute(tc_gemm_kernel<false, bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
   if (err == cudaSuccess)
+    err = cudaFuncSetAttribute(tc_gemm_kernel<false, float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+  if (err == cudaSuccess)
+    err = cudaFuncSetAttribute(tc_gemm_kernel<false, bf16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
+  if (err == cudaSuccess)
     err = cudaFuncSetAttribute(tc_gemm_persistent_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
   if (err == cudaSuccess)
     err = cudaFuncSetAttribute(tc_gemm_persistent_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 2048);
@@ -591,6 +620,35 @@ inline int tc_launch(const CUtensorMap& mx, const CUtensorMap& my, const TcParam
   cudaError_t err = cudaLaunchKernelEx(&cfg, tc_gemm_kernel<kSwap, TC>, mx, my, tp);
   if (err != cudaSuccess) {
     set_error(std::string("tc_gemm launch: ") + cudaGetErrorString(err));
+    return LVX_ERR_CUDA;
+  }
+  return LVX_OK;
+}
+
+// Grouped launch (see TcGroup): n_groups problems of at most max_M x max_N, 128 x 128 tiles, no split-K.  mx / my: tensor
+// maps (box 128 rows x 64 columns) of the two shared matrices; p carries alpha and the output base pointer.
+inline int tc_gemm_grouped(const CUtensorMap& mx, const CUtensorMap& my, const GemmParams& p, const TcGroup* d_groups, int n_groups, int max_M,
+                           int max_N, int max_kb, bool c_bf16, cudaStream_t st) {
+  if (n_groups <= 0) return LVX_OK;
+  TcParams tp;
+  tp.g = p;
+  tp.groups = d_groups;
+  tp.num_kb = max_kb;
+  tp.BN = 128;
+  tp.tmem_cols = 128;
+  tp.splits = 1;
+  const int stage_bytes = TC_X_BYTES + tp.BN * TC_BK * 2;
+  tp.stages = std::max(2, std::min(std::min(TC_MAX_STAGES, max_kb), (110 * 1024 - 1024) / stage_bytes));
+  const size_t smem = (size_t)tp.stages * stage_bytes + 1024;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ceil_div(max_N, tp.BN), ceil_div(max_M, TC_BM), n_groups);
+  cfg.blockDim = dim3(TcShape<false>::kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaError_t err = c_bf16 ? cudaLaunchKernelEx(&cfg, tc_gemm_kernel<false, bf16, true>, mx, my, tp)
+                           : cudaLaunchKernelEx(&cfg, tc_gemm_kernel<false, float, true>, mx, my, tp);
+  if (err != cudaSuccess) {
+    set_error(std::string("tc_gemm grouped launch: ") + cudaGetErrorString(err));
     return LVX_ERR_CUDA;
   }
   return LVX_OK;

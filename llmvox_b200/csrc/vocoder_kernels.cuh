@@ -15,7 +15,7 @@ struct ChunkInfo {
   int row0;  // first row of the chunk in the padded layout
   int len;   // frames
   int out0;  // first frame in the packed (unpadded) order == h_cu[i]
-  int s_off; // element offset of this chunk's L x Lp score matrix
+  int s_off; // unused (scores live in the launch group's [padded rows][sld] matrices)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -183,20 +183,21 @@ __global__ void __launch_bounds__(256) dwconv_adaln_kernel(const float* __restri
 
 // ---------------------------------------------------------------------------------------------------
 // Row softmax of the pos_net attention scores (models.py:117-118; the C^-0.5 scale is the GEMM's alpha).
-// Scores of chunk i: L x Lp fp32 at s_off (Lp = L rounded up to 8; pad columns are written as zeros so the
-// P.V GEMM may read them).  One warp per row.  Output type = GEMM operand type, in place for fp32.
+// Scores of padded row r: S[r * sld .. + L) fp32 (sld = the launch group's longest chunk rounded up to 64); P gets the
+// same layout, with columns [L, L rounded up to 64) written as zeros so the P.V GEMM's last k-block may read them.  One
+// warp per row.  Output type = GEMM operand type, in place for fp32.
 // ---------------------------------------------------------------------------------------------------
 template <typename TOut>
 __global__ void __launch_bounds__(256) attn_softmax_kernel(const float* __restrict__ S, TOut* __restrict__ P,
                                                            const ChunkInfo* __restrict__ chunks,
-                                                           const int* __restrict__ row_chunk, int rows) {
+                                                           const int* __restrict__ row_chunk, int rows, int sld) {
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const int ch = row_chunk[row];
   if (ch < 0) return;
   const ChunkInfo ci = chunks[ch];
-  const int L = ci.len, Lp = (L + 7) & ~7;
-  const size_t off = (size_t)ci.s_off + (size_t)(row - ci.row0) * Lp;
+  const int L = ci.len, Lp = min(sld, (L + 63) & ~63);
+  const size_t off = (size_t)row * sld;
   const float* s = S + off;
   float mx = -INFINITY;
   for (int j = lane; j < L; j += 32) mx = fmaxf(mx, s[j]);

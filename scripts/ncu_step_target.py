@@ -10,7 +10,7 @@ from llmvox_b200.engine import Engine
 from llmvox_b200.streaming import LaneRunner
 sd = W.make_random_weights(bench.SEED, wpe_rows=256)
 S = bench.STREAMS
-e = Engine(sd, device=0, precision="bf16", max_sessions=2 * S, max_batch=S, max_context=208, max_vocode_frames=S * 96, decode_lanes=1)
+e = Engine(sd, device=0, precision=os.environ.get("TARGET_PRECISION", "exact"), max_sessions=2 * S, max_batch=S, max_context=208, max_vocode_frames=S * 96, decode_lanes=1)
 texts = bench.synthetic_text(S, 1000)
 pcm = torch.empty((S * bench.TOKENS * 320,), dtype=torch.float32, device=e.device)
 runner = LaneRunner(e, 1)

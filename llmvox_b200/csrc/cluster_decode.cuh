@@ -109,9 +109,9 @@ struct CdG {
   static constexpr int OFF_SMALL = OFF_YST + 8 * CD_HD * (X ? 4 : 2);   // slot[16], t[16], code[16], wcand[8][8] x 8 B
   static constexpr int SMEM_BYTES = OFF_SMALL + 1024 + 1024;            // + alignment slack
   static_assert(SMEM_BYTES <= 232448 - 1024, "dynamic + static shared memory must fit one SM");
-  // per-warp attention staging tile inside A1 | A2 (LN1(x) has been consumed by the qkv MMAs, the LN2 gather and the GELU
-  // slice come later): X = 0 16 tokens x 208 B, X = 1 8 tokens x 400 B
-  static constexpr int ATT_TILE = X ? 3200 : 3328;
+  // per-warp attention staging inside A1 | A2 (LN1(x) has been consumed by the qkv MMAs, the LN2 gather and the GELU
+  // slice come later): X = 0 one tile of 16 tokens x 208 B, X = 1 the cp.async slots of one half page (K 3 KB | V 3 KB)
+  static constexpr int ATT_TILE = X ? 6144 : 3328;   // X = 1: lane-private cp.async slots, K | V of one half page
   static_assert(8 * ATT_TILE <= (CD_C / 64 + CD_FR / 64) * ABLK, "attention staging must fit A1 | A2");
 };
 
@@ -594,13 +594,22 @@ __device__ __noinline__ uint4 cd_attention_mma_warp(const bf16* kbase, int pt0, 
   return *reinterpret_cast<const uint4*>(yst + 4 * cc);
 }
 
-// ---- exact mode (X = 1) attention of one (session, head) by one warp, fp32 throughout: the cache is fp32 in the same
-// layout ([layer][k|v][page][head][16 tokens][96], one page of one head = 6 KB contiguous), scores, softmax and P V run on
-// the FMA pipe.  Per half page (8 tokens = 3 KB, the byte size of a bf16 page): 6 fully coalesced 512-byte loads each for
-// K and V -> registers -> per-warp shared-memory tile (row pitch 400 B: conflict-free float4 rows) ->
-//   scores : lane (token t = lane & 7, part = lane >> 3) sums 24 dims, two shuffles finish the dot product
-//   P V    : lane owns dims lane, lane + 32, lane + 64; p_t by shuffle, V[t][d] from the tile
-// with an online-softmax rescale per half page; K of the next half page and V of this one are in flight during the math.
+// ---- exact mode (X = 1) attention of one (session, head) by one warp, fp32 throughout, on the FMA pipe.  The fp32 pool
+// is LANE-MAJOR per 8-token half page (decode_kernels.cuh: kv_tile_offset): the six fully coalesced 512-byte loads a warp
+// issues for K (and six for V) of a half page land directly in the lane that uses them -- lane (t8 = lane & 7, part =
+// lane >> 3) holds dims [24 part, +24) of token 8 hp + t8 -- so there is no shared-memory staging, no ldmatrix and no
+// __syncwarp in the loop:
+//   scores : 24 FMAs per lane against q (shared memory, broadcast reads), two shuffles finish the dot product
+//   softmax: online, per half page (max over the 8 token lanes: three shuffles)
+//   P V    : every lane keeps 24 partial sums for ITS token slot and dims (24 FMAs per half page); the eight token slots
+//            are merged once, after the loop, by a 21-shuffle reduce-scatter that leaves dims 3 lane .. 3 lane + 2 in lane.
+// Two half pages are in flight per warp without a second register set: even half pages arrive in registers (LDG), odd
+// ones through cp.async into this warp's lane-private slots of the idle A1 | A2 operand area (every lane reads back only
+// what it copied itself: no __syncwarp), so K and V of half page hp + 1 are on their way while hp is consumed.  (A second
+// register set did the same at 160+ registers and pushed the rest of the kernel into spills.  History: the row-major
+// version staged every half page through a per-warp shared-memory tile -- 4 __syncwarp, 12 STS.128 + LDS round trips and
+// a serial 8-step shuffle + FMA chain per half page, with only K one stage ahead: 0.12 us per cached token and layer
+// against 0.08 here; profiles/r02_cluster_decode.md.)
 // Output: 96 fp32 values in yst.
 __device__ __forceinline__ uint4 cd_ld_stream_f32(const float* p) {
   uint4 v;
@@ -611,13 +620,14 @@ __device__ __forceinline__ const float* cd_attention_kbase_f32(const float* kv, 
   return kv + (size_t)(layer * 2) * ((size_t)pool_pages * (CD_H * 16 * CD_HD)) + h * (16 * CD_HD) + 4 * (threadIdx.x & 31);
 }
 __device__ __noinline__ void cd_attention_f32_warp(const float* kbase, int pt0, int pt1, const int* pt, int n_pages, long long pool_pages,
-                                                   int T, const float* qkv, float* tile, float* yst) {
-  constexpr int HD = CD_HD, PITCH = 100;   // floats
+                                                   int T, const float* qkv, uint32_t stage, float* yst) {
+  constexpr int HD = CD_HD;
   constexpr uint32_t head_stride = 16 * HD, page_stride = CD_H * head_stride;
   const int lane = threadIdx.x & 31;
   const int t8 = lane & 7, part = lane >> 3;
   const size_t plane = (size_t)pool_pages * page_stride;
   const float* const vbase = kbase + plane;
+  stage += 16u * (uint32_t)lane;   // this lane's slots: K chunk k at + 512 k, V chunk k at + 3072 + 512 k
   int win = 0;   // pt0 / pt1 hold page-table entries [64 win, 64 win + 64); contexts beyond 1024 tokens reload the window
   auto half_at = [&](int hp) -> uint32_t {   // warp-uniform argument: element offset of half page hp of this head
     const int pidx = hp >> 1;
@@ -629,76 +639,95 @@ __device__ __noinline__ void cd_attention_f32_warp(const float* kbase, int pt0, 
     const int a = __shfl_sync(0xffffffffu, pt0, pidx & 31), c = __shfl_sync(0xffffffffu, pt1, pidx & 31);
     return (uint32_t)((pidx & 32) ? c : a) * page_stride + (uint32_t)(hp & 1) * (8 * HD);
   };
-  // the new token's k / v rows join the cache unrounded (fp32): lanes 0-23 append one float4 each
+  const int halves = (T + 7) >> 3;
+  uint4 kr[6], vr[6];
+  auto request_regs = [&](int hp) {
+    const uint32_t pg = half_at(hp);   // past the end: entry 0 = a mapped page, never consumed
+#pragma unroll
+    for (int k = 0; k < 6; ++k) kr[k] = cd_ld_stream_f32(kbase + pg + 128 * k);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) vr[k] = cd_ld_stream_f32(vbase + pg + 128 * k);
+  };
+  auto request_smem = [&](int hp) {
+    const uint32_t pg = half_at(hp);
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage + 512u * k), "l"(kbase + pg + 128 * k) : "memory");
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage + 3072u + 512u * k), "l"(vbase + pg + 128 * k) : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  request_regs(0);
+  request_smem(1);
+  // the new token's k / v rows join the cache unrounded (fp32): lanes 0-23 append one float4 each (dims 4 lane .. + 4)
   {
-    const uint32_t o = half_at((T >> 4) << 1) + (uint32_t)(T & 15) * HD;
+    const int tn = T & 15;
+    const uint32_t o = half_at((T >> 4) << 1) - (uint32_t)(4 * lane) + kv_tile_offset<float, HD>(tn, 4 * lane);
     if (lane < HD / 4) {
       *reinterpret_cast<float4*>(const_cast<float*>(kbase) + o) = *reinterpret_cast<const float4*>(qkv + HD + 4 * lane);
       *reinterpret_cast<float4*>(const_cast<float*>(vbase) + o) = *reinterpret_cast<const float4*>(qkv + 2 * HD + 4 * lane);
     }
   }
   const float scale = 0.10206207261596577f;   // 96^-0.5
-  // staging offsets (floats) of this lane's six 16-byte chunks of a half page: chunk 32k + lane -> token chunk / 24, column chunk % 24
-  uint32_t soff[6];
-#pragma unroll
-  for (int k = 0; k < 6; ++k) soff[k] = (uint32_t)(((32 * k + lane) / 24) * PITCH + ((32 * k + lane) % 24) * 4);
   const float* const qp = qkv + 24 * part;
-  const float* const krow = tile + t8 * PITCH + 24 * part;
-  float m = -INFINITY, l = 0.f, acc0 = 0.f, acc1 = 0.f, acc2 = 0.f;
-  uint4 kr[6], vr[6];
-  const int halves = (T + 7) >> 3;
-  uint32_t pg = half_at(0);
+  float m = -INFINITY, l = 0.f, acc[24];
 #pragma unroll
-  for (int k = 0; k < 6; ++k) kr[k] = cd_ld_stream_f32(kbase + pg + 128 * k);
-#pragma unroll 1
-  for (int hp = 0; hp < halves; ++hp) {
-#pragma unroll
-    for (int k = 0; k < 6; ++k) vr[k] = cd_ld_stream_f32(vbase + pg + 128 * k);
-    // ---- scores of the 8 tokens
-#pragma unroll
-    for (int k = 0; k < 6; ++k) *reinterpret_cast<uint4*>(tile + soff[k]) = kr[k];
-    __syncwarp();
+  for (int i = 0; i < 24; ++i) acc[i] = 0.f;
+  // FROM_SMEM: the half page sits in this lane's slots (cp.async group complete), else in kr / vr
+  auto absorb = [&](int hp, auto from_smem) {
+    constexpr bool FS = decltype(from_smem)::value;
+    auto chunk = [&](uint32_t off, const uint4& r) -> float4 {
+      if constexpr (FS) {
+        float4 v;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(stage + off));
+        return v;
+      } else {
+        return make_float4(__uint_as_float(r.x), __uint_as_float(r.y), __uint_as_float(r.z), __uint_as_float(r.w));
+      }
+    };
     float s = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 6; i += 2) {
-      const float4 a = *reinterpret_cast<const float4*>(krow + 4 * i), b = *reinterpret_cast<const float4*>(qp + 4 * i);
-      const float4 c = *reinterpret_cast<const float4*>(krow + 4 * i + 4), d = *reinterpret_cast<const float4*>(qp + 4 * i + 4);
-      s = fmaf(a.x, b.x, s); s = fmaf(a.y, b.y, s); s = fmaf(a.z, b.z, s); s = fmaf(a.w, b.w, s);
-      s2 = fmaf(c.x, d.x, s2); s2 = fmaf(c.y, d.y, s2); s2 = fmaf(c.z, d.z, s2); s2 = fmaf(c.w, d.w, s2);
+    for (int k = 0; k < 6; k += 2) {
+      const float4 a = *reinterpret_cast<const float4*>(qp + 4 * k), b = *reinterpret_cast<const float4*>(qp + 4 * k + 4);
+      const float4 x = chunk(512u * k, kr[k]), y = chunk(512u * (k + 1), kr[k + 1]);
+      s = fmaf(x.x, a.x, s); s = fmaf(x.y, a.y, s); s = fmaf(x.z, a.z, s); s = fmaf(x.w, a.w, s);
+      s2 = fmaf(y.x, b.x, s2); s2 = fmaf(y.y, b.y, s2); s2 = fmaf(y.z, b.z, s2); s2 = fmaf(y.w, b.w, s2);
     }
     s += s2;
     s += __shfl_xor_sync(0xffffffffu, s, 8);
     s += __shfl_xor_sync(0xffffffffu, s, 16);
-    __syncwarp();
-    pg = half_at(hp + 1);   // past the end: entry 0 = a mapped page, never consumed
-#pragma unroll
-    for (int k = 0; k < 6; ++k) kr[k] = cd_ld_stream_f32(kbase + pg + 128 * k);
-    // ---- online softmax over the 8 tokens (select, not arithmetic, for rows >= T: they may hold anything)
-    s = (8 * hp + t8 < T) ? s * scale : -INFINITY;
+    // online softmax over the 8 tokens (select, not arithmetic, for rows >= T: they may hold anything)
+    const bool valid = 8 * hp + t8 < T;
+    s = valid ? s * scale : -INFINITY;
     float mx = s;
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
     mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 4));
     const float mn = fmaxf(m, mx);   // finite: token 8 hp < T
     const float corr = expf(m - mn), p = expf(s - mn);
-    l = l * corr + p;   // per-token partial (4 copies per token), merged at the end over lanes 0-7
+    l = l * corr + p;   // per-token-slot partial (4 copies per slot), merged at the end over the 8 token lanes
     m = mn;
-    // ---- P V
 #pragma unroll
-    for (int k = 0; k < 6; ++k) *reinterpret_cast<uint4*>(tile + soff[k]) = vr[k];
-    __syncwarp();
-    acc0 *= corr; acc1 *= corr; acc2 *= corr;
-    const int cnt = min(8, T - 8 * hp);   // warp-uniform: rows past T are never read
-#pragma unroll 1
-    for (int t = 0; t < cnt; ++t) {
-      const float pt = __shfl_sync(0xffffffffu, p, t);
-      const float* vrow = tile + t * PITCH + lane;
-      acc0 = fmaf(pt, vrow[0], acc0);
-      acc1 = fmaf(pt, vrow[32], acc1);
-      acc2 = fmaf(pt, vrow[64], acc2);
+    for (int k = 0; k < 6; ++k) {
+      float4 v = chunk(3072u + 512u * k, vr[k]);
+      if (!valid) v = make_float4(0.f, 0.f, 0.f, 0.f);   // 0 x (whatever the pool holds past T) must stay 0
+      acc[4 * k + 0] = fmaf(acc[4 * k + 0], corr, p * v.x);
+      acc[4 * k + 1] = fmaf(acc[4 * k + 1], corr, p * v.y);
+      acc[4 * k + 2] = fmaf(acc[4 * k + 2], corr, p * v.z);
+      acc[4 * k + 3] = fmaf(acc[4 * k + 3], corr, p * v.w);
     }
-    __syncwarp();
+  };
+#pragma unroll 1
+  for (int hp = 0; hp < halves; hp += 2) {
+    absorb(hp, std::false_type());
+    if (hp + 1 >= halves) break;
+    request_regs(hp + 2);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    absorb(hp + 1, std::true_type());
+    request_smem(hp + 3);   // after this lane's reads of its slots (program order)
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");   // nothing may land in A1 | A2 once the LN2 gather can start
   // the new token: q . k_new over lanes 0-23 (4 dims each) + warp sum
   float sc = 0.f;
   if (lane < HD / 4) {
@@ -706,17 +735,39 @@ __device__ __noinline__ void cd_attention_f32_warp(const float* kbase, int pt0, 
     sc = fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
   }
   sc = warp_sum(sc) * scale;
+  // merge the eight token slots: every lane's (m, l, acc) is relative to the same running maximum m (warp-uniform)
   l += __shfl_xor_sync(0xffffffffu, l, 1);
   l += __shfl_xor_sync(0xffffffffu, l, 2);
   l += __shfl_xor_sync(0xffffffffu, l, 4);
+  float r12[12], r6[6], r3[3];
+  {
+    const bool up = (t8 & 4) != 0;   // keeps the upper half of its 24 dims
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+      const float send = up ? acc[i] : acc[12 + i], keep = up ? acc[12 + i] : acc[i];
+      r12[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    const bool up2 = (t8 & 2) != 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+      const float send = up2 ? r12[i] : r12[6 + i], keep = up2 ? r12[6 + i] : r12[i];
+      r6[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    const bool up1 = (t8 & 1) != 0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const float send = up1 ? r6[i] : r6[3 + i], keep = up1 ? r6[3 + i] : r6[i];
+      r3[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+  }
   const float mn = fmaxf(m, sc);
   const float corr = expf(m - mn), pn = expf(sc - mn);
   l = l * corr + pn;
   const float inv = 1.0f / l;
-  const float* vn = qkv + 2 * HD + lane;
-  yst[lane] = (acc0 * corr + pn * vn[0]) * inv;
-  yst[lane + 32] = (acc1 * corr + pn * vn[32]) * inv;
-  yst[lane + 64] = (acc2 * corr + pn * vn[64]) * inv;
+  // lane holds dims 24 part + 12 b2 + 6 b1 + 3 b0 + i = 3 lane + i
+  const float* vn = qkv + 2 * HD + 3 * lane;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) yst[3 * lane + i] = (r3[i] * corr + pn * vn[i]) * inv;
   __syncwarp();
 }
 
@@ -1098,7 +1149,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
               float* yst = reinterpret_cast<float*>(sgen + G::OFF_YST) + ww * CD_HD;
               if (n < nloc) {   // warp-uniform
                 cd_attention_f32_warp(cd_attention_kbase_f32(reinterpret_cast<const float*>(P.kv), P.pool_pages, l, head), pt0, pt1,
-                                      pt, n_pages, P.pool_pages, sm_t[n], qkvb + ww * 288, reinterpret_cast<float*>(sgen + G::OFF_A1 + ww * G::ATT_TILE), yst);
+                                      pt, n_pages, P.pool_pages, sm_t[n], qkvb + ww * 288, sbase + G::OFF_A1 + ww * G::ATT_TILE, yst);
                 const float4 f0 = *reinterpret_cast<const float4*>(yst + 8 * ch), f1 = *reinterpret_cast<const float4*>(yst + 8 * ch + 4);
                 const float f[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
                 cd_split8(f, val, val_lo);

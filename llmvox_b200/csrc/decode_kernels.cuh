@@ -199,8 +199,22 @@ __global__ void fold_dup_kernel(const float* __restrict__ Wt, const float* __res
 // softmax per group, merged through shared memory.  The new token's K/V come from the qkv GEMM output and
 // are appended to the cache here (the O(1) replacement of the reference's torch.cat, model.py:74-77).
 //
-// KV pool layout: [layer][k|v][page][head][page_tokens][HD], element type TKV.
+// KV pool layout: [layer][k|v][page][head][tile of page_tokens x HD elements], element type TKV.  Inside a tile the
+// bf16 pool is token-major ([token][dim]).  The fp32 pool (fp32 and exact precisions) is LANE-MAJOR per 8-token half page:
+// [half][k = 0..5][lane = 8 part + t8][4 floats] with token = 8 half + t8 and dim = 24 part + 4 k + e, so that the six
+// fully coalesced 512-byte loads a warp of the cluster kernel issues per half page land directly in the lane that
+// multiplies them (lane (t8, part) owns 24 dims of token t8: no shared-memory staging, cluster_decode.cuh).
 // ---------------------------------------------------------------------------------------------------
+template <typename TKV, int HD>
+__device__ __forceinline__ uint32_t kv_tile_offset(int t, int d) {
+  if constexpr (sizeof(TKV) == 4) {
+    static_assert(HD == 96, "lane-major fp32 KV tiles are laid out for head_dim 96");
+    const int part = d / 24, r = d - 24 * part;
+    return (uint32_t)((t >> 3) * (8 * HD) + (r >> 2) * 128 + ((part << 3) + (t & 7)) * 4 + (r & 3));
+  } else {
+    return (uint32_t)(t * HD + d);
+  }
+}
 template <typename TKV, typename TOut, int HD>
 __global__ void __launch_bounds__(128) decode_attention_kernel(const float* __restrict__ qkv, TKV* __restrict__ kv,
                                                                const int* __restrict__ slots, SessionState st,
@@ -239,12 +253,13 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const float* __re
   // append the new token (group 0 holds all HD dims across its 8 lanes)
   if (g == 0) {
     const int page = pt[T / page_tokens], off = T % page_tokens;
-    TKV* kd = kbase + (size_t)page * page_stride + (size_t)off * HD + sub * DPL;
-    TKV* vd = vbase + (size_t)page * page_stride + (size_t)off * HD + sub * DPL;
+    TKV* kd = kbase + (size_t)page * page_stride;
+    TKV* vd = vbase + (size_t)page * page_stride;
 #pragma unroll
     for (int i = 0; i < DPL; i += 4) {
-      store4(kd + i, make_float4(kn[i], kn[i + 1], kn[i + 2], kn[i + 3]));
-      store4(vd + i, make_float4(vn[i], vn[i + 1], vn[i + 2], vn[i + 3]));
+      const uint32_t o = kv_tile_offset<TKV, HD>(off, sub * DPL + i);
+      store4(kd + o, make_float4(kn[i], kn[i + 1], kn[i + 2], kn[i + 3]));
+      store4(vd + o, make_float4(vn[i], vn[i + 1], vn[i + 2], vn[i + 3]));
     }
   }
 
@@ -272,12 +287,13 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const float* __re
 
   for (int tok = g; tok < T; tok += NG) {
     const int page = pt[tok / page_tokens], off = tok % page_tokens;
-    const TKV* kp = kbase + (size_t)page * page_stride + (size_t)off * HD + sub * DPL;
-    const TKV* vp = vbase + (size_t)page * page_stride + (size_t)off * HD + sub * DPL;
+    const TKV* kp = kbase + (size_t)page * page_stride;
+    const TKV* vp = vbase + (size_t)page * page_stride;
     float kk[DPL], vv[DPL];
 #pragma unroll
     for (int i = 0; i < DPL; i += 4) {
-      const float4 a = load4(kp + i), c = load4(vp + i);
+      const uint32_t o = kv_tile_offset<TKV, HD>(off, sub * DPL + i);
+      const float4 a = load4(kp + o), c = load4(vp + o);
       kk[i] = a.x; kk[i + 1] = a.y; kk[i + 2] = a.z; kk[i + 3] = a.w;
       vv[i] = c.x; vv[i + 1] = c.y; vv[i + 2] = c.z; vv[i + 3] = c.w;
     }

@@ -544,6 +544,8 @@ extern "C" int lvx_engine_create(const lvx_config* cfg, int device, lvx_engine**
   LVX_CHECK(c.max_sessions > 0 && c.max_batch > 0 && c.max_batch <= c.max_sessions, LVX_ERR_INVALID, "bad session capacity");
   LVX_CHECK(c.max_context > 0 && c.max_context <= c.block_size, LVX_ERR_INVALID, "max_context must be <= block_size");
   LVX_CHECK(c.kv_page_tokens > 0 && c.max_vocode_frames > 0, LVX_ERR_INVALID, "bad capacity");
+  LVX_CHECK(c.precision == LVX_PRECISION_BF16 || c.kv_page_tokens % 8 == 0, LVX_ERR_INVALID,
+            "the fp32 KV pool is laid out in 8-token half pages: kv_page_tokens must be a multiple of 8");
   LVX_CHECK(c.voc_inter % 64 == 0 && c.code_dim % 64 == 0, LVX_ERR_INVALID, "voc_inter / code_dim must be multiples of 64");
   LVX_CHECK(c.precision == LVX_PRECISION_FP32 || c.precision == LVX_PRECISION_BF16 || c.precision == LVX_PRECISION_EXACT,
             LVX_ERR_INVALID, "bad precision");

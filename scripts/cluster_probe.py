@@ -58,12 +58,14 @@ def timed(n, lanes, iters=100, prefill=0):
 
 
 for n, lanes in [(16, 1), (1, 1), (64, 1), (64, 4), (128, 1), (128, 8), (256, 1)]:
-    if n > N:
+    if n > N or os.environ.get("PROBE_QUICK") == "1":
         continue
     print(f"n={n:4d} lanes={lanes}: {timed(n, lanes):8.1f} us/iter  T=20..120", flush=True)
-print(f"n={min(N, 64)} lanes=1 context 110..210: {timed(min(N, 64), 1, prefill=100):8.1f} us/iter", flush=True)
+if os.environ.get("PROBE_QUICK") != "1":
+    print(f"n={min(N, 64)} lanes=1 context 110..210: {timed(min(N, 64), 1, prefill=100):8.1f} us/iter", flush=True)
 if os.environ.get("PROBE_TRACE") == "1":
-    timed(16, 1, iters=50, prefill=50)
+    timed(int(os.environ.get("PROBE_TRACE_N", "16")), 1, iters=int(os.environ.get("PROBE_TRACE_ITERS", "50")),
+          prefill=int(os.environ.get("PROBE_TRACE_PREFILL", "50")))
     tr = e.peek_trace(250) if hasattr(e, "peek_trace") else None
     if tr is not None:
         t0 = tr[0]

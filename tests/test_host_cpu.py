@@ -183,7 +183,7 @@ def test_lane_runner_picks_the_decode_path_by_batch_size():
     r.HYBRID_ABOVE_MAX_BATCH = True                                # opt-in split of one call between both paths
     assert r.plan(256, greedy) == (224, 32)
     r.HYBRID_ABOVE_MAX_BATCH = False
-    assert r.plan(64, sampled) == (0, 64)                         # sampled decoding: sampler kernel of the per-op chain
+    assert r.plan(64, sampled) == (64, 0)                         # sampled decoding runs inside the cluster kernel too (S = 1)
     r.e.precision = "fp32"
     assert r.plan(64, greedy) == (0, 64)                          # fp32 parity mode: FMA-pipe GEMMs
     r.e.precision = "exact"

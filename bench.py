@@ -296,7 +296,11 @@ def measure(args, precision, streams, K, Wm, rank, local, world, sd, barrier, fi
     n_cluster, n_lanes = runner.plan(streams, None)
     path = []
     if n_cluster:
-        path.append("%d sessions on the cluster-resident kernel (%d clusters of 16 CTAs, waves of <= 7)" % (n_cluster, (n_cluster + 15) // 16))
+        w16, w8 = e.cluster_capacity()
+        if w8 and precision == "bf16" and n_cluster > w16:
+            path.append("%d sessions on the cluster-resident kernel (8-CTA clusters, %d co-resident per wave)" % (n_cluster, w8 // 16))
+        else:
+            path.append("%d sessions on the cluster-resident kernel (%d clusters of 16 CTAs, waves of <= %d)" % (n_cluster, (n_cluster + 15) // 16, max(1, w16 // 16)))
     if n_lanes:
         path.append("%d sessions on the kernel-per-op chain (%d lanes)" % (n_lanes, args.lanes))
     e.close()

@@ -126,8 +126,23 @@ int lvx_decode_steps_lane(lvx_engine* e, int lane, const int32_t* h_slots, int n
 #define LVX_PATH_AUTO 0
 #define LVX_PATH_CLUSTER 1
 #define LVX_PATH_PER_OP 2
+/* The cluster-resident kernel exists in two cuts of the same weights: 16-CTA clusters (lowest latency, one wave holds
+ * 7 x 16 sessions on a B200) and 8-CTA clusters (bf16 greedy only; one wave holds 15 x 16 sessions: the 256-streams
+ * operating point).  LVX_PATH_CLUSTER picks by batch size (16-CTA up to one wave of them, 8-CTA above); the two values
+ * below force one cut (an error when it does not apply).  Within a cut a session's codes do not depend on how calls are
+ * composed; across cuts they agree within the bf16 contract (teacher-forced logits within 2e-2), not bit for bit. */
+#define LVX_PATH_CLUSTER16 3
+#define LVX_PATH_CLUSTER8 4
+/* The kernel-per-op chain sized for the SMs a resident wave of 8-CTA clusters leaves free: the tail of a batch slightly
+ * larger than one wave (256 streams = 240 on the clusters + 16 here, at the same time). */
+#define LVX_PATH_PER_OP_TAIL 5
 int lvx_decode_steps_ex(lvx_engine* e, int lane, const int32_t* h_slots, int n, int n_steps, const lvx_sampling* s,
                         int path, void* stream);
+
+/* Sessions ONE wave of the cluster-resident kernel advances together: *wave16 for 16-CTA clusters, *wave8 for 8-CTA
+ * clusters (0 where the cut does not exist: fp32 precision has neither, exact precision only the first).  Host
+ * schedulers use it to size batches (streaming.py: LaneRunner.plan). */
+int lvx_cluster_capacity(lvx_engine* e, int32_t* wave16, int32_t* wave8);
 
 /* Per-session progress for the host's chunk scheduler (streaming_server.py:357-422): writes (eoa_pos, ctx_len) pairs
  * -- the position of the sentence's first end-of-audio code (eoa_token_id; -1 = none yet) and the codes decoded so far

@@ -11,7 +11,7 @@ LVX_OK = 0
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
 PRECISION_EXACT = 2
-PATH_AUTO, PATH_CLUSTER, PATH_PER_OP = 0, 1, 2
+PATH_AUTO, PATH_CLUSTER, PATH_PER_OP, PATH_CLUSTER16, PATH_CLUSTER8, PATH_PER_OP_TAIL = 0, 1, 2, 3, 4, 5
 
 
 class LvxConfig(C.Structure):
@@ -47,6 +47,7 @@ SYMBOLS = [
     ("lvx_decode_steps_ex", C.c_int, [_VP, C.c_int, _I32P, C.c_int, C.c_int, C.POINTER(LvxSampling), C.c_int, _VP]),
     ("lvx_session_progress", C.c_int, [_VP, _I32P, C.c_int, _VP, _VP]),
     ("lvx_set_cluster_decode", C.c_int, [_VP, C.c_int]),
+    ("lvx_cluster_capacity", C.c_int, [_VP, _I32P, _I32P]),
     ("lvx_decode_step_logits", C.c_int, [_VP, _I32P, C.c_int, C.POINTER(LvxSampling), _VP, _VP, _VP, _VP]),
     ("lvx_peek_buffer", C.c_int, [_VP, C.c_int, C.c_int, _VP, C.c_int64]),
     ("lvx_peek_trace", C.c_int, [_VP, C.c_int, C.POINTER(C.c_int64), C.c_int]),

@@ -38,13 +38,9 @@
 
 namespace lvx {
 
-constexpr int CD_CLUSTER = 16;
+constexpr int CD_CLUSTER = 16;                 // largest cluster (the latency variant); the throughput variant uses 8
 constexpr int CD_NB = 16;                      // sessions per cluster = UMMA N
 constexpr int CD_C = 768, CD_H = 8, CD_HD = 96, CD_FF = 3072, CD_V = 4096;
-constexpr int CD_XR = CD_C / CD_CLUSTER;       // 48
-constexpr int CD_QR = 3 * CD_C / CD_CLUSTER;   // 144
-constexpr int CD_FR = CD_FF / CD_CLUSTER;      // 192
-constexpr int CD_VR = CD_V / CD_CLUSTER;       // 256
 constexpr int CD_MAX_LAYERS = 8;
 constexpr int CD_SLOT = 16384;                 // bytes per ring slot (one 128-row x 64-column tile)
 constexpr int CD_NI = 2;                       // MMA issuer warps
@@ -57,62 +53,83 @@ constexpr int CD_NI = 2;                       // MMA issuer warps
 constexpr int CD_THREADS = 32 * (1 + CD_NI + 8);   // warp 0 producer, warps 1..CD_NI MMA issuers, then 8 worker warps
 constexpr int CD_WORKER0 = 32 * (1 + CD_NI);       // first worker thread
 constexpr int CD_WORKERS = 256;
-// Weight stream items (one bulk copy + one ring slot each, <= 16 KB so that 8 are in flight).  Per layer:
-//   qkv  : 12 x [128 rows x 64 k] (rows 0..127), then the 16-row tail as 3 x [4 k-blocks x 2 KB]
-//   proj : 6 x [2 k-blocks x 48 rows]
-//   fc   : 12 x [128 rows x 64 k], then the 64-row tail as 6 x [2 k-blocks x 8 KB]
-//   proj2: 18 x [128 rows x 64 k]  (row tile m = s / 3, k-block s % 3 of this CTA's k-slice)
-// then lm_head: 24 x [128 rows x 64 k] (k-block major; item j = row tile (j ^ (j >> 1)) & 1)
 constexpr int CD_TILE = 16384;
-constexpr int CD_QT = (CD_QR - 128) * 128;     // one k-block of the qkv tail (16 rows)
-constexpr int CD_PT = CD_XR * 128;             // one k-block of proj (48 rows)
-constexpr int CD_FT = (CD_FR - 128) * 128;     // one k-block of the fc tail (64 rows)
-constexpr long long CD_LAYER_BYTES = (long long)CD_QR * CD_C * 2 + (long long)CD_XR * CD_C * 2 + (long long)CD_FR * CD_C * 2 +
-                                     (long long)CD_C * CD_FR * 2;
-constexpr long long CD_LM_BYTES = (long long)CD_VR * CD_C * 2;
-// ---- geometry of the two variants.  X = 0: bf16 activations, UMMA N = 16 (one operand row per session).  X = 1 (exact
-// mode, LVX_PRECISION_EXACT): every activation operand row is a bf16 hi | lo pair -- rows [0, 16) of a k-block hold
-// hi = bf16(v), rows [16, 32) hold lo = bf16(v - hi) of the same sessions, UMMA N = 32, and the epilogues add the two
-// accumulator columns: w . hi + w . lo = w . v to 2^-18 |v| per element with exact bf16 x bf16 products and fp32
-// accumulation, i.e. fp32-class activations against the same 62.9 MB bf16 weight stream.  x travels between CTAs as the
-// two 16-bit halves of its fp32 word (lossless), the KV cache is fp32, attention runs on the FMA pipe in fp32.
-template <int X>
+// ---- geometry.  CL = CTAs per cluster.  CL = 16 is the LATENCY variant (every CTA streams 1/16 of the weights: shortest
+// iteration, at most 7 clusters = 112 sessions co-resident on a B200); CL = 8 is the THROUGHPUT variant (1/8 of the
+// weights per CTA, a whole attention head per CTA -- no q/k/v pair exchange --, 16+ clusters = 256+ sessions co-resident:
+// the 256-streams-per-GPU operating point in ONE wave).  Rank r of CL owns
+//   residual stream x[:, XR r .. +XR), XR = 768 / CL
+//   qkv rows: CL = 16: head r / 2, even r -> q (96) + k[0:48), odd r -> k[48:96) + v (96)   (QR = 144 rows)
+//             CL = 8 : head r, q | k | v                                                    (QR = 288 rows)
+//   proj rows [XR r, +XR); fc rows [FR r, +FR), FR = 3072 / CL; proj2 k-slice [FR r, +FR) for all 768 rows;
+//   lm_head rows [VR r, +VR), VR = 4096 / CL
+// Weight stream items (one bulk copy + one ring slot each, <= 16 KB).  Per layer:
+//   qkv  : Q_FULL x 12 x [128 rows x 64 k], then the Q_TAIL-row tail as 3 x [4 k-blocks]
+//   proj : 12 / P_PER x [P_PER k-blocks x XR rows]
+//   fc   : F_FULL x 12 x [128 rows x 64 k], then (CL = 16) the 64-row tail as 6 x [2 k-blocks x 8 KB]
+//   proj2: 6 x KS x [128 rows x 64 k]  (row tile m = s / KS, k-block s % KS of this CTA's k-slice)
+// then lm_head: 12 x NT_LM x [128 rows x 64 k] (k-block major; item j = row tile ((j % NT) + (j / NT)) % NT, so that a
+// tile's items alternate between the two issuers and each issuer's first item of a tile starts its accumulator copy).
+// X = 0: bf16 activations, UMMA N = 16 (one operand row per session).  X = 1 (exact mode, LVX_PRECISION_EXACT): every
+// activation operand row is a bf16 hi | lo pair -- rows [0, 16) of a k-block hold hi = bf16(v), rows [16, 32) hold
+// lo = bf16(v - hi) of the same sessions, UMMA N = 32, and the epilogues add the two accumulator columns: w . hi + w . lo
+// = w . v to 2^-18 |v| per element with exact bf16 x bf16 products and fp32 accumulation, i.e. fp32-class activations
+// against the same 62.9 MB bf16 weight stream.  x travels between CTAs as the two 16-bit halves of its fp32 word
+// (lossless), the KV cache is fp32, attention runs on the FMA pipe in fp32.
+template <int X, int CL = 16>
 struct CdG {
+  static_assert(CL == 16 || (CL == 8 && X == 0), "cluster sizes: 16 (bf16 and exact) or 8 (bf16)");
+  static constexpr int CLN = CL, XM = X;
+  static constexpr int XR = CD_C / CL, QR = 3 * CD_C / CL, FR = CD_FF / CL, VR = CD_V / CL;
   static constexpr int NCOL = X ? 32 : 16;        // UMMA N = operand rows per k-block
   static constexpr int ABLK = NCOL * 128;         // one 64-wide k-block of an activation operand
-  static constexpr int STAGES = X ? 6 : 8;        // weight ring depth (the larger operands of X = 1 take 30 KB of it)
+  static constexpr int STAGES = (X || CL == 8) ? 6 : 8;   // weight ring depth (what the operands leave of the shared memory)
   // Issuer w takes the ring items at positions = w (mod CD_NI).  The ring depth MUST be a multiple of CD_NI (see above).
   static_assert(STAGES % CD_NI == 0, "every ring slot must belong to exactly one issuer");
+  // stream items
+  static constexpr int Q_FULL = QR / 128, Q_TAIL = QR % 128, Q_PER = 4;     // 1 x 128 + 16 | 2 x 128 + 32
+  static constexpr int F_FULL = FR / 128, F_TAIL = FR % 128, F_PER = 2;     // 1 x 128 + 64 | 3 x 128
+  static constexpr int P_PER = (XR * 128 * 2 <= CD_SLOT) ? 2 : 1;           // proj k-blocks per item
+  static constexpr int KS = FR / 64;                                        // proj2 k-blocks of this CTA's k-slice
+  static constexpr int NT_LM = VR / 128;                                    // lm_head row tiles
+  static constexpr int QT = Q_TAIL * 128, PT = XR * 128, FT = F_TAIL * 128; // bytes of one k-block of the tails / of proj
+  static_assert(Q_PER * QT <= CD_SLOT && F_PER * FT <= CD_SLOT && P_PER * PT <= CD_SLOT, "items must fit a ring slot");
+  static constexpr long long LAYER_BYTES = (long long)QR * CD_C * 2 + (long long)XR * CD_C * 2 + (long long)FR * CD_C * 2 +
+                                           (long long)CD_C * FR * 2;
+  static constexpr long long LM_BYTES = (long long)VR * CD_C * 2;
   // TMEM accumulator columns.  CD_NI copies of every accumulator, TM_BANK columns apart, one per MMA issuer warp: issuer
   // w takes the ring items at positions = w (mod CD_NI), accumulating into its own copy, and the epilogue adds them.
   // With N = 16 a GEMM phase is bound by the issuing warp's serial per-item latency (barrier poll, fence, 4 MMAs, commit:
   // ~300 cycles per 16 KB item, measured; M = 64 instead of 128 changed it by only 13 %), not by the tensor pipe.
-  static constexpr int TM_QKV = 0, TM_PROJ = 2 * NCOL, TM_PROJ2 = 0, TM_FC = 6 * NCOL, TM_LM = 6 * NCOL, TM_BANK = 8 * NCOL,
-                       TM_COLS = CD_NI * TM_BANK;
-  static_assert(TM_COLS <= 512, "accumulator copies must fit TMEM");
+  static constexpr int F_TILES = F_FULL + (F_TAIL ? 1 : 0);
+  static constexpr int TM_QKV = 0, TM_PROJ = (Q_FULL + 1) * NCOL, TM_PROJ2 = 0, TM_FC = 6 * NCOL, TM_LM = 6 * NCOL,
+                       TM_BANK = (6 + (F_TILES > NT_LM ? F_TILES : NT_LM)) * NCOL, TM_COLS = CD_NI * TM_BANK,
+                       TM_ALLOC = TM_COLS <= 256 ? 256 : 512;
+  static_assert(TM_PROJ + NCOL <= 6 * NCOL && TM_COLS <= 512, "accumulator copies must fit TMEM");
   // shared-memory carve (offsets from the 1024-aligned base)
   static constexpr int OFF_RING = 0;
   static constexpr int OFF_A1 = OFF_RING + STAGES * CD_SLOT;            // [12 k-blocks][NCOL x 128 B]: LN(x) operand
-  static constexpr int OFF_A2 = OFF_A1 + (CD_C / 64) * ABLK;            // [3 k-blocks]: this CTA's GELU(fc) slice
-  static constexpr int OFF_RED = OFF_A2 + (CD_FR / 64) * ABLK;          // [16 src][4 session quads][48 rows] float4 proj2 partials
+  static constexpr int OFF_A2 = OFF_A1 + (CD_C / 64) * ABLK;            // [KS k-blocks]: this CTA's GELU(fc) slice
+  static constexpr int OFF_RED = OFF_A2 + KS * ABLK;                    // [CL src][4 session quads][XR rows] float4 proj2 partials
   // attention output operand of proj, aliases the partials: A1 cannot take it (a fast peer's LN2 gather would land in A1
   // while this CTA's proj MMAs still read y), and every store into one of the two uses is separated from the other's
   // reads by an exchange.  X = 1: 12 x 4 KB = the 48 KB of the partials exactly.
   static constexpr int OFF_AY = OFF_RED;
-  static constexpr int RED_BYTES = CD_CLUSTER * CD_XR * CD_NB * 4;
+  static constexpr int RED_BYTES = CL * XR * CD_NB * 4;
   static_assert((CD_C / 64) * ABLK <= RED_BYTES, "y operand must fit the partials buffer it aliases");
-  static constexpr int OFF_QKV = OFF_RED + RED_BYTES;                   // [8 sessions][q 96 | k 96 | v 96] fp32
-  static constexpr int OFF_XS = OFF_QKV + 8 * 288 * 4;                  // [16 sessions][48] fp32 residual slice
-  static constexpr int OFF_STATS = OFF_XS + CD_NB * CD_XR * 4;          // [16 src][16 sessions] (mean, M2)
-  static constexpr int OFF_CAND = OFF_STATS + CD_CLUSTER * CD_NB * 8;   // [16 src][16 sessions] (value, index)
-  static constexpr int OFF_YST = OFF_CAND + CD_CLUSTER * CD_NB * 8;     // [8 warps][96] attention output staging (bf16 / fp32)
+  static constexpr int ATT_SESS = CD_NB * CD_H / CL;                    // attention sessions per CTA: 8 | 16
+  static constexpr int OFF_QKV = OFF_RED + RED_BYTES;                   // [ATT_SESS sessions][q 96 | k 96 | v 96] fp32
+  static constexpr int OFF_XS = OFF_QKV + ATT_SESS * 288 * 4;           // [16 sessions][XR] fp32 residual slice
+  static constexpr int OFF_STATS = OFF_XS + CD_NB * XR * 4;             // [CL src][16 sessions] (mean, M2)
+  static constexpr int OFF_CAND = OFF_STATS + CL * CD_NB * 8;           // [CL src][16 sessions] (value, index)
+  static constexpr int OFF_YST = OFF_CAND + CL * CD_NB * 8;             // [8 warps][96] attention output staging (bf16 / fp32)
   static constexpr int OFF_SMALL = OFF_YST + 8 * CD_HD * (X ? 4 : 2);   // slot[16], t[16], code[16], wcand[8][8] x 8 B
   static constexpr int SMEM_BYTES = OFF_SMALL + 1024 + 1024;            // + alignment slack
   static_assert(SMEM_BYTES <= 232448 - 1024, "dynamic + static shared memory must fit one SM");
   // per-warp attention staging inside A1 | A2 (LN1(x) has been consumed by the qkv MMAs, the LN2 gather and the GELU
   // slice come later): X = 0 one tile of 16 tokens x 208 B, X = 1 the cp.async slots of one half page (K 3 KB | V 3 KB)
   static constexpr int ATT_TILE = X ? 6144 : 3328;   // X = 1: lane-private cp.async slots, K | V of one half page
-  static_assert(8 * ATT_TILE <= (CD_C / 64 + CD_FR / 64) * ABLK, "attention staging must fit A1 | A2");
+  static_assert(8 * ATT_TILE <= (CD_C / 64 + KS) * ABLK, "attention staging must fit A1 | A2");
 };
 
 struct ClusterParams {
@@ -237,8 +254,9 @@ __device__ __forceinline__ void cd_proxy_fence_cta() { asm volatile("fence.proxy
 __device__ __forceinline__ void cd_proxy_fence_cluster() { asm volatile("fence.proxy.async.shared::cluster;" ::: "memory"); }
 // 32 lanes x 8 consecutive fp32 columns (8 sessions) of the accumulator copies, summed; X = 1 also adds the columns of
 // the lo halves, 16 columns further on.  Fixed order: (issuer 0 hi + issuer 1 hi) + (issuer 0 lo + issuer 1 lo).
-template <int X>
+template <class G>
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+  constexpr int X = G::XM;
   constexpr int NP = X ? 2 : 1;
   uint32_t r[NP][CD_NI][8];
 #pragma unroll
@@ -248,7 +266,7 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
       asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                    : "=r"(r[h][j][0]), "=r"(r[h][j][1]), "=r"(r[h][j][2]), "=r"(r[h][j][3]), "=r"(r[h][j][4]), "=r"(r[h][j][5]),
                      "=r"(r[h][j][6]), "=r"(r[h][j][7])
-                   : "r"(taddr + (uint32_t)(CdG<X>::TM_BANK * j + CD_NB * h))
+                   : "r"(taddr + (uint32_t)(G::TM_BANK * j + CD_NB * h))
                    : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
@@ -368,42 +386,48 @@ __device__ __forceinline__ void cd_kblock(uint32_t d, uint32_t a, uint32_t b, ui
 #pragma unroll
   for (int ks = 0; ks < 4; ++ks) umma_bf16(d, da + (uint64_t)(2 * ks), db + (uint64_t)(2 * ks), idesc, (acc || ks) ? 1u : 0u);
 }
-template <int X>
+template <class G>
 __device__ __forceinline__ uint32_t cd_stage_wait(uint32_t sbase, uint32_t bars, unsigned gi) {
-  constexpr unsigned ST = CdG<X>::STAGES;
+  constexpr unsigned ST = G::STAGES;
   cd_wait(cd_bar_full(bars, gi % ST), (gi / ST) & 1u);
   tc_fence_after();
-  return sbase + CdG<X>::OFF_RING + (gi % ST) * CD_SLOT;
+  return sbase + G::OFF_RING + (gi % ST) * CD_SLOT;
 }
-// `128 + tail`-row weight slice against the K = 768 operand `act`: 12 full tiles into `d`, then the tail rows
-// (tail_bytes per k-block, `per` k-blocks per item) into d + 16.  This warp takes the items at ring positions = par
-// (mod CD_NI) (d already points at its accumulator copy).  Returns the advanced ring position.
-template <int X>
+// `n_full x 128 + tail`-row weight slice against the K = 768 operand `act`: 12 full tiles per 128 rows into d, d + NCOL, ..,
+// then the tail rows (tail_bytes per k-block, `per` k-blocks per item; tail_bytes == 0: none) into d + n_full NCOL.  This
+// warp takes the items at ring positions = par (mod CD_NI) (d already points at its accumulator copy).  Returns the
+// advanced ring position.
+template <class G>
 __device__ __forceinline__ unsigned cd_mma_rowsplit(uint32_t sbase, uint32_t bars, uint32_t idesc, unsigned gi, unsigned par, uint32_t act,
-                                                    uint32_t d, int tail_bytes, int per) {
-  constexpr unsigned ST = CdG<X>::STAGES;
-  constexpr int ABLK = CdG<X>::ABLK, NCOL = CdG<X>::NCOL;
+                                                    uint32_t d, int n_full, int tail_bytes, int per) {
+  constexpr unsigned ST = G::STAGES;
+  constexpr int ABLK = G::ABLK, NCOL = G::NCOL;
 #pragma unroll 1
-  for (int kb = 0; kb < CD_C / 64; ++kb, ++gi) {
-    if (gi % CD_NI != par) continue;
-    const uint32_t a = cd_stage_wait<X>(sbase, bars, gi);
-    if (cd_elect()) {
-      cd_kblock(d, a, act + kb * ABLK, idesc, kb >= CD_NI ? 1u : 0u);   // each warp's first item of the tile starts its copy
-      umma_commit(cd_bar_empty(bars, gi % ST));
+  for (int t = 0; t < n_full; ++t) {
+#pragma unroll 1
+    for (int kb = 0; kb < CD_C / 64; ++kb, ++gi) {
+      if (gi % CD_NI != par) continue;
+      const uint32_t a = cd_stage_wait<G>(sbase, bars, gi);
+      if (cd_elect()) {
+        cd_kblock(d + NCOL * t, a, act + kb * ABLK, idesc, kb >= CD_NI ? 1u : 0u);   // each warp's first item of the tile starts its copy
+        umma_commit(cd_bar_empty(bars, gi % ST));
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
+  if (tail_bytes) {
 #pragma unroll 1
-  for (int kb = 0, it = 0; kb < CD_C / 64; kb += per, ++it, ++gi) {
-    if (gi % CD_NI != par) continue;
-    const uint32_t a = cd_stage_wait<X>(sbase, bars, gi);
-    if (cd_elect()) {
+    for (int kb = 0, it = 0; kb < CD_C / 64; kb += per, ++it, ++gi) {
+      if (gi % CD_NI != par) continue;
+      const uint32_t a = cd_stage_wait<G>(sbase, bars, gi);
+      if (cd_elect()) {
 #pragma unroll 1
-      for (int kk = 0; kk < per && kb + kk < CD_C / 64; ++kk)
-        cd_kblock(d + NCOL, a + kk * tail_bytes, act + (kb + kk) * ABLK, idesc, (it >= CD_NI || kk) ? 1u : 0u);
-      umma_commit(cd_bar_empty(bars, gi % ST));
+        for (int kk = 0; kk < per && kb + kk < CD_C / 64; ++kk)
+          cd_kblock(d + NCOL * n_full, a + kk * tail_bytes, act + (kb + kk) * ABLK, idesc, (it >= CD_NI || kk) ? 1u : 0u);
+        umma_commit(cd_bar_empty(bars, gi % ST));
+      }
+      __syncwarp();
     }
-    __syncwarp();
   }
   if (cd_elect()) umma_commit(cd_bar_tmem(bars));
   __syncwarp();
@@ -772,14 +796,15 @@ __device__ __noinline__ void cd_attention_f32_warp(const float* kbase, int pt0, 
 }
 
 // text-table elements (features below text_dim), position-row elements and the text row's sum of squares for position t
-__device__ __forceinline__ void cd_prefetch_text(const ClusterParams& P, int slot, int t, int rank, int wt, float (&e)[3], float (&pe)[3],
-                                                 float& ss) {
+template <int XR>
+__device__ __forceinline__ void cd_prefetch_text(const ClusterParams& P, int slot, int t, int rank, int wt, float (&e)[XR / 16],
+                                                 float (&pe)[XR / 16], float& ss) {
   int text_id = P.pad_id;
   if (t < P.st.text_len[slot]) text_id = P.st.text_ids[(size_t)slot * P.st.max_context + t];
   ss = __ldg(P.text_ss + text_id);
 #pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    const int f = CD_XR * rank + (wt & 15) + 16 * i;
+  for (int i = 0; i < XR / 16; ++i) {
+    const int f = XR * rank + (wt & 15) + 16 * i;
     e[i] = f < P.text_dim ? __ldg(P.text_table + (size_t)text_id * P.text_dim + f) : 0.f;
     pe[i] = __ldg(P.wpe + (size_t)t * CD_C + f);
   }
@@ -793,9 +818,11 @@ struct CdWorkersSync {
   __device__ __forceinline__ void operator()() const { cd_workers_sync(); }
 };
 
-template <int X, int S>
+template <int X, int S, int CL>
 __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __grid_constant__ ClusterParams P) {
-  using G = CdG<X>;
+  using G = CdG<X, CL>;
+  static_assert(CL == 16 || S == 0, "the 8-CTA variant is greedy-only");
+  constexpr int XR = G::XR, QR = G::QR, FR = G::FR, VR = G::VR, XF = XR / 16;
   extern __shared__ uint8_t smem_raw[];
   // barriers [0, 26) + status words [32, 40) (progress of each role, dumped by a timed-out spin); 512-byte aligned so that
   // cd_timeout finds the block from any barrier address
@@ -805,7 +832,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform for the compiler
   const int rank = (int)cluster_ctarank();
-  const int cid = (int)blockIdx.x / CD_CLUSTER;
+  const int cid = (int)blockIdx.x / CL;
   const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const sgen = smem_raw + (sbase - smem_u32(smem_raw));
   const uint32_t bars = smem_u32(bars_sh);
@@ -819,14 +846,14 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
     }
     mbar_init(cd_bar_act(bars), 1);
     mbar_init(cd_bar_tmem(bars), CD_NI);   // one commit per MMA issuer warp
-    mbar_init(cd_bar_x(bars, 0), CD_CLUSTER);
-    mbar_init(cd_bar_x(bars, 1), CD_CLUSTER);
-    for (unsigned m = 0; m < 6; ++m) mbar_init(cd_bar_tile(bars, m), 3);   // one commit per k-block item of the tile
+    mbar_init(cd_bar_x(bars, 0), CL);
+    mbar_init(cd_bar_x(bars, 1), CL);
+    for (unsigned m = 0; m < 6; ++m) mbar_init(cd_bar_tile(bars, m), G::KS);   // one commit per k-block item of the tile
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
     __syncwarp();
-    tmem_alloc(smem_u32(&tmem_base_sh), G::TM_COLS);
+    tmem_alloc(smem_u32(&tmem_base_sh), G::TM_ALLOC);
   }
   if (warp > CD_NI) {   // session scalars of this cluster
     const int wt = tid - CD_WORKER0;
@@ -848,8 +875,9 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
     // ------------------------------------------------------------------ weight producer: free-running bulk copies
     {
       // (items, bytes) runs of the stream: 7 per layer, then lm_head
-      const int run_count[8] = {12, 3, 0, 6, 12, 6, 18, 24};
-      const int run_bytes[8] = {CD_TILE, 4 * CD_QT, 0, 2 * CD_PT, CD_TILE, 2 * CD_FT, CD_TILE, CD_TILE};
+      const int run_count[8] = {12 * G::Q_FULL, 12 / G::Q_PER, 0, 12 / G::P_PER, 12 * G::F_FULL, G::F_TAIL ? 12 / G::F_PER : 0, 6 * G::KS,
+                                12 * G::NT_LM};
+      const int run_bytes[8] = {CD_TILE, G::Q_PER * G::QT, 0, G::P_PER * G::PT, CD_TILE, G::F_PER * G::FT, CD_TILE, CD_TILE};
       const uint8_t* const src0 = P.wstream + (size_t)rank * (size_t)P.stream_bytes;
       // the stream is re-read every iteration by every cluster: keep it in L2 (measured: evict_first is 3 % slower)
       const uint64_t policy = cd_policy_evict_last();
@@ -898,11 +926,12 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
           tc_fence_after();
           if (sl == 2 * n_layer) {
 #pragma unroll 1
-            for (int j = 0; j < 24; ++j, ++gi) {   // lm_head: k-block j / 2, row tile (j ^ (j >> 1)) & 1: a tile's items alternate issuers
+            for (int j = 0; j < 12 * G::NT_LM; ++j, ++gi) {   // lm_head: k-block j / NT, row tile (j % NT + j / NT) % NT: a tile's items alternate issuers
               if (gi % CD_NI != par) continue;
-              const uint32_t a = cd_stage_wait<X>(sbase, bars, gi);
+              const uint32_t a = cd_stage_wait<G>(sbase, bars, gi);
               if (cd_elect()) {
-                cd_kblock(tm + G::TM_LM + G::NCOL * ((j ^ (j >> 1)) & 1), a, a1 + (j >> 1) * G::ABLK, idesc, j >= 2 * CD_NI ? 1u : 0u);
+                cd_kblock(tm + G::TM_LM + G::NCOL * (((j % G::NT_LM) + (j / G::NT_LM)) % G::NT_LM), a, a1 + (j / G::NT_LM) * G::ABLK, idesc,
+                          j >= G::NT_LM * CD_NI ? 1u : 0u);
                 umma_commit(cd_bar_empty(bars, gi % G::STAGES));
               }
               __syncwarp();
@@ -910,18 +939,18 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
             if (cd_elect()) umma_commit(cd_bar_tmem(bars));
             __syncwarp();
           } else if (!(sl & 1)) {
-            gi = cd_mma_rowsplit<X>(sbase, bars, idesc, gi, par, a1, tm + G::TM_QKV, CD_QT, 4);
+            gi = cd_mma_rowsplit<G>(sbase, bars, idesc, gi, par, a1, tm + G::TM_QKV, G::Q_FULL, G::QT, G::Q_PER);
             CD_STATUS(warp, (iter << 8) | sl | 0x80, (g << 16) | (gi & 0xffffu));
             cd_wait(cd_bar_act(bars), g & 1u);   // attention output operand ready
             g += 1;
             tc_fence_after();
 #pragma unroll 1
-            for (int j = 0; j < 6; ++j, ++gi) {   // proj: 2 k-blocks of 48 rows per item
+            for (int j = 0; j < 12 / G::P_PER; ++j, ++gi) {   // proj: P_PER k-blocks of XR rows per item
               if (gi % CD_NI != par) continue;
-              const uint32_t a = cd_stage_wait<X>(sbase, bars, gi);
+              const uint32_t a = cd_stage_wait<G>(sbase, bars, gi);
               if (cd_elect()) {
-                cd_kblock(tm + G::TM_PROJ, a, ay + (2 * j) * G::ABLK, idesc, j >= CD_NI ? 1u : 0u);
-                cd_kblock(tm + G::TM_PROJ, a + CD_PT, ay + (2 * j + 1) * G::ABLK, idesc, 1u);
+                cd_kblock(tm + G::TM_PROJ, a, ay + (G::P_PER * j) * G::ABLK, idesc, j >= CD_NI ? 1u : 0u);
+                if constexpr (G::P_PER == 2) cd_kblock(tm + G::TM_PROJ, a + G::PT, ay + (2 * j + 1) * G::ABLK, idesc, 1u);
                 umma_commit(cd_bar_empty(bars, gi % G::STAGES));
               }
               __syncwarp();
@@ -929,16 +958,16 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
             if (cd_elect()) umma_commit(cd_bar_tmem(bars));
             __syncwarp();
           } else {
-            gi = cd_mma_rowsplit<X>(sbase, bars, idesc, gi, par, a1, tm + G::TM_FC, CD_FT, 2);
+            gi = cd_mma_rowsplit<G>(sbase, bars, idesc, gi, par, a1, tm + G::TM_FC, G::F_FULL, G::FT, G::F_PER);
             CD_STATUS(warp, (iter << 8) | sl | 0x80, (g << 16) | (gi & 0xffffu));
             cd_wait(cd_bar_act(bars), g & 1u);   // GELU(fc) slice ready
             g += 1;
             tc_fence_after();
 #pragma unroll 1
-            for (int s2 = 0; s2 < 18; ++s2, ++gi) {   // proj2: row tile m, k-block kb of this CTA's k-slice
+            for (int s2 = 0; s2 < 6 * G::KS; ++s2, ++gi) {   // proj2: row tile m, k-block kb of this CTA's k-slice
               if (gi % CD_NI != par) continue;
-              const int m = s2 / 3, kb = s2 - 3 * m;
-              const uint32_t a = cd_stage_wait<X>(sbase, bars, gi);
+              const int m = s2 / G::KS, kb = s2 - G::KS * m;
+              const uint32_t a = cd_stage_wait<G>(sbase, bars, gi);
               if (cd_elect()) {
                 cd_kblock(tm + G::TM_PROJ2 + G::NCOL * m, a, a2 + kb * G::ABLK, idesc, kb >= CD_NI ? 1u : 0u);
                 umma_commit(cd_bar_empty(bars, gi % G::STAGES));
@@ -962,32 +991,40 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
     int* const sm_code = sm_slot + 32;
     uint2* const wcand = reinterpret_cast<uint2*>(sgen + G::OFF_SMALL + 256);
     const uint32_t trow = tmem + ((uint32_t)(q * 32) << 16);
-    const int head = rank >> 1, odd = rank & 1;
+    // attention: CL = 16: head rank / 2, sessions [8 (rank & 1), +8), one per warp; CL = 8: head rank, all 16 sessions,
+    // warp ww takes sessions ww and ww + 8 one after the other
+    constexpr int APW = G::ATT_SESS / 8;   // attention sessions per warp
+    const int head = CL == 16 ? rank >> 1 : rank, odd = CL == 16 ? (rank & 1) : 0;
     unsigned xphase = 0, gcount = 0;
     long long* trp = nullptr;
-    float pre_e[3] = {0.f, 0.f, 0.f}, pre_pe[3] = {0.f, 0.f, 0.f}, pre_ss = 0.f;   // next iteration's text / position part
-    // page table of this warp's attention session (8 * odd + ww), whole launch: the host allocated every page the launch
-    // needs before it (lane i holds entries i and i + 32; unallocated entries read as page 0, a mapped page)
-    int pt0 = 0, pt1 = 0, n_pages = 0;
-    const int* pt = P.st.page_table;
-    {
-      const int n = 8 * odd + ww;
+    float pre_e[XF], pre_pe[XF], pre_ss = 0.f;   // next iteration's text / position part
+#pragma unroll
+    for (int i = 0; i < XF; ++i) pre_e[i] = pre_pe[i] = 0.f;
+    // page tables of this warp's attention sessions (8 odd + ww [, + 8]), whole launch: the host allocated every page the
+    // launch needs before it (lane i holds entries i and i + 32; unallocated entries read as page 0, a mapped page)
+    int pt0[APW], pt1[APW], n_pages[APW];
+    const int* pt[APW];
+#pragma unroll
+    for (int a = 0; a < APW; ++a) {
+      const int n = 8 * odd + ww + 8 * a;
+      pt0[a] = pt1[a] = n_pages[a] = 0;
+      pt[a] = P.st.page_table;
       if (n < nloc) {
-        pt = P.st.page_table + (size_t)sm_slot[n] * P.st.max_pages;
-        n_pages = ((sm_t[n] + n_iters - 1) >> 4) + 1;
-        pt0 = (lane < n_pages) ? __ldg(pt + lane) : 0;
-        pt1 = (lane + 32 < n_pages) ? __ldg(pt + lane + 32) : 0;
+        pt[a] = P.st.page_table + (size_t)sm_slot[n] * P.st.max_pages;
+        n_pages[a] = ((sm_t[n] + n_iters - 1) >> 4) + 1;
+        pt0[a] = (lane < n_pages[a]) ? __ldg(pt[a] + lane) : 0;
+        pt1[a] = (lane + 32 < n_pages[a]) ? __ldg(pt[a] + lane + 32) : 0;
       }
     }
 
     // Cluster barrier of the worker warps: everything this CTA's workers stored (locally or into peers) before it is
-    // visible to every peer's workers after it.  Two alternating mbarriers (count 16 = one arrival per peer): a fast
+    // visible to every peer's workers after it.  Two alternating mbarriers (count CL = one arrival per peer): a fast
     // peer's arrival for exchange p+1 can never complete a slow CTA's exchange p.
     auto exchange = [&](bool for_tensor_core) {
       if (for_tensor_core) cd_proxy_fence_cluster();
       cd_workers_sync();
       const uint32_t bar = cd_bar_x(bars, xphase & 1u);
-      if (wt < CD_CLUSTER) cd_mbar_arrive_remote(cd_mapa(bar, (uint32_t)wt));
+      if (wt < CL) cd_mbar_arrive_remote(cd_mapa(bar, (uint32_t)wt));
       cd_wait_cluster(bar, (xphase >> 1) & 1u);   // (a cta-scope acquire here is no faster and failed the parity test: measured)
       xphase += 1;
     };
@@ -1008,29 +1045,31 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
     for (int iter = 0; iter < n_iters; ++iter) {
       if (P.trace && cid == 0 && rank == 0 && wt == 0 && iter == n_iters - 1) trp = P.trace;
       CD_T();
-      {   // ---- input assembly (streaming_server.py:313-334, src/model.py:206-212): 48 features of every session.
+      {   // ---- input assembly (streaming_server.py:313-334, src/model.py:206-212): XR features of every session.
           // The text row, its norm and the position row only depend on t: they were fetched during the previous
           // iteration (pre_*); only the previous code's codebook row is looked up here.
         const int n = wt >> 4;
-        float v[3] = {0.f, 0.f, 0.f};
+        float v[XF];
+#pragma unroll
+        for (int i = 0; i < XF; ++i) v[i] = 0.f;
         if (n < nloc) {
           const int slot = sm_slot[n], t = sm_t[n];
-          if (iter == 0) cd_prefetch_text(P, slot, t, rank, wt, pre_e, pre_pe, pre_ss);
+          if (iter == 0) cd_prefetch_text<XR>(P, slot, t, rank, wt, pre_e, pre_pe, pre_ss);
           int prev = -1;
           if (t > 0) prev = iter > 0 ? sm_code[n] : P.st.codes[(size_t)slot * P.st.max_context + t - 1];
           const float ss = pre_ss + (prev >= 0 ? __ldg(P.code_ss + prev) : 0.f);
           const float inv = 1.0f / fmaxf(sqrtf(ss), 1e-8f);
 #pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const int f = CD_XR * rank + (wt & 15) + 16 * i;
+          for (int i = 0; i < XF; ++i) {
+            const int f = XR * rank + (wt & 15) + 16 * i;
             float e = pre_e[i];
             if (f >= P.text_dim) e = prev >= 0 ? __ldg(P.codebook + (size_t)prev * P.code_dim + (f - P.text_dim)) : 0.f;
             v[i] = e * inv + pre_pe[i];
           }
-          if (iter + 1 < n_iters) cd_prefetch_text(P, slot, t + 1, rank, wt, pre_e, pre_pe, pre_ss);   // lands during this iteration
+          if (iter + 1 < n_iters) cd_prefetch_text<XR>(P, slot, t + 1, rank, wt, pre_e, pre_pe, pre_ss);   // lands during this iteration
         }
 #pragma unroll
-        for (int i = 0; i < 3; ++i) xs[n * CD_XR + (wt & 15) + 16 * i] = v[i];
+        for (int i = 0; i < XF; ++i) xs[n * XR + (wt & 15) + 16 * i] = v[i];
       }
       CD_T();
 #pragma unroll 1
@@ -1039,33 +1078,42 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
         if (ww == 0) CD_STATUS(0, (iter << 8) | sl, (xphase << 16) | (gcount & 0xffffu));
         // ================= x all-gather + LayerNorm (src/model.py:29-38; weight folded into the GEMM) -> A1
         cd_workers_sync();   // xs complete
-        {   // partial statistics of sessions 2ww, 2ww+1 over this CTA's 48 features, one (mean, M2) pair to every peer.
-            // One pass: the two shuffle chains run side by side; M2 = sum(x^2) - 48 mean^2 over 48 fp32 values.
+        {   // partial statistics of sessions 2ww, 2ww+1 over this CTA's XR features, one (mean, M2) pair to every peer.
+            // One pass: the two shuffle chains run side by side; M2 = sum(x^2) - XR mean^2 over XR fp32 values.
           const int hw = lane >> 4, l16 = lane & 15, n = 2 * ww + hw;
-          const float* row = xs + n * CD_XR;
-          const float v0 = row[l16], v1 = row[l16 + 16], v2 = row[l16 + 32];
-          float s1 = v0 + v1 + v2, s2 = fmaf(v0, v0, fmaf(v1, v1, v2 * v2));
+          const float* row = xs + n * XR;
+          float vv[XF];
+#pragma unroll
+          for (int i = 0; i < XF; ++i) vv[i] = row[l16 + 16 * i];
+          float s1 = vv[0], s2 = vv[XF - 1] * vv[XF - 1];
+#pragma unroll
+          for (int i = 1; i < XF; ++i) {
+            s1 += vv[i];
+            s2 = fmaf(vv[XF - 1 - i], vv[XF - 1 - i], s2);
+          }
 #pragma unroll
           for (int o = 8; o > 0; o >>= 1) {
             s1 += __shfl_xor_sync(0xffffffffu, s1, o);
             s2 += __shfl_xor_sync(0xffffffffu, s2, o);
           }
-          const float mean = s1 * (1.0f / CD_XR);
-          const float m2 = fmaxf(s2 - (float)CD_XR * mean * mean, 0.f);
-          cd_st_remote_v2(cd_mapa(sbase + G::OFF_STATS + (uint32_t)((rank * CD_NB + n) * 8), (uint32_t)l16), __float_as_uint(mean),
-                          __float_as_uint(m2));
+          const float mean = s1 * (1.0f / XR);
+          const float m2 = fmaxf(s2 - (float)XR * mean * mean, 0.f);
+          if (l16 < CL)
+            cd_st_remote_v2(cd_mapa(sbase + G::OFF_STATS + (uint32_t)((rank * CD_NB + n) * 8), (uint32_t)l16), __float_as_uint(mean),
+                            __float_as_uint(m2));
         }
 #pragma unroll 1
-        for (int dd = 0; dd < 2; ++dd) {   // copies of the slice into the operand image of peers 2ww, 2ww+1: fp16 (X = 0), or
-                                           // the fp32 words as 16-bit halves in the hi / lo rows (X = 1: lossless)
-          const uint32_t rbase = cd_mapa(sbase + G::OFF_A1, (uint32_t)(2 * ww + dd));
+        for (int dd = 0; dd < CL / 8; ++dd) {   // copies of the slice into the operand image of peers (CL / 8) ww + dd: fp16 (X = 0),
+                                                // or the fp32 words as 16-bit halves in the hi / lo rows (X = 1: lossless)
+          const uint32_t rbase = cd_mapa(sbase + G::OFF_A1, (uint32_t)((CL / 8) * ww + dd));
 #pragma unroll
-          for (int i = 0; i < 3; ++i) {
-            const int item = lane + 32 * i, n = item / 6, ch = item - 6 * n;
-            const float4 f0 = *reinterpret_cast<const float4*>(xs + n * CD_XR + 8 * ch);
-            const float4 f1 = *reinterpret_cast<const float4*>(xs + n * CD_XR + 8 * ch + 4);
+          for (int i = 0; i < XR / 16; ++i) {
+            constexpr int CPS = XR / 8;   // 16-byte chunks per session
+            const int item = lane + 32 * i, n = item / CPS, ch = item - CPS * n;
+            const float4 f0 = *reinterpret_cast<const float4*>(xs + n * XR + 8 * ch);
+            const float4 f1 = *reinterpret_cast<const float4*>(xs + n * XR + 8 * ch + 4);
             const float f[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
-            const uint32_t a = rbase + cd_act_chunk<X>(n, CD_XR * rank + 8 * ch);
+            const uint32_t a = rbase + cd_act_chunk<X>(n, XR * rank + 8 * ch);
             if constexpr (X) {
               uint4 up, dn;
               cd_bits_split8(f, up, dn);
@@ -1079,21 +1127,21 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
         CD_T();
         exchange(true);
         CD_T();
-        {   // merge the 16 partials (Chan), normalise the gathered row in place
+        {   // merge the CL partials (Chan), normalise the gathered row in place
           const int n = wt >> 4;
           const float2* st = reinterpret_cast<const float2*>(sgen + G::OFF_STATS) + n;
           float mean = 0.f, m2 = 0.f, sq = 0.f;
 #pragma unroll
-          for (int r = 0; r < CD_CLUSTER; ++r) {
+          for (int r = 0; r < CL; ++r) {
             const float2 p = st[r * CD_NB];
             mean += p.x;
             m2 += p.y;
             sq = fmaf(p.x, p.x, sq);
           }
-          mean *= (1.0f / CD_CLUSTER);
-          // sum_r (mean_r - mean)^2 = sum_r mean_r^2 - 16 mean^2 (means of 48 values each: no cancellation issue at fp32)
-          const float dev = fmaxf(sq - (float)CD_CLUSTER * mean * mean, 0.f);
-          const float rstd = rsqrtf((m2 + (float)CD_XR * dev) * (1.0f / CD_C) + 1e-5f);
+          mean *= (1.0f / CL);
+          // sum_r (mean_r - mean)^2 = sum_r mean_r^2 - CL mean^2 (means of XR values each: no cancellation issue at fp32)
+          const float dev = fmaxf(sq - (float)CL * mean * mean, 0.f);
+          const float rstd = rsqrtf((m2 + (float)XR * dev) * (1.0f / CD_C) + 1e-5f);
           const float shift = -mean * rstd;
 #pragma unroll 2
           for (int i = 0; i < 6; ++i) {
@@ -1116,31 +1164,37 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
         CD_T();
         if (sl == 2 * n_layer) break;
         if (!(sl & 1)) {
-          // ================= qkv epilogue: rows to the CTA of the pair that owns the session's attention
+          // ================= qkv epilogue: rows to the CTA that owns the session's attention (CL = 16: of the pair; CL = 8: this one)
           wait_acc();
           CD_T();
           {
-            const uint32_t dest = (uint32_t)((rank & ~1) + hh);
-            const uint32_t qb = cd_mapa(sbase + G::OFF_QKV, dest);
+            const uint32_t qb = CL == 16 ? cd_mapa(sbase + G::OFF_QKV, (uint32_t)((rank & ~1) + hh)) : 0u;
 #pragma unroll 1
-            for (int tile = 0; tile < 2; ++tile) {
-              if (tile == 1 && q != 0) break;
+            for (int tile = 0; tile <= G::Q_FULL; ++tile) {
+              if (tile == G::Q_FULL && 32 * q >= G::Q_TAIL) break;
               float v[8];
-              tmem_ld8<X>(trow + (uint32_t)(G::TM_QKV + G::NCOL * tile + 8 * hh), v);
+              tmem_ld8<G>(trow + (uint32_t)(G::TM_QKV + G::NCOL * tile + 8 * hh), v);
               const int lr = 128 * tile + 32 * q + lane;
-              if (lr < CD_QR) {
-                const uint32_t a = qb + (uint32_t)((CD_QR * odd + lr) * 4);
+              if (lr < QR) {
+                if constexpr (CL == 16) {
+                  const uint32_t a = qb + (uint32_t)((QR * odd + lr) * 4);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) cd_st_remote_f32(a + (uint32_t)(i * 288 * 4), v[i]);
+                  for (int i = 0; i < 8; ++i) cd_st_remote_f32(a + (uint32_t)(i * 288 * 4), v[i]);
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) qkvb[(8 * hh + i) * 288 + lr] = v[i];
+                }
               }
             }
           }
           tc_fence_before();
-          exchange(false);
+          if constexpr (CL == 16) exchange(false); else cd_workers_sync();
           CD_T();
-          // ================= attention: warp ww = session 8 * odd + ww of the group, head = rank / 2
-          {
-            const int n = 8 * odd + ww;
+          // ================= attention: warp ww = session 8 * odd + ww (+ 8) of the group, head = rank / 2 | rank
+#pragma unroll 1
+          for (int ai = 0; ai < APW; ++ai) {
+            const int n = 8 * odd + ww + 8 * ai;
+            const float* const qrow = qkvb + (ww + 8 * ai) * 288;
             uint4 val = make_uint4(0u, 0u, 0u, 0u), val_lo = make_uint4(0u, 0u, 0u, 0u);
             const int ch = lane % 12, d0 = (lane / 12) * 8;
             // per-warp staging tile inside A1 | A2 (LN1(x) has been consumed by the qkv MMAs, the LN2 gather and the GELU
@@ -1148,20 +1202,20 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
             if constexpr (X) {
               float* yst = reinterpret_cast<float*>(sgen + G::OFF_YST) + ww * CD_HD;
               if (n < nloc) {   // warp-uniform
-                cd_attention_f32_warp(cd_attention_kbase_f32(reinterpret_cast<const float*>(P.kv), P.pool_pages, l, head), pt0, pt1,
-                                      pt, n_pages, P.pool_pages, sm_t[n], qkvb + ww * 288, sbase + G::OFF_A1 + ww * G::ATT_TILE, yst);
+                cd_attention_f32_warp(cd_attention_kbase_f32(reinterpret_cast<const float*>(P.kv), P.pool_pages, l, head), pt0[ai], pt1[ai],
+                                      pt[ai], n_pages[ai], P.pool_pages, sm_t[n], qrow, sbase + G::OFF_A1 + ww * G::ATT_TILE, yst);
                 const float4 f0 = *reinterpret_cast<const float4*>(yst + 8 * ch), f1 = *reinterpret_cast<const float4*>(yst + 8 * ch + 4);
                 const float f[8] = {f0.x, f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, f1.w};
                 cd_split8(f, val, val_lo);
               }
             } else {
               if (n < nloc)   // warp-uniform
-                val = cd_attention_mma_warp(cd_attention_kbase(reinterpret_cast<bf16*>(P.kv), P.pool_pages, l, head), pt0, pt1, pt, n_pages,
-                                            P.pool_pages, sm_t[n], qkvb + ww * 288, sgen + G::OFF_A1 + ww * G::ATT_TILE,
+                val = cd_attention_mma_warp(cd_attention_kbase(reinterpret_cast<bf16*>(P.kv), P.pool_pages, l, head), pt0[ai], pt1[ai], pt[ai],
+                                            n_pages[ai], P.pool_pages, sm_t[n], qrow, sgen + G::OFF_A1 + ww * G::ATT_TILE,
                                             reinterpret_cast<uint32_t*>(sgen + G::OFF_YST) + ww * 48);
             }
-            // output row to every peer's y operand: lanes 0-11 / 12-23 hold the 12 chunks, 8 peers each
-            if (lane < 24) {
+            // output row to every peer's y operand: lanes 0-11 (/ 12-23) hold the 12 chunks, 8 peers each
+            if (lane < 12 * (CL / 8)) {
               const uint32_t off = sbase + G::OFF_AY + cd_act_chunk<X>(n, CD_HD * head + 8 * ch);
 #pragma unroll 1
               for (int d2 = 0; d2 < 8; ++d2) {
@@ -1175,16 +1229,16 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
           exchange(true);
           signal_act();
           CD_T();
-          // ================= proj epilogue: x += y W^T on the 48 owned features
+          // ================= proj epilogue: x += y W^T on the XR owned features
           wait_acc();
           CD_T();
-          if (q < 2) {
+          if (32 * q < XR) {
             float v[8];
-            tmem_ld8<X>(trow + (uint32_t)(G::TM_PROJ + 8 * hh), v);
+            tmem_ld8<G>(trow + (uint32_t)(G::TM_PROJ + 8 * hh), v);
             const int lr = 32 * q + lane;
-            if (lr < CD_XR) {
+            if (lr < XR) {
 #pragma unroll
-              for (int i = 0; i < 8; ++i) xs[(8 * hh + i) * CD_XR + lr] += v[i];
+              for (int i = 0; i < 8; ++i) xs[(8 * hh + i) * XR + lr] += v[i];
             }
           }
           tc_fence_before();
@@ -1193,10 +1247,10 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
           wait_acc();
           CD_T();
 #pragma unroll 1
-          for (int tile = 0; tile < 2; ++tile) {
-            if (tile == 1 && q >= 2) break;
+          for (int tile = 0; tile < G::F_TILES; ++tile) {
+            if (128 * tile + 32 * q >= FR) break;
             float v[8];
-            tmem_ld8<X>(trow + (uint32_t)(G::TM_FC + G::NCOL * tile + 8 * hh), v);
+            tmem_ld8<G>(trow + (uint32_t)(G::TM_FC + G::NCOL * tile + 8 * hh), v);
             const int j = 128 * tile + 32 * q + lane;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -1220,13 +1274,13 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
             cd_wait(cd_bar_tile(bars, (unsigned)m), (unsigned)(iter * n_layer + l) & 1u);
             tc_fence_after();
             float v[8];
-            tmem_ld8<X>(trow + (uint32_t)(G::TM_PROJ2 + G::NCOL * m + 8 * hh), v);
+            tmem_ld8<G>(trow + (uint32_t)(G::TM_PROJ2 + G::NCOL * m + 8 * hh), v);
             // partials buffer of the owner: [source rank][session quad][row] float4, so that the 32 lanes of a store
             // (consecutive rows) write 512 contiguous bytes (16-byte pieces at a 64-byte stride ran at 4 B / clock)
-            const int j = 128 * m + 32 * q + lane, owner = j / CD_XR, lr = j - owner * CD_XR;
-            const uint32_t base = cd_mapa(sbase + G::OFF_RED + (uint32_t)(((rank * 4 + 2 * hh) * CD_XR + lr) * 16), (uint32_t)owner);
+            const int j = 128 * m + 32 * q + lane, owner = j / XR, lr = j - owner * XR;
+            const uint32_t base = cd_mapa(sbase + G::OFF_RED + (uint32_t)(((rank * 4 + 2 * hh) * XR + lr) * 16), (uint32_t)owner);
             cd_st_remote_v4(base, make_uint4(__float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3])));
-            cd_st_remote_v4(base + (uint32_t)(CD_XR * 16),
+            cd_st_remote_v4(base + (uint32_t)(XR * 16),
                             make_uint4(__float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7])));
           }
           wait_acc();   // (already complete: keeps the accumulator barrier's phase in step)
@@ -1234,19 +1288,20 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
           CD_T();
           exchange(false);
           CD_T();
-          if (wt < 4 * CD_XR) {   // fixed source order: deterministic
-            const int c4 = wt / CD_XR, lr = wt - c4 * CD_XR;
-            const uint8_t* rp = sgen + G::OFF_RED + (c4 * CD_XR + lr) * 16;
+#pragma unroll 1
+          for (int idx = wt; idx < 4 * XR; idx += CD_WORKERS) {   // fixed source order: deterministic
+            const int c4 = idx / XR, lr = idx - c4 * XR;
+            const uint8_t* rp = sgen + G::OFF_RED + (c4 * XR + lr) * 16;
             float4 a = *reinterpret_cast<const float4*>(rp);
 #pragma unroll
-            for (int r = 1; r < CD_CLUSTER; ++r) {
-              const float4 t = *reinterpret_cast<const float4*>(rp + r * (4 * CD_XR * 16));
+            for (int r = 1; r < CL; ++r) {
+              const float4 t = *reinterpret_cast<const float4*>(rp + r * (4 * XR * 16));
               a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
             }
-            xs[(4 * c4 + 0) * CD_XR + lr] += a.x;
-            xs[(4 * c4 + 1) * CD_XR + lr] += a.y;
-            xs[(4 * c4 + 2) * CD_XR + lr] += a.z;
-            xs[(4 * c4 + 3) * CD_XR + lr] += a.w;
+            xs[(4 * c4 + 0) * XR + lr] += a.x;
+            xs[(4 * c4 + 1) * XR + lr] += a.y;
+            xs[(4 * c4 + 2) * XR + lr] += a.z;
+            xs[(4 * c4 + 3) * XR + lr] += a.w;
           }
         }
       }
@@ -1258,9 +1313,9 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
         // the sampler of the kernel-per-op path (decode_kernels.cuh: sample_pick) with its 8 worker warps and tells every
         // peer the code.  Same draws as sampler_kernel: Philox4x32-10(seed; slot, step).
         float v0[8], v1[8];
-        tmem_ld8<X>(trow + (uint32_t)(G::TM_LM + 8 * hh), v0);
-        tmem_ld8<X>(trow + (uint32_t)(G::TM_LM + G::NCOL + 8 * hh), v1);
-        const int row = CD_VR * rank + 32 * q + lane;
+        tmem_ld8<G>(trow + (uint32_t)(G::TM_LM + 8 * hh), v0);
+        tmem_ld8<G>(trow + (uint32_t)(G::TM_LM + G::NCOL + 8 * hh), v1);
+        const int row = VR * rank + 32 * q + lane;
 #pragma unroll 1
         for (int i = 0; i < 8; ++i) {
           const int n = 8 * hh + i;
@@ -1283,7 +1338,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
           const float u = philox_uniform(P.seed, (uint32_t)slot, (uint32_t)sm_t[rank]);
           const int code = sample_pick(reinterpret_cast<float*>(sgen + G::OFF_RED), CD_V, false, P.top_k, P.temperature, u, scr, wt,
                                        CdWorkersSync());
-          if (wt < CD_CLUSTER) cd_st_remote_v2(cd_mapa(sbase + G::OFF_CAND + (uint32_t)(rank * 8), (uint32_t)wt), 0u, (uint32_t)code);
+          if (wt < CL) cd_st_remote_v2(cd_mapa(sbase + G::OFF_CAND + (uint32_t)(rank * 8), (uint32_t)wt), 0u, (uint32_t)code);
         }
         exchange(false);
         if (wt < CD_NB) {
@@ -1301,21 +1356,32 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
         }
       } else {
       {
-          float v0[8], v1[8];
-          tmem_ld8<X>(trow + (uint32_t)(G::TM_LM + 8 * hh), v0);
-          tmem_ld8<X>(trow + (uint32_t)(G::TM_LM + G::NCOL + 8 * hh), v1);
-          const int row = CD_VR * rank + 32 * q + lane;
+          float v[G::NT_LM][8];
+#pragma unroll
+          for (int tl = 0; tl < G::NT_LM; ++tl) tmem_ld8<G>(trow + (uint32_t)(G::TM_LM + G::NCOL * tl + 8 * hh), v[tl]);
+          const int row = VR * rank + 32 * q + lane;
 #pragma unroll 1
           for (int i = 0; i < 8; ++i) {
+            float vi[G::NT_LM];
+#pragma unroll
+            for (int tl = 0; tl < G::NT_LM; ++tl) {   // (v[tl][i] with a runtime i: select, the rows stay in registers)
+              float x = v[tl][0];
+#pragma unroll
+              for (int k = 1; k < 8; ++k) x = (i == k) ? v[tl][k] : x;
+              vi[tl] = x;
+            }
             if (P.logits && iter == n_iters - 1 && 8 * hh + i < nloc) {   // only the launch's last iteration is ever read back
               float* lg = P.logits + (size_t)(n0 + 8 * hh + i) * CD_V + row;
-              lg[0] = v0[i];
-              lg[128] = v1[i];
+#pragma unroll
+              for (int tl = 0; tl < G::NT_LM; ++tl) lg[128 * tl] = vi[tl];
             }
-            const uint32_t k0 = cd_fkey(v0[i]), k1 = cd_fkey(v1[i]);
-            const uint32_t key = max(k0, k1);
+            uint32_t key = cd_fkey(vi[0]);
+#pragma unroll
+            for (int tl = 1; tl < G::NT_LM; ++tl) key = max(key, cd_fkey(vi[tl]));
             const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
-            const uint32_t idx = (k0 == kmax) ? (uint32_t)row : (k1 == kmax) ? (uint32_t)(row + 128) : 0xffffffffu;
+            uint32_t idx = 0xffffffffu;
+#pragma unroll
+            for (int tl = G::NT_LM - 1; tl >= 0; --tl) idx = (cd_fkey(vi[tl]) == kmax) ? (uint32_t)(row + 128 * tl) : idx;   // lowest row wins
             const uint32_t imin = __reduce_min_sync(0xffffffffu, idx);
             if (lane == 0) wcand[ww * 8 + i] = make_uint2(kmax, imin);
           }
@@ -1330,14 +1396,15 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
             const uint2 o = wcand[(4 * h2 + w) * 8 + i];
             if (o.x > b.x || (o.x == b.x && o.y < b.y)) b = o;
           }
-          cd_st_remote_v2(cd_mapa(sbase + G::OFF_CAND + (uint32_t)((rank * CD_NB + n) * 8), (uint32_t)(wt & 15)), b.x, b.y);
+          if ((wt & 15) < CL)
+            cd_st_remote_v2(cd_mapa(sbase + G::OFF_CAND + (uint32_t)((rank * CD_NB + n) * 8), (uint32_t)(wt & 15)), b.x, b.y);
         }
         exchange(false);
         if (wt < CD_NB) {
           const uint2* cand = reinterpret_cast<const uint2*>(sgen + G::OFF_CAND);
           uint2 b = cand[wt];
 #pragma unroll
-          for (int r = 1; r < CD_CLUSTER; ++r) {
+          for (int r = 1; r < CL; ++r) {
             const uint2 o = cand[r * CD_NB + wt];
             if (o.x > b.x || (o.x == b.x && o.y < b.y)) b = o;
           }
@@ -1365,7 +1432,7 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
   if (warp == 1) {
     __syncwarp();
     tc_fence_after();
-    tmem_dealloc(tmem, G::TM_COLS);
+    tmem_dealloc(tmem, G::TM_ALLOC);
   }
 }
 #undef CD_T
@@ -1408,79 +1475,111 @@ struct CdLayerW {
   int ld_qkv, ld_proj, ld_fc, ld_proj2;
   const float *ln1_w, *ln2_w;             // folded into the columns of qkv / fc
 };
-// descriptors of the whole stream (all ranks); returns bytes per rank
+// descriptors of the whole stream of a CL-CTA cluster (all ranks); returns bytes per rank
+template <int CL>
 inline long long cd_build_descs(const CdLayerW* layers, int n_layer, const float* lm_head, int ld_lm, const float* lnf_w,
                                 std::vector<CdPackDesc>* out) {
-  const long long per_rank = (long long)n_layer * CD_LAYER_BYTES + CD_LM_BYTES;
-  for (int r = 0; r < CD_CLUSTER; ++r) {
+  using G = CdG<0, CL>;   // the stream does not depend on the precision variant
+  const long long per_rank = (long long)n_layer * G::LAYER_BYTES + G::LM_BYTES;
+  for (int r = 0; r < CL; ++r) {
     long long o = (long long)r * per_rank;
-    const int h = r / 2, odd = r & 1;
     auto seg = [&](const float* src, const float* scale, int ld, int row0, int rows, int k0, long long off, int dst_row0) {
       out->push_back(CdPackDesc{src, scale, off, ld, row0, rows, k0, dst_row0});
     };
+    // qkv rows of this rank in stream order, as runs of the (3 C, C) matrix:
+    //   CL = 16: head r / 2; even r = q (96) + k[0:48), odd r = k[48:96) + v (96);  CL = 8: head r, q | k | v
+    int run0[3], runn[3], nrun;
+    if (CL == 16) {
+      const int h = r / 2, odd = r & 1;
+      run0[0] = odd ? CD_C + CD_HD * h + 48 : CD_HD * h;
+      runn[0] = odd ? 48 : 96;
+      run0[1] = odd ? 2 * CD_C + CD_HD * h : CD_C + CD_HD * h;
+      runn[1] = G::QR - runn[0];
+      nrun = 2;
+    } else {
+      for (int i = 0; i < 3; ++i) {
+        run0[i] = i * CD_C + CD_HD * r;
+        runn[i] = CD_HD;
+      }
+      nrun = 3;
+    }
+    // rows [lo, lo + cnt) of the rank's concatenated qkv rows -> destination rows [0, cnt) of the image at `off`
+    auto qkv_rows = [&](const CdLayerW& L, int lo, int cnt, int k0, long long off) {
+      int pos = 0, dst = 0;
+      for (int i = 0; i < nrun; ++i) {
+        const int a = std::max(lo, pos), b = std::min(lo + cnt, pos + runn[i]);
+        if (b > a) {
+          seg(L.qkv, L.ln1_w, L.ld_qkv, run0[i] + (a - pos), b - a, k0, off, dst);
+          dst += b - a;
+        }
+        pos += runn[i];
+      }
+    };
     for (int l = 0; l < n_layer; ++l) {
       const CdLayerW& L = layers[l];
-      // qkv rows of this rank in stream order: even = q(96) + k[0:48), odd = k[48:96) + v(96); first 128, then 16
-      const int s0 = odd ? CD_C + CD_HD * h + 48 : CD_HD * h, n_s0 = odd ? 48 : 96;
-      const int s1 = odd ? 2 * CD_C + CD_HD * h : CD_C + CD_HD * h;
+      for (int t = 0; t < G::Q_FULL; ++t)
+        for (int kb = 0; kb < 12; ++kb) {
+          qkv_rows(L, 128 * t, 128, 64 * kb, o);
+          o += CD_TILE;
+        }
       for (int kb = 0; kb < 12; ++kb) {
-        seg(L.qkv, L.ln1_w, L.ld_qkv, s0, n_s0, 64 * kb, o, 0);
-        seg(L.qkv, L.ln1_w, L.ld_qkv, s1, 128 - n_s0, 64 * kb, o, n_s0);
-        o += CD_TILE;
+        qkv_rows(L, 128 * G::Q_FULL, G::Q_TAIL, 64 * kb, o);
+        o += G::QT;
       }
       for (int kb = 0; kb < 12; ++kb) {
-        seg(L.qkv, L.ln1_w, L.ld_qkv, s1 + 128 - n_s0, CD_QR - 128, 64 * kb, o, 0);
-        o += CD_QT;
+        seg(L.proj, nullptr, L.ld_proj, G::XR * r, G::XR, 64 * kb, o, 0);
+        o += G::PT;
       }
-      for (int kb = 0; kb < 12; ++kb) {
-        seg(L.proj, nullptr, L.ld_proj, CD_XR * r, CD_XR, 64 * kb, o, 0);
-        o += CD_PT;
-      }
-      for (int kb = 0; kb < 12; ++kb) {
-        seg(L.fc, L.ln2_w, L.ld_fc, CD_FR * r, 128, 64 * kb, o, 0);
-        o += CD_TILE;
-      }
-      for (int kb = 0; kb < 12; ++kb) {
-        seg(L.fc, L.ln2_w, L.ld_fc, CD_FR * r + 128, CD_FR - 128, 64 * kb, o, 0);
-        o += CD_FT;
-      }
-      for (int s2 = 0; s2 < 18; ++s2) {
-        const int m = s2 / 3, kb = s2 % 3;
-        seg(L.proj2, nullptr, L.ld_proj2, 128 * m, 128, CD_FR * r + 64 * kb, o, 0);
+      for (int t = 0; t < G::F_FULL; ++t)
+        for (int kb = 0; kb < 12; ++kb) {
+          seg(L.fc, L.ln2_w, L.ld_fc, G::FR * r + 128 * t, 128, 64 * kb, o, 0);
+          o += CD_TILE;
+        }
+      if (G::F_TAIL)
+        for (int kb = 0; kb < 12; ++kb) {
+          seg(L.fc, L.ln2_w, L.ld_fc, G::FR * r + 128 * G::F_FULL, G::F_TAIL, 64 * kb, o, 0);
+          o += G::FT;
+        }
+      for (int s2 = 0; s2 < 6 * G::KS; ++s2) {
+        const int m = s2 / G::KS, kb = s2 % G::KS;
+        seg(L.proj2, nullptr, L.ld_proj2, 128 * m, 128, G::FR * r + 64 * kb, o, 0);
         o += CD_TILE;
       }
     }
-    for (int j = 0; j < 24; ++j) {   // k-block j / 2, row tile (j ^ (j >> 1)) & 1: a tile's items alternate between the two issuers
-      seg(lm_head, lnf_w, ld_lm, CD_VR * r + 128 * ((j ^ (j >> 1)) & 1), 128, 64 * (j >> 1), o, 0);
+    for (int j = 0; j < 12 * G::NT_LM; ++j) {   // k-block j / NT, row tile (j % NT + j / NT) % NT: a tile's items alternate between the two issuers
+      seg(lm_head, lnf_w, ld_lm, G::VR * r + 128 * (((j % G::NT_LM) + (j / G::NT_LM)) % G::NT_LM), 128, 64 * (j / G::NT_LM), o, 0);
       o += CD_TILE;
     }
   }
   return per_rank;
 }
 
-template <int X>
+template <int X, int CL>
 inline int cluster_decode_configure_x(int* max_clusters) {
-  cudaError_t err = cudaFuncSetAttribute(cluster_decode_kernel<X, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, CdG<X>::SMEM_BYTES);
-  if (err == cudaSuccess) err = cudaFuncSetAttribute(cluster_decode_kernel<X, 0>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-  if (err == cudaSuccess) err = cudaFuncSetAttribute(cluster_decode_kernel<X, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CdG<X>::SMEM_BYTES);
-  if (err == cudaSuccess) err = cudaFuncSetAttribute(cluster_decode_kernel<X, 1>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  using G = CdG<X, CL>;
+  cudaError_t err = cudaFuncSetAttribute(cluster_decode_kernel<X, 0, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(cluster_decode_kernel<X, 0, CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  if constexpr (CL == 16) {
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(cluster_decode_kernel<X, 1, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
+    if (err == cudaSuccess) err = cudaFuncSetAttribute(cluster_decode_kernel<X, 1, CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+  }
   if (err != cudaSuccess) {
     set_error(std::string("cudaFuncSetAttribute(cluster_decode): ") + cudaGetErrorString(err));
     return LVX_ERR_CUDA;
   }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(CD_CLUSTER * 8);
+  cfg.gridDim = dim3(CL * 32);
   cfg.blockDim = dim3(CD_THREADS);
-  cfg.dynamicSmemBytes = CdG<X>::SMEM_BYTES;
+  cfg.dynamicSmemBytes = G::SMEM_BYTES;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CD_CLUSTER;
+  attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   int mc = 0;
-  err = cudaOccupancyMaxActiveClusters(&mc, cluster_decode_kernel<X, 0>, &cfg);
+  err = cudaOccupancyMaxActiveClusters(&mc, cluster_decode_kernel<X, 0, CL>, &cfg);
   if (err != cudaSuccess) {
     cudaGetLastError();
     mc = 0;
@@ -1488,28 +1587,41 @@ inline int cluster_decode_configure_x(int* max_clusters) {
   *max_clusters = mc;
   return LVX_OK;
 }
-inline int cluster_decode_configure(bool exact, int* max_clusters) {
-  return exact ? cluster_decode_configure_x<1>(max_clusters) : cluster_decode_configure_x<0>(max_clusters);
+// co-resident clusters of the 16-CTA variant (max_clusters) and of the 8-CTA variant (max_clusters8; 0 = not built: exact)
+inline int cluster_decode_configure(bool exact, int* max_clusters, int* max_clusters8) {
+  *max_clusters8 = 0;
+  if (exact) return cluster_decode_configure_x<1, 16>(max_clusters);
+  int st = cluster_decode_configure_x<0, 16>(max_clusters);
+  if (st == LVX_OK) st = cluster_decode_configure_x<0, 8>(max_clusters8);
+  return st;
 }
 
-inline int cluster_decode_launch(bool exact, bool sampled, const ClusterParams& P, cudaStream_t st) {
+// cl = CTAs per cluster: 16, or 8 (bf16 greedy only)
+inline int cluster_decode_launch(bool exact, bool sampled, int cl, const ClusterParams& P, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(CD_CLUSTER * ceil_div(P.n, P.per_cluster));
+  cfg.gridDim = dim3(cl * ceil_div(P.n, P.per_cluster));
   cfg.blockDim = dim3(CD_THREADS);
-  cfg.dynamicSmemBytes = exact ? CdG<1>::SMEM_BYTES : CdG<0>::SMEM_BYTES;
+  cfg.dynamicSmemBytes = exact ? CdG<1, 16>::SMEM_BYTES : cl == 8 ? CdG<0, 8>::SMEM_BYTES : CdG<0, 16>::SMEM_BYTES;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CD_CLUSTER;
+  attr[0].val.clusterDim.x = cl;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t err;
-  if (exact)
-    err = sampled ? cudaLaunchKernelEx(&cfg, cluster_decode_kernel<1, 1>, P) : cudaLaunchKernelEx(&cfg, cluster_decode_kernel<1, 0>, P);
-  else
-    err = sampled ? cudaLaunchKernelEx(&cfg, cluster_decode_kernel<0, 1>, P) : cudaLaunchKernelEx(&cfg, cluster_decode_kernel<0, 0>, P);
+  if (cl == 8) {
+    if (exact || sampled) {
+      set_error("cluster_decode launch: the 8-CTA variant is bf16 greedy only");
+      return LVX_ERR_INVALID;
+    }
+    err = cudaLaunchKernelEx(&cfg, cluster_decode_kernel<0, 0, 8>, P);
+  } else if (exact) {
+    err = sampled ? cudaLaunchKernelEx(&cfg, cluster_decode_kernel<1, 1, 16>, P) : cudaLaunchKernelEx(&cfg, cluster_decode_kernel<1, 0, 16>, P);
+  } else {
+    err = sampled ? cudaLaunchKernelEx(&cfg, cluster_decode_kernel<0, 1, 16>, P) : cudaLaunchKernelEx(&cfg, cluster_decode_kernel<0, 0, 16>, P);
+  }
   if (err != cudaSuccess) {
     set_error(std::string("cluster_decode launch: ") + cudaGetErrorString(err));
     return LVX_ERR_CUDA;

@@ -210,6 +210,7 @@ struct lvx_engine {
     void *h = nullptr, *y = nullptr, *g = nullptr;
     float *yf = nullptr, *gf = nullptr;   // exact mode: fp32 attention output / fc output before the hi | lo split
     std::map<std::string, StepGraph> graphs;
+    int cta_budget = 0;   // CTAs the kernel-per-op chain of the current call sizes its grids for; 0 = lane_cta_budget
   };
   std::vector<Lane> lanes;
   int lane_cta_budget = 0;
@@ -223,10 +224,12 @@ struct lvx_engine {
   // cluster-resident decode kernel (cluster_decode.cuh): per-rank weight streams + table norms, built on first use
   bool use_cluster = false;
   bool cd_ready = false;
-  uint8_t* cd_stream = nullptr;
+  uint8_t* cd_stream = nullptr;    // 16-CTA clusters (latency variant)
   long long cd_stream_bytes = 0;
+  uint8_t* cd_stream8 = nullptr;   // 8-CTA clusters (throughput variant, bf16 greedy)
+  long long cd_stream8_bytes = 0;
   float *cd_text_ss = nullptr, *cd_code_ss = nullptr;
-  int cd_max_clusters = 0;
+  int cd_max_clusters = 0, cd_max_clusters8 = 0;   // co-resident clusters of each variant (cudaOccupancyMaxActiveClusters)
   // spread a call's sessions over all co-resident clusters instead of filling clusters to 16 (LLMVOX_B200_CD_SPREAD=1).
   // Measured (profiles/r02_cluster_decode.md): 64 sessions as 7 clusters of 9-10 run at 148.7 us / iteration at T = 20..120
   // (4 clusters of 16: 149.8) but 202.8 vs 184.1 at T = 110..210 -- seven weight streams contend in L2 with the K/V
@@ -1031,7 +1034,7 @@ static int gpt_body(lvx_engine* e, lvx_engine::Lane& ln, int n, const int* pos_o
   const lvx_config& c = e->cfg;
   const int C = c.n_embd;
   const DT a = e->adt();
-  const int budget = e->lane_cta_budget;
+  const int budget = ln.cta_budget ? ln.cta_budget : e->lane_cta_budget;
   const bool pdl = e->use_pdl && !e->prof_on;
   for (int l = 0; l < c.n_layer; ++l) {
     auto& L = e->layers[l];
@@ -1087,7 +1090,7 @@ static int split2(lvx_engine* e, const float* in, int n, int width, int act, bf1
 static int gpt_body_exact(lvx_engine* e, lvx_engine::Lane& ln, int n, const int* pos_override, cudaStream_t st) {
   const lvx_config& c = e->cfg;
   const int C = c.n_embd;
-  const int budget = e->lane_cta_budget;
+  const int budget = ln.cta_budget ? ln.cta_budget : e->lane_cta_budget;
   const bool pdl = e->use_pdl && !e->prof_on;
   for (int l = 0; l < c.n_layer; ++l) {
     auto& L = e->layers[l];
@@ -1123,7 +1126,7 @@ static int gpt_body_exact(lvx_engine* e, lvx_engine::Lane& ln, int n, const int*
 static int lm_head_logits(lvx_engine* e, lvx_engine::Lane& ln, int n, float* d_logits, cudaStream_t st) {
   GemmParams p;
   const int kd = e->exact() ? 2 : 1;
-  p.A = ln.h; p.C = d_logits; p.M = n; p.lda = kd * e->cfg.n_embd; p.ldc = e->cfg.vocab_size; p.cta_budget = e->lane_cta_budget;
+  p.A = ln.h; p.C = d_logits; p.M = n; p.lda = kd * e->cfg.n_embd; p.ldc = e->cfg.vocab_size; p.cta_budget = ln.cta_budget ? ln.cta_budget : e->lane_cta_budget;
   p.pdl = e->use_pdl && !e->prof_on;
   p.kdup = kd;
   return run_gemm(e, p, e->exact() ? e->lm_head_x2 : e->lm_head, e->adt(), F32, st);
@@ -1175,9 +1178,9 @@ static int prepare_decode(lvx_engine* e, lvx_engine::Lane& ln, const int32_t* h_
 // Graph of `iters` decode iterations for (n sessions, sampler) on this lane: every iteration launches the same
 // kernels with the same arguments (all per-session state lives on the device), so it is captured once.
 static int lane_graph(lvx_engine* e, lvx_engine::Lane& ln, int n, int iters, const SamplerArgs& sa, lvx_engine::StepGraph** out) {
-  char key[112];
-  snprintf(key, sizeof(key), "%d|%d|%d|%d|%.9g|%llu", n, iters, sa.greedy, sa.top_k, (double)sa.temperature,
-           (unsigned long long)sa.seed);
+  char key[128];
+  snprintf(key, sizeof(key), "%d|%d|%d|%d|%.9g|%llu|%d", n, iters, sa.greedy, sa.top_k, (double)sa.temperature,
+           (unsigned long long)sa.seed, ln.cta_budget);
   auto it = ln.graphs.find(key);
   if (it == ln.graphs.end()) {
     cudaGraph_t graph = nullptr;
@@ -1215,22 +1218,34 @@ extern "C" const unsigned long long* lvx_cluster_diag(void) { return g_cd_diag_h
 static int cluster_init(lvx_engine* e) {
   if (e->cd_ready) return LVX_OK;
   const lvx_config& c = e->cfg;
-  LVX_TRY(cluster_decode_configure(e->exact(), &e->cd_max_clusters));
+  LVX_TRY(cluster_decode_configure(e->exact(), &e->cd_max_clusters, &e->cd_max_clusters8));
   LVX_CHECK(e->cd_max_clusters >= 1, LVX_ERR_CUDA, "cluster decode: no 16-CTA cluster fits on this device");
-  if (getenv("LLMVOX_B200_TRACE")) fprintf(stderr, "[llmvox_b200] cluster decode: %d co-resident clusters of %d CTAs\n", e->cd_max_clusters, CD_CLUSTER);
+  if (getenv("LLMVOX_B200_TRACE"))
+    fprintf(stderr, "[llmvox_b200] cluster decode: %d co-resident clusters of 16 CTAs, %d of 8 CTAs\n", e->cd_max_clusters, e->cd_max_clusters8);
   std::vector<CdLayerW> lw(c.n_layer);
   for (int l = 0; l < c.n_layer; ++l) {
     auto& L = e->layers[l];
     lw[l] = CdLayerW{L.attn.f32, L.proj.f32, L.fc.f32, L.proj2.f32, L.attn.ld, L.proj.ld, L.fc.ld, L.proj2.ld, L.ln1_w, L.ln2_w};
   }
   std::vector<CdPackDesc> descs;
-  e->cd_stream_bytes = cd_build_descs(lw.data(), c.n_layer, e->lm_head.f32, e->lm_head.ld, e->lnf_w, &descs);
-  LVX_TRY(dev_alloc_bytes(e, (void**)&e->cd_stream, (size_t)e->cd_stream_bytes * CD_CLUSTER));
+  e->cd_stream_bytes = cd_build_descs<16>(lw.data(), c.n_layer, e->lm_head.f32, e->lm_head.ld, e->lnf_w, &descs);
+  LVX_TRY(dev_alloc_bytes(e, (void**)&e->cd_stream, (size_t)e->cd_stream_bytes * 16));
   CdPackDesc* d_descs = nullptr;
   LVX_CUDA(cudaMalloc(&d_descs, descs.size() * sizeof(CdPackDesc)));
   LVX_CUDA(cudaMemcpy(d_descs, descs.data(), descs.size() * sizeof(CdPackDesc), cudaMemcpyHostToDevice));
   cd_pack_kernel<<<(unsigned)descs.size(), 256>>>(d_descs, e->cd_stream);
   LAUNCHED(e);
+  if (e->cd_max_clusters8 > 0) {   // the same weights cut for 8-CTA clusters (another 62.9 MB)
+    LVX_CUDA(cudaDeviceSynchronize());
+    cudaFree(d_descs);
+    descs.clear();
+    e->cd_stream8_bytes = cd_build_descs<8>(lw.data(), c.n_layer, e->lm_head.f32, e->lm_head.ld, e->lnf_w, &descs);
+    LVX_TRY(dev_alloc_bytes(e, (void**)&e->cd_stream8, (size_t)e->cd_stream8_bytes * 8));
+    LVX_CUDA(cudaMalloc(&d_descs, descs.size() * sizeof(CdPackDesc)));
+    LVX_CUDA(cudaMemcpy(d_descs, descs.data(), descs.size() * sizeof(CdPackDesc), cudaMemcpyHostToDevice));
+    cd_pack_kernel<<<(unsigned)descs.size(), 256>>>(d_descs, e->cd_stream8);
+    LAUNCHED(e);
+  }
   LVX_TRY(dev_alloc(e, &e->cd_text_ss, (size_t)c.text_vocab));
   LVX_TRY(dev_alloc(e, &e->cd_code_ss, (size_t)c.vocab_size));
   cd_row_ss_kernel<<<ceil_div(c.text_vocab, 8), 256>>>(W(e, "text_table"), c.text_vocab, c.text_dim, e->cd_text_ss);
@@ -1272,12 +1287,24 @@ static bool cluster_applicable(const lvx_engine* e, const SamplerArgs& sa) {
 // belonged to different issuers and the parity wait could pass on stale data) that are fixed (cd_wait; CD_NI = 2 with the
 // static_assert in CdG).  scripts/cluster_stress.py runs the kernel with the cap lifted (LLMVOX_B200_CD_CAP, a
 // measurement knob that does not change results) as a regression test of those fixes.
+// variant: 0 = by batch size, 16 / 8 = forced cut
 static int cluster_launch(lvx_engine* e, lvx_engine::Lane& ln, const int32_t* h_slots, int n, int n_steps, const SamplerArgs& sa,
-                          cudaStream_t st) {
+                          int variant, cudaStream_t st) {
   LVX_TRY(cluster_init(e));
   const lvx_config& c = e->cfg;
   // LLMVOX_B200_CD_CAP overrides the cap (experiments only: scripts/cluster_stress.py)
-  const int cap = getenv("LLMVOX_B200_CD_CAP") ? std::max(1, atoi(getenv("LLMVOX_B200_CD_CAP"))) : std::max(1, e->cd_max_clusters);
+  const int cap16 = getenv("LLMVOX_B200_CD_CAP") ? std::max(1, atoi(getenv("LLMVOX_B200_CD_CAP"))) : std::max(1, e->cd_max_clusters);
+  // Variant.  Up to one wave of 16-CTA clusters (7 x 16 = 112 sessions on a B200) the latency variant runs: every CTA
+  // streams 1/16 of the weights.  Above that the greedy bf16 path switches to 8-CTA clusters: 1/8 of the weights per CTA
+  // makes an iteration ~1.4x longer, but 15 clusters are co-resident, so up to 240 sessions advance in ONE wave where the
+  // 16-CTA variant needs two or three.  (LLMVOX_B200_CD_NO8=1: measurement knob, results do not depend on the variant's
+  // choice beyond the bf16 tolerance both meet.)
+  const bool can8 = !e->exact() && sa.greedy && e->cd_max_clusters8 > 0;
+  LVX_CHECK(variant != 8 || can8, LVX_ERR_INVALID, "the 8-CTA cluster cut exists for greedy bf16 decoding only");
+  const bool use8 = variant == 8 || (variant == 0 && can8 && n > cap16 * CD_NB && !getenv("LLMVOX_B200_CD_NO8"));
+  const int cl = use8 ? 8 : 16;
+  const int cap = use8 ? e->cd_max_clusters8 : cap16;
+  const int unit = use8 ? 1 : 2, unit_cap = use8 ? e->cd_max_clusters8 : 2 * cap16;   // in-flight accounting in 8-CTA units
   ClusterParams P;
   memset(&P, 0, sizeof(P));
   P.n_iters = n_steps; P.n_layer = c.n_layer;
@@ -1287,7 +1314,8 @@ static int cluster_launch(lvx_engine* e, lvx_engine::Lane& ln, const int32_t* h_
   P.wpe = W(e, "transformer.wpe.weight");
   P.text_ss = e->cd_text_ss; P.code_ss = e->cd_code_ss;
   P.text_dim = c.text_dim; P.code_dim = c.code_dim; P.pad_id = c.pad_token_id;
-  P.wstream = e->cd_stream; P.stream_bytes = e->cd_stream_bytes;
+  P.wstream = use8 ? e->cd_stream8 : e->cd_stream;
+  P.stream_bytes = use8 ? e->cd_stream8_bytes : e->cd_stream_bytes;
   P.top_k = sa.top_k; P.temperature = sa.temperature; P.seed = sa.seed;
   P.kv = e->kv; P.pool_pages = e->pool_pages;
   P.page_shift = 0;
@@ -1298,8 +1326,11 @@ static int cluster_launch(lvx_engine* e, lvx_engine::Lane& ln, const int32_t* h_
   const int per_wave = ceil_div(n, waves);
   for (int pos = 0; pos < n; pos += per_wave) {
     const int cnt = std::min(per_wave, n - pos);
-    P.per_cluster = e->cd_spread ? ceil_div(cnt, std::min(cap, cnt)) : CD_NB;
-    const int clusters = ceil_div(cnt, P.per_cluster);
+    // 8-CTA clusters: spread the wave over all co-resident clusters, 8 sessions or more each (a CTA's eight attention
+    // warps take a second pass only for sessions 9..16 of its cluster)
+    if (use8) P.per_cluster = ceil_div(cnt, std::min(cap, ceil_div(cnt, 8)));
+    else P.per_cluster = e->cd_spread ? ceil_div(cnt, std::min(cap, cnt)) : CD_NB;
+    const int clusters = ceil_div(cnt, P.per_cluster) * unit;
     P.n = cnt;
     P.slots = ln.d_slots + pos;
     P.logits = ln.logits + (size_t)pos * c.vocab_size;
@@ -1313,7 +1344,7 @@ static int cluster_launch(lvx_engine* e, lvx_engine::Lane& ln, const int32_t* h_
     for (auto& f : e->cd_inflight)
       if (f.st != st) inflight += f.clusters;   // launches on this stream are ordered before this one anyway
     for (auto& f : e->cd_inflight) {
-      if (inflight + clusters <= cap) break;
+      if (inflight + clusters <= unit_cap) break;
       if (f.st == st) continue;
       LVX_CUDA(cudaStreamWaitEvent(st, f.ev, 0));
       inflight -= f.clusters;
@@ -1328,7 +1359,7 @@ static int cluster_launch(lvx_engine* e, lvx_engine::Lane& ln, const int32_t* h_
     }
     {
       ProfScope prof_scope(e, "cluster_decode", st, 0.0, bytes);
-      LVX_TRY(cluster_decode_launch(e->exact(), !sa.greedy, P, st));
+      LVX_TRY(cluster_decode_launch(e->exact(), !sa.greedy, cl, P, st));
     }
     e->launches += 1;
     lvx_engine::CdInflight rec{e->get_event(), st, clusters};
@@ -1341,7 +1372,8 @@ static int cluster_launch(lvx_engine* e, lvx_engine::Lane& ln, const int32_t* h_
 extern "C" int lvx_decode_steps_ex(lvx_engine* e, int lane, const int32_t* h_slots, int n, int n_steps, const lvx_sampling* s,
                                    int path, void* stream) {
   LVX_TRY(check_engine(e));
-  LVX_CHECK(path == LVX_PATH_AUTO || path == LVX_PATH_CLUSTER || path == LVX_PATH_PER_OP, LVX_ERR_INVALID, "bad decode path");
+  LVX_CHECK(path >= LVX_PATH_AUTO && path <= LVX_PATH_PER_OP_TAIL, LVX_ERR_INVALID, "bad decode path");
+  const bool forced_cluster = path == LVX_PATH_CLUSTER || path == LVX_PATH_CLUSTER16 || path == LVX_PATH_CLUSTER8;
   LVX_CHECK(lane >= 0 && lane < (int)e->lanes.size(), LVX_ERR_INVALID, "decode lane out of range");
   LVX_CHECK(n_steps > 0, LVX_ERR_INVALID, "n_steps must be positive");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1353,11 +1385,18 @@ extern "C" int lvx_decode_steps_ex(lvx_engine* e, int lane, const int32_t* h_slo
   SamplerArgs sa = sampler_args(s);
   LVX_CHECK(sa.greedy || sa.temperature > 0.f, LVX_ERR_INVALID, "temperature must be positive");
   LVX_CHECK(!(sa.uniform && n_steps > 1), LVX_ERR_INVALID, "d_uniform supplies one draw per session: use n_steps == 1");
-  const bool want_cluster = path == LVX_PATH_CLUSTER || (path == LVX_PATH_AUTO && e->use_cluster);
-  LVX_CHECK(path != LVX_PATH_CLUSTER || cluster_applicable(e, sa), LVX_ERR_INVALID,
+  const bool want_cluster = forced_cluster || (path == LVX_PATH_AUTO && e->use_cluster);
+  // the tail of a batch that runs beside a resident wave of 8-CTA clusters sizes its grids for the SMs the wave leaves
+  // (split-K factors depend on the budget: it is part of the call, never of timing, so results are reproducible)
+  ln.cta_budget = 0;
+  if (path == LVX_PATH_PER_OP_TAIL) {
+    const int free_sms = (e->tcw.num_sms > 0 ? e->tcw.num_sms : 148) - 8 * e->cd_max_clusters8;
+    ln.cta_budget = getenv("LLMVOX_B200_TAIL_BUDGET") ? atoi(getenv("LLMVOX_B200_TAIL_BUDGET")) : std::max(8, (2 * free_sms) / 3);
+  }
+  LVX_CHECK(!forced_cluster || cluster_applicable(e, sa), LVX_ERR_INVALID,
             "the cluster-resident decode kernel does not apply to this engine / sampler");
   if (want_cluster && cluster_applicable(e, sa)) {
-    LVX_TRY(cluster_launch(e, ln, h_slots, n, n_steps, sa, st));
+    LVX_TRY(cluster_launch(e, ln, h_slots, n, n_steps, sa, path == LVX_PATH_CLUSTER16 ? 16 : path == LVX_PATH_CLUSTER8 ? 8 : 0, st));
   } else if (e->use_graphs && !e->prof_on && !sa.uniform) {
     const int unroll = 10;   // iterations per graph launch for long runs
     int left = n_steps;
@@ -1390,6 +1429,18 @@ extern "C" int lvx_session_progress(lvx_engine* e, const int32_t* h_slots, int n
   gather_progress_kernel<<<ceil_div(n, 256), 256, 0, st>>>(e->d_slots, n, e->st, reinterpret_cast<int2*>(e->d_aux));
   LAUNCHED(e);
   LVX_CUDA(cudaMemcpyAsync(h_pinned_out, e->d_aux, (size_t)n * 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  return LVX_OK;
+}
+
+extern "C" int lvx_cluster_capacity(lvx_engine* e, int32_t* wave16, int32_t* wave8) {
+  LVX_TRY(check_engine(e));
+  LVX_CHECK(wave16 && wave8, LVX_ERR_INVALID, "NULL argument");
+  *wave16 = *wave8 = 0;
+  SamplerArgs greedy = sampler_args(nullptr);
+  if (!cluster_applicable(e, greedy)) return LVX_OK;
+  LVX_TRY(cluster_init(e));
+  *wave16 = e->cd_max_clusters * CD_NB;
+  *wave8 = e->exact() ? 0 : e->cd_max_clusters8 * CD_NB;
   return LVX_OK;
 }
 

@@ -133,7 +133,7 @@ class Engine:
                      path: int = _lib.PATH_AUTO):
         """n_steps decode iterations for `slots` on decode lane `lane`.  Calls on different lanes may be enqueued on
         different streams and run concurrently (sessions are independent).  `path`: _lib.PATH_AUTO / PATH_CLUSTER /
-        PATH_PER_OP (lvx_decode_steps_ex)."""
+        PATH_PER_OP / PATH_CLUSTER16 / PATH_CLUSTER8 (lvx_decode_steps_ex)."""
         s = (sampling or Sampling()).to_c()
         check(self.lib.lvx_decode_steps_ex(self._h, lane, i32_array(slots), len(slots), n_steps, C.byref(s), int(path),
                                            self._stream(stream)))
@@ -148,6 +148,13 @@ class Engine:
         """Greedy bf16 decode path for the calls that follow: the cluster-resident kernel (default) or the kernel-per-op
         chain (better above ~224 sessions per batch)."""
         check(self.lib.lvx_set_cluster_decode(self._h, int(bool(on))))
+
+    def cluster_capacity(self) -> Tuple[int, int]:
+        """Sessions one wave of the cluster-resident kernel advances together: (16-CTA clusters, 8-CTA clusters); 0 where
+        the cut does not exist (lvx_cluster_capacity).  (112, 240) for bf16 on a B200."""
+        a, b = C.c_int32(), C.c_int32()
+        check(self.lib.lvx_cluster_capacity(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def cluster_decode_applicable(self, sampling: Optional[Sampling] = None) -> bool:
         """Host-side mirror of the engine's own test (engine.cu: cluster_applicable): would a decode_steps call with this

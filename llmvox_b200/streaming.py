@@ -8,6 +8,7 @@ chunks, and all ready chunks of a round are vocoded as ONE ragged batch -- each 
 exactly as the reference.  PCM leaves through a pinned host buffer with an asynchronous copy."""
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass, field
 from typing import Dict, Iterator, List, Optional, Sequence, Tuple
 
@@ -18,14 +19,22 @@ from .engine import Engine, Sampling
 from .scheduler import ChunkScheduler, INITIAL_DUMP_SIZE_1, MAX_DUMP_SIZE
 
 
+def os_environ_no8() -> bool:
+    """LLMVOX_B200_CD_NO8=1: measurement knob of the engine (cluster_launch), mirrored here so that plan() agrees."""
+    import os
+    return os.environ.get("LLMVOX_B200_CD_NO8") == "1"
+
+
 class LaneRunner:
     """Runs the decode iterations of a batch off the control stream, so that the control stream's work (gather / vocode /
     copies) overlaps with the next iterations.  The decode path is chosen PER CALL (lvx_decode_steps_ex), never through
     engine state:
 
-    * cluster-resident decode kernel (bf16 / exact precision, greedy): ONE call on the side stream; the engine cuts it
-      into balanced waves of at most 7 co-resident clusters (7 x 16 sessions on a B200), which run back to back.  A wave
-      costs the same ~150 us per iteration however many of its clusters are used.
+    * cluster-resident decode kernel (bf16 / exact precision): ONE call on the side stream; the engine cuts it into
+      balanced waves of co-resident clusters, which run back to back: 7 x 16 sessions per wave of 16-CTA clusters
+      (~150 us per iteration however many of the clusters are used), and for greedy bf16 batches above that 15 x 16
+      sessions per wave of 8-CTA clusters (each CTA streams twice the weights: a longer iteration, but 240 sessions
+      abreast).
     * kernel-per-op chain (fp32 precision, sampled decoding, and the part of a batch the cluster waves do not take):
       `lanes` independent groups on their own streams.  A decode iteration there is a chain of ~35 dependent,
       latency-bound kernels that leaves most of the GPU idle; sessions never interact, so disjoint groups advance
@@ -40,22 +49,33 @@ class LaneRunner:
     a session may move between streams from round to round (the active set shrinks, the path changes with the batch
     size), and its context length / KV pages must be ordered across that move."""
 
-    # two waves of 7 clusters; measured (bench.py --short, audio-s/s, cluster vs kernel-per-op): 112: 8341 / 5418,
-    # 128: 5780 / 5992, 192: 8300 / 7624, 224: 9062 / 7457, 256: 7647 / 8251.  Just above one full wave (113..139 sessions)
-    # the second wave is nearly empty and the kernel-per-op lanes win.
+    # 16-CTA clusters only (exact precision, sampled decoding): two waves of 7 clusters; measured (bench.py --short,
+    # audio-s/s, cluster vs kernel-per-op): 112: 8341 / 5418, 128: 5780 / 5992, 192: 8300 / 7624, 224: 9062 / 7457,
+    # 256: 7647 / 8251.  Just above one full wave (113..139 sessions) the second wave is nearly empty and the kernel-per-op
+    # lanes win.
     CLUSTER_DECODE_MAX_BATCH = 224
     CLUSTER_DECODE_GAP = (113, 139)
     HYBRID_ABOVE_MAX_BATCH = False
+    # greedy bf16: above one wave of 16-CTA clusters the engine switches to 8-CTA clusters, 15 x 16 = 240 sessions per wave
+    # (engine.cluster_capacity()).  A batch slightly above a wave (256 streams) runs the wave on the cluster kernel and the
+    # rest on the kernel-per-op lanes AT THE SAME TIME (the 28 SMs fifteen 8-CTA clusters leave idle); larger batches take
+    # further waves, and beyond CLUSTER8_MAX_WAVES waves the kernel-per-op chain's large-M GEMMs win (config 4).
+    HYBRID_TAIL_MAX = 32
+    CLUSTER8_MAX_WAVES = 2
 
     def __init__(self, engine: Engine, lanes: Optional[int] = None):
         import os
         self.e = engine
         self.G = max(1, min(engine.decode_lanes, lanes or engine.decode_lanes))
-        self.streams = [torch.cuda.Stream(device=engine.device) for _ in range(self.G)]
+        # high priority: the decode chains are the critical path; the control stream's vocoder kernels (default priority)
+        # fill whatever SMs they leave
+        self.streams = [torch.cuda.Stream(device=engine.device, priority=-1) for _ in range(self.G)]
         self.side = self.streams[0]                                   # cluster-kernel launches
         self.cluster_default = os.environ.get("LLMVOX_B200_CLUSTER", "1") != "0"
-        if "LLMVOX_B200_CLUSTER_MAX_BATCH" in os.environ:      # measurement override of the threshold above
+        if "LLMVOX_B200_CLUSTER_MAX_BATCH" in os.environ:      # measurement overrides of the thresholds above
             self.CLUSTER_DECODE_MAX_BATCH = int(os.environ["LLMVOX_B200_CLUSTER_MAX_BATCH"])
+        if "LLMVOX_B200_HYBRID_TAIL" in os.environ:
+            self.HYBRID_TAIL_MAX = int(os.environ["LLMVOX_B200_HYBRID_TAIL"])
         self._prev: List[Tuple[torch.cuda.Stream, torch.cuda.Event]] = []
 
     def split(self, slots: Sequence[int], groups: Optional[int] = None) -> List[List[int]]:
@@ -75,10 +95,25 @@ class LaneRunner:
         for st in self.streams:
             st.wait_event(ev)
 
+    def wave8(self, sampling: Optional[Sampling]) -> int:
+        """Sessions per wave of the 8-CTA cut for this sampler (0: the cut does not apply)."""
+        if self.e.precision != "bf16" or (sampling is not None and not sampling.greedy and sampling.top_k != 1):
+            return 0
+        if not hasattr(self, "_caps"):
+            self._caps = self.e.cluster_capacity() if hasattr(self.e, "cluster_capacity") else (112, 240)
+        return 0 if os_environ_no8() else self._caps[1]
+
     def plan(self, n: int, sampling: Optional[Sampling]) -> Tuple[int, int]:
         """-> (sessions for the cluster-resident kernel, sessions for the kernel-per-op lanes)."""
         if not self.cluster_default or not self.e.cluster_decode_applicable(sampling):
             return 0, n
+        w8 = self.wave8(sampling)
+        if w8:
+            if n <= w8:
+                return n, 0
+            if n - w8 <= self.HYBRID_TAIL_MAX and self.G > 1:
+                return w8, n - w8
+            return (n, 0) if n <= self.CLUSTER8_MAX_WAVES * w8 else (0, n)
         if n <= self.CLUSTER_DECODE_MAX_BATCH:
             gap = self.CLUSTER_DECODE_GAP[0] <= n <= self.CLUSTER_DECODE_GAP[1] and self.e.precision == "bf16"
             return (0, n) if gap else (n, 0)
@@ -91,16 +126,25 @@ class LaneRunner:
 
     def launch(self, slots: Sequence[int], n_steps: int, sampling: Optional[Sampling] = None) -> List[torch.cuda.Event]:
         """Enqueues n_steps iterations for the batch on the side streams; returns their completion events."""
-        from ._lib import PATH_CLUSTER, PATH_PER_OP
+        from ._lib import PATH_CLUSTER, PATH_PER_OP, PATH_PER_OP_TAIL
         n_cluster, n_lanes = self.plan(len(slots), sampling)
+        if n_cluster and n_lanes and os.environ.get("LLMVOX_B200_SERIAL", "1") == "1":
+            # a full wave of 8-CTA clusters holds 120 of the 148 SMs: vocoder kernels squeezed into the rest run ~5x
+            # slower and starve the kernel-per-op tail (measured at 256 streams: 72.9 ms per step overlapped, 69.3 taking
+            # turns), so with a tail the decode rounds and the control stream's vocoder batches take turns on the whole
+            # GPU; without one (<= 240 streams) overlapping stays better (57.7 vs 65.5 ms at 240)
+            self.sync_from_control()
         calls = []                                                   # (stream, lane, slots, path)
         if n_cluster:
             calls.append((self.side, 0, list(slots[:n_cluster]), PATH_CLUSTER))
         if n_lanes:
             lane0 = 1 if (n_cluster and self.G > 1) else 0            # lane 0's workspace belongs to the cluster call
-            groups = self.split(slots[n_cluster:], max(1, self.G - lane0))
+            tail_lanes = max(1, self.G - lane0)
+            if n_cluster:
+                tail_lanes = min(tail_lanes, int(os.environ.get("LLMVOX_B200_TAIL_LANES", "1")))
+            groups = self.split(slots[n_cluster:], tail_lanes)
             for g, grp in enumerate(groups):
-                calls.append((self.streams[lane0 + g], lane0 + g, grp, PATH_PER_OP))
+                calls.append((self.streams[lane0 + g], lane0 + g, grp, PATH_PER_OP_TAIL if n_cluster else PATH_PER_OP))
         used = {id(st): st for st, _, _, _ in calls}
         for st in used.values():
             for pst, pev in self._prev:

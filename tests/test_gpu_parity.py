@@ -440,15 +440,18 @@ def test_decode_lanes_do_not_change_results(weights, precision):
     e.close()
 
 
-@pytest.mark.parametrize("n", [1, 5, 16, 17, 64])
-def test_cluster_decode_kernel(weights, n):
+@pytest.mark.parametrize("n,cut", [(1, 16), (5, 16), (16, 16), (17, 16), (64, 16), (1, 8), (9, 8), (16, 8), (40, 8), (130, 8)])
+def test_cluster_decode_kernel(weights, n, cut):
     """The cluster-resident decode kernel (cluster_decode.cuh; bf16, greedy: the default decode path) against the fp32
     engine (pinned to the reference within 1e-4) and the kernel-per-op bf16 path on twin engines.  The twins are
     teacher-forced with the cluster kernel's pick at every step, so all three see identical histories: logits within
     the north-star bf16 bound of the fp32 ones, every pick the argmax of its own logits, and n iterations inside one
-    launch equal to n launches of one iteration (fixed reduction orders: bit-identical)."""
+    launch equal to n launches of one iteration (fixed reduction orders: bit-identical).  Both cuts of the kernel: 16-CTA
+    clusters and 8-CTA clusters (forced through the decode path argument; 130 sessions = 15 clusters of 8-9)."""
     import os
+    from llmvox_b200 import _lib
     from llmvox_b200.engine import Engine
+    path = _lib.PATH_CLUSTER16 if cut == 16 else _lib.PATH_CLUSTER8
     kw = dict(device=0, max_sessions=n, max_context=48, max_vocode_frames=256)
     clus = Engine(weights, precision="bf16", **kw)
     os.environ["LLMVOX_B200_CLUSTER"] = "0"          # read at engine creation
@@ -466,7 +469,7 @@ def test_cluster_decode_kernel(weights, n):
     l0 = clus.kernel_launches
     worst = worst_pair = 0.0
     for t in range(36):                               # crosses two KV page boundaries (16 tokens per page)
-        clus.decode_steps(slots, 1)
+        clus.decode_steps(slots, 1, path=path)
         codes = clus.gather_codes(slots, t, 1).view(-1).contiguous()
         lc = clus.peek_logits(n)
         lr, _ = ref.decode_step_logits(slots, forced=codes)
@@ -480,7 +483,7 @@ def test_cluster_decode_kernel(weights, n):
     first = clus.gather_codes(slots, 0, 36).cpu()
     clus.open(slots)
     clus.feed_text(slots, texts)
-    clus.decode_steps(slots, 36)
+    clus.decode_steps(slots, 36, path=path)
     again = clus.gather_codes(slots, 0, 36).cpu()
     assert clus.session_length(0) == 36
     assert (again == first).all()
@@ -537,22 +540,27 @@ def test_cluster_decode_ragged_contexts_and_long_runs(weights):
     ref.close()
 
 
-def test_cluster_decode_large_call_is_split_and_batch_invariant(weights):
-    """A call with more sessions than 7 clusters hold (130 -> launches of 112 + 18) must give every session exactly the
-    codes it gets when the same sessions are decoded in differently composed calls (a session's arithmetic does not
-    depend on its neighbours or on its place in a cluster), also when the calls are spread over three streams / lanes."""
+@pytest.mark.parametrize("cut", [16, 8])
+def test_cluster_decode_large_call_is_split_and_batch_invariant(weights, cut):
+    """A call with more sessions than one wave of 16-CTA clusters holds (130 -> two launches of 65 on 16-CTA clusters, or
+    one launch of fifteen 8-CTA clusters) must give every session exactly the codes it gets when the same sessions are
+    decoded in differently composed calls of the same cut (a session's arithmetic does not depend on its neighbours or
+    on its place in a cluster), also when the calls are spread over three streams / lanes."""
+    from llmvox_b200 import _lib
     from llmvox_b200.engine import Engine
+    path = _lib.PATH_CLUSTER16 if cut == 16 else _lib.PATH_CLUSTER8
     n = 130
     kw = dict(device=0, precision="bf16", max_sessions=n, max_context=48, max_vocode_frames=256, decode_lanes=3)
     rng = np.random.RandomState(11)
     texts = [rng.randint(3, 259, size=rng.randint(0, 40)).tolist() for _ in range(n)]
     slots = list(range(n))
     a = Engine(weights, **kw)
+    assert a.cluster_capacity()[0] >= 16 and a.cluster_capacity()[1] >= 16
     a.open(slots)
     a.feed_text(slots, texts)
     l0 = a.kernel_launches
-    a.decode_steps(slots, 24)
-    assert a.kernel_launches - l0 <= 8               # two cluster launches (+ stream packing on first use, page patches), not 24 x 33 kernels
+    a.decode_steps(slots, 24, path=path)
+    assert a.kernel_launches - l0 <= 10              # one or two cluster launches (+ stream packing on first use, page patches), not 24 x 33 kernels
     ca = a.gather_codes(slots, 0, 24).cpu()
     b = Engine(weights, **kw)
     b.open(slots)
@@ -562,7 +570,7 @@ def test_cluster_decode_large_call_is_split_and_batch_invariant(weights):
     ev.record()
     for lane, (lo, hi) in enumerate([(0, 50), (50, 57), (57, 130)]):
         streams[lane].wait_event(ev)
-        b.decode_steps(slots[lo:hi], 24, stream=streams[lane], lane=lane)
+        b.decode_steps(slots[lo:hi], 24, stream=streams[lane], lane=lane, path=path)
     torch.cuda.synchronize()
     cb = b.gather_codes(slots, 0, 24).cpu()
     assert (ca == cb).all()

@@ -159,9 +159,11 @@ def test_chunk_scheduler_properties_against_the_oracle_schedule():
 
 
 def test_lane_runner_picks_the_decode_path_by_batch_size():
-    """LaneRunner's host-side policy (no GPU needed): the cluster-resident kernel gets batches of one or two waves of 7
-    clusters (up to 112 and 140-224 sessions) when the engine can run it (bf16, greedy, english-tiny dimensions); the
-    kernel-per-op lanes get the rest."""
+    """LaneRunner's host-side policy (no GPU needed).  Greedy bf16: the cluster-resident kernel takes everything up to one
+    wave of 8-CTA clusters (240 sessions on a B200; the engine itself uses 16-CTA clusters up to 112), a batch slightly
+    above a wave keeps the wave on the cluster kernel and puts the rest on the kernel-per-op lanes, two waves are still
+    cluster work, beyond that the lanes take all.  Exact precision and sampled decoding have 16-CTA clusters only: one or
+    two waves of 7 (up to 112 and 140-224 sessions)."""
     from llmvox_b200.engine import Engine, Sampling
     from llmvox_b200.streaming import LaneRunner
 
@@ -173,21 +175,32 @@ def test_lane_runner_picks_the_decode_path_by_batch_size():
         precision = "bf16"
         cluster_decode_applicable = Engine.cluster_decode_applicable
 
+        def cluster_capacity(self):
+            return (112, 240) if self.precision == "bf16" else (112, 0)
+
     r = object.__new__(LaneRunner)
     r.e = FakeEngine()
+    r.G = 4
     r.cluster_default = True
     greedy, sampled = Sampling(), Sampling(greedy=False, top_k=50, temperature=0.8)
     # (sessions on the cluster kernel, sessions on the kernel-per-op lanes)
-    assert [r.plan(n, greedy) for n in (1, 64, 112, 113, 139, 140, 224, 225, 256)] == \
-        [(1, 0), (64, 0), (112, 0), (0, 113), (0, 139), (140, 0), (224, 0), (0, 225), (0, 256)]
+    assert [r.plan(n, greedy) for n in (1, 64, 112, 113, 139, 240, 241, 256, 272, 273, 480, 481, 2048)] == \
+        [(1, 0), (64, 0), (112, 0), (113, 0), (139, 0), (240, 0), (240, 1), (240, 16), (240, 32), (273, 0), (480, 0), (0, 481), (0, 2048)]
+    r.G = 1                                                        # no second lane to run the tail beside the wave
+    assert r.plan(256, greedy) == (256, 0)
+    r.G = 4
+    # sampled decoding runs inside the cluster kernel too (S = 1), on 16-CTA clusters only
+    assert [r.plan(n, sampled) for n in (64, 112, 113, 139, 140, 224, 225, 256)] == \
+        [(64, 0), (112, 0), (0, 113), (0, 139), (140, 0), (224, 0), (0, 225), (0, 256)]
     r.HYBRID_ABOVE_MAX_BATCH = True                                # opt-in split of one call between both paths
-    assert r.plan(256, greedy) == (224, 32)
+    assert r.plan(256, sampled) == (224, 32)
     r.HYBRID_ABOVE_MAX_BATCH = False
-    assert r.plan(64, sampled) == (64, 0)                         # sampled decoding runs inside the cluster kernel too (S = 1)
     r.e.precision = "fp32"
     assert r.plan(64, greedy) == (0, 64)                          # fp32 parity mode: FMA-pipe GEMMs
     r.e.precision = "exact"
-    assert r.plan(64, greedy) == (64, 0) and r.plan(120, greedy) == (120, 0)   # exact mode: hi | lo cluster kernel
+    del r._caps
+    assert r.plan(64, greedy) == (64, 0) and r.plan(120, greedy) == (120, 0)   # exact mode: hi | lo cluster kernel, 16-CTA clusters
+    assert r.plan(256, greedy) == (0, 256)
     r.e.precision = "bf16"
     r.e.cfg.max_context = 8192
     assert r.plan(64, greedy) == (64, 0)                          # the reference's block_size: page-table windows of 64 pages

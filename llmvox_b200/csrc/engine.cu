@@ -1303,8 +1303,9 @@ static int cluster_launch(lvx_engine* e, lvx_engine::Lane& ln, const int32_t* h_
   LVX_CHECK(variant != 8 || can8, LVX_ERR_INVALID, "the 8-CTA cluster cut exists for greedy bf16 decoding only");
   const bool use8 = variant == 8 || (variant == 0 && can8 && n > cap16 * CD_NB && !getenv("LLMVOX_B200_CD_NO8"));
   const int cl = use8 ? 8 : 16;
-  const int cap = use8 ? e->cd_max_clusters8 : cap16;
-  const int unit = use8 ? 1 : 2, unit_cap = use8 ? e->cd_max_clusters8 : 2 * cap16;   // in-flight accounting in 8-CTA units
+  const int cap8 = getenv("LLMVOX_B200_CD_CAP8") ? std::max(1, atoi(getenv("LLMVOX_B200_CD_CAP8"))) : e->cd_max_clusters8;   // (stress only)
+  const int cap = use8 ? cap8 : cap16;
+  const int unit = use8 ? 1 : 2, unit_cap = use8 ? cap8 : 2 * cap16;   // in-flight accounting in 8-CTA units
   ClusterParams P;
   memset(&P, 0, sizeof(P));
   P.n_iters = n_steps; P.n_layer = c.n_layer;

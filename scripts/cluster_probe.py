@@ -41,17 +41,21 @@ if os.environ.get("PROBE_CHECK", "1") == "1":
     p.close()
 
 
+FORCED = {"16": 3, "8": 4}.get(os.environ.get("PROBE_CUT", ""))   # _lib.PATH_CLUSTER16 / PATH_CLUSTER8: bypass LaneRunner's policy
+
+
 def timed(n, lanes, iters=100, prefill=0):
     slots = list(range(n))
     e.open(slots)
     e.feed_text(slots, [rng.randint(3, 259, size=200).tolist() for _ in slots])
     r = LaneRunner(e, lanes)
     r.sync_from_control()
-    r.decode(slots, 10 + prefill)
+    run = (lambda k: e.decode_steps(slots, k, path=FORCED)) if FORCED else (lambda k: r.decode(slots, k))
+    run(10 + prefill)
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record()
-    r.decode(slots, iters)
+    run(iters)
     b.record()
     torch.cuda.synchronize()
     return 1e3 * a.elapsed_time(b) / iters

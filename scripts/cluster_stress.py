@@ -1,7 +1,9 @@
-"""Stress of the cluster-resident decode kernel above its co-residency (7 clusters): batches of 144..256 sessions forced
-through the cluster path (the engine splits a call into launches of <= 7 clusters and keeps <= 7 in flight across
-streams), repeated open / feed / decode / vocode rounds through BatchSynthesizer, 1 and 4 lanes.  Prints the timeout
-records of the bounded spins (LLMVOX_B200_CD_DIAG=1) if a launch dies."""
+"""Stress of the cluster-resident decode kernel at and above its co-residency: batches of 144..256 sessions forced
+through the cluster path, repeated open / feed / decode / vocode rounds through BatchSynthesizer, 1 and 4 lanes.
+bf16 greedy batches above 112 sessions run on the 8-CTA cut (15 co-resident clusters; LLMVOX_B200_CD_CAP8=64 lifts the
+cap, LLMVOX_B200_CD_NO8=1 selects the 16-CTA cut with its cap of 7, LLMVOX_B200_CD_CAP=64 lifts that one); exact
+precision always runs the 16-CTA cut.  Prints the timeout records of the bounded spins (LLMVOX_B200_CD_DIAG=1) if a
+launch dies."""
 import ctypes
 import os
 import sys
@@ -17,6 +19,8 @@ from llmvox_b200.engine import Engine
 from llmvox_b200.streaming import BatchSynthesizer, LaneRunner
 
 LaneRunner.CLUSTER_DECODE_MAX_BATCH = 1 << 30       # force the cluster path at every batch size
+LaneRunner.HYBRID_TAIL_MAX = 0
+LaneRunner.CLUSTER8_MAX_WAVES = 1 << 20
 REPS = int(os.environ.get("STRESS_REPS", "40"))
 sd = W.make_random_weights(1234, wpe_rows=256)
 e = Engine(sd, device=0, precision=os.environ.get("STRESS_PRECISION", "bf16"), max_sessions=256, max_batch=256, max_context=256, max_vocode_frames=256 * 170, decode_lanes=8)

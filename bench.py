@@ -195,9 +195,17 @@ def decode_bytes(streams, tokens, kv_bytes):
 
 
 def roofline_of(prof, peaks):
-    """The launch class that took the most time in the profiled step."""
+    """The launch class that took the most time in the profiled step.  When part of a batch runs on the kernel-per-op chain
+    BESIDE a wave of the cluster-resident kernel (256 streams: 240 + 16), the chain's ~35 kernels per iteration are timed
+    while they overlap the one cluster launch: summed, they can exceed it although the cluster kernel bounds the wall
+    clock.  The dominant kernel is then the cluster kernel as long as its own time is at least half of the largest sum
+    (`concurrent_classes` names what ran beside it)."""
     total_ms = sum(v["ms"] for v in prof.values())
     name, r = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    beside = None
+    if name != "cluster_decode" and "cluster_decode" in prof and "tc_gemm_swap" in prof and prof["cluster_decode"]["ms"] >= 0.5 * r["ms"]:
+        beside = {k: round(v["ms"], 3) for k, v in prof.items() if k in ("tc_gemm_swap", "layernorm", "decode_attention", "assemble_input", "sampler")}
+        name, r = "cluster_decode", prof["cluster_decode"]
     if name.startswith("tc_gemm") and name != "tc_gemm_swap":
         ach = r["flops"] / (r["ms"] / 1e3) / 1e12
         roof = {"kernel": name, "bound": "tensor", "achieved": ach, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
@@ -210,6 +218,10 @@ def roofline_of(prof, peaks):
     roof.update({"traffic": None, "traffic_source": "not measured in-run; ncu --set full capture under profiles/ (DRAM bytes per launch vs algorithmic)",
                  "launches_per_step": r["launches"], "avg_launch_us": 1e3 * r["ms"] / max(1, r["launches"]),
                  "share_of_step": r["ms"] / total_ms, "peak_source": peaks["source"] + " (MEASURED_PEAKS.json)"})
+    if beside:
+        wall = total_ms - sum(beside.values())
+        roof.update({"share_of_step": r["ms"] / wall, "concurrent_classes": beside,
+                     "note": "kernel-per-op tail (16 of 256 sessions) timed while it overlaps the cluster launches: share = cluster time / (profiled total - tail)"})
     return roof
 
 

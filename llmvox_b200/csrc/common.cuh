@@ -134,11 +134,11 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-enum { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_GELU_ERF = 2 };
+enum { ACT_NONE = 0, ACT_GELU_TANH = 1, ACT_GELU_ERF = 2, ACT_GELU_ERF_BF16 = 3 };   // 3: tensor-core path, bf16 destination (tc_gemm.cuh)
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_GELU_TANH) return gelu_tanh(v);
-  if (act == ACT_GELU_ERF) return gelu_erf(v);
+  if (act == ACT_GELU_ERF || act == ACT_GELU_ERF_BF16) return gelu_erf(v);
   return v;
 }
 

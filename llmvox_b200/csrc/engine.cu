@@ -1812,7 +1812,8 @@ static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes
     LAUNCHED(e);
     }
     GemmParams p;
-    p.A = e->v_h; p.C = e->v_big; p.M = g.R; p.lda = D; p.ldc = I; p.bias = X.b1; p.act = ACT_GELU_ERF; p.row_chunk = e->row_chunk;
+    p.A = e->v_h; p.C = e->v_big; p.M = g.R; p.lda = D; p.ldc = I; p.bias = X.b1; p.row_chunk = e->row_chunk;
+    p.act = (a == B16 && !getenv("LLMVOX_B200_GELU_AS")) ? ACT_GELU_ERF_BF16 : ACT_GELU_ERF;   // bf16 destination: tanh form (tc_gemm.cuh)
     if (e->prof_detail) p.tag = "tc_gemm:pw1_gelu";
     LVX_TRY(run_gemm(e, p, X.pw1, a, a, st));
     GemmParams q;

@@ -40,9 +40,12 @@ class LaneRunner:
       latency-bound kernels that leaves most of the GPU idle; sessions never interact, so disjoint groups advance
       concurrently (engine decode lanes).
     * a call may also be split between both (`plan` returns the two counts and `launch` runs them at the same time on
-      different streams), but that is not used by default: measured at 256 streams (bench.py streams256, bf16), 224 on the
-      cluster kernel + 32 on the lanes ran at 6858 audio-s/s against 8251 for all 256 on the lanes -- the lanes' GEMMs are
-      left with the 36 SMs the clusters do not hold and become the critical path.
+      different streams): a greedy bf16 batch slightly above one wave of 8-CTA clusters (256 streams = 240 + 16) keeps the
+      wave on the cluster kernel and runs the tail on ONE kernel-per-op lane (LVX_PATH_PER_OP_TAIL: grids sized for the 28
+      SMs the wave leaves free) while decode rounds and vocoder batches take turns on the GPU.  Measured (bench.py --streams
+      256, bf16, ms per step): all on the lanes 86.8, two waves 98.6, 240 + 16 on three tail lanes with the vocoder
+      overlapped 92.4, one tail lane overlapped 72.4, one tail lane taking turns 69.3.  (With 16-CTA clusters only -- exact
+      precision, sampled decoding -- the split is off by default: 224 + 32 ran at 6858 audio-s/s against 8251 on the lanes.)
 
     `launch()` enqueues on the side streams and returns the completion events; `join()` makes the control stream wait
     for them.  Every launch first waits, on every stream it uses, for the previous round's events of the OTHER streams:

@@ -309,7 +309,7 @@ def measure(args, precision, streams, K, Wm, rank, local, world, sd, barrier, fi
     path = []
     if n_cluster:
         w16, w8 = e.cluster_capacity()
-        if w8 and precision == "bf16" and n_cluster > w16:
+        if w8 and n_cluster > w16:
             path.append("%d sessions on the cluster-resident kernel (8-CTA clusters, %d co-resident per wave)" % (n_cluster, w8 // 16))
         else:
             path.append("%d sessions on the cluster-resident kernel (%d clusters of 16 CTAs, waves of <= %d)" % (n_cluster, (n_cluster + 15) // 16, max(1, w16 // 16)))
@@ -442,6 +442,9 @@ def run_gpu(args):
     # ---- north-star operating point: 256 concurrent streams per GPU
     K256 = max(2, min(K, 5))
     s256 = measure(args, "bf16", 256, K256, 3, rank, local, world, sd, barrier) if (STREAMS != 256 and not args.no_256) else None
+    # the same point and one full wave of 8-CTA clusters (240 streams) in the exact precision / bf16: value + e2e only
+    x256 = measure(args, "exact", 256, K256, 3, rank, local, world, sd, barrier, first_chunk=False) if s256 else None
+    s240 = measure(args, "bf16", 240, K256, 3, rank, local, world, sd, barrier, first_chunk=False) if s256 else None
     voc = vocoder_bulk(args, local, sd, peaks) if (rank == 0 and not args.no_vocoder) else None
     barrier()
     c4 = config4(args, rank, local, world, sd, barrier) if (world > 1 or args.config4) else None
@@ -453,6 +456,8 @@ def run_gpu(args):
     lm = line_of(main, STREAMS, K)
     la = line_of(alt, STREAMS, K) if alt else None
     l256 = line_of(s256, 256, K256) if s256 else None
+    lx256 = line_of(x256, 256, K256) if x256 else None
+    l240 = line_of(s240, 240, K256) if s240 else None
 
     if rank == 0:
         threads = os.cpu_count() or 1
@@ -505,7 +510,12 @@ def run_gpu(args):
                                                     "frac": by256 / (l256["ms_per_step"] / 1e3) / 1e9 / peaks["hbm_gbs"], "unit": "GB/s"},
                                   "kernels": {k: {"launches": v["launches"], "ms": round(v["ms"], 3)}
                                               for k, v in sorted(s256["prof"].items(), key=lambda kv: -kv[1]["ms"])[:6]},
-                                  "gpu_launches": s256["launches"]}
+                                  "gpu_launches": s256["launches"],
+                                  "exact": {"value": lx256["value"], "e2e": lx256["e2e_value"], "ms_per_step": lx256["ms_per_step"],
+                                            "decode_path": x256["decode_path"], "roofline": roofline_of(x256["prof"], peaks)},
+                                  "streams240_bf16": {"value": l240["value"], "e2e": l240["e2e_value"], "ms_per_step": l240["ms_per_step"],
+                                                      "decode_path": s240["decode_path"], "roofline": roofline_of(s240["prof"], peaks),
+                                                      "what": "one full wave of 8-CTA clusters (15 x 16 sessions), no kernel-per-op tail"}}
         line["vocoder_bulk"] = voc
         if c4:
             line["config4"] = c4

@@ -78,12 +78,12 @@ constexpr int CD_TILE = 16384;
 // (lossless), the KV cache is fp32, attention runs on the FMA pipe in fp32.
 template <int X, int CL = 16>
 struct CdG {
-  static_assert(CL == 16 || (CL == 8 && X == 0), "cluster sizes: 16 (bf16 and exact) or 8 (bf16)");
+  static_assert(CL == 16 || CL == 8, "cluster sizes: 16 or 8");
   static constexpr int CLN = CL, XM = X;
   static constexpr int XR = CD_C / CL, QR = 3 * CD_C / CL, FR = CD_FF / CL, VR = CD_V / CL;
   static constexpr int NCOL = X ? 32 : 16;        // UMMA N = operand rows per k-block
   static constexpr int ABLK = NCOL * 128;         // one 64-wide k-block of an activation operand
-  static constexpr int STAGES = (X || CL == 8) ? 6 : 8;   // weight ring depth (what the operands leave of the shared memory)
+  static constexpr int STAGES = (X && CL == 8) ? 4 : (X || CL == 8) ? 6 : 8;   // weight ring depth (what the operands leave of the shared memory)
   // Issuer w takes the ring items at positions = w (mod CD_NI).  The ring depth MUST be a multiple of CD_NI (see above).
   static_assert(STAGES % CD_NI == 0, "every ring slot must belong to exactly one issuer");
   // stream items
@@ -101,11 +101,15 @@ struct CdG {
   // w takes the ring items at positions = w (mod CD_NI), accumulating into its own copy, and the epilogue adds them.
   // With N = 16 a GEMM phase is bound by the issuing warp's serial per-item latency (barrier poll, fence, 4 MMAs, commit:
   // ~300 cycles per 16 KB item, measured; M = 64 instead of 128 changed it by only 13 %), not by the tensor pipe.
+  // Map: qkv tiles | proj share [0, 6 NCOL) with proj2's six tiles (dead by then); fc / lm_head sit behind them -- except
+  // for X = 1 with CL = 8, where 10 x 32 columns per copy would not fit: there fc and lm_head start at 0 too (the fc
+  // accumulators are fully read, and the workers synchronised, before the proj2 MMAs that overwrite them are released).
   static constexpr int F_TILES = F_FULL + (F_TAIL ? 1 : 0);
-  static constexpr int TM_QKV = 0, TM_PROJ = (Q_FULL + 1) * NCOL, TM_PROJ2 = 0, TM_FC = 6 * NCOL, TM_LM = 6 * NCOL,
-                       TM_BANK = (6 + (F_TILES > NT_LM ? F_TILES : NT_LM)) * NCOL, TM_COLS = CD_NI * TM_BANK,
+  static constexpr bool TM_OVERLAY = X && CL == 8;
+  static constexpr int TM_QKV = 0, TM_PROJ = (Q_FULL + 1) * NCOL, TM_PROJ2 = 0, TM_FC = TM_OVERLAY ? 0 : 6 * NCOL, TM_LM = TM_FC,
+                       TM_BANK = TM_OVERLAY ? 6 * NCOL : (6 + (F_TILES > NT_LM ? F_TILES : NT_LM)) * NCOL, TM_COLS = CD_NI * TM_BANK,
                        TM_ALLOC = TM_COLS <= 256 ? 256 : 512;
-  static_assert(TM_PROJ + NCOL <= 6 * NCOL && TM_COLS <= 512, "accumulator copies must fit TMEM");
+  static_assert(TM_PROJ + NCOL <= 6 * NCOL && TM_COLS <= 512 && F_TILES <= 6 && NT_LM <= 6, "accumulator copies must fit TMEM");
   // shared-memory carve (offsets from the 1024-aligned base)
   static constexpr int OFF_RING = 0;
   static constexpr int OFF_A1 = OFF_RING + STAGES * CD_SLOT;            // [12 k-blocks][NCOL x 128 B]: LN(x) operand
@@ -1587,21 +1591,20 @@ inline int cluster_decode_configure_x(int* max_clusters) {
   *max_clusters = mc;
   return LVX_OK;
 }
-// co-resident clusters of the 16-CTA variant (max_clusters) and of the 8-CTA variant (max_clusters8; 0 = not built: exact)
+// co-resident clusters of the 16-CTA variant (max_clusters) and of the 8-CTA variant (max_clusters8)
 inline int cluster_decode_configure(bool exact, int* max_clusters, int* max_clusters8) {
   *max_clusters8 = 0;
-  if (exact) return cluster_decode_configure_x<1, 16>(max_clusters);
-  int st = cluster_decode_configure_x<0, 16>(max_clusters);
-  if (st == LVX_OK) st = cluster_decode_configure_x<0, 8>(max_clusters8);
+  int st = exact ? cluster_decode_configure_x<1, 16>(max_clusters) : cluster_decode_configure_x<0, 16>(max_clusters);
+  if (st == LVX_OK) st = exact ? cluster_decode_configure_x<1, 8>(max_clusters8) : cluster_decode_configure_x<0, 8>(max_clusters8);
   return st;
 }
 
-// cl = CTAs per cluster: 16, or 8 (bf16 greedy only)
+// cl = CTAs per cluster: 16, or 8 (greedy only)
 inline int cluster_decode_launch(bool exact, bool sampled, int cl, const ClusterParams& P, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cl * ceil_div(P.n, P.per_cluster));
   cfg.blockDim = dim3(CD_THREADS);
-  cfg.dynamicSmemBytes = exact ? CdG<1, 16>::SMEM_BYTES : cl == 8 ? CdG<0, 8>::SMEM_BYTES : CdG<0, 16>::SMEM_BYTES;
+  cfg.dynamicSmemBytes = exact ? (cl == 8 ? CdG<1, 8>::SMEM_BYTES : CdG<1, 16>::SMEM_BYTES) : (cl == 8 ? CdG<0, 8>::SMEM_BYTES : CdG<0, 16>::SMEM_BYTES);
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1612,11 +1615,11 @@ inline int cluster_decode_launch(bool exact, bool sampled, int cl, const Cluster
   cfg.numAttrs = 1;
   cudaError_t err;
   if (cl == 8) {
-    if (exact || sampled) {
-      set_error("cluster_decode launch: the 8-CTA variant is bf16 greedy only");
+    if (sampled) {
+      set_error("cluster_decode launch: the 8-CTA variant is greedy only");
       return LVX_ERR_INVALID;
     }
-    err = cudaLaunchKernelEx(&cfg, cluster_decode_kernel<0, 0, 8>, P);
+    err = exact ? cudaLaunchKernelEx(&cfg, cluster_decode_kernel<1, 0, 8>, P) : cudaLaunchKernelEx(&cfg, cluster_decode_kernel<0, 0, 8>, P);
   } else if (exact) {
     err = sampled ? cudaLaunchKernelEx(&cfg, cluster_decode_kernel<1, 1, 16>, P) : cudaLaunchKernelEx(&cfg, cluster_decode_kernel<1, 0, 16>, P);
   } else {

@@ -32,7 +32,7 @@ class LaneRunner:
 
     * cluster-resident decode kernel (bf16 / exact precision): ONE call on the side stream; the engine cuts it into
       balanced waves of co-resident clusters, which run back to back: 7 x 16 sessions per wave of 16-CTA clusters
-      (~150 us per iteration however many of the clusters are used), and for greedy bf16 batches above that 15 x 16
+      (~150 us per iteration however many of the clusters are used), and for greedy batches above that 15 x 16
       sessions per wave of 8-CTA clusters (each CTA streams twice the weights: a longer iteration, but 240 sessions
       abreast).
     * kernel-per-op chain (fp32 precision, sampled decoding, and the part of a batch the cluster waves do not take):
@@ -40,12 +40,12 @@ class LaneRunner:
       latency-bound kernels that leaves most of the GPU idle; sessions never interact, so disjoint groups advance
       concurrently (engine decode lanes).
     * a call may also be split between both (`plan` returns the two counts and `launch` runs them at the same time on
-      different streams): a greedy bf16 batch slightly above one wave of 8-CTA clusters (256 streams = 240 + 16) keeps the
+      different streams): a greedy batch slightly above one wave of 8-CTA clusters (256 streams = 240 + 16) keeps the
       wave on the cluster kernel and runs the tail on ONE kernel-per-op lane (LVX_PATH_PER_OP_TAIL: grids sized for the 28
       SMs the wave leaves free) while decode rounds and vocoder batches take turns on the GPU.  Measured (bench.py --streams
       256, bf16, ms per step): all on the lanes 86.8, two waves 98.6, 240 + 16 on three tail lanes with the vocoder
-      overlapped 92.4, one tail lane overlapped 72.4, one tail lane taking turns 69.3.  (With 16-CTA clusters only -- exact
-      precision, sampled decoding -- the split is off by default: 224 + 32 ran at 6858 audio-s/s against 8251 on the lanes.)
+      overlapped 92.4, one tail lane overlapped 72.4, one tail lane taking turns 69.3.  (With 16-CTA clusters only -- sampled
+      decoding -- the split is off by default: 224 + 32 ran at 6858 audio-s/s against 8251 on the lanes.)
 
     `launch()` enqueues on the side streams and returns the completion events; `join()` makes the control stream wait
     for them.  Every launch first waits, on every stream it uses, for the previous round's events of the OTHER streams:
@@ -59,7 +59,7 @@ class LaneRunner:
     CLUSTER_DECODE_MAX_BATCH = 224
     CLUSTER_DECODE_GAP = (113, 139)
     HYBRID_ABOVE_MAX_BATCH = False
-    # greedy bf16: above one wave of 16-CTA clusters the engine switches to 8-CTA clusters, 15 x 16 = 240 sessions per wave
+    # greedy decoding: above one wave of 16-CTA clusters the engine switches to 8-CTA clusters, 15 x 16 = 240 sessions per wave
     # (engine.cluster_capacity()).  A batch slightly above a wave (256 streams) runs the wave on the cluster kernel and the
     # rest on the kernel-per-op lanes AT THE SAME TIME (the 28 SMs fifteen 8-CTA clusters leave idle); larger batches take
     # further waves, and beyond CLUSTER8_MAX_WAVES waves the kernel-per-op chain's large-M GEMMs win (config 4).
@@ -100,7 +100,7 @@ class LaneRunner:
 
     def wave8(self, sampling: Optional[Sampling]) -> int:
         """Sessions per wave of the 8-CTA cut for this sampler (0: the cut does not apply)."""
-        if self.e.precision != "bf16" or (sampling is not None and not sampling.greedy and sampling.top_k != 1):
+        if self.e.precision not in ("bf16", "exact") or (sampling is not None and not sampling.greedy and sampling.top_k != 1):
             return 0
         if not hasattr(self, "_caps"):
             self._caps = self.e.cluster_capacity() if hasattr(self.e, "cluster_capacity") else (112, 240)

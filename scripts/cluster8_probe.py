@@ -1,5 +1,6 @@
 """us per decode iteration of the two cuts of the cluster-resident kernel (16-CTA / 8-CTA clusters) and of the
-kernel-per-op chain over batch sizes, bf16 greedy; direct engine calls on one stream (no LaneRunner policy)."""
+kernel-per-op chain over batch sizes, greedy, PROBE_PRECISION = bf16 | exact; direct engine calls on one stream (no
+LaneRunner policy)."""
 import os
 import sys
 
@@ -15,7 +16,8 @@ T0 = int(os.environ.get("PROBE_T0", "20"))
 ITERS = int(os.environ.get("PROBE_ITERS", "100"))
 sd = W.make_random_weights(1234, wpe_rows=512)
 rng = np.random.RandomState(0)
-e = Engine(sd, device=0, precision="bf16", max_sessions=N, max_batch=N, max_context=T0 + 2 * ITERS + 32, max_vocode_frames=256, decode_lanes=4)
+PRECISION = os.environ.get("PROBE_PRECISION", "bf16")
+e = Engine(sd, device=0, precision=PRECISION, max_sessions=N, max_batch=N, max_context=T0 + 2 * ITERS + 32, max_vocode_frames=256, decode_lanes=4)
 print("cluster capacity (sessions per wave: 16-CTA, 8-CTA):", e.cluster_capacity(), flush=True)
 
 

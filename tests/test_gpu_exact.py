@@ -36,6 +36,12 @@ def _report(tag, got, ref, logits):
     return div, msg
 
 
+def _path(path):
+    """decode path argument of a test variant: the engine's choice, or the 8-CTA cut of the cluster kernel forced"""
+    from llmvox_b200 import _lib
+    return _lib.PATH_CLUSTER8 if path == "cluster8" else _lib.PATH_AUTO
+
+
 def _engine(weights, path, n, ctx):
     import os
     from llmvox_b200.engine import Engine
@@ -47,7 +53,7 @@ def _engine(weights, path, n, ctx):
         os.environ.pop("LLMVOX_B200_CLUSTER", None)
 
 
-@pytest.mark.parametrize("path", ["cluster", "per_op"])
+@pytest.mark.parametrize("path", ["cluster", "cluster8", "per_op"])
 def test_exact_greedy_tokens_identical_config0(weights, folded, gold, path):
     """BASELINE config 0: the 20-word sentence, all 130 steps of the fixture's length, every token."""
     g = gold("config0_loop.npz")
@@ -57,10 +63,10 @@ def test_exact_greedy_tokens_identical_config0(weights, folded, gold, path):
     e.open([1])
     e.feed_text([1], [ids])
     l0 = e.kernel_launches
-    e.decode_steps([1], n)
+    e.decode_steps([1], n, path=_path(path))
     launches = e.kernel_launches - l0
-    # the path under test really ran: one cluster-kernel launch (+ the page-table patch) against ~40 kernels per step
-    assert (launches <= 8) if path == "cluster" else (launches > 30 * n), launches
+    # the path under test really ran: one cluster-kernel launch (+ the page-table patch, stream packing) against ~40 kernels per step
+    assert (launches <= 12) if path != "per_op" else (launches > 30 * n), launches
     got = e.gather_codes([1], 0, n).cpu().numpy()[0].tolist()
     e.close()
     div, msg = _report(f"exact/{path} config0", got, ref, logits)
@@ -68,7 +74,7 @@ def test_exact_greedy_tokens_identical_config0(weights, folded, gold, path):
     assert got == ref
 
 
-@pytest.mark.parametrize("path", ["cluster", "per_op"])
+@pytest.mark.parametrize("path", ["cluster", "cluster8", "per_op"])
 def test_exact_greedy_tokens_identical_config1_streams(weights, folded, path):
     """BASELINE config 1 shape: 8 of the concurrent streams x 200 steps each, every token of every stream, decoded as
     one batch (and, on the cluster kernel, cut into launches of 10/30/90/70 iterations like the chunk schedule)."""
@@ -80,7 +86,7 @@ def test_exact_greedy_tokens_identical_config1_streams(weights, folded, path):
     e.open(slots)
     e.feed_text(slots, texts)
     for k in (10, 30, 90, 70):
-        e.decode_steps(slots, k)
+        e.decode_steps(slots, k, path=_path(path))
     got = e.gather_codes(slots, 0, n).cpu().numpy()
     e.close()
     bad = []
@@ -161,17 +167,20 @@ def test_exact_long_context_2000_steps(weights, folded):
     texts = [ids] + [rng.randint(3, 259, size=k).tolist() for k in (0, 300, 1500)]
     slots = [0, 1, 2, 3]
     out = {}
-    for path in ("cluster", "per_op"):
+    for path in ("cluster", "cluster8", "per_op"):
         e = _engine(weights, path, 4, 2048)
         e.open(slots)
         e.feed_text(slots, texts)
         for k in (1000, 30, 970):                   # launches that start below, straddle and start above the 1024-token window
-            e.decode_steps(slots, k)
+            e.decode_steps(slots, k, path=_path(path))
         out[path] = e.gather_codes(slots, 0, n).cpu().numpy()
         assert e.session_length(0) == n
         e.close()
     div, msg = _report("exact/cluster 2000 steps", out["cluster"][0].tolist(), ref, logits)
     assert div is None, msg
+    div, msg = _report("exact/cluster8 2000 steps", out["cluster8"][0].tolist(), ref, logits)
+    assert div is None, msg
     for i in range(4):
-        same = out["cluster"][i] == out["per_op"][i]
-        assert same.all(), (i, int(np.argmin(same)))
+        for path in ("cluster", "cluster8"):
+            same = out[path][i] == out["per_op"][i]
+            assert same.all(), (path, i, int(np.argmin(same)))

@@ -159,11 +159,11 @@ def test_chunk_scheduler_properties_against_the_oracle_schedule():
 
 
 def test_lane_runner_picks_the_decode_path_by_batch_size():
-    """LaneRunner's host-side policy (no GPU needed).  Greedy bf16: the cluster-resident kernel takes everything up to one
+    """LaneRunner's host-side policy (no GPU needed).  Greedy bf16 / exact: the cluster-resident kernel takes everything up to one
     wave of 8-CTA clusters (240 sessions on a B200; the engine itself uses 16-CTA clusters up to 112), a batch slightly
     above a wave keeps the wave on the cluster kernel and puts the rest on the kernel-per-op lanes, two waves are still
-    cluster work, beyond that the lanes take all.  Exact precision and sampled decoding have 16-CTA clusters only: one or
-    two waves of 7 (up to 112 and 140-224 sessions)."""
+    cluster work, beyond that the lanes take all.  Sampled decoding has 16-CTA clusters only: one or two waves of 7 (up to
+    112 and 140-224 sessions)."""
     from llmvox_b200.engine import Engine, Sampling
     from llmvox_b200.streaming import LaneRunner
 
@@ -176,7 +176,7 @@ def test_lane_runner_picks_the_decode_path_by_batch_size():
         cluster_decode_applicable = Engine.cluster_decode_applicable
 
         def cluster_capacity(self):
-            return (112, 240) if self.precision == "bf16" else (112, 0)
+            return (112, 240)
 
     r = object.__new__(LaneRunner)
     r.e = FakeEngine()
@@ -198,9 +198,9 @@ def test_lane_runner_picks_the_decode_path_by_batch_size():
     r.e.precision = "fp32"
     assert r.plan(64, greedy) == (0, 64)                          # fp32 parity mode: FMA-pipe GEMMs
     r.e.precision = "exact"
-    del r._caps
-    assert r.plan(64, greedy) == (64, 0) and r.plan(120, greedy) == (120, 0)   # exact mode: hi | lo cluster kernel, 16-CTA clusters
-    assert r.plan(256, greedy) == (0, 256)
+    assert r.plan(64, greedy) == (64, 0) and r.plan(120, greedy) == (120, 0)   # exact mode: hi | lo cluster kernel, both cuts
+    assert r.plan(256, greedy) == (240, 16)
+    assert r.plan(140, sampled) == (140, 0) and r.plan(256, sampled) == (0, 256)   # sampled: 16-CTA clusters only
     r.e.precision = "bf16"
     r.e.cfg.max_context = 8192
     assert r.plan(64, greedy) == (64, 0)                          # the reference's block_size: page-table windows of 64 pages

@@ -370,6 +370,119 @@ __device__ __forceinline__ void tc_epilogue_chunk(const GemmParams& p, int i, in
   }
 }
 
+// Normal-mode epilogue of a full 16-column chunk with COALESCED global accesses (persistent kernel).  In TMEM a lane owns a
+// D row, so the plain epilogue above makes every warp-wide load / store touch 32 different rows (16 bytes each: 32
+// sectors per instruction, every sector fetched twice by successive instructions).  Measured on the ConvNeXt GEMMs at
+// 61,440 rows: the residual read alone cost pw2 27 % (697 vs 947 TFLOP/s without it), the row-strided bf16 stores pw1 about
+// as much.  Here a warp's 32 x 16 block goes through a per-warp shared-memory scratch (row pitch 80 B: conflict-free
+// 16-byte writes per quarter warp) so that global instructions move whole 64-byte row segments, 8 rows per instruction,
+// every sector touched once (bf16 destinations: two chunks side by side).
+//   row0  = first D row of the warp (lane = row - row0), j0 = first column, v = this lane's 16 accumulator values
+//   Requirements (checked by the caller): j0 + 16 <= N, ldc / ldr multiples of 4 elements (8 for bf16).
+constexpr int TC_EPI_SCRATCH = 32 * 80;   // bytes per epilogue warp
+//   vmask = ballot of the rows that exist and are not padding (computed once per tile by the caller: the row_chunk load
+//   cost 17 % of the epilogue's stall samples when it sat in front of every chunk)
+__device__ __forceinline__ unsigned tc_row_mask(const GemmParams& p, int m) {
+  const bool valid = m < p.M && (!p.row_chunk || p.row_chunk[m] >= 0);
+  return __ballot_sync(0xffffffffu, valid);
+}
+template <typename TC, int ACT>
+__device__ __forceinline__ void tc_epilogue_chunk_coalesced(const GemmParams& p, int row0, int lane, int j0, const float* v, float* scratch,
+                                                            int pair, unsigned vmask) {
+  if (vmask == 0u) return;   // warp-uniform
+  float r[16];
+  if (p.residual) {
+    const int seg = 4 * (lane & 3);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int R = 8 * k + (lane >> 2);
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if ((vmask >> R) & 1u) t = __ldcg(reinterpret_cast<const float4*>(p.residual + (size_t)(row0 + R) * p.ldr + j0 + seg));
+      *reinterpret_cast<float4*>(scratch + R * 20 + seg) = t;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(scratch + lane * 20 + j);
+      r[j] = t.x; r[j + 1] = t.y; r[j + 2] = t.z; r[j + 3] = t.w;
+    }
+    __syncwarp();
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) r[j] = 0.f;
+  }
+  float o[16];
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) {
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f), cs = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (p.bias) b = load4(p.bias + j0 + j);
+    if (p.col_scale) cs = load4(p.col_scale + j0 + j);
+    o[j] = tc_act<ACT>(v[j] * p.alpha + b.x) * cs.x + r[j];
+    o[j + 1] = tc_act<ACT>(v[j + 1] * p.alpha + b.y) * cs.y + r[j + 1];
+    o[j + 2] = tc_act<ACT>(v[j + 2] * p.alpha + b.z) * cs.z + r[j + 2];
+    o[j + 3] = tc_act<ACT>(v[j + 3] * p.alpha + b.w) * cs.w + r[j + 3];
+  }
+  TC* C = reinterpret_cast<TC*>(p.C);
+  if (sizeof(TC) == 2) {
+    // bf16: a chunk is only 32 bytes per row, so two consecutive chunks (j0 a multiple of 32, then j0 + 16) are packed side
+    // by side into the scratch rows (pitch 80 B) and leave as 64-byte row segments, four lanes per row, after the second
+    // one (`pair` = 0: first half, stored later; 1: second half, stores both; 2: a lone chunk, 32-byte segments).
+    uint4* sc = reinterpret_cast<uint4*>(scratch);
+    const int half = pair == 1 ? 2 : 0;
+#pragma unroll
+    for (int j = 0; j < 16; j += 8) {
+      uint4 u;
+      __nv_bfloat162 h0 = __floats2bfloat162_rn(o[j], o[j + 1]), h1 = __floats2bfloat162_rn(o[j + 2], o[j + 3]);
+      __nv_bfloat162 h2 = __floats2bfloat162_rn(o[j + 4], o[j + 5]), h3 = __floats2bfloat162_rn(o[j + 6], o[j + 7]);
+      u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+      u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+      sc[lane * 5 + half + (j >> 3)] = u;
+    }
+    if (pair == 0) return;   // (the next call, for the same rows, completes the pair)
+    __syncwarp();
+    if (pair == 1) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int R = 8 * k + (lane >> 2), piece = lane & 3;
+        if ((vmask >> R) & 1u)
+          *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(C) + (size_t)(row0 + R) * p.ldc + (j0 - 16) + 8 * piece) = sc[R * 5 + piece];
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int R = 16 * k + (lane >> 1), piece = lane & 1;
+        if ((vmask >> R) & 1u)
+          *reinterpret_cast<uint4*>(reinterpret_cast<bf16*>(C) + (size_t)(row0 + R) * p.ldc + j0 + 8 * piece) = sc[R * 5 + piece];
+      }
+    }
+    __syncwarp();
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(scratch + lane * 20 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+    __syncwarp();
+    const int seg = 4 * (lane & 3);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int R = 8 * k + (lane >> 2);
+      if ((vmask >> R) & 1u)
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(C) + (size_t)(row0 + R) * p.ldc + j0 + seg) = *reinterpret_cast<const float4*>(scratch + R * 20 + seg);
+    }
+    __syncwarp();
+  }
+}
+template <typename TC>
+__device__ __forceinline__ void tc_epilogue_dispatch_coalesced(const GemmParams& p, int row0, int lane, int j0, const float* v, float* scratch,
+                                                               int pair, unsigned vmask) {
+  if (p.act == ACT_GELU_ERF_BF16)
+    tc_epilogue_chunk_coalesced<TC, ACT_GELU_ERF_BF16>(p, row0, lane, j0, v, scratch, pair, vmask);
+  else if (p.act == ACT_GELU_ERF)
+    tc_epilogue_chunk_coalesced<TC, ACT_GELU_ERF>(p, row0, lane, j0, v, scratch, pair, vmask);
+  else if (p.act == ACT_GELU_TANH)
+    tc_epilogue_chunk_coalesced<TC, ACT_GELU_TANH>(p, row0, lane, j0, v, scratch, pair, vmask);
+  else
+    tc_epilogue_chunk_coalesced<TC, ACT_NONE>(p, row0, lane, j0, v, scratch, pair, vmask);
+}
+
 template <bool kSwap, typename TC>
 __device__ __forceinline__ void tc_epilogue_dispatch(const GemmParams& p, int i, int j0, const float* v, int ncols) {
   if (p.act == ACT_GELU_ERF_BF16)
@@ -779,6 +892,10 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
   } else {
     const int q = warp & 3, half = (warp - 2) >> 2;
     const int drow = q * 32 + lane;
+    // per-warp scratch of the coalesced epilogue, behind the operand ring
+    float* const scratch = reinterpret_cast<float*>(smem_raw + (tiles - smem_u32(smem_raw)) + TCP_STAGES * TCP_STAGE_BYTES + (warp - 2) * TC_EPI_SCRATCH);
+    const bool coalesced = (p.ldc & (sizeof(TC) == 2 ? 7 : 3)) == 0 && (!p.residual || (p.ldr & 3) == 0) &&
+                           (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0;
     int i = 0;
     for (int w = cluster_id; w < n_items; w += n_clusters, ++i) {
       const int acc = i & 1;
@@ -788,11 +905,19 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
       tc_fence_after();
       const uint32_t trow = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TCP_BN);
       const int c_lo = half * (TCP_BN / 2), c_hi = c_lo + TCP_BN / 2;
+      const unsigned vmask = tc_row_mask(p, x0 + drow);
       for (int c = c_lo; c < c_hi; c += 16) {
         if (y0 + c >= p.N) break;   // warp-uniform: columns past N (last N tile)
         float v[16];
-        tmem_ld16(trow + (uint32_t)c, v);
-        tc_epilogue_dispatch<false, TC>(p, x0 + drow, y0 + c, v, 16);   // rows >= M (odd tile count: the pair's second tile) store nothing
+        tmem_ld16(trow + (uint32_t)c, v);   // (issuing the next chunk's load before processing this one: 160 registers, 8 % slower)
+        if (coalesced && y0 + c + 16 <= p.N) {   // warp-uniform
+          // bf16 destination: chunks leave in pairs (c is a multiple of 16; the pair starts at a multiple of 32)
+          // (not with a residual: its staging uses the same scratch rows between the two halves)
+          const int pair = (sizeof(TC) == 2 && !p.residual) ? ((c & 16) ? 1 : (y0 + c + 32 <= p.N ? 0 : 2)) : 2;
+          tc_epilogue_dispatch_coalesced<TC>(p, x0 + q * 32, lane, y0 + c, v, scratch, pair, vmask);
+        }
+        else
+          tc_epilogue_dispatch<false, TC>(p, x0 + drow, y0 + c, v, 16);   // rows >= M (odd tile count: the pair's second tile) store nothing
       }
       tc_fence_before();
       __syncwarp();
@@ -811,7 +936,7 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
 
 template <typename TC>
 inline int tc_launch_persistent(const CUtensorMap& mx, const CUtensorMap& my, const TcParams& tp, int grid, cudaStream_t st) {
-  const size_t smem = (size_t)TCP_STAGES * TCP_STAGE_BYTES + 1024;
+  const size_t smem = (size_t)TCP_STAGES * TCP_STAGE_BYTES + 8 * TC_EPI_SCRATCH + 1024;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)(grid & ~1));
   cfg.blockDim = dim3(TCP_THREADS);

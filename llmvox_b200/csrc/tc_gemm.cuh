@@ -178,6 +178,27 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// The same load split into issue and wait: the coalesced epilogue starts the TMEM load, then fetches residual / bias /
+// scale, and only then waits.  The wait names the registers as in / out operands: nothing that reads them may be
+// scheduled above it.
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t (&r)[16], float* v) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                 "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 // TMA load multicast to the CTAs of `mask`: the tile lands at the same shared-memory offset in each of them and each CTA's
 // mbarrier (same offset) receives the byte count
 __device__ __forceinline__ void tma_load_2d_mcast(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, uint16_t mask) {
@@ -387,9 +408,11 @@ __device__ __forceinline__ unsigned tc_row_mask(const GemmParams& p, int m) {
   return __ballot_sync(0xffffffffu, valid);
 }
 template <typename TC, int ACT>
-__device__ __forceinline__ void tc_epilogue_chunk_coalesced(const GemmParams& p, int row0, int lane, int j0, const float* v, float* scratch,
+__device__ __forceinline__ void tc_epilogue_chunk_coalesced(const GemmParams& p, int row0, int lane, int j0, uint32_t taddr, float* scratch,
                                                             int pair, unsigned vmask) {
   if (vmask == 0u) return;   // warp-uniform
+  uint32_t acc_raw[16];
+  tmem_ld16_issue(taddr, acc_raw);   // on its way while the residual / bias / scale loads below are issued
   float r[16];
   if (p.residual) {
     const int seg = 4 * (lane & 3);
@@ -411,12 +434,18 @@ __device__ __forceinline__ void tc_epilogue_chunk_coalesced(const GemmParams& p,
 #pragma unroll
     for (int j = 0; j < 16; ++j) r[j] = 0.f;
   }
+  float4 bb[4], cc[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    bb[j] = p.bias ? load4(p.bias + j0 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    cc[j] = p.col_scale ? load4(p.col_scale + j0 + 4 * j) : make_float4(1.f, 1.f, 1.f, 1.f);
+  }
+  float v[16];
+  tmem_ld16_wait(acc_raw, v);
   float o[16];
 #pragma unroll
   for (int j = 0; j < 16; j += 4) {
-    float4 b = make_float4(0.f, 0.f, 0.f, 0.f), cs = make_float4(1.f, 1.f, 1.f, 1.f);
-    if (p.bias) b = load4(p.bias + j0 + j);
-    if (p.col_scale) cs = load4(p.col_scale + j0 + j);
+    const float4 b = bb[j >> 2], cs = cc[j >> 2];
     o[j] = tc_act<ACT>(v[j] * p.alpha + b.x) * cs.x + r[j];
     o[j + 1] = tc_act<ACT>(v[j + 1] * p.alpha + b.y) * cs.y + r[j + 1];
     o[j + 2] = tc_act<ACT>(v[j + 2] * p.alpha + b.z) * cs.z + r[j + 2];
@@ -471,16 +500,16 @@ __device__ __forceinline__ void tc_epilogue_chunk_coalesced(const GemmParams& p,
   }
 }
 template <typename TC>
-__device__ __forceinline__ void tc_epilogue_dispatch_coalesced(const GemmParams& p, int row0, int lane, int j0, const float* v, float* scratch,
+__device__ __forceinline__ void tc_epilogue_dispatch_coalesced(const GemmParams& p, int row0, int lane, int j0, uint32_t taddr, float* scratch,
                                                                int pair, unsigned vmask) {
   if (p.act == ACT_GELU_ERF_BF16)
-    tc_epilogue_chunk_coalesced<TC, ACT_GELU_ERF_BF16>(p, row0, lane, j0, v, scratch, pair, vmask);
+    tc_epilogue_chunk_coalesced<TC, ACT_GELU_ERF_BF16>(p, row0, lane, j0, taddr, scratch, pair, vmask);
   else if (p.act == ACT_GELU_ERF)
-    tc_epilogue_chunk_coalesced<TC, ACT_GELU_ERF>(p, row0, lane, j0, v, scratch, pair, vmask);
+    tc_epilogue_chunk_coalesced<TC, ACT_GELU_ERF>(p, row0, lane, j0, taddr, scratch, pair, vmask);
   else if (p.act == ACT_GELU_TANH)
-    tc_epilogue_chunk_coalesced<TC, ACT_GELU_TANH>(p, row0, lane, j0, v, scratch, pair, vmask);
+    tc_epilogue_chunk_coalesced<TC, ACT_GELU_TANH>(p, row0, lane, j0, taddr, scratch, pair, vmask);
   else
-    tc_epilogue_chunk_coalesced<TC, ACT_NONE>(p, row0, lane, j0, v, scratch, pair, vmask);
+    tc_epilogue_chunk_coalesced<TC, ACT_NONE>(p, row0, lane, j0, taddr, scratch, pair, vmask);
 }
 
 template <bool kSwap, typename TC>
@@ -908,16 +937,17 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
       const unsigned vmask = tc_row_mask(p, x0 + drow);
       for (int c = c_lo; c < c_hi; c += 16) {
         if (y0 + c >= p.N) break;   // warp-uniform: columns past N (last N tile)
-        float v[16];
-        tmem_ld16(trow + (uint32_t)c, v);   // (issuing the next chunk's load before processing this one: 160 registers, 8 % slower)
+        // (issuing the NEXT chunk's TMEM load before processing this one: 160 registers, 8 % slower -- measured)
         if (coalesced && y0 + c + 16 <= p.N) {   // warp-uniform
           // bf16 destination: chunks leave in pairs (c is a multiple of 16; the pair starts at a multiple of 32)
           // (not with a residual: its staging uses the same scratch rows between the two halves)
           const int pair = (sizeof(TC) == 2 && !p.residual) ? ((c & 16) ? 1 : (y0 + c + 32 <= p.N ? 0 : 2)) : 2;
-          tc_epilogue_dispatch_coalesced<TC>(p, x0 + q * 32, lane, y0 + c, v, scratch, pair, vmask);
-        }
-        else
+          tc_epilogue_dispatch_coalesced<TC>(p, x0 + q * 32, lane, y0 + c, trow + (uint32_t)c, scratch, pair, vmask);
+        } else {
+          float v[16];
+          tmem_ld16(trow + (uint32_t)c, v);
           tc_epilogue_dispatch<false, TC>(p, x0 + drow, y0 + c, v, 16);   // rows >= M (odd tile count: the pair's second tile) store nothing
+        }
       }
       tc_fence_before();
       __syncwarp();

@@ -570,6 +570,15 @@ extern "C" int lvx_engine_create(const lvx_config* cfg, int device, lvx_engine**
   declare_tensors(e);
   int s = engine_alloc(e);
   if (s == LVX_OK && c.precision != LVX_PRECISION_FP32) s = tc_init(&e->tcw, prop.multiProcessorCount);
+  if (s == LVX_OK) {   // the tiled depthwise-conv kernel keeps a 32-frame fp32 tile (96 KB) in shared memory
+    cudaError_t ce = cudaFuncSetAttribute(dwconv_adaln_tiled_kernel<float, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_R * 768 * 4);
+    if (ce == cudaSuccess)
+      ce = cudaFuncSetAttribute(dwconv_adaln_tiled_kernel<bf16, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_R * 768 * 4);
+    if (ce != cudaSuccess) {
+      set_error(std::string("cudaFuncSetAttribute(dwconv_adaln_tiled): ") + cudaGetErrorString(ce));
+      s = LVX_ERR_CUDA;
+    }
+  }
   if (s == LVX_OK) {
     const char* env = getenv("LLMVOX_B200_NO_GRAPH");
     e->use_graphs = !(env && env[0] == '1');
@@ -1801,7 +1810,19 @@ static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes
     auto& X = e->cnx[i];
     {
     PROF(e, "dwconv_adaln", st);
-    if (a == F32)
+    // bulk shapes: strips of DW_R frames with register-resident weights; small batches (fewer strips than two per SM): one
+    // warp per frame, which keeps every SM busy
+    const size_t dw_smem = (size_t)DW_R * 768 * sizeof(float);
+    const bool tiled = g.R >= 2 * DW_R * (e->tcw.num_sms > 0 ? e->tcw.num_sms : 148);
+    if (tiled && a == F32)
+      dwconv_adaln_tiled_kernel<float, 768><<<ceil_div(g.R, DW_R), 192, dw_smem, st>>>(e->v_x, g.R, e->row_chunk, X.dw_w, X.dw_b,
+                                                                                        X.scale + (size_t)bw * D, X.shift + (size_t)bw * D,
+                                                                                        1e-6f, (float*)e->v_h);
+    else if (tiled)
+      dwconv_adaln_tiled_kernel<bf16, 768><<<ceil_div(g.R, DW_R), 192, dw_smem, st>>>(e->v_x, g.R, e->row_chunk, X.dw_w, X.dw_b,
+                                                                                       X.scale + (size_t)bw * D, X.shift + (size_t)bw * D,
+                                                                                       1e-6f, (bf16*)e->v_h);
+    else if (a == F32)
       dwconv_adaln_kernel<float, 768><<<ceil_div(g.R, 8), 256, 0, st>>>(e->v_x, g.R, e->row_chunk, e->d_chunks, X.dw_w, X.dw_b,
                                                                          X.scale + (size_t)bw * D, X.shift + (size_t)bw * D, 1e-6f,
                                                                          (float*)e->v_h);

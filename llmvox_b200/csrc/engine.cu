@@ -1734,12 +1734,13 @@ static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes
     }
     int large_max = 0;
     if (nl) {
-      // V^T for the whole group: Vt[c, r] = (Wv . h^T)[c, r] + bv[c]  (swap-mode tiles, transposed store)
-      GemmParams t;
-      t.A = e->v_h; t.C = e->v_vt; t.M = g.R; t.lda = D; t.ldc = e->R_max; t.bias = e->at_qkv_b + 2 * D; t.c_transposed = 1;
-      t.a_cap = e->R_max;
-      if (e->prof_detail) t.tag = "tc_gemm:attn_vt";
-      LVX_TRY(run_gemm(e, t, e->at_v, a, a, st));
+      // V^T for the whole group: the v third of the fused q|k|v output, transposed (Vt[c, r] = V[r, c]; padding rows = 0)
+      {
+        PROF(e, "transpose_v", st);
+        transpose_v_kernel<<<dim3(ceil_div(g.R, 64), D / 64), 256, 0, st>>>((const bf16*)e->v_big, 3 * D, 2 * D, g.R, e->row_chunk, e->v_vt,
+                                                                             e->R_max);
+        LAUNCHED(e);
+      }
       std::vector<TcGroup> gs(nl), gp(nl);
       double fl = 0;
       for (int j = 0; j < nl; ++j) {

@@ -187,6 +187,36 @@ __global__ void __launch_bounds__(256) dwconv_adaln_kernel(const float* __restri
 // same layout, with columns [L, L rounded up to 64) written as zeros so the P.V GEMM's last k-block may read them.  One
 // warp per row.  Output type = GEMM operand type, in place for fp32.
 // ---------------------------------------------------------------------------------------------------
+// V^T operand of the pos_net attention's P V GEMM: Vt[c][r] = V[r][c], V = columns [v0, v0 + C) of the fused q|k|v
+// output (bf16, row stride ld).  64 x 64 tiles through shared memory; padding rows become zeros (the grouped P V GEMM
+// reads its K tail up to the next multiple of 64 rows, against P columns that are zero there).  Replaces a second
+// projection GEMM with a transposed store (0.57 ms per 61,440 frames at 128 TFLOP/s; this copy: 0.05 ms).
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transpose_v_kernel(const bf16* __restrict__ qkv, int ld, int v0, int rows,
+                                                          const int* __restrict__ row_chunk, bf16* __restrict__ vt, int ldt) {
+  __shared__ __align__(4) bf16 tile[64][66];
+  const int r0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int item = threadIdx.x + 256 * it, r = item >> 3, ch = item & 7;
+    uint4 u = make_uint4(0u, 0u, 0u, 0u);
+    if (r0 + r < rows && row_chunk[r0 + r] >= 0) u = *reinterpret_cast<const uint4*>(qkv + (size_t)(r0 + r) * ld + v0 + c0 + 8 * ch);
+    uint32_t* d = reinterpret_cast<uint32_t*>(&tile[r][8 * ch]);
+    d[0] = u.x; d[1] = u.y; d[2] = u.z; d[3] = u.w;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const int item = threadIdx.x + 256 * it, c = item >> 3, rb = (item & 7) * 8;
+    if (r0 + rb >= rows) continue;   // the last 8-row piece may run up to 7 columns past `rows` (zeros; ldt has the room)
+    __align__(16) bf16 o[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) o[k] = tile[rb + k][c];
+    *reinterpret_cast<uint4*>(vt + (size_t)(c0 + c) * ldt + r0 + rb) = *reinterpret_cast<const uint4*>(o);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // The same operation, tiled (the bulk path).  The one-warp-per-frame kernel above re-reads every input row 7 times and the
 // 21 KB of depthwise weights once per frame through L1: ~42 KB of L1 traffic per frame, which bounds it at a third of the
 // HBM rate (136 us per launch at 61,440 frames against 43 us of HBM time).  Here a CTA of 6 warps owns a strip of DW_R

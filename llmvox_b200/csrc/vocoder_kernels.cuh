@@ -20,7 +20,7 @@ struct ChunkInfo {
 
 // ---------------------------------------------------------------------------------------------------
 // GroupNorm statistics (WavTokenizer/decoder/models.py:15-16: 32 groups, eps 1e-6): mean / rstd over
-// (C/32 channels x L frames) per (chunk, group).  One CTA per (group, chunk); two passes.
+// (C/32 channels x L frames) per (chunk, group).  One CTA per (group, chunk); one shifted pass.
 // ---------------------------------------------------------------------------------------------------
 template <int C>
 __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const float* __restrict__ x,
@@ -32,20 +32,21 @@ __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const float* __res
   const ChunkInfo ci = chunks[ch];
   const int items = ci.len * V;
   const float* base = x + (size_t)ci.row0 * C + g * CPG;
-  float s = 0.f;
+  // ONE pass over the strip: sums of (x - K) and (x - K)^2 with K = the strip's first element (a value of the same
+  // distribution, so |mean - K| is a few standard deviations at most and the cancellation in q - s^2 / n costs a few ulps;
+  // the plain two-pass form read the strip twice, the second time from L2)
+  const float K = base[0];
+  float s = 0.f, q = 0.f;
   for (int i = threadIdx.x; i < items; i += 256) {
     const float4 v = load4(base + (size_t)(i / V) * C + (i % V) * 4);
-    s += (v.x + v.y) + (v.z + v.w);
-  }
-  const float n = (float)(ci.len * CPG);
-  const float mean = block_sum(s, red) / n;
-  float q = 0.f;
-  for (int i = threadIdx.x; i < items; i += 256) {
-    const float4 v = load4(base + (size_t)(i / V) * C + (i % V) * 4);
-    const float a = v.x - mean, b = v.y - mean, c = v.z - mean, d = v.w - mean;
+    const float a = v.x - K, b = v.y - K, c = v.z - K, d = v.w - K;
+    s += (a + b) + (c + d);
     q += (a * a + b * b) + (c * c + d * d);
   }
-  const float var = block_sum(q, red) / n;
+  const float n = (float)(ci.len * CPG);
+  const float ds = block_sum(s, red) / n;
+  const float mean = K + ds;
+  const float var = fmaxf(block_sum(q, red) / n - ds * ds, 0.f);
   if (threadIdx.x == 0) stats[(size_t)ch * G + g] = make_float2(mean, 1.0f / sqrtf(var + eps));
 }
 

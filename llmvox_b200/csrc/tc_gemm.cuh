@@ -499,6 +499,71 @@ __device__ __forceinline__ void tc_epilogue_chunk_coalesced(const GemmParams& p,
     __syncwarp();
   }
 }
+// bf16 destination without a residual (the ConvNeXt pw1 GEMM: K = 768, so the epilogue of a 128 x 256 tile has to keep
+// up with 12 k-blocks of MMAs): 32 columns per step -- both TMEM loads in flight together, one wait, one __syncwarp, and
+// the 64-byte row segments leave four lanes per row.
+template <int ACT>
+__device__ __forceinline__ void tc_epilogue_pair_bf16(const GemmParams& p, int row0, int lane, int j0, uint32_t taddr, float* scratch,
+                                                      unsigned vmask) {
+  if (vmask == 0u) return;   // warp-uniform
+  uint32_t ra[16], rb[16];
+  tmem_ld16_issue(taddr, ra);
+  tmem_ld16_issue(taddr + 16u, rb);
+  float4 bb[8], cc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    bb[j] = p.bias ? load4(p.bias + j0 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+    cc[j] = p.col_scale ? load4(p.col_scale + j0 + 4 * j) : make_float4(1.f, 1.f, 1.f, 1.f);
+  }
+  float v[32];
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(ra[0]), "+r"(ra[1]), "+r"(ra[2]), "+r"(ra[3]), "+r"(ra[4]), "+r"(ra[5]), "+r"(ra[6]), "+r"(ra[7]), "+r"(ra[8]), "+r"(ra[9]),
+                 "+r"(ra[10]), "+r"(ra[11]), "+r"(ra[12]), "+r"(ra[13]), "+r"(ra[14]), "+r"(ra[15]), "+r"(rb[0]), "+r"(rb[1]), "+r"(rb[2]),
+                 "+r"(rb[3]), "+r"(rb[4]), "+r"(rb[5]), "+r"(rb[6]), "+r"(rb[7]), "+r"(rb[8]), "+r"(rb[9]), "+r"(rb[10]), "+r"(rb[11]),
+                 "+r"(rb[12]), "+r"(rb[13]), "+r"(rb[14]), "+r"(rb[15])
+               :
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    v[i] = __uint_as_float(ra[i]);
+    v[16 + i] = __uint_as_float(rb[i]);
+  }
+  uint4* sc = reinterpret_cast<uint4*>(scratch);
+#pragma unroll
+  for (int j = 0; j < 32; j += 8) {
+    const float4 b0 = bb[j >> 2], b1 = bb[(j >> 2) + 1], c0 = cc[j >> 2], c1 = cc[(j >> 2) + 1];
+    const float o0 = tc_act<ACT>(v[j] * p.alpha + b0.x) * c0.x, o1 = tc_act<ACT>(v[j + 1] * p.alpha + b0.y) * c0.y;
+    const float o2 = tc_act<ACT>(v[j + 2] * p.alpha + b0.z) * c0.z, o3 = tc_act<ACT>(v[j + 3] * p.alpha + b0.w) * c0.w;
+    const float o4 = tc_act<ACT>(v[j + 4] * p.alpha + b1.x) * c1.x, o5 = tc_act<ACT>(v[j + 5] * p.alpha + b1.y) * c1.y;
+    const float o6 = tc_act<ACT>(v[j + 6] * p.alpha + b1.z) * c1.z, o7 = tc_act<ACT>(v[j + 7] * p.alpha + b1.w) * c1.w;
+    uint4 u;
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(o0, o1), h1 = __floats2bfloat162_rn(o2, o3);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(o4, o5), h3 = __floats2bfloat162_rn(o6, o7);
+    u.x = *reinterpret_cast<uint32_t*>(&h0); u.y = *reinterpret_cast<uint32_t*>(&h1);
+    u.z = *reinterpret_cast<uint32_t*>(&h2); u.w = *reinterpret_cast<uint32_t*>(&h3);
+    sc[lane * 5 + (j >> 3)] = u;
+  }
+  __syncwarp();
+  bf16* C = reinterpret_cast<bf16*>(p.C);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int R = 8 * k + (lane >> 2), piece = lane & 3;
+    if ((vmask >> R) & 1u) *reinterpret_cast<uint4*>(C + (size_t)(row0 + R) * p.ldc + j0 + 8 * piece) = sc[R * 5 + piece];
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void tc_epilogue_pair_bf16_dispatch(const GemmParams& p, int row0, int lane, int j0, uint32_t taddr, float* scratch,
+                                                               unsigned vmask) {
+  if (p.act == ACT_GELU_ERF_BF16)
+    tc_epilogue_pair_bf16<ACT_GELU_ERF_BF16>(p, row0, lane, j0, taddr, scratch, vmask);
+  else if (p.act == ACT_GELU_ERF)
+    tc_epilogue_pair_bf16<ACT_GELU_ERF>(p, row0, lane, j0, taddr, scratch, vmask);
+  else if (p.act == ACT_GELU_TANH)
+    tc_epilogue_pair_bf16<ACT_GELU_TANH>(p, row0, lane, j0, taddr, scratch, vmask);
+  else
+    tc_epilogue_pair_bf16<ACT_NONE>(p, row0, lane, j0, taddr, scratch, vmask);
+}
+
 template <typename TC>
 __device__ __forceinline__ void tc_epilogue_dispatch_coalesced(const GemmParams& p, int row0, int lane, int j0, uint32_t taddr, float* scratch,
                                                                int pair, unsigned vmask) {
@@ -938,6 +1003,11 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
       for (int c = c_lo; c < c_hi; c += 16) {
         if (y0 + c >= p.N) break;   // warp-uniform: columns past N (last N tile)
         // (issuing the NEXT chunk's TMEM load before processing this one: 160 registers, 8 % slower -- measured)
+        if (sizeof(TC) == 2 && coalesced && !p.residual && y0 + c + 32 <= p.N) {   // warp-uniform: 32 columns per step
+          tc_epilogue_pair_bf16_dispatch(p, x0 + q * 32, lane, y0 + c, trow + (uint32_t)c, scratch, vmask);
+          c += 16;
+          continue;
+        }
         if (coalesced && y0 + c + 16 <= p.N) {   // warp-uniform
           // bf16 destination: chunks leave in pairs (c is a multiple of 16; the pair starts at a multiple of 32)
           // (not with a residual: its staging uses the same scratch rows between the two halves)

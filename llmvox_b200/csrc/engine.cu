@@ -1615,13 +1615,10 @@ static int groupnorm(lvx_engine* e, const VocGroup& g, const float* x, const flo
   dim3 grid(32, (unsigned)g.chunks.size());
   groupnorm_stats_kernel<768><<<grid, 256, 0, st>>>(x, e->d_chunks, 1e-6f, e->v_stats);
   LAUNCHED(e);
-  const long long items = (long long)g.R * (768 / 4);
   if (e->adt() == F32)
-    groupnorm_apply_kernel<float, 768><<<(unsigned)((items + 255) / 256), 256, 0, st>>>(x, g.R, e->row_chunk, e->v_stats, w, b,
-                                                                                         swish, (float*)out);
+    groupnorm_apply_kernel<float, 768><<<ceil_div(g.R, 8), 256, 0, st>>>(x, g.R, e->row_chunk, e->v_stats, w, b, swish, (float*)out);
   else
-    groupnorm_apply_kernel<bf16, 768><<<(unsigned)((items + 255) / 256), 256, 0, st>>>(x, g.R, e->row_chunk, e->v_stats, w, b,
-                                                                                        swish, (bf16*)out);
+    groupnorm_apply_kernel<bf16, 768><<<ceil_div(g.R, 8), 256, 0, st>>>(x, g.R, e->row_chunk, e->v_stats, w, b, swish, (bf16*)out);
   LAUNCHED(e);
   return LVX_OK;
 }

@@ -50,31 +50,39 @@ __global__ void __launch_bounds__(256) groupnorm_stats_kernel(const float* __res
   if (threadIdx.x == 0) stats[(size_t)ch * G + g] = make_float2(mean, 1.0f / sqrtf(var + eps));
 }
 
-// GroupNorm apply (+ optional swish, models.py:10-12) -> GEMM operand type.  One thread per float4.
+// GroupNorm apply (+ optional swish, models.py:10-12) -> GEMM operand type.  One warp per row (6 float4 per lane, no
+// index divisions; swish through the fast exponential: relative error 2^-21).
 template <typename TOut, int C>
 __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float* __restrict__ x, int rows,
                                                               const int* __restrict__ row_chunk,
                                                               const float2* __restrict__ stats,
                                                               const float* __restrict__ w, const float* __restrict__ b,
                                                               int swish, TOut* __restrict__ out) {
-  constexpr int G = 32, CPG = C / G;
-  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
-  const int row = (int)(i / (C / 4)), c = (int)(i % (C / 4)) * 4;
+  constexpr int G = 32, CPG = C / G, V = C / 128;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (row >= rows) return;
   const int ch = row_chunk[row];
   if (ch < 0) {  // padding row: the k=3 conv that follows must read zeros here
-    store4(out + (size_t)row * C + c, make_float4(0.f, 0.f, 0.f, 0.f));
+#pragma unroll
+    for (int i = 0; i < V; ++i) store4(out + (size_t)row * C + (lane + 32 * i) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
     return;
   }
-  const float2 st = stats[(size_t)ch * G + c / CPG];
-  const float4 v = load4(x + (size_t)row * C + c), ww = load4(w + c), bb = load4(b + c);
-  float r[4] = {(v.x - st.x) * st.y * ww.x + bb.x, (v.y - st.x) * st.y * ww.y + bb.y,
-                (v.z - st.x) * st.y * ww.z + bb.z, (v.w - st.x) * st.y * ww.w + bb.w};
-  if (swish) {
+  float4 v[V];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) r[k] = r[k] / (1.0f + expf(-r[k]));
+  for (int i = 0; i < V; ++i) v[i] = load4(x + (size_t)row * C + (lane + 32 * i) * 4);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    const float2 st = stats[(size_t)ch * G + c / CPG];
+    const float4 ww = load4(w + c), bb = load4(b + c);
+    float r[4] = {(v[i].x - st.x) * st.y * ww.x + bb.x, (v[i].y - st.x) * st.y * ww.y + bb.y,
+                  (v[i].z - st.x) * st.y * ww.z + bb.z, (v[i].w - st.x) * st.y * ww.w + bb.w};
+    if (swish) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) r[k] = r[k] / (1.0f + __expf(-r[k]));
+    }
+    store4(out + (size_t)row * C + c, make_float4(r[0], r[1], r[2], r[3]));
   }
-  store4(out + (size_t)row * C + c, make_float4(r[0], r[1], r[2], r[3]));
 }
 
 // ---------------------------------------------------------------------------------------------------

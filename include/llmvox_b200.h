@@ -127,7 +127,7 @@ int lvx_decode_steps_lane(lvx_engine* e, int lane, const int32_t* h_slots, int n
 #define LVX_PATH_CLUSTER 1
 #define LVX_PATH_PER_OP 2
 /* The cluster-resident kernel exists in two cuts of the same weights: 16-CTA clusters (lowest latency, one wave holds
- * 7 x 16 sessions on a B200) and 8-CTA clusters (greedy decoding only; one wave holds 15 x 16 sessions: the 256-streams
+ * 7 x 16 sessions on a B200) and 8-CTA clusters (one wave holds 15 x 16 sessions: the 256-streams
  * operating point).  LVX_PATH_CLUSTER picks by batch size (16-CTA up to one wave of them, 8-CTA above); the two values
  * below force one cut (an error when it does not apply).  Within a cut a session's codes do not depend on how calls are
  * composed; across cuts they agree within the bf16 contract (teacher-forced logits within 2e-2), not bit for bit. */

@@ -825,7 +825,6 @@ struct CdWorkersSync {
 template <int X, int S, int CL>
 __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __grid_constant__ ClusterParams P) {
   using G = CdG<X, CL>;
-  static_assert(CL == 16 || S == 0, "the 8-CTA variant is greedy-only");
   constexpr int XR = G::XR, QR = G::QR, FR = G::FR, VR = G::VR, XF = XR / 16;
   extern __shared__ uint8_t smem_raw[];
   // barriers [0, 26) + status words [32, 40) (progress of each role, dumped by a timed-out spin); 512-byte aligned so that
@@ -1313,36 +1312,50 @@ __global__ void __launch_bounds__(CD_THREADS, 1) cluster_decode_kernel(const __g
       wait_acc();
       CD_T();
       if constexpr (S) {
-        // ---- sampled pick: session n's 4096 logits are gathered at CTA n (into the partials buffer, idle here), which runs
-        // the sampler of the kernel-per-op path (decode_kernels.cuh: sample_pick) with its 8 worker warps and tells every
-        // peer the code.  Same draws as sampler_kernel: Philox4x32-10(seed; slot, step).
-        float v0[8], v1[8];
-        tmem_ld8<G>(trow + (uint32_t)(G::TM_LM + 8 * hh), v0);
-        tmem_ld8<G>(trow + (uint32_t)(G::TM_LM + G::NCOL + 8 * hh), v1);
+        // ---- sampled pick: session n's 4096 logits are gathered at CTA n % CL (into the partials buffer, idle here: 16 KB per
+        // session, two sessions per CTA with 8-CTA clusters), which runs the sampler of the kernel-per-op path
+        // (decode_kernels.cuh: sample_pick) with its 8 worker warps and tells every peer the code.  Same draws as
+        // sampler_kernel: Philox4x32-10(seed; slot, step).
+        float v[G::NT_LM][8];
+#pragma unroll
+        for (int tl = 0; tl < G::NT_LM; ++tl) tmem_ld8<G>(trow + (uint32_t)(G::TM_LM + G::NCOL * tl + 8 * hh), v[tl]);
         const int row = VR * rank + 32 * q + lane;
 #pragma unroll 1
         for (int i = 0; i < 8; ++i) {
           const int n = 8 * hh + i;
+          float vi[G::NT_LM];
+#pragma unroll
+          for (int tl = 0; tl < G::NT_LM; ++tl) {   // (v[tl][i] with a runtime i: select, the rows stay in registers)
+            float x = v[tl][0];
+#pragma unroll
+            for (int k = 1; k < 8; ++k) x = (i == k) ? v[tl][k] : x;
+            vi[tl] = x;
+          }
           if (P.logits && iter == n_iters - 1 && n < nloc) {
             float* lg = P.logits + (size_t)(n0 + n) * CD_V + row;
-            lg[0] = v0[i];
-            lg[128] = v1[i];
+#pragma unroll
+            for (int tl = 0; tl < G::NT_LM; ++tl) lg[128 * tl] = vi[tl];
           }
-          const uint32_t dst = cd_mapa(sbase + G::OFF_RED + (uint32_t)(row * 4), (uint32_t)n);
-          cd_st_remote_f32(dst, v0[i]);
-          cd_st_remote_f32(dst + 128 * 4, v1[i]);
+          const uint32_t dst = cd_mapa(sbase + G::OFF_RED + (uint32_t)(((n / CL) * CD_V + row) * 4), (uint32_t)(n % CL));
+#pragma unroll
+          for (int tl = 0; tl < G::NT_LM; ++tl) cd_st_remote_f32(dst + (uint32_t)(128 * 4 * tl), vi[tl]);
         }
         tc_fence_before();
         exchange(false);
-        if (rank < nloc) {   // CTA-uniform: this CTA owns session `rank`
-          // scratch in the q/k/v buffer (idle outside the attention phases; the candidates buffer next to the statistics
-          // is NOT free: peers that finish first already write their codes into it)
-          SamplerScratch& scr = *reinterpret_cast<SamplerScratch*>(sgen + G::OFF_QKV);
-          const int slot = sm_slot[rank];
-          const float u = philox_uniform(P.seed, (uint32_t)slot, (uint32_t)sm_t[rank]);
-          const int code = sample_pick(reinterpret_cast<float*>(sgen + G::OFF_RED), CD_V, false, P.top_k, P.temperature, u, scr, wt,
-                                       CdWorkersSync());
-          if (wt < CL) cd_st_remote_v2(cd_mapa(sbase + G::OFF_CAND + (uint32_t)(rank * 8), (uint32_t)wt), 0u, (uint32_t)code);
+#pragma unroll 1
+        for (int a = 0; a < CD_NB / CL; ++a) {
+          const int n = rank + CL * a;
+          if (n < nloc) {   // CTA-uniform: this CTA owns session n
+            // scratch in the q/k/v buffer (idle outside the attention phases; the candidates buffer next to the statistics
+            // is NOT free: peers that finish first already write their codes into it)
+            SamplerScratch& scr = *reinterpret_cast<SamplerScratch*>(sgen + G::OFF_QKV);
+            const int slot = sm_slot[n];
+            const float u = philox_uniform(P.seed, (uint32_t)slot, (uint32_t)sm_t[n]);
+            const int code = sample_pick(reinterpret_cast<float*>(sgen + G::OFF_RED) + a * CD_V, CD_V, false, P.top_k, P.temperature, u, scr,
+                                         wt, CdWorkersSync());
+            if (wt < CL) cd_st_remote_v2(cd_mapa(sbase + G::OFF_CAND + (uint32_t)(n * 8), (uint32_t)wt), 0u, (uint32_t)code);
+            cd_workers_sync();   // the scratch is reused by the CTA's second session
+          }
         }
         exchange(false);
         if (wt < CD_NB) {
@@ -1563,10 +1576,8 @@ inline int cluster_decode_configure_x(int* max_clusters) {
   using G = CdG<X, CL>;
   cudaError_t err = cudaFuncSetAttribute(cluster_decode_kernel<X, 0, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
   if (err == cudaSuccess) err = cudaFuncSetAttribute(cluster_decode_kernel<X, 0, CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-  if constexpr (CL == 16) {
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(cluster_decode_kernel<X, 1, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
-    if (err == cudaSuccess) err = cudaFuncSetAttribute(cluster_decode_kernel<X, 1, CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-  }
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(cluster_decode_kernel<X, 1, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, G::SMEM_BYTES);
+  if (err == cudaSuccess) err = cudaFuncSetAttribute(cluster_decode_kernel<X, 1, CL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
   if (err != cudaSuccess) {
     set_error(std::string("cudaFuncSetAttribute(cluster_decode): ") + cudaGetErrorString(err));
     return LVX_ERR_CUDA;
@@ -1599,7 +1610,7 @@ inline int cluster_decode_configure(bool exact, int* max_clusters, int* max_clus
   return st;
 }
 
-// cl = CTAs per cluster: 16, or 8 (greedy only)
+// cl = CTAs per cluster: 16 or 8
 inline int cluster_decode_launch(bool exact, bool sampled, int cl, const ClusterParams& P, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(cl * ceil_div(P.n, P.per_cluster));
@@ -1614,12 +1625,10 @@ inline int cluster_decode_launch(bool exact, bool sampled, int cl, const Cluster
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t err;
-  if (cl == 8) {
-    if (sampled) {
-      set_error("cluster_decode launch: the 8-CTA variant is greedy only");
-      return LVX_ERR_INVALID;
-    }
-    err = exact ? cudaLaunchKernelEx(&cfg, cluster_decode_kernel<1, 0, 8>, P) : cudaLaunchKernelEx(&cfg, cluster_decode_kernel<0, 0, 8>, P);
+  if (cl == 8 && exact) {
+    err = sampled ? cudaLaunchKernelEx(&cfg, cluster_decode_kernel<1, 1, 8>, P) : cudaLaunchKernelEx(&cfg, cluster_decode_kernel<1, 0, 8>, P);
+  } else if (cl == 8) {
+    err = sampled ? cudaLaunchKernelEx(&cfg, cluster_decode_kernel<0, 1, 8>, P) : cudaLaunchKernelEx(&cfg, cluster_decode_kernel<0, 0, 8>, P);
   } else if (exact) {
     err = sampled ? cudaLaunchKernelEx(&cfg, cluster_decode_kernel<1, 1, 16>, P) : cudaLaunchKernelEx(&cfg, cluster_decode_kernel<1, 0, 16>, P);
   } else {

@@ -226,7 +226,7 @@ struct lvx_engine {
   bool cd_ready = false;
   uint8_t* cd_stream = nullptr;    // 16-CTA clusters (latency variant)
   long long cd_stream_bytes = 0;
-  uint8_t* cd_stream8 = nullptr;   // 8-CTA clusters (throughput variant, greedy decoding)
+  uint8_t* cd_stream8 = nullptr;   // 8-CTA clusters (throughput variant)
   long long cd_stream8_bytes = 0;
   float *cd_text_ss = nullptr, *cd_code_ss = nullptr;
   int cd_max_clusters = 0, cd_max_clusters8 = 0;   // co-resident clusters of each variant (cudaOccupancyMaxActiveClusters)
@@ -1304,12 +1304,12 @@ static int cluster_launch(lvx_engine* e, lvx_engine::Lane& ln, const int32_t* h_
   // LLMVOX_B200_CD_CAP overrides the cap (experiments only: scripts/cluster_stress.py)
   const int cap16 = getenv("LLMVOX_B200_CD_CAP") ? std::max(1, atoi(getenv("LLMVOX_B200_CD_CAP"))) : std::max(1, e->cd_max_clusters);
   // Variant.  Up to one wave of 16-CTA clusters (7 x 16 = 112 sessions on a B200) the latency variant runs: every CTA
-  // streams 1/16 of the weights.  Above that greedy decoding switches to 8-CTA clusters: 1/8 of the weights per CTA
+  // streams 1/16 of the weights.  Above that decoding switches to 8-CTA clusters: 1/8 of the weights per CTA
   // makes an iteration ~1.4x longer, but 15 clusters are co-resident, so up to 240 sessions advance in ONE wave where the
   // 16-CTA variant needs two or three.  (LLMVOX_B200_CD_NO8=1: measurement knob, results do not depend on the variant's
   // choice beyond the bf16 tolerance both meet.)
-  const bool can8 = sa.greedy && e->cd_max_clusters8 > 0;
-  LVX_CHECK(variant != 8 || can8, LVX_ERR_INVALID, "the 8-CTA cluster cut exists for greedy decoding only");
+  const bool can8 = e->cd_max_clusters8 > 0;
+  LVX_CHECK(variant != 8 || can8, LVX_ERR_INVALID, "no 8-CTA cluster fits on this device");
   const bool use8 = variant == 8 || (variant == 0 && can8 && n > cap16 * CD_NB && !getenv("LLMVOX_B200_CD_NO8"));
   const int cl = use8 ? 8 : 16;
   const int cap8 = getenv("LLMVOX_B200_CD_CAP8") ? std::max(1, atoi(getenv("LLMVOX_B200_CD_CAP8"))) : e->cd_max_clusters8;   // (stress only)

@@ -44,15 +44,14 @@ class LaneRunner:
       wave on the cluster kernel and runs the tail on ONE kernel-per-op lane (LVX_PATH_PER_OP_TAIL: grids sized for the 28
       SMs the wave leaves free) while decode rounds and vocoder batches take turns on the GPU.  Measured (bench.py --streams
       256, bf16, ms per step): all on the lanes 86.8, two waves 98.6, 240 + 16 on three tail lanes with the vocoder
-      overlapped 92.4, one tail lane overlapped 72.4, one tail lane taking turns 69.3.  (With 16-CTA clusters only -- sampled
-      decoding -- the split is off by default: 224 + 32 ran at 6858 audio-s/s against 8251 on the lanes.)
+      overlapped 92.4, one tail lane overlapped 72.4, one tail lane taking turns 69.3.  (With 16-CTA clusters only the split is off by default: 224 + 32 ran at 6858 audio-s/s against 8251 on the lanes.)
 
     `launch()` enqueues on the side streams and returns the completion events; `join()` makes the control stream wait
     for them.  Every launch first waits, on every stream it uses, for the previous round's events of the OTHER streams:
     a session may move between streams from round to round (the active set shrinks, the path changes with the batch
     size), and its context length / KV pages must be ordered across that move."""
 
-    # 16-CTA clusters only (exact precision, sampled decoding): two waves of 7 clusters; measured (bench.py --short,
+    # 16-CTA clusters only (LLMVOX_B200_CD_NO8=1, or a device without room for 8-CTA clusters): two waves of 7; measured (bench.py --short,
     # audio-s/s, cluster vs kernel-per-op): 112: 8341 / 5418, 128: 5780 / 5992, 192: 8300 / 7624, 224: 9062 / 7457,
     # 256: 7647 / 8251.  Just above one full wave (113..139 sessions) the second wave is nearly empty and the kernel-per-op
     # lanes win.
@@ -101,7 +100,7 @@ class LaneRunner:
 
     def wave8(self, sampling: Optional[Sampling]) -> int:
         """Sessions per wave of the 8-CTA cut for this sampler (0: the cut does not apply)."""
-        if self.e.precision not in ("bf16", "exact") or (sampling is not None and not sampling.greedy and sampling.top_k != 1):
+        if self.e.precision not in ("bf16", "exact"):
             return 0
         if not hasattr(self, "_caps"):
             self._caps = self.e.cluster_capacity() if hasattr(self.e, "cluster_capacity") else (112, 240)

@@ -609,15 +609,17 @@ def _philox_uniform(seed, slot, step):
     return np.float32(c[0] >> 8) * np.float32(1.0 / 16777216.0)
 
 
+@pytest.mark.parametrize("cut", [16, 8])
 @pytest.mark.parametrize("precision", ["exact", "bf16"])
 @pytest.mark.parametrize("temp,topk", [(0.8, 50), (1.0, 5), (1.2, 0)])
-def test_cluster_kernel_sampled_decoding(weights, precision, temp, topk):
+def test_cluster_kernel_sampled_decoding(weights, precision, temp, topk, cut):
     """Temperature / top-k / multinomial inside the cluster-resident kernel (north_star kernel 3; src/model.py:397-406):
     every pick equals the oracle's inverse-CDF draw on the kernel's own logits against the same Philox uniform, the
     kernel-per-op sampler_kernel makes the same draws from the same state, and 12 iterations in one launch equal 12
     launches of one (fixed reduction orders + counter-based RNG)."""
     from llmvox_b200 import _lib
     from llmvox_b200.engine import Engine, Sampling
+    path = _lib.PATH_CLUSTER16 if cut == 16 else _lib.PATH_CLUSTER8      # both cuts of the kernel
     n, steps, seed = 19, 12, 77
     s = Sampling(greedy=False, top_k=topk, temperature=temp, seed=seed)
     e = Engine(weights, device=0, precision=precision, max_sessions=2 * n, max_context=48, max_vocode_frames=256)
@@ -629,8 +631,8 @@ def test_cluster_kernel_sampled_decoding(weights, precision, temp, topk):
     edge = 0
     for t in range(steps):
         l0 = e.kernel_launches
-        e.decode_steps(slots, 1, s, path=_lib.PATH_CLUSTER)
-        assert e.kernel_launches - l0 <= 8                       # one cluster launch (+ one-time set-up), not the per-op chain
+        e.decode_steps(slots, 1, s, path=path)
+        assert e.kernel_launches - l0 <= 12                      # one cluster launch (+ one-time set-up), not the per-op chain
         codes = e.gather_codes(slots, t, 1).view(-1).cpu()
         logits = e.peek_logits(n).cpu()
         u = torch.tensor([_philox_uniform(seed, sl, t) for sl in slots])
@@ -660,7 +662,7 @@ def test_cluster_kernel_sampled_decoding(weights, precision, temp, topk):
     # the Philox counter is (slot, step): give the second batch the draws of the first by decoding it in the same slots
     e.open(slots)
     e.feed_text(slots, texts)
-    e.decode_steps(slots, steps, s2, path=_lib.PATH_CLUSTER)
+    e.decode_steps(slots, steps, s2, path=path)
     again = e.gather_codes(slots, 0, steps).cpu()
     assert (again == first).all()
     # the kernel-per-op sampler makes the same draws (same logits class in exact mode; bf16 logits differ by < 2e-2, so

@@ -162,8 +162,8 @@ def test_lane_runner_picks_the_decode_path_by_batch_size():
     """LaneRunner's host-side policy (no GPU needed).  Greedy bf16 / exact: the cluster-resident kernel takes everything up to one
     wave of 8-CTA clusters (240 sessions on a B200; the engine itself uses 16-CTA clusters up to 112), a batch slightly
     above a wave keeps the wave on the cluster kernel and puts the rest on the kernel-per-op lanes, two waves are still
-    cluster work, beyond that the lanes take all.  Sampled decoding has 16-CTA clusters only: one or two waves of 7 (up to
-    112 and 140-224 sessions)."""
+    cluster work, beyond that the lanes take all; sampled decoding follows the same plan.  Without the 8-CTA cut: one or two
+    waves of 7 16-CTA clusters (up to 112 and 140-224 sessions)."""
     from llmvox_b200.engine import Engine, Sampling
     from llmvox_b200.streaming import LaneRunner
 
@@ -189,18 +189,21 @@ def test_lane_runner_picks_the_decode_path_by_batch_size():
     r.G = 1                                                        # no second lane to run the tail beside the wave
     assert r.plan(256, greedy) == (256, 0)
     r.G = 4
-    # sampled decoding runs inside the cluster kernel too (S = 1), on 16-CTA clusters only
-    assert [r.plan(n, sampled) for n in (64, 112, 113, 139, 140, 224, 225, 256)] == \
+    # sampled decoding runs inside the cluster kernel too (S = 1), on both cuts
+    assert [r.plan(n, sampled) for n in (64, 112, 113, 240, 256, 481)] == [(64, 0), (112, 0), (113, 0), (240, 0), (240, 16), (0, 481)]
+    # without the 8-CTA cut (measurement knob / a device with no room for it): one or two waves of 16-CTA clusters
+    r._caps = (112, 0)
+    assert [r.plan(n, greedy) for n in (64, 112, 113, 139, 140, 224, 225, 256)] == \
         [(64, 0), (112, 0), (0, 113), (0, 139), (140, 0), (224, 0), (0, 225), (0, 256)]
     r.HYBRID_ABOVE_MAX_BATCH = True                                # opt-in split of one call between both paths
-    assert r.plan(256, sampled) == (224, 32)
+    assert r.plan(256, greedy) == (224, 32)
     r.HYBRID_ABOVE_MAX_BATCH = False
+    r._caps = (112, 240)
     r.e.precision = "fp32"
     assert r.plan(64, greedy) == (0, 64)                          # fp32 parity mode: FMA-pipe GEMMs
     r.e.precision = "exact"
     assert r.plan(64, greedy) == (64, 0) and r.plan(120, greedy) == (120, 0)   # exact mode: hi | lo cluster kernel, both cuts
-    assert r.plan(256, greedy) == (240, 16)
-    assert r.plan(140, sampled) == (140, 0) and r.plan(256, sampled) == (0, 256)   # sampled: 16-CTA clusters only
+    assert r.plan(256, greedy) == (240, 16) and r.plan(256, sampled) == (240, 16)
     r.e.precision = "bf16"
     r.e.cfg.max_context = 8192
     assert r.plan(64, greedy) == (64, 0)                          # the reference's block_size: page-table windows of 64 pages

@@ -112,23 +112,6 @@ __global__ void gather_code_ranges_kernel(const int* __restrict__ slots, const i
   for (int j = threadIdx.x; j < cnt; j += blockDim.x)
     out[offs[b] + j] = st.codes[(size_t)slot * st.max_context + starts[b] + j];
 }
-// LayerNorm output split into bf16 hi / lo / hi thirds of a (rows, 3C) operand ("bf16x3" along K)
-template <int C>
-__global__ void __launch_bounds__(256) split3_kernel(const float* __restrict__ x, int rows, int width, int ld_in,
-                                                     bf16* __restrict__ out, int seg, int ld_out) {
-  // out[r, 0:seg) = hi, [seg, 2seg) = lo, [2seg, 3seg) = hi; columns >= width are zero
-  const int r = blockIdx.x;   // rows on grid.x: a launch group may hold more than 65535 rows
-  const int j = blockIdx.y * 256 + threadIdx.x;
-  if (r >= rows || j >= seg) return;
-  float v = j < width ? x[(size_t)r * ld_in + j] : 0.f;
-  const bf16 hi = __float2bfloat16_rn(v);
-  const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-  bf16* o = out + (size_t)r * ld_out;
-  o[j] = hi;
-  o[seg + j] = lo;
-  o[2 * seg + j] = hi;
-}
-
 }  // namespace lvx
 
 using namespace lvx;
@@ -165,7 +148,7 @@ struct lvx_engine {
   float* embed_b = nullptr;
   Res res[4];
   float *at_nw = nullptr, *at_nb = nullptr, *at_qkv_b = nullptr, *at_proj_b = nullptr;
-  GemmW at_qkv, at_proj, at_v;   // at_v: the v rows of at_qkv (bf16 mode, transposed-V GEMM of the tensor-core attention)
+  GemmW at_qkv, at_proj;
   float *pn5_w = nullptr, *pn5_b = nullptr, *norm_scale = nullptr, *norm_shift = nullptr;
   std::vector<CNX> cnx;
   float *fln_w = nullptr, *fln_b = nullptr, *head_b = nullptr, *window = nullptr;
@@ -777,11 +760,6 @@ extern "C" int lvx_finalize_weights(lvx_engine* e) {
     }
     e->at_qkv_b = bq;
     LVX_TRY(make_gemm_w(e, &e->at_qkv, wq, 3 * D, D, D));
-    if (e->adt() == B16) {
-      e->at_v.b16 = e->at_qkv.b16 + (size_t)2 * D * D;
-      e->at_v.N = D; e->at_v.K = D; e->at_v.ld = D;
-      LVX_TRY(tc_make_desc(&e->at_v.tma, e->at_v.b16, D, D, D));
-    }
     LVX_TRY(make_gemm_w(e, &e->at_proj, W(e, p + "proj_out.weight"), D, D, D));
     e->at_proj_b = W(e, p + "proj_out.bias");
   }
@@ -1857,25 +1835,27 @@ static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes
     q.A = e->v_spec; q.C = e->v_frames; q.M = g.R; q.lda = e->spec_ld; q.ldc = NF; q.row_chunk = e->row_chunk;
     LVX_TRY(run_gemm(e, q, e->idft, a, F32, st));
   } else {
-    layernorm_kernel<float, 768><<<ceil_div(g.R, 8), 256, 0, st>>>(e->v_x, g.R, e->fln_w, e->fln_b, 1e-6f, e->row_chunk, e->v_t);
-    LAUNCHED(e);
-    if (stage == 4) return dump(e->v_t, D, D);
-    dim3 g3(g.R, ceil_div(D, 256));
-    split3_kernel<768><<<g3, 256, 0, st>>>(e->v_t, g.R, D, D, (bf16*)e->v_h3, D, 3 * D);
-    LAUNCHED(e);
+    if (stage == 4) {   // test hook: the LayerNorm output itself
+      layernorm_kernel<float, 768><<<ceil_div(g.R, 8), 256, 0, st>>>(e->v_x, g.R, e->fln_w, e->fln_b, 1e-6f, e->row_chunk, e->v_t);
+      LAUNCHED(e);
+      return dump(e->v_t, D, D);
+    }
+    {
+      PROF(e, "layernorm_split3", st);
+      layernorm_split3_kernel<768><<<ceil_div(g.R, 8), 256, 0, st>>>(e->v_x, g.R, e->fln_w, e->fln_b, 1e-6f, e->row_chunk, (bf16*)e->v_h3);
+      LAUNCHED(e);
+    }
     GemmParams p;
     p.kdup = 3;
     p.A = e->v_h3; p.C = e->v_raw; p.M = g.R; p.lda = 3 * D; p.ldc = e->raw_ld; p.bias = e->head_b; p.row_chunk = e->row_chunk;
     if (e->prof_detail) p.tag = "tc_gemm:head_x3";
     LVX_TRY(run_gemm(e, p, e->head, a, F32, st));
-    dim3 grid(g.R, ceil_div(e->spec_ld, 256));
-    // fp32 spectrum into v_frames' storage is not possible (needed later); reuse v_big as fp32 scratch
-    float* spec32 = (float*)e->v_big;
-    head_activation_kernel<float><<<grid, 256, 0, st>>>(e->v_raw, e->raw_ld, g.R, e->row_chunk, bins, spec32, e->spec_ld);
-    LAUNCHED(e);
-    dim3 g4(g.R, ceil_div(e->spec_ld, 256));
-    split3_kernel<768><<<g4, 256, 0, st>>>(spec32, g.R, e->spec_ld, e->spec_ld, (bf16*)e->v_spec, e->spec_ld, 3 * e->spec_ld);
-    LAUNCHED(e);
+    {
+      PROF(e, "head_act_split3", st);
+      dim3 grid(g.R, ceil_div(std::max(bins, e->spec_ld - 2 * bins), 256));
+      head_act_split3_kernel<<<grid, 256, 0, st>>>(e->v_raw, e->raw_ld, g.R, e->row_chunk, bins, (bf16*)e->v_spec, e->spec_ld);
+      LAUNCHED(e);
+    }
     GemmParams q;
     q.kdup = 3;
     q.A = e->v_spec; q.C = e->v_frames; q.M = g.R; q.lda = 3 * e->spec_ld; q.ldc = NF; q.row_chunk = e->row_chunk;

@@ -196,6 +196,96 @@ __global__ void __launch_bounds__(256) dwconv_adaln_kernel(const float* __restri
 // same layout, with columns [L, L rounded up to 64) written as zeros so the P.V GEMM's last k-block may read them.  One
 // warp per row.  Output type = GEMM operand type, in place for fp32.
 // ---------------------------------------------------------------------------------------------------
+// bf16x3 operand builders of the iSTFT head (the head and iDFT GEMMs keep ~fp32 accuracy on bf16 tensor cores by laying
+// hi | lo | hi thirds side by side along K): out[r, 0:seg) = hi, [seg, 2 seg) = lo, [2 seg, 3 seg) = hi.
+//   layernorm_split3_kernel : backbone final LayerNorm (models.py:229) straight into the head GEMM's operand -- one warp per
+//                             row; the fp32 copy the separate split kernel re-read is gone
+//   head_act_split3_kernel  : ISTFTHead activation (heads.py:57-63: mag = min(exp(.), 100), S = mag (cos p + i sin p)) straight
+//                             into the iDFT GEMM's operand -- one thread per frequency bin computes exp and sincos ONCE and
+//                             writes real and imaginary part (the per-output-element kernel computed exp twice and went
+//                             through an fp32 spectrum: 0.46 + 0.23 ms per 61,440 frames, this one 0.2)
+// Padding rows become zeros (the GEMMs mask them on the way out).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void store_hi_lo_hi(bf16* o, int col, int seg, float v) {
+  const bf16 hi = __float2bfloat16_rn(v);
+  const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+  o[col] = hi;
+  o[seg + col] = lo;
+  o[2 * seg + col] = hi;
+}
+template <int C>
+__global__ void __launch_bounds__(256) layernorm_split3_kernel(const float* __restrict__ x, int rows, const float* __restrict__ w,
+                                                               const float* __restrict__ bias, float eps,
+                                                               const int* __restrict__ row_chunk, bf16* __restrict__ out) {
+  constexpr int V = C / 128;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  bf16* o = out + (size_t)row * (3 * C);
+  if (row_chunk[row] < 0) {
+    for (int c = lane * 8; c < 3 * C; c += 256) *reinterpret_cast<uint4*>(o + c) = make_uint4(0u, 0u, 0u, 0u);
+    return;
+  }
+  const float* xr = x + (size_t)row * C;
+  float4 v[V];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    v[i] = load4(xr + (lane + 32 * i) * 4);
+    s += v[i].x + v[i].y + v[i].z + v[i].w;
+  }
+  const float mean = warp_sum(s) * (1.0f / C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += a * a + b * b + c * c + d * d;
+  }
+  const float rstd = rsqrtf(warp_sum(q) * (1.0f / C) + eps);
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    const int c = (lane + 32 * i) * 4;
+    const float4 ww = load4(w + c), bb = load4(bias + c);
+    const float r[4] = {(v[i].x - mean) * rstd * ww.x + bb.x, (v[i].y - mean) * rstd * ww.y + bb.y,
+                        (v[i].z - mean) * rstd * ww.z + bb.z, (v[i].w - mean) * rstd * ww.w + bb.w};
+    __nv_bfloat162 h[2], l[2];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      h[k] = __floats2bfloat162_rn(r[2 * k], r[2 * k + 1]);
+      const float2 hf = __bfloat1622float2(h[k]);
+      l[k] = __floats2bfloat162_rn(r[2 * k] - hf.x, r[2 * k + 1] - hf.y);
+    }
+    const uint2 hu = make_uint2(*reinterpret_cast<uint32_t*>(&h[0]), *reinterpret_cast<uint32_t*>(&h[1]));
+    const uint2 lu = make_uint2(*reinterpret_cast<uint32_t*>(&l[0]), *reinterpret_cast<uint32_t*>(&l[1]));
+    *reinterpret_cast<uint2*>(o + c) = hu;
+    *reinterpret_cast<uint2*>(o + C + c) = lu;
+    *reinterpret_cast<uint2*>(o + 2 * C + c) = hu;
+  }
+}
+__global__ void __launch_bounds__(256) head_act_split3_kernel(const float* __restrict__ raw, int ld_raw, int rows,
+                                                              const int* __restrict__ row_chunk, int bins, bf16* __restrict__ out,
+                                                              int seg) {
+  const int row = blockIdx.x;   // rows on grid.x: a launch group may hold more than 65535 rows
+  const int k = blockIdx.y * 256 + threadIdx.x;
+  if (row >= rows) return;
+  bf16* o = out + (size_t)row * (3 * seg);
+  const bool pad = row_chunk[row] < 0;
+  if (k < bins) {
+    float re = 0.f, im = 0.f;
+    if (!pad) {
+      const float* r = raw + (size_t)row * ld_raw;
+      const float mag = fminf(expf(r[k]), 100.0f);
+      float sn, cs;
+      sincosf(r[bins + k], &sn, &cs);
+      re = mag * cs;
+      im = mag * sn;
+    }
+    store_hi_lo_hi(o, k, seg, re);
+    store_hi_lo_hi(o, bins + k, seg, im);
+  }
+  if (k < seg - 2 * bins) store_hi_lo_hi(o, 2 * bins + k, seg, 0.f);   // alignment columns of the operand
+}
+
+// ---------------------------------------------------------------------------------------------------
 // V^T operand of the pos_net attention's P V GEMM: Vt[c][r] = V[r][c], V = columns [v0, v0 + C) of the fused q|k|v
 // output (bf16, row stride ld).  64 x 64 tiles through shared memory; padding rows become zeros (the grouped P V GEMM
 // reads its K tail up to the next multiple of 64 rows, against P columns that are zero there).  Replaces a second

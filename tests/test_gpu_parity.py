@@ -265,6 +265,22 @@ def test_vocoder_launch_group_above_65535_rows(weights):
     big.close()
 
 
+def test_vocoder_bulk_kernels_in_fp32(weights):
+    """The bulk-shape kernels (tiled depthwise conv + AdaLN from 9,472 padded rows on) in the fp32 parity mode, where the
+    comparison is tight: chunks inside an 8 x 1280-frame batch equal their solo decodes (one warp per frame kernel)."""
+    from llmvox_b200.engine import Engine
+    e = Engine(weights, device=0, precision="fp32", max_sessions=2, max_context=32, max_vocode_frames=11000)
+    g = torch.Generator().manual_seed(21)
+    n, L = 8, 1280
+    codes = torch.randint(0, 4096, (n * L,), generator=g).to("cuda", torch.int32)
+    pcm = e.vocode(codes, list(range(0, (n + 1) * L, L))).cpu().numpy()
+    for k in (0, 5, 7):
+        alone = e.vocode(codes[k * L:(k + 1) * L].contiguous(), [0, L]).cpu().numpy()
+        seg = pcm[k * L * 320:(k + 1) * L * 320]
+        assert np.abs(seg - alone).max() < 1e-5 * max(1.0, np.abs(alone).max()), k
+    e.close()
+
+
 def test_vocoder_groups_split_transparently(weights):
     """More frames than max_vocode_frames: the call is cut into launch groups without changing results."""
     from llmvox_b200.engine import Engine

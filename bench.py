@@ -261,6 +261,7 @@ def measure(args, precision, streams, K, Wm, rank, local, world, sd, barrier, fi
 
     # e2e: host text ids in, PCM out to pinned host memory, through the public batched API
     bs = BatchSynthesizer(e, streams, SCHEDULE[0], stop_on_eoa=False, slots=groups[n_groups], lanes=args.lanes)
+    bs_b = BatchSynthesizer(e, streams, SCHEDULE[0], stop_on_eoa=False, slots=groups[0], lanes=args.lanes)
     e2e_steps = max(3, min(K, 10))
 
     def e2e_step():
@@ -269,7 +270,31 @@ def measure(args, precision, streams, K, Wm, rank, local, world, sd, barrier, fi
         for chunks in bs.run(TOKENS, flush_tail=True, copy=False):     # D2H of every chunk into pinned memory
             n += sum(c.length for c in chunks)
         return n
+
+    def e2e_steps_back_to_back(steps):
+        """`steps` batches through the public API the way a server runs them: two synthesizers on alternating slot groups,
+        batch i + 1 is started (H2D of its ids, its first decode rounds) as soon as all of batch i's GPU work is enqueued,
+        THEN the host waits for batch i's last PCM.  Every batch's inputs still come from the host and every PCM sample
+        still lands in pinned host memory inside the timed region."""
+        def begin(b):
+            b.start(texts)
+            g = b.run(TOKENS, flush_tail=True, copy=False, yield_when_enqueued=True)
+            n = 0
+            for chunks in g:                                           # until everything of this batch is enqueued
+                if not chunks:
+                    break
+                n += sum(c.length for c in chunks)
+            return g, n
+        total, prev = 0, None
+        for i in range(steps):
+            cur = begin(bs if i % 2 == 0 else bs_b)
+            if prev is not None:
+                total += prev[1] + sum(c.length for chunks in prev[0] for c in chunks)
+            prev = cur
+        total += prev[1] + sum(c.length for chunks in prev[0] for c in chunks)
+        return total
     e2e_step()
+    assert e2e_steps_back_to_back(4) == 4 * streams * TOKENS      # both synthesizers' pinned rings reach their final size
     fc = {}
     if first_chunk:   # p50 first-chunk latency: host text ids -> the first chunk's PCM of every stream in host memory
         for dump in (10, 160):
@@ -290,10 +315,16 @@ def measure(args, precision, streams, K, Wm, rank, local, world, sd, barrier, fi
             fc[dump] = float(np.median(lat[2:]))
     barrier()
     t0 = time.perf_counter()
+    assert e2e_steps_back_to_back(e2e_steps) == e2e_steps * streams * TOKENS
+    torch.cuda.synchronize()
+    e2e_ms = 1e3 * (time.perf_counter() - t0)
+    barrier()
+    # the same without overlapping consecutive batches (each batch drained before the next starts): reported beside it
+    t0 = time.perf_counter()
     for _ in range(e2e_steps):
         assert e2e_step() == streams * TOKENS
     torch.cuda.synchronize()
-    e2e_ms = 1e3 * (time.perf_counter() - t0)
+    e2e_serial_ms = 1e3 * (time.perf_counter() - t0)
     barrier()
 
     # per-kernel profile of one step (events around every launch), beside the timed region
@@ -316,7 +347,7 @@ def measure(args, precision, streams, K, Wm, rank, local, world, sd, barrier, fi
     if n_lanes:
         path.append("%d sessions on the kernel-per-op chain (%d lanes)" % (n_lanes, args.lanes))
     e.close()
-    return {"ms": ms, "e2e_ms": e2e_ms, "e2e_steps": e2e_steps, "first_chunk": fc, "prof": prof, "launches": int(launches), "clocks": clk,
+    return {"ms": ms, "e2e_ms": e2e_ms, "e2e_serial_ms": e2e_serial_ms, "e2e_steps": e2e_steps, "first_chunk": fc, "prof": prof, "launches": int(launches), "clocks": clk,
             "decode_path": " + ".join(path)}
 
 
@@ -450,9 +481,10 @@ def run_gpu(args):
     c4 = config4(args, rank, local, world, sd, barrier) if (world > 1 or args.config4) else None
 
     def line_of(m, streams, k):
-        ms, e2e_ms = reduce_max([m["ms"], m["e2e_ms"]], world, dev)
+        ms, e2e_ms, e2e_serial_ms = reduce_max([m["ms"], m["e2e_ms"], m["e2e_serial_ms"]], world, dev)
         audio = world * streams * TOKENS / CODES_PER_SEC
-        return {"value": audio * k / (ms / 1e3), "ms_per_step": ms / k, "e2e_value": audio * m["e2e_steps"] / (e2e_ms / 1e3)}
+        return {"value": audio * k / (ms / 1e3), "ms_per_step": ms / k, "e2e_value": audio * m["e2e_steps"] / (e2e_ms / 1e3),
+                "e2e_drained": audio * m["e2e_steps"] / (e2e_serial_ms / 1e3)}
     lm = line_of(main, STREAMS, K)
     la = line_of(alt, STREAMS, K) if alt else None
     l256 = line_of(s256, 256, K256) if s256 else None
@@ -490,7 +522,11 @@ def run_gpu(args):
                                  "sample": f"{cpu_streams} of the {STREAMS} streams, sequential batch-1: {TOKENS} codes + chunks {SCHEDULE} each"},
                 "e2e": {"value": lm["e2e_value"], "unit": "audio-s/s", "steps": main["e2e_steps"],
                         "h2d_bytes_per_step": STREAMS * TOKENS * 4 + (STREAMS + 1) * 4 + STREAMS * 4,
-                        "d2h_bytes_per_step": STREAMS * TOKENS * 320 * 4},
+                        "d2h_bytes_per_step": STREAMS * TOKENS * 320 * 4,
+                        "what": "BatchSynthesizer from host text ids to PCM in pinned host memory, consecutive batches back to back on two "
+                                "alternating slot groups (batch i + 1 starts once batch i's GPU work is enqueued, as a server would); "
+                                "value_drained = every batch drained on the host before the next starts",
+                        "value_drained": lm["e2e_drained"]},
                 "first_chunk_latency": {"p50_ms": main["first_chunk"].get(10), "p50_ms_160": main["first_chunk"].get(160), "streams": STREAMS,
                                         "codes": [10, 160],
                                         "what": "host text ids -> PCM of every stream's first chunk (replica 0: 10 codes, replica 1: 160) in pinned host memory"},

@@ -195,14 +195,19 @@ class ChunkEmitter:
         self.bw = bandwidth_id
         self._ring: List[Optional[torch.Tensor]] = [None] * buffers
         self._next = 0
+        self._cap = 1 << 20
 
     def _pinned(self, n: int) -> torch.Tensor:
         """Pinned buffers used round-robin: a ticket's PCM (and, with copy=False, the arrays handed out) stays valid until
-        `buffers - 1` further tickets have been enqueued."""
+        `buffers - 1` further tickets have been enqueued.  Every buffer is kept at the size of the LARGEST ticket seen so
+        far (plus a quarter): allocating pinned memory synchronises the device and costs milliseconds, so the ring must stop
+        growing after the first batch instead of reallocating a slot whenever a bigger round happens to land on it."""
         i = self._next
         self._next = (i + 1) % len(self._ring)
-        if self._ring[i] is None or self._ring[i].numel() < n:
-            self._ring[i] = torch.empty((max(n, 1 << 20),), dtype=torch.float32, pin_memory=True)
+        if n > self._cap:
+            self._cap = max(n + n // 4, 1 << 20)
+        if self._ring[i] is None or self._ring[i].numel() < self._cap:
+            self._ring[i] = torch.empty((self._cap,), dtype=torch.float32, pin_memory=True)
         return self._ring[i]
 
     def enqueue(self, ready: Sequence[Tuple[int, int, int]]):
@@ -301,8 +306,13 @@ class BatchSynthesizer:
         out.sort(key=lambda ch: (ch.session, ch.start))
         return out
 
-    def run(self, max_steps: int, flush_tail: bool = False, copy: bool = True) -> Iterator[List[Chunk]]:
+    def run(self, max_steps: int, flush_tail: bool = False, copy: bool = True, yield_when_enqueued: bool = False) -> Iterator[List[Chunk]]:
         """Decodes up to `max_steps` codes per session, yielding the chunks of each round as they are ready.
+
+        `yield_when_enqueued`: yields one EMPTY list at the point where all of this batch's GPU work has been enqueued and
+        only host waits remain, so that a caller serving several batches can start the next one (another BatchSynthesizer on
+        other slots) before it blocks on this batch's last PCM -- the next batch's first decode rounds then overlap this
+        batch's last vocoder batch and copy on the GPU.
 
         Software-pipelined: round r+1's decode iterations are enqueued on the lanes BEFORE the host waits for round
         r's PCM, so the vocoder and the copies of round r overlap the decode of round r+1.  With stop_on_eoa the
@@ -340,18 +350,20 @@ class BatchSynthesizer:
             self.steps_done += k
             pending = self._enqueue_emit(ready)
             active = [i for i in active if not self.sched[i].done]
-        if pending is not None:
-            chunks = self._finish_emit(pending, copy)
-            if chunks:
-                yield chunks
+        tail = None
         if flush_tail:
             ready = []
             for i in range(self.n):
                 if not self.sched[i].done:
                     ready.extend((i, s, c) for (s, c) in self.sched[i].flush())
-            chunks = self._finish_emit(self._enqueue_emit(ready), copy)
-            if chunks:
-                yield chunks
+            tail = self._enqueue_emit(ready)
+        if yield_when_enqueued:
+            yield []
+        for ticket in (pending, tail):
+            if ticket is not None:
+                chunks = self._finish_emit(ticket, copy)
+                if chunks:
+                    yield chunks
 
     def codes(self, count: Optional[int] = None) -> np.ndarray:
         """(n_sessions, count) codes decoded so far (host copy)."""

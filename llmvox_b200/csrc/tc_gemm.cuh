@@ -721,7 +721,22 @@ __global__ void __launch_bounds__(TcShape<kSwap>::kThreads, kSwap ? 1 : 2) tc_ge
     pdl_wait();   // residual reads and output writes must follow the predecessor's completion
     const int c_lo = half * (BN / kHalves), c_hi = (half + 1) * (BN / kHalves);   // multiples of 8 (BN % 16 == 0)
     if (S == 1) {
+      // normal mode: the coalesced epilogue of the persistent kernel, with the (now idle) operand ring as its scratch
+      float* const scratch = reinterpret_cast<float*>(smem_raw + (tiles - smem_u32(smem_raw)) + (warp - 2) * TC_EPI_SCRATCH);
+      const bool coalesced = !kSwap && (size_t)stages * stage_bytes >= (size_t)TcShape<kSwap>::kEpiWarps * TC_EPI_SCRATCH &&
+                             (p.ldc & (sizeof(TC) == 2 ? 7 : 3)) == 0 && (!p.residual || (p.ldr & 3) == 0) &&
+                             (reinterpret_cast<uintptr_t>(p.C) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0;
+      const unsigned vmask = coalesced ? tc_row_mask(p, x0 + drow) : 0u;
       for (int c = c_lo; c < c_hi; c += 16) {
+        if (!kSwap && coalesced && c + 16 <= c_hi && y0 + c + 16 <= p.N) {   // warp-uniform
+          if (sizeof(TC) == 2 && !p.residual && c + 32 <= c_hi && y0 + c + 32 <= p.N) {
+            tc_epilogue_pair_bf16_dispatch(p, x0 + q * 32, lane, y0 + c, trow + (uint32_t)c, scratch, vmask);
+            c += 16;
+          } else {
+            tc_epilogue_dispatch_coalesced<TC>(p, x0 + q * 32, lane, y0 + c, trow + (uint32_t)c, scratch, 2, vmask);
+          }
+          continue;
+        }
         float v[16];
         tmem_ld16(trow + (uint32_t)c, v);
         tc_epilogue_dispatch<kSwap, TC>(p, x0 + drow, y0 + c, v, min(16, c_hi - c));

@@ -216,7 +216,7 @@ __device__ __forceinline__ uint32_t kv_tile_offset(int t, int d) {
   }
 }
 template <typename TKV, typename TOut, int HD>
-__global__ void __launch_bounds__(128) decode_attention_kernel(const float* __restrict__ qkv, TKV* __restrict__ kv,
+__global__ void __launch_bounds__(128, 8) decode_attention_kernel(const float* __restrict__ qkv, TKV* __restrict__ kv,
                                                                const int* __restrict__ slots, SessionState st,
                                                                const int* __restrict__ pos_override, int layer,
                                                                int n_head, int page_tokens, long long pool_pages,
@@ -236,14 +236,23 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const float* __re
   const float scale = rsqrtf((float)HD);
 
   const float* qrow = qkv + (size_t)b * 3 * C + h * HD + sub * DPL;
-  float q[DPL], kn[DPL], vn[DPL];
+  float q[DPL];
 #pragma unroll
   for (int i = 0; i < DPL; i += 4) {
-    const float4 a = load4(qrow + i), k4 = load4(qrow + C + i), v4 = load4(qrow + 2 * C + i);
+    const float4 a = load4(qrow + i);
     q[i] = a.x; q[i + 1] = a.y; q[i + 2] = a.z; q[i + 3] = a.w;
-    kn[i] = round_to<TKV>(k4.x); kn[i + 1] = round_to<TKV>(k4.y); kn[i + 2] = round_to<TKV>(k4.z); kn[i + 3] = round_to<TKV>(k4.w);
-    vn[i] = round_to<TKV>(v4.x); vn[i + 1] = round_to<TKV>(v4.y); vn[i + 2] = round_to<TKV>(v4.z); vn[i + 3] = round_to<TKV>(v4.w);
   }
+  // the new token's k / v (rounded as they will be read back from the cache) are NOT kept in registers across the token
+  // loop: they are re-read from the qkv row (L2) where they are needed.  79 -> 56 registers = 8 instead of 6 CTAs per SM;
+  // the loop is latency-bound (60 % long_scoreboard stalls at 2048 sessions: ncu), so occupancy is bandwidth.
+  auto new_kv = [&](float (&kn)[DPL], float (&vn)[DPL]) {
+#pragma unroll
+    for (int i = 0; i < DPL; i += 4) {
+      const float4 k4 = load4(qrow + C + i), v4 = load4(qrow + 2 * C + i);
+      kn[i] = round_to<TKV>(k4.x); kn[i + 1] = round_to<TKV>(k4.y); kn[i + 2] = round_to<TKV>(k4.z); kn[i + 3] = round_to<TKV>(k4.w);
+      vn[i] = round_to<TKV>(v4.x); vn[i + 1] = round_to<TKV>(v4.y); vn[i + 2] = round_to<TKV>(v4.z); vn[i + 3] = round_to<TKV>(v4.w);
+    }
+  };
   const size_t head_stride = (size_t)page_tokens * HD;
   const size_t page_stride = (size_t)n_head * head_stride;
   TKV* kbase = kv + ((size_t)(layer * 2 + 0) * pool_pages) * page_stride + (size_t)h * head_stride;
@@ -252,6 +261,8 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const float* __re
 
   // append the new token (group 0 holds all HD dims across its 8 lanes)
   if (g == 0) {
+    float kn[DPL], vn[DPL];
+    new_kv(kn, vn);
     const int page = pt[T / page_tokens], off = T % page_tokens;
     TKV* kd = kbase + (size_t)page * page_stride;
     TKV* vd = vbase + (size_t)page * page_stride;
@@ -299,7 +310,11 @@ __global__ void __launch_bounds__(128) decode_attention_kernel(const float* __re
     }
     absorb(kk, vv);
   }
-  if (g == (T % NG)) absorb(kn, vn);  // the new token, taken by the group that would own index T
+  if (g == (T % NG)) {   // the new token, taken by the group that would own index T
+    float kn[DPL], vn[DPL];
+    new_kv(kn, vn);
+    absorb(kn, vn);
+  }
 
   if (sub == 0) { sm_m[g] = m; sm_l[g] = l; }
 #pragma unroll

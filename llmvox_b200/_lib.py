@@ -102,5 +102,11 @@ def check(status: int):
 
 
 def i32_array(values):
-    arr = (C.c_int32 * len(values))(*[int(v) for v in values])
-    return arr
+    """int32 pointer argument from a sequence / array.  Goes through numpy (a C loop): the ctypes array constructor cost
+    1.5 ms for the 12,800 text ids of a 64-stream batch, 40 % of its first-chunk latency.  The returned pointer keeps the
+    array alive (numpy: ctypes.data_as)."""
+    import numpy as np
+    arr = np.ascontiguousarray(values, dtype=np.int32)
+    if arr.size == 0:
+        arr = np.zeros((1,), dtype=np.int32)
+    return arr.ctypes.data_as(_I32P)

@@ -116,11 +116,12 @@ class Engine:
         check(self.lib.lvx_session_close(self._h, i32_array(slots), len(slots), self._stream(stream)))
 
     def feed_text(self, slots: Sequence[int], ids: Sequence[Sequence[int]], stream=None):
-        offs, flat = [0], []
-        for seq in ids:
-            flat.extend(int(x) for x in seq)
-            offs.append(len(flat))
-        check(self.lib.lvx_feed_text(self._h, i32_array(slots), i32_array(offs), i32_array(flat or [0]), len(slots),
+        import itertools
+        import numpy as np
+        offs = np.zeros((len(ids) + 1,), dtype=np.int32)
+        np.cumsum([len(seq) for seq in ids], out=offs[1:])
+        flat = np.fromiter(itertools.chain.from_iterable(ids), dtype=np.int32, count=int(offs[-1]))
+        check(self.lib.lvx_feed_text(self._h, i32_array(slots), i32_array(offs), i32_array(flat), len(slots),
                                      self._stream(stream)))
 
     def session_length(self, slot: int) -> int:

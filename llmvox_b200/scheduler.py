@@ -60,6 +60,33 @@ class ChunkScheduler:
         self.chunks.extend(out)
         return out
 
+    def push_many(self, k: int) -> List[Tuple[int, int]]:
+        """`k` pushes of codes that are not EOA (or whose value is irrelevant) in one call: the ranges that become ready, in
+        emission order -- identical to k calls of push(None), in O(emissions) instead of O(codes) (a 256-stream batch
+        costs the host 51,200 pushes per 200-code step otherwise)."""
+        assert not self.done, "sentence already ended; call new_sentence()"
+        out: List[Tuple[int, int]] = []
+        while k > 0:
+            if self.eoa_pending or self.dump_size > self.max_audio_len:  # rare shapes (the length cap can trigger before the
+                n0 = len(self.chunks)                                    # next cut): the reference's per-code order
+                for _ in range(k):
+                    if self.done:
+                        break
+                    self.push(None)
+                self.chunks[n0:n0] = out
+                return out + self.chunks[n0 + len(out):]
+            need = self.dump_size - (self.seen - self.emitted)           # codes until the next cut (>= 1)
+            if k < need:
+                self.seen += k
+                break
+            self.seen += need
+            k -= need
+            out.append((self.emitted, self.dump_size))
+            self.emitted += self.dump_size
+            self._grow()
+        self.chunks.extend(out)
+        return out
+
     def flush(self) -> List[Tuple[int, int]]:
         """Not in the reference (it only flushes on EOA): emits whatever is pending, for fixed-length
         benchmark utterances."""

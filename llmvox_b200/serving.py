@@ -363,6 +363,12 @@ class ContinuousBatcher:
                 break
             avail = s.known if s.eoa is None else min(s.known, s.eoa + 1)
             ended = False
+            plain = (avail - s.pushed) if s.eoa is None else (min(avail, s.eoa) - s.pushed)   # codes before the EOA: in one go
+            if plain > 1:
+                for (st, ln) in sc.push_many(plain):
+                    self._queue_chunk(req, r, s, st, ln, ready, pend)
+                s.pushed += plain
+                ended = sc.done
             while s.pushed < avail and not ended:
                 code = sc.eoa if (s.eoa is not None and s.pushed == s.eoa) else None
                 for (st, ln) in sc.push(code):

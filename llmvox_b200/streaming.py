@@ -341,10 +341,13 @@ class BatchSynthesizer:
             ready: List[Tuple[int, int, int]] = []
             for a, i in enumerate(active):
                 sc = self.sched[i]
+                if eoa_at is None or not (self.steps_done <= eoa_at[a] < self.steps_done + k):
+                    ready.extend((i, s, c) for (s, c) in sc.push_many(k))      # no EOA in this round: O(emissions)
+                    continue
                 for t in range(k):
                     if sc.done:
                         break
-                    code = sc.eoa if (eoa_at is not None and eoa_at[a] == self.steps_done + t) else None
+                    code = sc.eoa if eoa_at[a] == self.steps_done + t else None
                     for (s, c) in sc.push(code):
                         ready.append((i, s, c))
             self.steps_done += k

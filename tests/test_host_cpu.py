@@ -260,3 +260,27 @@ def test_resize_text_table_rows_are_running_means():
     assert torch.allclose(r[384], t.mean(0), atol=1e-6)
     assert torch.allclose(r[385], torch.cat([t, r[384:385]]).mean(0), atol=1e-6)
     assert torch.equal(resize_text_table(r), r)
+
+
+def test_scheduler_push_many_equals_repeated_push():
+    """ChunkScheduler.push_many(k) == k x push(None): same ranges, same state, for random round lengths, dump sizes and
+    length caps (including the shapes where the cap can trigger)."""
+    import random
+    from llmvox_b200.scheduler import ChunkScheduler
+    rnd = random.Random(5)
+    for _ in range(300):
+        kw = dict(dump_size=rnd.choice([1, 3, 10, 160]), max_dump=rnd.choice([10, 90, 1280]), stop_on_eoa=rnd.random() < 0.5,
+                  max_audio_len=rnd.choice([5, 50, 8000]))
+        a, b = ChunkScheduler(**kw), ChunkScheduler(**kw)
+        for _ in range(rnd.randint(1, 12)):
+            if a.done:
+                break
+            k = rnd.randint(1, 400)
+            got = a.push_many(k)
+            want = []
+            for _ in range(k):
+                if b.done:
+                    break
+                want.extend(b.push(None))
+            assert got == want
+            assert (a.seen, a.emitted, a.dump_size, a.done, a.chunks) == (b.seen, b.emitted, b.dump_size, b.done, b.chunks)

@@ -103,6 +103,16 @@ int lvx_session_close(lvx_engine* e, const int32_t* h_slots, int n, void* stream
 int lvx_feed_text(lvx_engine* e, const int32_t* h_slots, const int32_t* h_offsets, const int32_t* h_ids,
                   int n, void* stream);
 
+/* The same from raw text, tokenised on the device: sentence i is the UTF-8 bytes h_bytes[h_offsets[i] ..
+ * h_offsets[i+1]).  clean != 0 runs the reference's clean_text (streaming_server.py:106-149) first; the text
+ * is then split at spaces, every word stripped and byte-tokenised (byte + 3, "[PAD]" -> 384, "EOS" -> 385)
+ * with its own </s> = 1, and 385 follows the last word -- the ids the producer / generator threads of
+ * streaming_server.py:184-248, 297-310 feed for a whole sentence.  h_counts[i] receives the number of ids
+ * appended to session i.  Synchronous on `stream`.  LVX_ERR_CAPACITY if a sentence is longer than max_context
+ * bytes or its ids do not fit the session. */
+int lvx_feed_utf8(lvx_engine* e, const int32_t* h_slots, const int32_t* h_offsets, const uint8_t* h_bytes,
+                  int n, int clean, int32_t* h_counts, void* stream);
+
 /* n_steps decode steps for n sessions, batched: the loop body of streaming_server.py:323-354 (input
  * assembly a4, GPT.forward a5-a8 with a paged KV cache, pick a9) with no host sync per token.  Step t of a
  * session consumes text id t (pad_token_id beyond its text), the previous code's codebook row (zeros at
@@ -189,6 +199,9 @@ int lvx_gather_code_ranges(lvx_engine* e, const int32_t* h_slots, const int32_t*
                            int n, int32_t* d_out, void* stream);
 /* Host mirror of a slot's context length (codes decoded so far). */
 int lvx_session_length(lvx_engine* e, int slot, int32_t* out_len);
+/* The text ids a slot holds, read back from the device (synchronous on `stream`): up to `cap` ids into h_out,
+ * *out_n = the slot's text length. */
+int lvx_session_text(lvx_engine* e, int slot, int32_t* h_out, int cap, int32_t* out_n, void* stream);
 
 /* Replaces wavtokenizer.codes_to_features(codes) (pretrained.py:209-239): n codes -> n x code_dim fp32
  * rows (channels-last; the reference returns the transpose (1, 512, n)). */

@@ -42,6 +42,7 @@ SYMBOLS = [
     ("lvx_session_open", C.c_int, [_VP, _I32P, C.c_int, _VP]),
     ("lvx_session_close", C.c_int, [_VP, _I32P, C.c_int, _VP]),
     ("lvx_feed_text", C.c_int, [_VP, _I32P, _I32P, _I32P, C.c_int, _VP]),
+    ("lvx_feed_utf8", C.c_int, [_VP, _I32P, _I32P, C.c_char_p, C.c_int, C.c_int, _I32P, _VP]),
     ("lvx_decode_steps", C.c_int, [_VP, _I32P, C.c_int, C.c_int, C.POINTER(LvxSampling), _VP]),
     ("lvx_decode_steps_lane", C.c_int, [_VP, C.c_int, _I32P, C.c_int, C.c_int, C.POINTER(LvxSampling), _VP]),
     ("lvx_decode_steps_ex", C.c_int, [_VP, C.c_int, _I32P, C.c_int, C.c_int, C.POINTER(LvxSampling), C.c_int, _VP]),
@@ -56,6 +57,7 @@ SYMBOLS = [
     ("lvx_gather_codes", C.c_int, [_VP, _I32P, C.c_int, C.c_int, C.c_int, _VP, _VP]),
     ("lvx_gather_code_ranges", C.c_int, [_VP, _I32P, _I32P, _I32P, C.c_int, _VP, _VP]),
     ("lvx_session_length", C.c_int, [_VP, C.c_int, _I32P]),
+    ("lvx_session_text", C.c_int, [_VP, C.c_int, _I32P, C.c_int, _I32P, _VP]),
     ("lvx_codes_to_features", C.c_int, [_VP, _VP, C.c_int, _VP, _VP]),
     ("lvx_text_embed", C.c_int, [_VP, _VP, C.c_int, _VP, _VP]),
     ("lvx_vocode", C.c_int, [_VP, _VP, _I32P, C.c_int, C.c_int, _VP, _VP]),

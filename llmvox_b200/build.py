@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libllmvox_b200.so")
 SOURCES = ["engine.cu"]
-HEADERS = ["common.cuh", "decode_kernels.cuh", "gemm.cuh", "tc_gemm.cuh", "vocoder_kernels.cuh", "cluster_decode.cuh",
+HEADERS = ["common.cuh", "decode_kernels.cuh", "gemm.cuh", "tc_gemm.cuh", "vocoder_kernels.cuh", "cluster_decode.cuh", "text_kernels.cuh",
            os.path.join("..", "..", "include", "llmvox_b200.h")]
 
 

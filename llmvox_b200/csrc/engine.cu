@@ -19,6 +19,7 @@
 #include "gemm.cuh"
 #include "tc_gemm.cuh"
 #include "cluster_decode.cuh"
+#include "text_kernels.cuh"
 
 #include <deque>
 #include "vocoder_kernels.cuh"
@@ -161,6 +162,8 @@ struct lvx_engine {
   long long pool_pages = 0;
   int max_pages = 0;
   std::vector<int> h_len, h_text_len, h_open, h_npages, free_pages, stamp;
+  uint8_t *tx_bytes = nullptr, *tx_scratch = nullptr;   // device text front-end (lvx_feed_utf8): raw bytes, rewrite scratch
+  int* tx_status = nullptr;
   std::vector<std::vector<int>> h_pages;
   int stamp_ctr = 0;
   int *d_slots = nullptr, *d_aux = nullptr, *d_ids = nullptr;   // staging of the control calls (open / feed / gather)
@@ -1013,6 +1016,45 @@ extern "C" int lvx_feed_text(lvx_engine* e, const int32_t* h_slots, const int32_
   return LVX_OK;
 }
 
+// Text front-end on the device (text_kernels.cuh): raw UTF-8 sentences -> [clean_text ->] ByT5 ids appended to the sessions' text.
+// Synchronous on `stream` (the id counts come back to the host, which tracks every session's text length).
+extern "C" int lvx_feed_utf8(lvx_engine* e, const int32_t* h_slots, const int32_t* h_offsets, const uint8_t* h_bytes, int n, int clean,
+                             int32_t* h_counts, void* stream) {
+  LVX_TRY(check_engine(e));
+  LVX_TRY(check_slots(e, h_slots, n, true));
+  LVX_CHECK(h_offsets && h_bytes && h_counts, LVX_ERR_INVALID, "NULL argument");
+  LVX_CHECK(h_offsets[0] == 0, LVX_ERR_INVALID, "offsets must start at 0");
+  const int S = e->cfg.max_sessions, ctx = e->cfg.max_context;
+  for (int i = 0; i < n; ++i) {
+    const int cnt = h_offsets[i + 1] - h_offsets[i];
+    LVX_CHECK(cnt >= 0, LVX_ERR_INVALID, "offsets must be non-decreasing");
+    LVX_CHECK(cnt <= ctx, LVX_ERR_CAPACITY, "sentence longer than max_context bytes");
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int cap = 12 * ctx + 64;   // the longest rewrite (one backslash -> " backslash ") grows a sentence 11x
+  if (!e->tx_bytes) {
+    LVX_TRY(dev_alloc_bytes(e, (void**)&e->tx_bytes, (size_t)S * ctx));
+    LVX_TRY(dev_alloc_bytes(e, (void**)&e->tx_scratch, (size_t)2 * S * cap));
+    LVX_TRY(dev_alloc_bytes(e, (void**)&e->tx_status, (size_t)S * sizeof(int)));
+  }
+  const int total = h_offsets[n];
+  LVX_TRY(upload_slots(e, h_slots, n, st));
+  LVX_CUDA(cudaMemcpyAsync(e->d_aux, h_offsets, (n + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (total) LVX_CUDA(cudaMemcpyAsync(e->tx_bytes, h_bytes, total, cudaMemcpyHostToDevice, st));
+  text_frontend_kernel<<<ceil_div(n, 64), 64, 0, st>>>(e->tx_bytes, e->d_aux, e->d_slots, n, clean, e->tx_scratch, cap, e->st, e->tx_status);
+  LAUNCHED(e);
+  LVX_CUDA(cudaMemcpyAsync(h_counts, e->tx_status, n * sizeof(int), cudaMemcpyDeviceToHost, st));
+  LVX_CUDA(cudaStreamSynchronize(st));
+  int worst = 0;   // a sentence that does not fit leaves its session untouched; the others of the batch are appended
+  for (int i = 0; i < n; ++i) {
+    if (h_counts[i] >= 0) e->h_text_len[h_slots[i]] += h_counts[i];
+    else worst = std::min(worst, h_counts[i]);
+  }
+  LVX_CHECK(worst != -1, LVX_ERR_CAPACITY, "clean_text scratch overflow");
+  LVX_CHECK(worst == 0, LVX_ERR_CAPACITY, "text longer than max_context");
+  return LVX_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ decode
 // One GPT.forward over n session rows whose residual stream x is already assembled (src/model.py:220-234).
 static int gpt_body_exact(lvx_engine* e, lvx_engine::Lane& ln, int n, const int* pos_override, cudaStream_t st);
@@ -1555,6 +1597,20 @@ extern "C" int lvx_session_length(lvx_engine* e, int slot, int32_t* out_len) {
   LVX_CHECK(e && out_len, LVX_ERR_INVALID, "NULL argument");
   LVX_CHECK(slot >= 0 && slot < e->cfg.max_sessions, LVX_ERR_INVALID, "slot out of range");
   *out_len = e->h_len[slot];
+  return LVX_OK;
+}
+
+extern "C" int lvx_session_text(lvx_engine* e, int slot, int32_t* h_out, int cap, int32_t* out_n, void* stream) {
+  LVX_TRY(check_engine(e));
+  LVX_CHECK(h_out && out_n && cap >= 0, LVX_ERR_INVALID, "bad argument");
+  LVX_CHECK(slot >= 0 && slot < e->cfg.max_sessions, LVX_ERR_INVALID, "slot out of range");
+  const int n = e->h_text_len[slot];
+  *out_n = n;
+  if (std::min(n, cap) > 0) {
+    LVX_CUDA(cudaMemcpyAsync(h_out, e->st.text_ids + (size_t)slot * e->cfg.max_context, std::min(n, cap) * sizeof(int),
+                             cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    LVX_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  }
   return LVX_OK;
 }
 

@@ -124,6 +124,27 @@ class Engine:
         check(self.lib.lvx_feed_text(self._h, i32_array(slots), i32_array(offs), i32_array(flat), len(slots),
                                      self._stream(stream)))
 
+    def feed_sentences(self, slots: Sequence[int], sentences: Sequence[str], clean: bool = True, stream=None) -> List[int]:
+        """Raw sentences -> [clean_text ->] ByT5 ids appended to the sessions' text, tokenised on the device
+        (lvx_feed_utf8): the ids `tokenizer.sentence_ids(protocol.clean_text(s))` would give.  Returns the id count
+        per sentence.  Synchronous on the stream."""
+        import numpy as np
+        raw = [s.encode("utf-8") for s in sentences]
+        offs = np.zeros((len(raw) + 1,), dtype=np.int32)
+        np.cumsum([len(b) for b in raw], out=offs[1:])
+        counts = np.zeros((len(raw),), dtype=np.int32)
+        check(self.lib.lvx_feed_utf8(self._h, i32_array(slots), i32_array(offs), b"".join(raw), len(slots), int(bool(clean)),
+                                     counts.ctypes.data_as(C.POINTER(C.c_int32)), self._stream(stream)))
+        return counts.tolist()
+
+    def session_text(self, slot: int, stream=None) -> List[int]:
+        """The text ids the slot holds, read back from the device."""
+        import numpy as np
+        out = np.zeros((self.cfg.max_context,), dtype=np.int32)
+        n = C.c_int32()
+        check(self.lib.lvx_session_text(self._h, slot, out.ctypes.data_as(C.POINTER(C.c_int32)), out.size, C.byref(n), self._stream(stream)))
+        return out[:n.value].tolist()
+
     def session_length(self, slot: int) -> int:
         out = C.c_int32()
         check(self.lib.lvx_session_length(self._h, slot, C.byref(out)))

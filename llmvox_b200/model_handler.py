@@ -184,10 +184,11 @@ class ModelHandler:
         return sentence_ids(sentence)
 
     def stream(self, sentences: Sequence[str], max_steps: Optional[int] = None, replica: int = 0, stop_on_eoa: bool = True,
-               flush_tail: bool = True, sampling: Optional[Sampling] = None) -> Iterator[List[Chunk]]:
+               flush_tail: bool = True, sampling: Optional[Sampling] = None, clean: bool = False) -> Iterator[List[Chunk]]:
         """Yields lists of ready chunks (float32 PCM) as the sessions advance; replica 0 / 1 selects
-        initial_dump_size_1 / _2 (streaming_server.py:521-531)."""
-        ids = [self.text_to_ids(s) for s in sentences]
+        initial_dump_size_1 / _2 (streaming_server.py:521-531).  The sentences are tokenised on the device (the ids
+        `text_to_ids` gives); `clean=True` runs the reference's clean_text (:106-149) there first."""
+        ids = list(sentences)
         if len(ids) > len(self._batch_slots):
             raise ValueError("more sentences than max_sessions")
         dump = self.config["initial_dump_size_1" if replica == 0 else "initial_dump_size_2"]
@@ -196,7 +197,7 @@ class ModelHandler:
         steps = max_steps if max_steps is not None else self.config["max_context"]
         bs = BatchSynthesizer(self.engine, len(ids), dump, self.config["max_dump_size"], stop_on_eoa, sampling,
                               slots=self._batch_slots[: len(ids)], max_audio_length=self.config["max_audio_length"])
-        bs.start(ids)
+        bs.start(ids, clean=clean)
         yield from bs.run(steps, flush_tail=flush_tail)
         self.truncated = [i for i, sc in enumerate(bs.sched) if stop_on_eoa and not sc.done]   # sessions cut by the step bound
 

@@ -10,7 +10,7 @@ from __future__ import annotations
 
 import os
 from dataclasses import dataclass, field
-from typing import Dict, Iterator, List, Optional, Sequence, Tuple
+from typing import Dict, Iterator, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
 import torch
@@ -277,13 +277,17 @@ class BatchSynthesizer:
         self.emitter = ChunkEmitter(engine, bandwidth_id)
         self._prog = None
 
-    def start(self, text_ids: Sequence[Sequence[int]], keep_schedule: bool = False):
-        """Opens the sessions (the per-sentence reset of :404-416) and hands them their text ids.  A new call is a new
-        request (fresh generator threads in the reference, so the dump size starts at its initial value again);
+    def start(self, text_ids: Sequence[Union[Sequence[int], str]], keep_schedule: bool = False, clean: bool = False):
+        """Opens the sessions (the per-sentence reset of :404-416) and hands them their text: lists of ids, or raw
+        sentences (str) that the engine tokenises on the device (`clean=True` runs clean_text there first).  A new call is
+        a new request (fresh generator threads in the reference, so the dump size starts at its initial value again);
         `keep_schedule=True` continues the same request, where the dump size only ever grows (:373-375)."""
         assert len(text_ids) == self.n
         self.e.open(self.slots)
-        self.e.feed_text(self.slots, text_ids)
+        if self.n and all(isinstance(t, str) for t in text_ids):
+            self.e.feed_sentences(self.slots, text_ids, clean=clean)
+        else:
+            self.e.feed_text(self.slots, text_ids)
         for s in self.sched:
             s.new_sentence()
             if not keep_schedule:

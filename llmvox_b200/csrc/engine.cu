@@ -556,12 +556,11 @@ extern "C" int lvx_engine_create(const lvx_config* cfg, int device, lvx_engine**
   declare_tensors(e);
   int s = engine_alloc(e);
   if (s == LVX_OK && c.precision != LVX_PRECISION_FP32) s = tc_init(&e->tcw, prop.multiProcessorCount);
-  if (s == LVX_OK) {   // the tiled depthwise-conv kernel keeps a 32-frame fp32 tile (96 KB) in shared memory
-    cudaError_t ce = cudaFuncSetAttribute(dwconv_adaln_tiled_kernel<float, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_R * 768 * 4);
-    if (ce == cudaSuccess)
-      ce = cudaFuncSetAttribute(dwconv_adaln_tiled_kernel<bf16, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, DW_R * 768 * 4);
+  if (s == LVX_OK) {   // the depthwise-conv strip kernel keeps DWB_R + 6 fp32 rows (54 KB) in shared memory
+    cudaError_t ce = cudaFuncSetAttribute(dwconv_adaln_bulk_kernel<float, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, DWB_SMEM);
+    if (ce == cudaSuccess) ce = cudaFuncSetAttribute(dwconv_adaln_bulk_kernel<bf16, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, DWB_SMEM);
     if (ce != cudaSuccess) {
-      set_error(std::string("cudaFuncSetAttribute(dwconv_adaln_tiled): ") + cudaGetErrorString(ce));
+      set_error(std::string("cudaFuncSetAttribute(dwconv_adaln_bulk): ") + cudaGetErrorString(ce));
       s = LVX_ERR_CUDA;
     }
   }
@@ -1842,18 +1841,17 @@ static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes
     auto& X = e->cnx[i];
     {
     PROF(e, "dwconv_adaln", st);
-    // bulk shapes: strips of DW_R frames with register-resident weights; small batches (fewer strips than two per SM): one
-    // warp per frame, which keeps every SM busy
-    const size_t dw_smem = (size_t)DW_R * 768 * sizeof(float);
-    const bool tiled = g.R >= 2 * DW_R * (e->tcw.num_sms > 0 ? e->tcw.num_sms : 148);
-    if (tiled && a == F32)
-      dwconv_adaln_tiled_kernel<float, 768><<<ceil_div(g.R, DW_R), 192, dw_smem, st>>>(e->v_x, g.R, e->row_chunk, X.dw_w, X.dw_b,
+    // strips of DWB_R frames brought in by the bulk-copy engine; LLMVOX_B200_DW_SIMPLE selects the one-warp-per-frame kernel
+    // (the cross-check of tests/test_gpu_parity.py; read per call so a test can switch)
+    const bool bulk = getenv("LLMVOX_B200_DW_SIMPLE") == nullptr;
+    if (bulk && a == F32)
+      dwconv_adaln_bulk_kernel<float, 768><<<ceil_div(g.R, DWB_R), 192, DWB_SMEM, st>>>(e->v_x, g.R, e->row_chunk, X.dw_w, X.dw_b,
+                                                                                         X.scale + (size_t)bw * D, X.shift + (size_t)bw * D,
+                                                                                         1e-6f, (float*)e->v_h);
+    else if (bulk)
+      dwconv_adaln_bulk_kernel<bf16, 768><<<ceil_div(g.R, DWB_R), 192, DWB_SMEM, st>>>(e->v_x, g.R, e->row_chunk, X.dw_w, X.dw_b,
                                                                                         X.scale + (size_t)bw * D, X.shift + (size_t)bw * D,
-                                                                                        1e-6f, (float*)e->v_h);
-    else if (tiled)
-      dwconv_adaln_tiled_kernel<bf16, 768><<<ceil_div(g.R, DW_R), 192, dw_smem, st>>>(e->v_x, g.R, e->row_chunk, X.dw_w, X.dw_b,
-                                                                                       X.scale + (size_t)bw * D, X.shift + (size_t)bw * D,
-                                                                                       1e-6f, (bf16*)e->v_h);
+                                                                                        1e-6f, (bf16*)e->v_h);
     else if (a == F32)
       dwconv_adaln_kernel<float, 768><<<ceil_div(g.R, 8), 256, 0, st>>>(e->v_x, g.R, e->row_chunk, e->d_chunks, X.dw_w, X.dw_b,
                                                                          X.scale + (size_t)bw * D, X.shift + (size_t)bw * D, 1e-6f,

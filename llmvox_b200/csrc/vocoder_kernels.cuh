@@ -316,95 +316,100 @@ __global__ void __launch_bounds__(256) transpose_v_kernel(const bf16* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------------
-// The same operation, tiled (the bulk path).  The one-warp-per-frame kernel above re-reads every input row 7 times and the
-// 21 KB of depthwise weights once per frame through L1: ~42 KB of L1 traffic per frame, which bounds it at a third of the
-// HBM rate (136 us per launch at 61,440 frames against 43 us of HBM time).  Here a CTA of 6 warps owns a strip of DW_R
-// frames; warp w owns channels [128 w, +128) with its 7 x 4 weights in REGISTERS and slides a 7-row window down the
-// strip (one coalesced 512-byte load per new row, 28 FMAs), writing the convolution into a shared-memory tile; after one
-// barrier the warps normalise the tile's rows (AdaLayerNorm over all 768 channels) and store.  Input rows are read
-// (DW_R + 6) / DW_R times, L1 / shared traffic per frame drops to ~10 KB.  Chunk edges: at least ROW_PAD = 3 padding rows
-// separate chunks, so a window never reaches another chunk's frames -- padding rows count as zeros (the reference's
-// per-chunk zero padding), whatever the residual stream holds there.  Same summation order as the kernel above.
+// The same operation in strips (the product path at every batch size).  The one-warp-per-frame kernel above re-reads every
+// input row 7 times and the 21 KB of depthwise weights once per frame through L1: ~42 KB of L1 traffic per frame, which
+// bounds it at a third of the HBM rate (136 us per launch at 61,440 frames against 43 us of HBM time).  Here a CTA of 6
+// warps owns a strip of DWB_R frames; warp w owns channels [128 w, +128) with its 7 x 4 weights in REGISTERS and slides a
+// 7-row window down the strip (28 FMAs per row), leaving the convolution in shared memory; after one barrier the warps
+// normalise the strip's rows (AdaLayerNorm over all 768 channels) and store.  Chunk edges: at least ROW_PAD = 3 padding
+// rows separate chunks, so a window never reaches another chunk's frames -- padding rows count as zeros (the reference's
+// per-chunk zero padding), whatever the residual stream holds there.
+//
+// A first version pulled the rows through registers (two sets of 8 prefetched rows, or every row costs a full HBM latency:
+// 193 us per launch without the prefetch, 111 with): 139 registers, 12 warps per SM, 0.44 of the HBM rate under ncu.
+// Now one thread issues cp.async.bulk copies of the whole strip (DWB_R + 6 contiguous rows)
+// into shared memory and the convolution runs IN PLACE from there (row o is stored to slot o once slot o + 6 has been read;
+// a thread only ever touches its own 4 channels), which frees the registers: short strips of 12 frames (54 KB) put four
+// CTAs on an SM, so three strips are in flight while one computes.  The 1.5x re-read of the halo rows hits L2.  Measured on
+// 61,440 frames (engine profiler, per launch incl. its events): 121 us registers -> 91 us (30 rows, 2 CTAs) -> 84 us
+// (12 rows, 4 CTAs); it also beats the one-warp-per-frame kernel on the small streaming batches (64 x 90 frames: 23 -> 15 us).
+// Same summation order as the kernel above (tests/test_gpu_parity.py compares the two bit for bit).
 // ---------------------------------------------------------------------------------------------------
-constexpr int DW_R = 32;
+constexpr int DWB_R = 12;
+constexpr int DWB_SMEM = (DWB_R + 6) * 768 * 4 + 64 * 4 + 16;
 template <typename TOut, int C>
-__global__ void __launch_bounds__(192, 2) dwconv_adaln_tiled_kernel(const float* __restrict__ x, int rows,
-                                                                    const int* __restrict__ row_chunk,
-                                                                    const float* __restrict__ dw_w, const float* __restrict__ dw_b,
-                                                                    const float* __restrict__ scale,
-                                                                    const float* __restrict__ shift, float eps,
-                                                                    TOut* __restrict__ out) {
+__global__ void __launch_bounds__(192, 4) dwconv_adaln_bulk_kernel(const float* __restrict__ x, int rows,
+                                                                   const int* __restrict__ row_chunk,
+                                                                   const float* __restrict__ dw_w, const float* __restrict__ dw_b,
+                                                                   const float* __restrict__ scale,
+                                                                   const float* __restrict__ shift, float eps,
+                                                                   TOut* __restrict__ out) {
   static_assert(C == 768, "6 warps x 128 channels");
-  extern __shared__ __align__(16) float dw_tile[];   // [DW_R][C]
+  constexpr int TR = DWB_R + 6;
+  extern __shared__ __align__(128) float dwb_tile[];   // [TR][C], then TR validity flags, then the mbarrier
+  int* valid = reinterpret_cast<int*>(dwb_tile + TR * C);
+  const uint32_t bar = smem_u32(dwb_tile + TR * C + 64);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c0 = warp * 128 + lane * 4;
-  const int r0 = blockIdx.x * DW_R;
+  const int r0 = blockIdx.x * DWB_R;
+  const int g_lo = max(r0 - 3, 0), g_hi = min(r0 + DWB_R + 3, rows);   // rows of x that exist
+  if (threadIdx.x == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (threadIdx.x < TR) {
+    const int r = r0 - 3 + (int)threadIdx.x;
+    valid[threadIdx.x] = (r >= 0 && r < rows && row_chunk[r] >= 0) ? 1 : 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(bar, (uint32_t)(g_hi - g_lo) * C * 4);
+    for (int r = g_lo; r < g_hi; r += 9) {   // a few copies rather than one: they spread over the copy engine's queues
+      const int nr = min(9, g_hi - r);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32(dwb_tile + (size_t)(r - (r0 - 3)) * C)),
+                   "l"(x + (size_t)r * C), "r"((uint32_t)nr * C * 4), "r"(bar)
+                   : "memory");
+    }
+  }
   float4 wt[7];
 #pragma unroll
   for (int t = 0; t < 7; ++t) wt[t] = load4(dw_w + t * C + c0);
   const float4 b4 = load4(dw_b + c0);
-  auto in_row = [&](int r) -> float4 {
-    if (r < 0 || r >= rows || row_chunk[r] < 0) return make_float4(0.f, 0.f, 0.f, 0.f);
-    return load4(x + (size_t)r * C + c0);
+  mbar_wait(bar, 0);
+  auto slot = [&](int i) -> float4 {   // padding rows and rows outside the batch count as zeros (their slots hold anything)
+    return valid[i] ? *reinterpret_cast<const float4*>(dwb_tile + i * C + c0) : make_float4(0.f, 0.f, 0.f, 0.f);
   };
-  // rows are requested a block of 8 ahead of their use (two register sets): a warp is a single dependent chain, so without
-  // this every row would cost a full L2 / HBM latency (measured: 193 us per launch against 78 with the prefetch)
-  float4 win[7], na[8], nb[8];
+  float4 win[7];
 #pragma unroll
-  for (int t = 0; t < 6; ++t) win[t] = in_row(r0 - 3 + t);
+  for (int t = 0; t < 6; ++t) win[t] = slot(t);
+#pragma unroll 3
+  for (int o = 0; o < DWB_R; ++o) {
+    win[6] = slot(o + 6);
+    float4 v = b4;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) na[k] = in_row(r0 + 3 + k);
-  static_assert(DW_R % 16 == 0, "two blocks of 8 rows per loop iteration");
-#pragma unroll 1
-  for (int o = 0; o < DW_R; o += 16) {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) nb[k] = in_row(r0 + o + 11 + k);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      win[6] = na[k];
-      float4 v = b4;
-#pragma unroll
-      for (int t = 0; t < 7; ++t) {
-        v.x = fmaf(win[t].x, wt[t].x, v.x);
-        v.y = fmaf(win[t].y, wt[t].y, v.y);
-        v.z = fmaf(win[t].z, wt[t].z, v.z);
-        v.w = fmaf(win[t].w, wt[t].w, v.w);
-      }
-      *reinterpret_cast<float4*>(dw_tile + (o + k) * C + c0) = v;
-#pragma unroll
-      for (int t = 0; t < 6; ++t) win[t] = win[t + 1];
+    for (int t = 0; t < 7; ++t) {
+      v.x = fmaf(win[t].x, wt[t].x, v.x);
+      v.y = fmaf(win[t].y, wt[t].y, v.y);
+      v.z = fmaf(win[t].z, wt[t].z, v.z);
+      v.w = fmaf(win[t].w, wt[t].w, v.w);
     }
-    if (o + 16 < DW_R) {
+    *reinterpret_cast<float4*>(dwb_tile + o * C + c0) = v;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) na[k] = in_row(r0 + o + 19 + k);
-    }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      win[6] = nb[k];
-      float4 v = b4;
-#pragma unroll
-      for (int t = 0; t < 7; ++t) {
-        v.x = fmaf(win[t].x, wt[t].x, v.x);
-        v.y = fmaf(win[t].y, wt[t].y, v.y);
-        v.z = fmaf(win[t].z, wt[t].z, v.z);
-        v.w = fmaf(win[t].w, wt[t].w, v.w);
-      }
-      *reinterpret_cast<float4*>(dw_tile + (o + 8 + k) * C + c0) = v;
-#pragma unroll
-      for (int t = 0; t < 6; ++t) win[t] = win[t + 1];
-    }
+    for (int t = 0; t < 6; ++t) win[t] = win[t + 1];
   }
   __syncthreads();
   constexpr int V = C / 128;
 #pragma unroll 1
-  for (int o = warp; o < DW_R; o += 6) {
+  for (int o = warp; o < DWB_R; o += 6) {
     const int row = r0 + o;
-    if (row >= rows || row_chunk[row] < 0) continue;   // warp-uniform
+    if (!valid[o + 3]) continue;   // warp-uniform
+    const float* src = dwb_tile + o * C;
     float4 v[V];
     float s = 0.f;
 #pragma unroll
     for (int i = 0; i < V; ++i) {
-      v[i] = *reinterpret_cast<const float4*>(dw_tile + o * C + (lane + 32 * i) * 4);
+      v[i] = *reinterpret_cast<const float4*>(src + (lane + 32 * i) * 4);
       s += v[i].x + v[i].y + v[i].z + v[i].w;
     }
     const float mean = warp_sum(s) * (1.0f / C);

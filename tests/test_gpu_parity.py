@@ -266,8 +266,10 @@ def test_vocoder_launch_group_above_65535_rows(weights):
 
 
 def test_vocoder_bulk_kernels_in_fp32(weights):
-    """The bulk-shape kernels (tiled depthwise conv + AdaLN from 9,472 padded rows on) in the fp32 parity mode, where the
-    comparison is tight: chunks inside an 8 x 1280-frame batch equal their solo decodes (one warp per frame kernel)."""
+    """The bulk shape in the fp32 parity mode, where the comparison is tight: chunks inside an 8 x 1280-frame batch equal
+    their solo decodes, and the strip kernel of the depthwise conv + AdaLN (bulk-copy engine, in-place window) gives the
+    PCM of the one-warp-per-frame kernel bit for bit (same summation order), ragged chunk lengths included."""
+    import os
     from llmvox_b200.engine import Engine
     e = Engine(weights, device=0, precision="fp32", max_sessions=2, max_context=32, max_vocode_frames=11000)
     g = torch.Generator().manual_seed(21)
@@ -278,6 +280,17 @@ def test_vocoder_bulk_kernels_in_fp32(weights):
         alone = e.vocode(codes[k * L:(k + 1) * L].contiguous(), [0, L]).cpu().numpy()
         seg = pcm[k * L * 320:(k + 1) * L * 320]
         assert np.abs(seg - alone).max() < 1e-5 * max(1.0, np.abs(alone).max()), k
+    lens = [1, 2, 3, 5, 7, 11, 12, 13, 23, 24, 25, 100, 333, 1280, 6, 9]
+    cu = np.concatenate([[0], np.cumsum(lens)]).tolist()
+    ragged = e.vocode(codes[: cu[-1]].contiguous(), cu).cpu().numpy()
+    os.environ["LLMVOX_B200_DW_SIMPLE"] = "1"
+    try:
+        simple = e.vocode(codes, list(range(0, (n + 1) * L, L))).cpu().numpy()
+        ragged_simple = e.vocode(codes[: cu[-1]].contiguous(), cu).cpu().numpy()
+    finally:
+        del os.environ["LLMVOX_B200_DW_SIMPLE"]
+    assert np.array_equal(pcm, simple)
+    assert np.array_equal(ragged, ragged_simple)
     e.close()
 
 

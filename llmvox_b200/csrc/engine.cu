@@ -1906,8 +1906,8 @@ static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes
     LVX_TRY(run_gemm(e, p, e->head, a, F32, st));
     {
       PROF(e, "head_act_split3", st);
-      dim3 grid(g.R, ceil_div(std::max(bins, e->spec_ld - 2 * bins), 256));
-      head_act_split3_kernel<<<grid, 256, 0, st>>>(e->v_raw, e->raw_ld, g.R, e->row_chunk, bins, (bf16*)e->v_spec, e->spec_ld);
+      head_act_split3_kernel<<<ceil_div(g.R, 8), 256, 16 * e->spec_ld * sizeof(bf16), st>>>(e->v_raw, e->raw_ld, g.R, e->row_chunk, bins, (bf16*)e->v_spec,
+                                                                              e->spec_ld);
       LAUNCHED(e);
     }
     GemmParams q;
@@ -1919,8 +1919,14 @@ static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes
   if (stage == 5) return dump(e->v_frames, NF, NF);
   // overlap-add + trim + envelope (spectral_ops.py:59-73)
   PROF(e, "overlap_add", st);
-  dim3 grid(ceil_div(g.max_len * c.hop, 256), nch);
-  overlap_add_kernel<<<grid, 256, 0, st>>>(e->v_frames, NF, e->d_chunks, e->window, NF, c.hop, d_pcm + (size_t)g.code0 * c.hop);
+  float* pcm0 = d_pcm + (size_t)g.code0 * c.hop;
+  if ((reinterpret_cast<uintptr_t>(pcm0) & 15) == 0 && c.hop % 4 == 0 && NF % 4 == 0 && ((NF - c.hop) / 2) % 4 == 0) {
+    dim3 grid(ceil_div(g.max_len * c.hop, 1024), nch);
+    overlap_add_kernel<4><<<grid, 256, 0, st>>>(e->v_frames, NF, e->d_chunks, e->window, NF, c.hop, pcm0);
+  } else {
+    dim3 grid(ceil_div(g.max_len * c.hop, 256), nch);
+    overlap_add_kernel<1><<<grid, 256, 0, st>>>(e->v_frames, NF, e->d_chunks, e->window, NF, c.hop, pcm0);
+  }
   LAUNCHED(e);
   return LVX_OK;
 }

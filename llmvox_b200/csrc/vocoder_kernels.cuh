@@ -201,18 +201,11 @@ __global__ void __launch_bounds__(256) dwconv_adaln_kernel(const float* __restri
 //   layernorm_split3_kernel : backbone final LayerNorm (models.py:229) straight into the head GEMM's operand -- one warp per
 //                             row; the fp32 copy the separate split kernel re-read is gone
 //   head_act_split3_kernel  : ISTFTHead activation (heads.py:57-63: mag = min(exp(.), 100), S = mag (cos p + i sin p)) straight
-//                             into the iDFT GEMM's operand -- one thread per frequency bin computes exp and sincos ONCE and
-//                             writes real and imaginary part (the per-output-element kernel computed exp twice and went
-//                             through an fp32 spectrum: 0.46 + 0.23 ms per 61,440 frames, this one 0.2)
+//                             into the iDFT GEMM's operand -- one thread per frequency bin computes exp and sincos ONCE for the
+//                             real and the imaginary part (the per-output-element kernel computed exp twice and went
+//                             through an fp32 spectrum: 0.46 + 0.23 ms per 61,440 frames)
 // Padding rows become zeros (the GEMMs mask them on the way out).
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void store_hi_lo_hi(bf16* o, int col, int seg, float v) {
-  const bf16 hi = __float2bfloat16_rn(v);
-  const bf16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-  o[col] = hi;
-  o[seg + col] = lo;
-  o[2 * seg + col] = hi;
-}
 template <int C>
 __global__ void __launch_bounds__(256) layernorm_split3_kernel(const float* __restrict__ x, int rows, const float* __restrict__ w,
                                                                const float* __restrict__ bias, float eps,
@@ -261,28 +254,75 @@ __global__ void __launch_bounds__(256) layernorm_split3_kernel(const float* __re
     *reinterpret_cast<uint2*>(o + 2 * C + c) = hu;
   }
 }
+// exp / sincos of the operand builder below.  Its output is a hi | lo bf16 pair (16 mantissa bits, 2^-17), so the accurate
+// libdevice routines (149 instructions per bin with them: the kernel was issue-bound at 57 % of the issue slots) buy
+// nothing: ex2.approx on x log2(e) (relative error ~1e-6 for |x| < 5; larger magnitudes clip at 100) and sin / cos.approx after a
+// two-term Cody-Waite reduction to [-pi, pi] (absolute error 2^-21.4); phases beyond 8192 rad take the libdevice path.
+__device__ __forceinline__ void sincos_reduced(float p, float* sn, float* cs) {
+  if (fabsf(p) > 8192.0f) {
+    sincosf(p, sn, cs);
+    return;
+  }
+  const float k = rintf(p * 0.15915494309189535f);
+  float r = fmaf(k, -6.2831854820251465f, p);   // fp32(2 pi) ...
+  r = fmaf(k, 1.7484555e-7f, r);                // ... minus the 1.7484555e-7 it exceeds 2 pi by
+  *sn = __sinf(r);
+  *cs = __cosf(r);
+}
+// One WARP per row, 8 rows per CTA: a lane loads the magnitude / phase pairs of 8 bins before it touches any (16 loads in flight
+// per lane -- with one bin per thread the kernel sat at 2.5 TB/s whatever its arithmetic and store pattern were: too few bytes in
+// flight per SM), the hi and lo halves of the row's operand are built in the warp's slice of shared memory and go out as whole
+// 16-byte pieces.  (One 2-byte store per element, with the imaginary parts starting at the odd column 641, also left every warp
+// store a 64-byte run across three partly written sectors: 405 MB of DRAM reads for 315 MB of input under ncu.)
 __global__ void __launch_bounds__(256) head_act_split3_kernel(const float* __restrict__ raw, int ld_raw, int rows,
                                                               const int* __restrict__ row_chunk, int bins, bf16* __restrict__ out,
                                                               int seg) {
-  const int row = blockIdx.x;   // rows on grid.x: a launch group may hold more than 65535 rows
-  const int k = blockIdx.y * 256 + threadIdx.x;
+  extern __shared__ __align__(16) bf16 has_rows[];   // per warp: hi[seg] | lo[seg]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + warp;
   if (row >= rows) return;
-  bf16* o = out + (size_t)row * (3 * seg);
-  const bool pad = row_chunk[row] < 0;
-  if (k < bins) {
-    float re = 0.f, im = 0.f;
-    if (!pad) {
-      const float* r = raw + (size_t)row * ld_raw;
-      const float mag = fminf(expf(r[k]), 100.0f);
-      float sn, cs;
-      sincosf(r[bins + k], &sn, &cs);
-      re = mag * cs;
-      im = mag * sn;
-    }
-    store_hi_lo_hi(o, k, seg, re);
-    store_hi_lo_hi(o, bins + k, seg, im);
+  bf16* hi = has_rows + (size_t)warp * 2 * seg;
+  bf16* lo = hi + seg;
+  uint4* o4 = reinterpret_cast<uint4*>(out + (size_t)row * (3 * seg));
+  const int n4 = seg / 8;
+  if (row_chunk[row] < 0) {
+    for (int i = lane; i < 3 * n4; i += 32) o4[i] = make_uint4(0u, 0u, 0u, 0u);
+    return;
   }
-  if (k < seg - 2 * bins) store_hi_lo_hi(o, 2 * bins + k, seg, 0.f);   // alignment columns of the operand
+  const float* r = raw + (size_t)row * ld_raw;
+  for (int k0 = 0; k0 < bins; k0 += 256) {
+    float m[8], ph[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + 32 * j + lane;
+      m[j] = k < bins ? r[k] : 0.f;
+      ph[j] = k < bins ? r[bins + k] : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = k0 + 32 * j + lane;
+      if (k >= bins) continue;
+      const float mag = fminf(__expf(m[j]), 100.0f);
+      float sn, cs;
+      sincos_reduced(ph[j], &sn, &cs);
+      const float re = mag * cs, im = mag * sn;
+      const bf16 rh = __float2bfloat16_rn(re), ih = __float2bfloat16_rn(im);
+      hi[k] = rh;
+      lo[k] = __float2bfloat16_rn(re - __bfloat162float(rh));
+      hi[bins + k] = ih;
+      lo[bins + k] = __float2bfloat16_rn(im - __bfloat162float(ih));
+    }
+  }
+  for (int k = 2 * bins + lane; k < seg; k += 32) hi[k] = lo[k] = __float2bfloat16_rn(0.f);   // alignment columns
+  __syncwarp();
+  const uint4* h4 = reinterpret_cast<const uint4*>(hi);
+  const uint4* l4 = reinterpret_cast<const uint4*>(lo);
+  for (int i = lane; i < n4; i += 32) {
+    const uint4 h = h4[i];
+    o4[i] = h;
+    o4[n4 + i] = l4[i];
+    o4[2 * n4 + i] = h;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -485,26 +525,43 @@ __global__ void __launch_bounds__(256) head_activation_kernel(const float* __res
 // p = t + (n_fft - hop) / 2 and sums frames i with i*hop <= p < i*hop + n_fft, 0 <= i < L; the envelope is
 // the same sum over window^2.  One thread per output sample.
 // ---------------------------------------------------------------------------------------------------
+template <int V>   // samples per thread: 4 (16-byte accesses; needs a 16-byte aligned PCM pointer) or 1
 __global__ void __launch_bounds__(256) overlap_add_kernel(const float* __restrict__ frames, int ldf,
                                                           const ChunkInfo* __restrict__ chunks,
                                                           const float* __restrict__ window, int n_fft, int hop,
                                                           float* __restrict__ pcm) {
+  // V consecutive samples per thread: hop, n_fft and the trim are multiples of 4, so the samples of a thread share their
+  // frames; per sample the same sums in the same order whatever V is
   const ChunkInfo ci = chunks[blockIdx.y];
-  const int t = blockIdx.x * 256 + threadIdx.x;
+  const int t = (blockIdx.x * 256 + threadIdx.x) * V;
   if (t >= ci.len * hop) return;
   const int p = t + (n_fft - hop) / 2;
   int i_lo = (p - n_fft + hop) / hop;  // ceil((p - n_fft + 1) / hop) for p - n_fft + 1 > 0
   if (p - n_fft + 1 <= 0) i_lo = 0;
   int i_hi = p / hop;
   if (i_hi > ci.len - 1) i_hi = ci.len - 1;
-  float y = 0.f, env = 0.f;
+  float y[V], env[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) y[j] = env[j] = 0.f;
   for (int i = i_lo; i <= i_hi; ++i) {
     const int n = p - i * hop;
-    const float w = window[n];
-    y += frames[(size_t)(ci.row0 + i) * ldf + n];
-    env += w * w;
+    float w[V], f[V];
+    if constexpr (V == 4) {
+      *reinterpret_cast<float4*>(w) = load4(window + n);
+      *reinterpret_cast<float4*>(f) = load4(frames + (size_t)(ci.row0 + i) * ldf + n);
+    } else {
+      w[0] = window[n];
+      f[0] = frames[(size_t)(ci.row0 + i) * ldf + n];
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      y[j] += f[j];
+      env[j] += w[j] * w[j];
+    }
   }
-  pcm[(size_t)ci.out0 * hop + t] = y / env;
+  float* o = pcm + (size_t)ci.out0 * hop + t;
+  if constexpr (V == 4) store4(o, make_float4(y[0] / env[0], y[1] / env[1], y[2] / env[2], y[3] / env[3]));
+  else o[0] = y[0] / env[0];
 }
 
 __global__ void build_row_chunk_kernel(const ChunkInfo* __restrict__ chunks, int n_chunks, int* __restrict__ row_chunk,

@@ -294,6 +294,22 @@ def test_vocoder_bulk_kernels_in_fp32(weights):
     e.close()
 
 
+def test_vocoder_pcm_pointer_alignment(weights):
+    """The overlap-add writes four samples per thread into a 16-byte aligned PCM buffer and one per thread otherwise: same bits."""
+    from llmvox_b200.engine import Engine
+    e = Engine(weights, device=0, precision="bf16", max_sessions=2, max_context=32, max_vocode_frames=512)
+    g = torch.Generator().manual_seed(8)
+    lens = [1, 10, 33, 160]
+    cu = np.concatenate([[0], np.cumsum(lens)]).tolist()
+    codes = torch.randint(0, 4096, (cu[-1],), generator=g).to("cuda", torch.int32)
+    buf = torch.zeros((cu[-1] * 320 + 4,), dtype=torch.float32, device="cuda")
+    aligned = e.vocode(codes, cu, out=buf[: cu[-1] * 320]).clone()
+    shifted = e.vocode(codes, cu, out=buf[1: 1 + cu[-1] * 320])
+    assert shifted.data_ptr() % 16 == 4
+    assert torch.equal(aligned, shifted)
+    e.close()
+
+
 def test_vocoder_groups_split_transparently(weights):
     """More frames than max_vocode_frames: the call is cut into launch groups without changing results."""
     from llmvox_b200.engine import Engine

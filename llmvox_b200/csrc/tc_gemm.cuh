@@ -1017,7 +1017,8 @@ __global__ void __launch_bounds__(TCP_THREADS, 1) tc_gemm_persistent_kernel(cons
       const unsigned vmask = tc_row_mask(p, x0 + drow);
       for (int c = c_lo; c < c_hi; c += 16) {
         if (y0 + c >= p.N) break;   // warp-uniform: columns past N (last N tile)
-        // (issuing the NEXT chunk's TMEM load before processing this one: 160 registers, 8 % slower -- measured)
+        // (issuing the NEXT chunk's TMEM load before processing this one: 160 registers, 8 % slower -- measured;
+        //  12 epilogue warps, three per lane quarter with 96 / 96 / 64 columns: pw1 2.88 ms against 2.85 with 8 -- no gain)
         if (sizeof(TC) == 2 && coalesced && !p.residual && y0 + c + 32 <= p.N) {   // warp-uniform: 32 columns per step
           tc_epilogue_pair_bf16_dispatch(p, x0 + q * 32, lane, y0 + c, trow + (uint32_t)c, scratch, vmask);
           c += 16;

@@ -1069,6 +1069,7 @@ static int gpt_body(lvx_engine* e, lvx_engine::Lane& ln, int n, const int* pos_o
     LVX_TRY(run_layernorm<768>(e, ln.x, n, L.ln1_w, L.ln1_b, 1e-5f, nullptr, ln.h, st, pdl));
     GemmParams p;
     p.A = ln.h; p.C = ln.qkv; p.M = n; p.lda = C; p.ldc = 3 * C; p.bias = L.attn_b; p.cta_budget = budget; p.pdl = pdl;
+    if (e->prof_detail) p.tag = "tc_gemm:dec_qkv";
     LVX_TRY(run_gemm(e, p, L.attn, a, F32, st));
     dim3 grid(n, c.n_head);
     {
@@ -1085,13 +1086,16 @@ static int gpt_body(lvx_engine* e, lvx_engine::Lane& ln, int n, const int* pos_o
     }
     GemmParams q;
     q.A = ln.y; q.C = ln.x; q.M = n; q.lda = C; q.ldc = C; q.bias = L.proj_b; q.residual = ln.x; q.ldr = C; q.cta_budget = budget; q.pdl = pdl;
+    if (e->prof_detail) q.tag = "tc_gemm:dec_proj";
     LVX_TRY(run_gemm(e, q, L.proj, a, F32, st));
     LVX_TRY(run_layernorm<768>(e, ln.x, n, L.ln2_w, L.ln2_b, 1e-5f, nullptr, ln.h, st, pdl));
     GemmParams f;
     f.A = ln.h; f.C = ln.g; f.M = n; f.lda = C; f.ldc = 4 * C; f.bias = L.fc_b; f.act = ACT_GELU_TANH; f.cta_budget = budget; f.pdl = pdl;
+    if (e->prof_detail) f.tag = "tc_gemm:dec_fc";
     LVX_TRY(run_gemm(e, f, L.fc, a, a, st));
     GemmParams r;
     r.A = ln.g; r.C = ln.x; r.M = n; r.lda = 4 * C; r.ldc = C; r.bias = L.proj2_b; r.residual = ln.x; r.ldr = C; r.cta_budget = budget; r.pdl = pdl;
+    if (e->prof_detail) r.tag = "tc_gemm:dec_proj2";
     LVX_TRY(run_gemm(e, r, L.proj2, a, F32, st));
   }
   LVX_TRY(run_layernorm<768>(e, ln.x, n, e->lnf_w, e->lnf_b, 1e-5f, nullptr, ln.h, st, pdl));

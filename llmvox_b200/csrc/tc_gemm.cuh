@@ -1099,9 +1099,12 @@ inline TcPlan tc_plan(const TcWorkspace* ws, const GemmParams& p) {
   const int tiles = gx * gy;
   const int all_sms = ws->num_sms > 0 ? ws->num_sms : 148;
   const int sms = p.cta_budget > 0 ? std::min(p.cta_budget, all_sms) : all_sms;
-  // few tiles: split K across a cluster so that about 1.5 CTAs per SM pull operands concurrently
+  // few tiles: split K across a cluster so that about 1.5 CTAs per SM pull operands concurrently.  Swap mode only (M <= 256,
+  // where the weights are the whole traffic): in normal mode the DSMEM reduction and the cluster barriers cost more than
+  // the extra CTAs bring -- measured on the kernel-per-op decode chain at T = 300: 288 sessions 675 -> 500 us per
+  // iteration, 512: 820 -> 680, 2048: 2011 -> 1926 (proj 31 -> 17 us, proj2 38 -> 30 us per launch); vocoder 64 x 10 frames 1.18 -> 1.07 ms
   int S = 1;
-  while (S < 8 && tiles * (S * 2) <= sms + sms / 2 && num_kb >= S * 2 && (pl.BN / (S * 2)) % 4 == 0 && pl.BN / (S * 2) >= 4) S *= 2;
+  while (pl.swap && S < 8 && tiles * (S * 2) <= sms + sms / 2 && num_kb >= S * 2 && (pl.BN / (S * 2)) % 4 == 0 && pl.BN / (S * 2) >= 4) S *= 2;
   pl.splits = S;
   pl.tmem_cols = 32;
   while (pl.tmem_cols < pl.BN) pl.tmem_cols *= 2;

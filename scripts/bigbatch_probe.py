@@ -7,7 +7,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from llmvox_b200 import weights as W
+from llmvox_b200 import _lib, weights as W
 from llmvox_b200.engine import Engine
 
 N = int(os.environ.get("PROBE_N", "2048"))
@@ -20,16 +20,17 @@ rng = np.random.RandomState(0)
 slots = list(range(N))
 e.open(slots)
 e.feed_text(slots, [rng.randint(3, 259, size=50).tolist() for _ in slots])
-e.decode_steps(slots, T0)
+PATH = {'per_op': _lib.PATH_PER_OP, 'cluster': _lib.PATH_CLUSTER, 'auto': _lib.PATH_AUTO}[os.environ.get('PROBE_PATH', 'per_op')]
+e.decode_steps(slots, T0, path=PATH)
 torch.cuda.synchronize()
 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 a.record()
-e.decode_steps(slots, STEPS)
+e.decode_steps(slots, STEPS, path=PATH)
 b.record()
 torch.cuda.synchronize()
 print(f"n={N} T={T0}..{T0 + STEPS}: {1e3 * a.elapsed_time(b) / STEPS:.1f} us / iteration (graphs + PDL)")
-e.profile(True)
-e.decode_steps(slots, STEPS)
+e.profile(2 if os.environ.get('PROBE_DETAIL') else True)
+e.decode_steps(slots, STEPS, path=PATH)
 rep = e.profile_report()
 e.profile(False)
 tot = sum(v["ms"] for v in rep.values())

@@ -1040,7 +1040,7 @@ extern "C" int lvx_feed_utf8(lvx_engine* e, const int32_t* h_slots, const int32_
   LVX_TRY(upload_slots(e, h_slots, n, st));
   LVX_CUDA(cudaMemcpyAsync(e->d_aux, h_offsets, (n + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
   if (total) LVX_CUDA(cudaMemcpyAsync(e->tx_bytes, h_bytes, total, cudaMemcpyHostToDevice, st));
-  text_frontend_kernel<<<ceil_div(n, 64), 64, 0, st>>>(e->tx_bytes, e->d_aux, e->d_slots, n, clean, e->tx_scratch, cap, e->st, e->tx_status);
+  text_frontend_kernel<<<ceil_div(n, TX_WARPS), 32 * TX_WARPS, 0, st>>>(e->tx_bytes, e->d_aux, e->d_slots, n, clean, e->tx_scratch, cap, e->st, e->tx_status);
   LAUNCHED(e);
   LVX_CUDA(cudaMemcpyAsync(h_counts, e->tx_status, n * sizeof(int), cudaMemcpyDeviceToHost, st));
   LVX_CUDA(cudaStreamSynchronize(st));

@@ -4,8 +4,9 @@
 // UTF-8 bytes straight into the sessions' device-side text ids -- one H2D copy and one launch for a batch of sentences
 // instead of host regexes and a Python list of ids per sentence.
 //
-// clean_text is a chain of 13 rewrite passes; every pass is a left-to-right scan, so ONE thread runs a sentence through
-// them between two scratch buffers (sentences are a few hundred bytes; all sentences of a batch run in parallel).  The
+// clean_text is a chain of 13 rewrite passes; every pass is a left-to-right scan, so ONE thread (lane 0 of the sentence's warp)
+// runs a sentence through them between two scratch buffers (sentences are a few hundred bytes; all sentences of a batch run in
+// parallel).  The
 // character classes are Python's: `\s` / str.strip = str.isspace (29 code points), `\d` = Unicode category Nd (64 runs of
 // ten digits, Unicode 15); bytes are decoded as UTF-8 where a class is tested.  tests/test_gpu_text.py compares the ids
 // with the host pipeline (protocol.clean_text + tokenizer.sentence_ids, themselves pinned to the reference's fixtures).
@@ -180,17 +181,38 @@ __device__ inline int tx_clean(const uint8_t* s, int n, uint8_t* a, uint8_t* b, 
   return n;
 }
 
-// One thread per sentence: [clean_text,] split at ' ', strip every word, tokenise ("[PAD]" -> 384 and "EOS" -> 385 as literal
+// One sentence per warp: [clean_text,] split at ' ', strip every word, tokenise ("[PAD]" -> 384 and "EOS" -> 385 as literal
 // substrings, else utf-8 byte + 3), </s> after every word, 385 after the last; ids to the slot's text buffer.
 // status[i]: number of ids written, or -1 (scratch overflow) / -2 (more ids than max_context).
-__global__ void text_frontend_kernel(const uint8_t* __restrict__ bytes, const int* __restrict__ offs, const int* __restrict__ slots, int n,
-                                     int clean, uint8_t* __restrict__ scratch, int cap, SessionState st, int* __restrict__ status) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// The rewrite passes read what the previous pass wrote, byte by byte: between two GLOBAL scratch buffers every such read is an
+// L1 miss, and threads of a warp working on different sentences diverge at every byte.  So a sentence gets a WARP: its lanes copy
+// the raw bytes into shared memory together, then lane 0 runs the passes between the warp's two shared-memory buffers (2 x TX_SCAP
+// bytes) and tokenises; only a sentence that outgrows them is redone in the global buffers.
+constexpr int TX_WARPS = 4;
+constexpr int TX_SCAP = 1024;
+__global__ void __launch_bounds__(32 * TX_WARPS) text_frontend_kernel(const uint8_t* __restrict__ bytes, const int* __restrict__ offs,
+                                                                      const int* __restrict__ slots, int n, int clean,
+                                                                      uint8_t* __restrict__ scratch, int cap, SessionState st,
+                                                                      int* __restrict__ status) {
+  __shared__ __align__(16) uint8_t tx_sm[TX_WARPS * 2 * TX_SCAP];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * TX_WARPS + warp;
   if (i >= n) return;
   const uint8_t* s = bytes + offs[i];
   int len = offs[i + 1] - offs[i];
+  uint8_t* sa = tx_sm + warp * (2 * TX_SCAP);
+  uint8_t* sb = sa + TX_SCAP;
+  const uint8_t* raw = s;
+  if (len <= TX_SCAP) {
+    for (int k = lane; k < len; k += 32) sb[k] = raw[k];
+    __syncwarp();
+    s = sb;
+  }
+  if (lane != 0) return;
   if (clean) {
-    len = tx_clean(s, len, scratch + (size_t)(2 * i) * cap, scratch + (size_t)(2 * i + 1) * cap, cap, &s);
+    const int raw_len = len;
+    len = raw_len <= TX_SCAP ? tx_clean(sb, raw_len, sa, sb, TX_SCAP, &s) : -1;   // pass 1 reads sb and writes sa; sb is free from pass 2 on
+    if (len < 0) len = tx_clean(raw, raw_len, scratch + (size_t)(2 * i) * cap, scratch + (size_t)(2 * i + 1) * cap, cap, &s);
     if (len < 0) { status[i] = -1; return; }
   }
   const int slot = slots[i];

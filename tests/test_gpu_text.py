@@ -131,3 +131,20 @@ def test_feed_sentences_capacity_errors(engine):
     e.feed_sentences([0], ["ok."])
     assert len(e.session_text(0)) == 5
     e.release([0])
+
+
+@pytest.mark.gpu
+def test_long_rewrites_fall_back_to_the_global_scratch():
+    """Sentences whose rewritten form outgrows the per-thread shared-memory scratch (1024 bytes) are redone in global memory."""
+    import torch
+    from llmvox_b200 import weights as W
+    from llmvox_b200.engine import Engine
+    e = Engine(W.make_random_weights(7, wpe_rows=4096), device=0, precision="bf16", max_sessions=8, max_context=4096, max_vocode_frames=256)
+    sents = ["&" * 300, "\\a" * 250, "x" * 1023 + ".", "y" * 1025, "#7, " * 150, "short one.", "", "a-b " * 400]
+    slots = list(range(len(sents)))
+    e.open(slots)
+    counts = e.feed_sentences(slots, sents)
+    for s_, slot, cnt in zip(sents, slots, counts):
+        want = _expect(s_, True)
+        assert cnt == len(want) and e.session_text(slot) == want, repr(s_[:20])
+    e.close()

@@ -29,8 +29,8 @@ def _nd_runs():
 def test_digit_and_space_tables_are_pythons():
     """The kernel's \\d table = this interpreter's Unicode category Nd; its \\s predicate = str.isspace."""
     src = open(os.path.join(ROOT, "llmvox_b200", "csrc", "text_kernels.cuh")).read()
-    body = src[src.index("tx_digit_runs[64]"):]
-    body = body[: body.index("};")]
+    body = src[src.index("#define TX_DIGIT_RUNS"):]
+    body = body[: body.index("\n")]
     table = [(int(a, 16), int(b, 16)) for a, b in re.findall(r"\{0x([0-9A-Fa-f]+), 0x([0-9A-Fa-f]+)\}", body)]
     assert table == _nd_runs()
     spaces = [c for c in range(0x110000) if chr(c).isspace()]

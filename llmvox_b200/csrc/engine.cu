@@ -1023,7 +1023,7 @@ extern "C" int lvx_feed_utf8(lvx_engine* e, const int32_t* h_slots, const int32_
   LVX_TRY(check_slots(e, h_slots, n, true));
   LVX_CHECK(h_offsets && h_bytes && h_counts, LVX_ERR_INVALID, "NULL argument");
   LVX_CHECK(h_offsets[0] == 0, LVX_ERR_INVALID, "offsets must start at 0");
-  const int S = e->cfg.max_sessions, ctx = e->cfg.max_context;
+  const int S = e->cfg.max_batch, ctx = e->cfg.max_context;   // a call holds at most max_batch sentences (check_slots)
   for (int i = 0; i < n; ++i) {
     const int cnt = h_offsets[i + 1] - h_offsets[i];
     LVX_CHECK(cnt >= 0, LVX_ERR_INVALID, "offsets must be non-decreasing");

@@ -1910,6 +1910,7 @@ static int vocode_group(lvx_engine* e, const VocGroup& g, const int32_t* d_codes
     LVX_TRY(run_gemm(e, p, e->head, a, F32, st));
     {
       PROF(e, "head_act_split3", st);
+      LVX_CHECK(16 * e->spec_ld * sizeof(bf16) <= 48 * 1024, LVX_ERR_CAPACITY, "n_fft too large for the head operand builder's shared-memory rows");
       head_act_split3_kernel<<<ceil_div(g.R, 8), 256, 16 * e->spec_ld * sizeof(bf16), st>>>(e->v_raw, e->raw_ld, g.R, e->row_chunk, bins, (bf16*)e->v_spec,
                                                                               e->spec_ld);
       LAUNCHED(e);
